@@ -1,0 +1,160 @@
+/*
+ * qmpc.h — C-ABI of the batched B200 quaternion-MPC solver.
+ *
+ * Drop-in boundary for the GRF solve of zixinz990/quaternion-mpc's legged_ctrl package:
+ *   legged::LeggedMpc::grf_update(LeggedState&)      legged_ctrl/include/mpc/LeggedMpc.h:26
+ *     QuatMpc::grf_update                            legged_ctrl/src/mpc/QuatMpc.cpp:109-276
+ *     ConvexMpc::grf_update                          legged_ctrl/src/mpc/ConvexMpc.cpp:81-198
+ * The structs below carry exactly the LeggedState fields those two functions read and write
+ * (file:line next to every field).  Everything is plain C: fixed-width types, caller-owned
+ * buffers, no exceptions, int return codes (0 = ok, <0 = error), per-problem `status`.
+ *
+ * One handle = one CUDA device + one solver configuration + all workspace (allocated once in
+ * qmpc_create, nothing is allocated per call).  Calls on one handle are not concurrent; use one
+ * handle per calling thread / stream.  There is NO CPU fallback: if the CUDA device or kernel
+ * image is unavailable the calls fail with QMPC_ERR_CUDA.
+ */
+#ifndef QMPC_H_
+#define QMPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMPC_ABI_VERSION 1
+
+/* ---- models ------------------------------------------------------------- */
+#define QMPC_MODEL_QUAT_4FOOT   0 /* QuatMpc: 13-state quaternion SRB, 4 feet, 24 cone rows
+                                     (AltroUtils.cpp:363-439, QuatMpc.cpp:109-276) */
+#define QMPC_MODEL_QUAT_2FOOT   1 /* 2-contact quaternion SRB, m=6, 12 cone rows
+                                     (AltroUtils.cpp:441-513, TestAltroTrotQuatMpc.cpp) */
+#define QMPC_MODEL_EULER_CONVEX 2 /* ConvexMpc: 12-state Euler SRB, LQR cost
+                                     (AltroUtils.cpp:224-359, ConvexMpc.cpp:81-198) */
+
+#define QMPC_MAX_HORIZON 32
+
+/* ---- return codes ----------------------------------------------------------------------------- */
+#define QMPC_OK            0
+#define QMPC_ERR_ARG      -1 /* null pointer, bad model / horizon / batch */
+#define QMPC_ERR_CUDA     -2 /* CUDA runtime error (no device, launch failure, ...) */
+#define QMPC_ERR_CAPACITY -3 /* batch larger than the handle's max_batch */
+
+/* ---- per-problem solve status (ALTRO's SolveStatus is discarded by the reference,
+ *      QuatMpc.cpp:256; we report it) ------------------------------------------------------------ */
+#define QMPC_STATUS_SUCCESS            0 /* stationarity and feasibility tolerances met */
+#define QMPC_STATUS_MAX_ITERATIONS     1 /* stopped at iterations_max (the usual case with active cones) */
+#define QMPC_STATUS_LINESEARCH_FAILED  2 /* no step length satisfied the Armijo test; last iterate returned */
+#define QMPC_STATUS_BACKWARD_FAILED    3 /* Quu not positive definite; last iterate returned */
+#define QMPC_STATUS_NONFINITE          4 /* NaN/Inf in the inputs or the initial rollout */
+
+/* Solver + robot configuration, constant over a batch.  Defaults: qmpc_default_config(). */
+typedef struct QmpcConfig {
+  int32_t model;             /* QMPC_MODEL_*                                                     */
+  int32_t horizon;           /* N = state.param.mpc_horizon                    QuatMpc.cpp:35      */
+  double  dt;                /* seconds = mpc_update_period/1000; rounded to float32 inside, as
+                                ALTRO passes `float h`                          QuatMpc.cpp:224,
+                                                                                AltroUtils.cpp:10   */
+  double  q_weights[13];     /* state.param.q_weights (12 used by EULER_CONVEX) QuatMpc.cpp:227     */
+  double  r_weights[12];     /* state.param.r_weights                                              */
+  double  w;                 /* quaternion (geodesic) weight state.param.w                         */
+  double  mu;                /* friction coefficient                            QuatMpc.cpp:37      */
+  double  fz_max;            /*                                                 QuatMpc.cpp:38      */
+  double  robot_mass;        /* state.param.robot_mass                          QuatMpc.cpp:122,185 */
+  double  inertia[9];        /* row-major body inertia ACTUALLY used by the dynamics, i.e.
+                                1.2 * trunk_inertia for QuatMpc                 QuatMpc.cpp:182     */
+  double  com_offset[3];     /* body_com (0.0223, 0.002, -0.0005)               AltroUtils.cpp:373  */
+  double  com_mass;          /* 5.204                                           AltroUtils.cpp:374  */
+  double  gravity;           /* 9.81                                                               */
+  double  quat_d_dt;         /* desired-attitude integration step, fixed 5 ms   QuatMpc.cpp:132     */
+  /* AltroOptions in force (QuatMpc.cpp:21-26, ConvexMpc.cpp:36-38; rest = library defaults) */
+  int32_t iterations_max;    /* 10 (QuatMpc) / 5 (ConvexMpc)                                       */
+  int32_t drop_omega0;       /* 1 = reproduce the reference's x_init quirk: measured angular
+                                velocity is NOT put into x0                     QuatMpc.cpp:232-245 */
+  double  penalty_initial;   /* 1.0                                                                */
+  double  penalty_scaling;   /* 20.0 (QuatMpc) / 10.0 (ConvexMpc)                                  */
+  double  penalty_max;       /* 1e8                                                                */
+  double  tol_cost_intermediate;   /* 1e-4 */
+  double  tol_primal_feasibility;  /* 1e-4 */
+  double  tol_stationarity;        /* 1e-4 */
+} QmpcConfig;
+
+/* One QuatMpc solve: the LeggedState fields QuatMpc::grf_update reads (QUAT_4FOOT / QUAT_2FOOT). */
+typedef struct QmpcProblem {
+  double  torso_quat[4];           /* fbk.torso_quat (w,x,y,z)                  QuatMpc.cpp:236-239 */
+  double  torso_lin_vel_world[3];  /* fbk.torso_lin_vel_world                   QuatMpc.cpp:231     */
+  double  torso_ang_vel_body[3];   /* fbk.torso_ang_vel_body (unused if drop_omega0) :243-245       */
+  double  foot_pos_body[12];       /* fbk.foot_pos_body, 3x4 column-major FL,FR,RL,RR  :185
+                                      (QUAT_2FOOT uses the first two columns)                       */
+  double  torso_pos_d_body[3];     /* filtered desired position offset          QuatMpc.cpp:156-158 */
+  double  torso_lin_vel_d_body[3]; /* filtered desired velocity                 QuatMpc.cpp:156-169 */
+  double  torso_quat_d[4];         /* ctrl.torso_quat_d BEFORE this tick's integration  :128-131    */
+  double  torso_ang_vel_d_body[3]; /* ctrl.torso_ang_vel_d_body                 QuatMpc.cpp:132     */
+  int32_t plan_contacts[4];        /* ctrl.plan_contacts (0/1)                  QuatMpc.cpp:119     */
+} QmpcProblem;
+
+/* One ConvexMpc solve: the fields ConvexMpc::grf_update reads (EULER_CONVEX). */
+typedef struct QmpcConvexProblem {
+  double  torso_euler[3];          /* fbk.torso_euler                           ConvexMpc.cpp:156   */
+  double  torso_pos_world[3];      /* fbk.torso_pos_world                       ConvexMpc.cpp:159   */
+  double  torso_ang_vel_world[3];  /* fbk.torso_ang_vel_world                   ConvexMpc.cpp:162   */
+  double  torso_lin_vel_world[3];  /* fbk.torso_lin_vel_world                   ConvexMpc.cpp:165   */
+  double  foot_pos_abs_com[12];    /* fbk.foot_pos_abs_com 3x4 column-major     ConvexMpc.cpp:117   */
+  double  torso_rot_mat[9];        /* fbk.torso_rot_mat row-major (output map)  ConvexMpc.cpp:191   */
+  double  torso_pos_d_world[3];    /* ctrl.torso_pos_d_world                    ConvexMpc.cpp:99-101 */
+  double  torso_lin_vel_d_world[3];/* ctrl.torso_lin_vel_d_world                ConvexMpc.cpp:105   */
+  double  yaw_rate_d;              /* ctrl.torso_ang_vel_d_body[2]              ConvexMpc.cpp:98    */
+  int32_t plan_contacts[4];        /* ctrl.plan_contacts                        ConvexMpc.cpp:91    */
+  int32_t pad_[2];
+} QmpcConvexProblem;
+
+/* What grf_update writes back. */
+typedef struct QmpcResult {
+  double  grf_body[12];      /* ctrl.optimized_input[0:12]   QuatMpc.cpp:269 / ConvexMpc.cpp:191  */
+  double  grf_world[12];     /* ctrl.mpc_grf_world           QuatMpc.cpp:268                      */
+  double  torso_quat_d[4];   /* ctrl.torso_quat_d after the 5 ms integration, QuatMpc.cpp:133-137
+                                (unchanged identity for EULER_CONVEX)                             */
+  double  max_violation;     /* max_k max(0, c) of the cone rows at the returned iterate          */
+  int32_t iterations;        /* AL-iLQR iterations executed                                       */
+  int32_t status;            /* QMPC_STATUS_*                                                     */
+} QmpcResult;
+
+typedef struct QmpcHandle QmpcHandle;
+
+/* Fill cfg with the shipped Go1 values: legged_ctrl/config/gazebo_go1_quat_mpc.yaml:35-75,115-122
+ * and QuatMpc.cpp:21-26 for QUAT_*;  gazebo_go1_convex_mpc.yaml + ConvexMpc.cpp:36-38 for
+ * EULER_CONVEX.  `horizon` <= QMPC_MAX_HORIZON. */
+int qmpc_default_config(int32_t model, int32_t horizon, QmpcConfig* cfg);
+
+/* Create a solver on CUDA device `device` able to solve up to `max_batch` problems per call.
+ * Replaces: QuatMpc::QuatMpc (QuatMpc.cpp:8-55) + the per-call `ALTROSolver solver(horizon)`
+ * construction (QuatMpc.cpp:218-229). */
+int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t device, QmpcHandle** out);
+
+/* Solve `batch` independent problems.  `d_in` / `d_out` are DEVICE pointers; the launch is
+ * enqueued on `cuda_stream` (a cudaStream_t, may be NULL = default stream) and the call returns
+ * without synchronising.  Replaces the body of QuatMpc::grf_update (QuatMpc.cpp:109-276). */
+int qmpc_solve_batch(QmpcHandle* h, const QmpcProblem* d_in, int32_t batch, QmpcResult* d_out,
+                     void* cuda_stream);
+int qmpc_solve_batch_convex(QmpcHandle* h, const QmpcConvexProblem* d_in, int32_t batch,
+                            QmpcResult* d_out, void* cuda_stream);
+
+/* Same with HOST buffers: H2D copy, solve, D2H copy, synchronise.  This is the call the
+ * CudaQuatMpc shim makes with batch = 1 from the 200 Hz mpc_thread (Main.cpp:88-120). */
+int qmpc_solve_batch_host(QmpcHandle* h, const QmpcProblem* in, int32_t batch, QmpcResult* out);
+int qmpc_solve_batch_convex_host(QmpcHandle* h, const QmpcConvexProblem* in, int32_t batch,
+                                 QmpcResult* out);
+
+void qmpc_destroy(QmpcHandle* h);
+
+/* Introspection: number of kernel launches issued by this handle so far; last CUDA error text. */
+int64_t     qmpc_launch_count(const QmpcHandle* h);
+const char* qmpc_last_error(const QmpcHandle* h);
+const char* qmpc_status_string(int32_t status);
+int32_t     qmpc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMPC_H_ */

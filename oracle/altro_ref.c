@@ -1,0 +1,524 @@
+/*
+ * altro_ref.c — fp64 CPU restatement of the AL-iLQR solve (see altro_ref.h for provenance).
+ * TEST INFRASTRUCTURE ONLY.
+ *
+ * One solve (mirrors oracle/altro_np.py line by line; the two are cross-checked in tests/):
+ *   open-loop rollout of the input guess from x0 (the SetState guesses are overwritten, as in
+ *   ALTRO's Solve()); merit phi = cost + augmented-Lagrangian terms
+ *   for it = 0 .. iterations_max-1
+ *     expansions at (X,U): error-state A_k = E(x+)^T A E(x), B_k = E(x+)^T B
+ *                          (convention: legged_ctrl/src/utils/AltroUtils.cpp:153-168),
+ *                          cost gradient/Hessian (quaternion geodesic term w(1-|qref.q|)),
+ *                          AL gradient + Gauss-Newton Hessian of the constraint block
+ *     it>0: stationarity = inf-norm residual of the KKT stationarity conditions evaluated with
+ *           the Riccati duals y_k = P_k dx_k + p_k of the accepted step;
+ *           converged if stationarity < tol and max violation < tol;
+ *           else if |cost decrease| < tol_cost_intermediate or stationarity < tol:
+ *                dual update  mu <- max(0, mu + rho c) (ineq) / mu + rho c (eq),
+ *                penalty rho <- min(rho * penalty_scaling, penalty_max)
+ *     Riccati backward pass, plain Cholesky of Quu (no regularisation)
+ *     forward pass: closed-loop rollout u = ubar + alpha d + K dx, dx in error coordinates
+ *                   (Cayley map, QuaternionUtils.cpp:10-18), back-tracking line search
+ *                   alpha = 1, 1/2, ... (<= ls_iters_max trials), Armijo c1 on the AL merit
+ */
+#include "altro_ref.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+void altro_ref_default_options(AltroRefOptions* o) {
+  o->iterations_max = 200;
+  o->tol_cost_intermediate = 1e-4;
+  o->tol_primal_feasibility = 1e-4;
+  o->tol_stationarity = 1e-4;
+  o->penalty_initial = 1.0;
+  o->penalty_scaling = 10.0;
+  o->penalty_max = 1e8;
+  o->use_quaternion = 0;
+  o->quat_start_index = 0;
+  o->ls_c1 = 1e-4;
+  o->ls_decrease = 0.5;
+  o->ls_iters_max = 25;
+}
+
+/* ------------------------------------------------------------------ small dense helpers (row-major) */
+/* C(r x c) = A(r x k) * B(k x c) */
+static void mm(double* C, const double* A, const double* B, int r, int k, int c) {
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < c; ++j) {
+      double s = 0;
+      for (int l = 0; l < k; ++l) s += A[i * k + l] * B[l * c + j];
+      C[i * c + j] = s;
+    }
+}
+/* C(r x c) = A(k x r)^T * B(k x c) */
+static void mtm(double* C, const double* A, const double* B, int k, int r, int c) {
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < c; ++j) {
+      double s = 0;
+      for (int l = 0; l < k; ++l) s += A[l * r + i] * B[l * c + j];
+      C[i * c + j] = s;
+    }
+}
+/* y(r) = A(k x r)^T x(k) */
+static void mtv(double* y, const double* A, const double* x, int k, int r) {
+  for (int i = 0; i < r; ++i) {
+    double s = 0;
+    for (int l = 0; l < k; ++l) s += A[l * r + i] * x[l];
+    y[i] = s;
+  }
+}
+static void mv(double* y, const double* A, const double* x, int r, int c) {
+  for (int i = 0; i < r; ++i) {
+    double s = 0;
+    for (int l = 0; l < c; ++l) s += A[i * c + l] * x[l];
+    y[i] = s;
+  }
+}
+static double dot(const double* a, const double* b, int n) {
+  double s = 0;
+  for (int i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+/* in-place lower Cholesky of the m x m row-major SPD matrix; returns 0 on success */
+static int chol(double* A, int m) {
+  for (int j = 0; j < m; ++j) {
+    double s = A[j * m + j];
+    for (int l = 0; l < j; ++l) s -= A[j * m + l] * A[j * m + l];
+    if (!(s > 0.0)) return 1;
+    double d = sqrt(s);
+    A[j * m + j] = d;
+    for (int i = j + 1; i < m; ++i) {
+      double t = A[i * m + j];
+      for (int l = 0; l < j; ++l) t -= A[i * m + l] * A[j * m + l];
+      A[i * m + j] = t / d;
+    }
+  }
+  return 0;
+}
+/* solve L L^T X = Bm for nrhs columns, Bm is m x nrhs row-major, in place */
+static void chol_solve(const double* L, double* Bm, int m, int nrhs) {
+  for (int c = 0; c < nrhs; ++c) {
+    for (int i = 0; i < m; ++i) {
+      double t = Bm[i * nrhs + c];
+      for (int l = 0; l < i; ++l) t -= L[i * m + l] * Bm[l * nrhs + c];
+      Bm[i * nrhs + c] = t / L[i * m + i];
+    }
+    for (int i = m - 1; i >= 0; --i) {
+      double t = Bm[i * nrhs + c];
+      for (int l = i + 1; l < m; ++l) t -= L[l * m + i] * Bm[l * nrhs + c];
+      Bm[i * nrhs + c] = t / L[i * m + i];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ quaternion error state */
+/* G(q) = L(q) H, 4x3 row-major (QuaternionUtils.cpp:30-52) */
+static void quat_G(const double* q, double* G) {
+  G[0] = -q[1]; G[1] = -q[2]; G[2] = -q[3];
+  G[3] = q[0];  G[4] = -q[3]; G[5] = q[2];
+  G[6] = q[3];  G[7] = q[0];  G[8] = -q[1];
+  G[9] = -q[2]; G[10] = q[1]; G[11] = q[0];
+}
+/* E(x): n x ne row-major, blkdiag(I, G(q), I) */
+static void err_jac(const double* x, int n, int ne, int qi, double* E) {
+  memset(E, 0, sizeof(double) * n * ne);
+  if (qi < 0) {
+    for (int i = 0; i < n; ++i) E[i * ne + i] = 1.0;
+    return;
+  }
+  for (int i = 0; i < qi; ++i) E[i * ne + i] = 1.0;
+  double G[12];
+  quat_G(x + qi, G);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 3; ++j) E[(qi + i) * ne + qi + j] = G[i * 3 + j];
+  for (int i = qi + 4; i < n; ++i) E[i * ne + i - 1] = 1.0;
+}
+/* dx = x (-) xbar ; attitude part = Cayley vector of conj(qbar) * q */
+static void state_diff(const double* x, const double* xb, int n, int qi, double* dx) {
+  if (qi < 0) {
+    for (int i = 0; i < n; ++i) dx[i] = x[i] - xb[i];
+    return;
+  }
+  for (int i = 0; i < qi; ++i) dx[i] = x[i] - xb[i];
+  const double* q = x + qi;
+  const double* b = xb + qi;
+  double s = b[0] * q[0] + b[1] * q[1] + b[2] * q[2] + b[3] * q[3];
+  /* vector part of L(qbar)^T q */
+  double v0 = -b[1] * q[0] + b[0] * q[1] + b[3] * q[2] - b[2] * q[3];
+  double v1 = -b[2] * q[0] - b[3] * q[1] + b[0] * q[2] + b[1] * q[3];
+  double v2 = -b[3] * q[0] + b[2] * q[1] - b[1] * q[2] + b[0] * q[3];
+  dx[qi] = v0 / s; dx[qi + 1] = v1 / s; dx[qi + 2] = v2 / s;
+  for (int i = qi + 4; i < n; ++i) dx[i - 1] = x[i] - xb[i];
+}
+
+/* ------------------------------------------------------------------ solver workspace */
+typedef struct WS {
+  int N, n, ne, m, pmax, qi;
+  double *A, *B, *lx, *lu, *lxx, *gx, *gu, *Hxx, *Huu, *Hux, *K, *d, *P, *pv, *Y, *mu, *rho;
+  double *Xn, *Un, *cval, *cjac, *E, *En, *J, *tmp;
+} WS;
+
+static double* take(double** cur, size_t cnt) {
+  double* r = *cur;
+  *cur += cnt;
+  return r;
+}
+
+static double stage_cost(const AltroRefProblem* P, int k, const double* x, const double* u, int qi) {
+  int n = P->n, m = P->m;
+  const double *Q = P->Q + k * n, *xr = P->xref + k * n;
+  double J = 0;
+  for (int i = 0; i < n; ++i) { double dxi = x[i] - xr[i]; J += 0.5 * Q[i] * dxi * dxi; }
+  if (k < P->N) {
+    const double *R = P->R + k * m, *ur = P->uref + k * m;
+    for (int i = 0; i < m; ++i) { double dui = u[i] - ur[i]; J += 0.5 * R[i] * dui * dui; }
+  }
+  if (qi >= 0 && P->w[k] != 0.0) {
+    double s = dot(xr + qi, x + qi, 4);
+    J += P->w[k] * (1.0 - fabs(s));
+  }
+  return J;
+}
+
+/* AL merit of a trajectory with the current duals/penalties; also the max violation */
+static double merit(const AltroRefProblem* P, WS* w, const double* X, const double* U, double* viol_out) {
+  int N = P->N, n = P->n, m = P->m;
+  double J = 0, viol = 0;
+  double uz[16] = {0};
+  for (int k = 0; k <= N; ++k) {
+    const double* u = k < N ? U + k * m : uz;
+    J += stage_cost(P, k, X + k * n, u, w->qi);
+    int p = P->p ? P->p[k] : 0;
+    if (p > 0) {
+      P->con(P->ctx, k, w->cval, X + k * n, u);
+      const double* mu = w->mu + k * w->pmax;
+      double r = w->rho[k], acc = 0;
+      for (int i = 0; i < p; ++i) {
+        double c = w->cval[i], est = mu[i] + r * c, lh;
+        if (P->ctype[k] == ALTRO_REF_INEQUALITY) {
+          lh = est > 0 ? est : 0;
+          if (c > viol) viol = c;
+        } else {
+          lh = est;
+          if (fabs(c) > viol) viol = fabs(c);
+        }
+        acc += lh * lh - mu[i] * mu[i];
+      }
+      J += acc / (2 * r);
+    }
+  }
+  *viol_out = viol;
+  return J;
+}
+
+/* AL gradient / Gauss-Newton Hessian terms at (X,U) with current duals */
+static void al_terms(const AltroRefProblem* P, WS* w, const double* X, const double* U) {
+  int N = P->N, n = P->n, m = P->m, ne = w->ne, nz = ne + m;
+  double uz[16] = {0};
+  for (int k = 0; k <= N; ++k) {
+    double *gx = w->gx + k * ne, *gu = w->gu + k * m;
+    double *Hxx = w->Hxx + k * ne * ne, *Huu = w->Huu + k * m * m, *Hux = w->Hux + k * m * ne;
+    memset(gx, 0, sizeof(double) * ne);
+    memset(gu, 0, sizeof(double) * m);
+    memset(Hxx, 0, sizeof(double) * ne * ne);
+    memset(Huu, 0, sizeof(double) * m * m);
+    memset(Hux, 0, sizeof(double) * m * ne);
+    int p = P->p ? P->p[k] : 0;
+    if (p == 0) continue;
+    const double* u = k < N ? U + k * m : uz;
+    P->con(P->ctx, k, w->cval, X + k * n, u);
+    memset(w->cjac, 0, sizeof(double) * p * nz);
+    P->conjac(P->ctx, k, w->cjac, X + k * n, u); /* column-major p x (ne+m) */
+    const double* mu = w->mu + k * w->pmax;
+    double r = w->rho[k];
+    for (int i = 0; i < p; ++i) {
+      double est = mu[i] + r * w->cval[i], lh, wt;
+      if (P->ctype[k] == ALTRO_REF_INEQUALITY) {
+        lh = est > 0 ? est : 0;
+        wt = est > 0 ? r : 0;
+      } else {
+        lh = est;
+        wt = r;
+      }
+      /* row i of the Jacobian: Jc(i, j) = cjac[j*p + i] */
+      for (int a = 0; a < ne; ++a) gx[a] += w->cjac[a * p + i] * lh;
+      for (int a = 0; a < m; ++a) gu[a] += w->cjac[(ne + a) * p + i] * lh;
+      if (wt != 0.0) {
+        for (int a = 0; a < ne; ++a)
+          for (int b = 0; b < ne; ++b) Hxx[a * ne + b] += wt * w->cjac[a * p + i] * w->cjac[b * p + i];
+        for (int a = 0; a < m; ++a) {
+          double ja = wt * w->cjac[(ne + a) * p + i];
+          for (int b = 0; b < m; ++b) Huu[a * m + b] += ja * w->cjac[(ne + b) * p + i];
+          for (int b = 0; b < ne; ++b) Hux[a * ne + b] += ja * w->cjac[b * p + i];
+        }
+      }
+    }
+  }
+}
+
+int altro_ref_solve(const AltroRefProblem* P, const AltroRefOptions* o, double* X, double* U,
+                    AltroRefStats* st) {
+  const int N = P->N, n = P->n, m = P->m;
+  const int qi = o->use_quaternion ? o->quat_start_index : -1;
+  const int ne = qi >= 0 ? n - 1 : n;
+  if (N < 1 || n < 1 || m < 1 || m > 16 || n > 32) return -1;
+  int pmax = 1;
+  if (P->p)
+    for (int k = 0; k <= N; ++k)
+      if (P->p[k] > pmax) pmax = P->p[k];
+  const int nz = ne + m;
+  const float h = P->h;
+
+  size_t per = (size_t)ne * ne * 4 + (size_t)ne * m * 3 + (size_t)m * m + (size_t)ne * 5 + (size_t)m * 3 +
+               pmax + 1 + n + m;
+  size_t total = per * (N + 1) + (size_t)pmax * (nz + 1) + (size_t)n * ne * 2 + (size_t)n * (n + m) +
+                 (size_t)(ne + m + n) * (ne + m + n) * 4 + 1024;
+  double* base = (double*)calloc(total, sizeof(double));
+  if (!base) return -1;
+  double* cur = base;
+  WS w;
+  w.N = N; w.n = n; w.ne = ne; w.m = m; w.pmax = pmax; w.qi = qi;
+  w.A = take(&cur, (size_t)(N + 1) * ne * ne);
+  w.B = take(&cur, (size_t)(N + 1) * ne * m);
+  w.lx = take(&cur, (size_t)(N + 1) * ne);
+  w.lu = take(&cur, (size_t)(N + 1) * m);
+  w.lxx = take(&cur, (size_t)(N + 1) * ne * ne);
+  w.gx = take(&cur, (size_t)(N + 1) * ne);
+  w.gu = take(&cur, (size_t)(N + 1) * m);
+  w.Hxx = take(&cur, (size_t)(N + 1) * ne * ne);
+  w.Huu = take(&cur, (size_t)(N + 1) * m * m);
+  w.Hux = take(&cur, (size_t)(N + 1) * m * ne);
+  w.K = take(&cur, (size_t)(N + 1) * m * ne);
+  w.d = take(&cur, (size_t)(N + 1) * m);
+  w.P = take(&cur, (size_t)(N + 1) * ne * ne);
+  w.pv = take(&cur, (size_t)(N + 1) * ne);
+  w.Y = take(&cur, (size_t)(N + 1) * ne);
+  w.mu = take(&cur, (size_t)(N + 1) * pmax);
+  w.rho = take(&cur, (size_t)(N + 1));
+  w.Xn = take(&cur, (size_t)(N + 1) * n);
+  w.Un = take(&cur, (size_t)(N + 1) * m);
+  w.cval = take(&cur, pmax);
+  w.cjac = take(&cur, (size_t)pmax * nz);
+  w.E = take(&cur, (size_t)n * ne);
+  w.En = take(&cur, (size_t)n * ne);
+  w.J = take(&cur, (size_t)n * (n + m));
+  w.tmp = take(&cur, (size_t)(ne + m + n) * (ne + m + n) * 4);
+
+  for (int k = 0; k <= N; ++k) w.rho[k] = o->penalty_initial;
+
+  /* initial open-loop rollout */
+  memcpy(X, P->x0, sizeof(double) * n);
+  for (int k = 0; k < N; ++k) P->dyn(P->ctx, X + (k + 1) * n, X + k * n, U + k * m, h);
+  double viol = 0;
+  double phi = merit(P, &w, X, U, &viol);
+  int status = ALTRO_REF_MAX_ITERATIONS, iters = 0, trials = 0;
+  double cost_decrease = INFINITY, stat = INFINITY;
+  if (!isfinite(phi)) status = ALTRO_REF_NONFINITE;
+
+  double *T1 = w.tmp, *T2 = T1 + (ne + m + n) * (ne + m + n), *T3 = T2 + (ne + m + n) * (ne + m + n),
+         *T4 = T3 + (ne + m + n) * (ne + m + n);
+
+  for (int it = 0; it < o->iterations_max && status == ALTRO_REF_MAX_ITERATIONS; ++it) {
+    /* ---------------- dynamics + cost expansions in error coordinates */
+    for (int k = 0; k <= N; ++k) {
+      const double* x = X + k * n;
+      const double *Q = P->Q + k * n, *xr = P->xref + k * n;
+      err_jac(x, n, ne, qi, w.E);
+      double g[32];
+      for (int i = 0; i < n; ++i) g[i] = Q[i] * (x[i] - xr[i]);
+      double* H = w.lxx + k * ne * ne;
+      /* H = E^T diag(Q) E */
+      for (int a = 0; a < ne; ++a)
+        for (int b = 0; b < ne; ++b) {
+          double s = 0;
+          for (int i = 0; i < n; ++i) s += w.E[i * ne + a] * Q[i] * w.E[i * ne + b];
+          H[a * ne + b] = s;
+        }
+      if (qi >= 0) {
+        const double *q = x + qi, *qb = xr + qi;
+        if (P->w[k] != 0.0) {
+          double s = dot(qb, q, 4) >= 0 ? 1.0 : -1.0;
+          for (int i = 0; i < 4; ++i) g[qi + i] += -P->w[k] * s * qb[i];
+        }
+        double corr = dot(g + qi, q, 4); /* manifold Hessian correction: -I3 (grad_q . q) */
+        for (int i = 0; i < 3; ++i) H[(qi + i) * ne + qi + i] -= corr;
+      }
+      mtv(w.lx + k * ne, w.E, g, n, ne);
+      if (k < N) {
+        const double *R = P->R + k * m, *ur = P->uref + k * m, *u = U + k * m;
+        for (int i = 0; i < m; ++i) w.lu[k * m + i] = R[i] * (u[i] - ur[i]);
+        memset(w.J, 0, sizeof(double) * n * (n + m));
+        P->jac(P->ctx, w.J, x, u, h); /* column-major n x (n+m) */
+        err_jac(X + (k + 1) * n, n, ne, qi, w.En);
+        /* T1 = Jx (n x n row-major), T2 = Ju (n x m) */
+        for (int i = 0; i < n; ++i) {
+          for (int j = 0; j < n; ++j) T1[i * n + j] = w.J[j * n + i];
+          for (int j = 0; j < m; ++j) T2[i * m + j] = w.J[(n + j) * n + i];
+        }
+        mm(T3, T1, w.E, n, n, ne);                   /* Jx E : n x ne */
+        mtm(w.A + k * ne * ne, w.En, T3, n, ne, ne); /* En^T Jx E */
+        mtm(w.B + k * ne * m, w.En, T2, n, ne, m);   /* En^T Ju */
+      }
+    }
+    al_terms(P, &w, X, U);
+
+    if (it > 0) {
+      /* ---------------- stationarity with the Riccati duals of the accepted step */
+      double rx = 0, ru = 0, t[32];
+      for (int a = 0; a < ne; ++a) {
+        double v = fabs(w.lx[N * ne + a] + w.gx[N * ne + a] - w.Y[N * ne + a]);
+        if (v > rx) rx = v;
+      }
+      for (int k = 0; k < N; ++k) {
+        mtv(t, w.A + k * ne * ne, w.Y + (k + 1) * ne, ne, ne);
+        for (int a = 0; a < ne; ++a) {
+          double v = fabs(w.lx[k * ne + a] + w.gx[k * ne + a] + t[a] - w.Y[k * ne + a]);
+          if (v > rx) rx = v;
+        }
+        mtv(t, w.B + k * ne * m, w.Y + (k + 1) * ne, ne, m);
+        for (int a = 0; a < m; ++a) {
+          double v = fabs(w.lu[k * m + a] + w.gu[k * m + a] + t[a]);
+          if (v > ru) ru = v;
+        }
+      }
+      stat = rx > ru ? rx : ru;
+      if (stat < o->tol_stationarity && viol < o->tol_primal_feasibility) {
+        status = ALTRO_REF_SUCCESS;
+        break;
+      }
+      if (fabs(cost_decrease) < o->tol_cost_intermediate || stat < o->tol_stationarity) {
+        double uz[16] = {0};
+        for (int k = 0; k <= N; ++k) {
+          int p = P->p ? P->p[k] : 0;
+          if (p == 0) continue;
+          P->con(P->ctx, k, w.cval, X + k * n, k < N ? U + k * m : uz);
+          double* mu = w.mu + k * pmax;
+          for (int i = 0; i < p; ++i) {
+            double est = mu[i] + w.rho[k] * w.cval[i];
+            mu[i] = (P->ctype[k] == ALTRO_REF_INEQUALITY) ? (est > 0 ? est : 0) : est;
+          }
+          double r = w.rho[k] * o->penalty_scaling;
+          w.rho[k] = r < o->penalty_max ? r : o->penalty_max;
+        }
+        al_terms(P, &w, X, U);
+        phi = merit(P, &w, X, U, &viol);
+      }
+    }
+
+    /* ---------------- Riccati backward pass */
+    double* Pm = w.P + N * ne * ne;
+    double* pv = w.pv + N * ne;
+    for (int i = 0; i < ne * ne; ++i) Pm[i] = w.lxx[N * ne * ne + i] + w.Hxx[N * ne * ne + i];
+    for (int i = 0; i < ne; ++i) pv[i] = w.lx[N * ne + i] + w.gx[N * ne + i];
+    double dphi0 = 0;
+    int bp_ok = 1;
+    for (int k = N - 1; k >= 0 && bp_ok; --k) {
+      const double *A = w.A + k * ne * ne, *B = w.B + k * ne * m;
+      const double* Pn = w.P + (k + 1) * ne * ne;
+      const double* pn = w.pv + (k + 1) * ne;
+      double Qx[32], Qu[16];
+      double *Qxx = T1, *Quu = T2, *Qux = T3, *PA = T4;
+      double* PB = T4 + ne * ne;
+      double* L = PB + ne * m;
+      double* S = L + m * m; /* m x (ne+1) right-hand sides */
+      mtv(Qx, A, pn, ne, ne);
+      mtv(Qu, B, pn, ne, m);
+      for (int i = 0; i < ne; ++i) Qx[i] += w.lx[k * ne + i] + w.gx[k * ne + i];
+      for (int i = 0; i < m; ++i) Qu[i] += w.lu[k * m + i] + w.gu[k * m + i];
+      mm(PA, Pn, A, ne, ne, ne);
+      mm(PB, Pn, B, ne, ne, m);
+      mtm(Qxx, A, PA, ne, ne, ne);
+      mtm(Quu, B, PB, ne, m, m);
+      mtm(Qux, B, PA, ne, m, ne);
+      for (int i = 0; i < ne * ne; ++i) Qxx[i] += w.lxx[k * ne * ne + i] + w.Hxx[k * ne * ne + i];
+      for (int i = 0; i < m * m; ++i) Quu[i] += w.Huu[k * m * m + i];
+      for (int i = 0; i < m; ++i) Quu[i * m + i] += P->R[k * m + i];
+      for (int i = 0; i < m * ne; ++i) Qux[i] += w.Hux[k * m * ne + i];
+      memcpy(L, Quu, sizeof(double) * m * m);
+      if (chol(L, m)) { bp_ok = 0; break; }
+      for (int i = 0; i < m; ++i) {
+        for (int j = 0; j < ne; ++j) S[i * (ne + 1) + j] = Qux[i * ne + j];
+        S[i * (ne + 1) + ne] = Qu[i];
+      }
+      chol_solve(L, S, m, ne + 1);
+      double *K = w.K + k * m * ne, *d = w.d + k * m;
+      for (int i = 0; i < m; ++i) {
+        for (int j = 0; j < ne; ++j) K[i * ne + j] = -S[i * (ne + 1) + j];
+        d[i] = -S[i * (ne + 1) + ne];
+      }
+      /* P = Qxx + K^T Quu K + K^T Qux + Qux^T K ; p = Qx + K^T Quu d + K^T Qu + Qux^T d */
+      double* QuuK = PA; /* m x ne, reuse */
+      mm(QuuK, Quu, K, m, m, ne);
+      double* Pk = w.P + k * ne * ne;
+      for (int a = 0; a < ne; ++a)
+        for (int b = 0; b < ne; ++b) {
+          double s = Qxx[a * ne + b];
+          for (int i = 0; i < m; ++i)
+            s += K[i * ne + a] * QuuK[i * ne + b] + K[i * ne + a] * Qux[i * ne + b] +
+                 Qux[i * ne + a] * K[i * ne + b];
+          Pk[a * ne + b] = s;
+        }
+      for (int a = 0; a < ne; ++a)
+        for (int b = a + 1; b < ne; ++b) {
+          double s = 0.5 * (Pk[a * ne + b] + Pk[b * ne + a]);
+          Pk[a * ne + b] = s;
+          Pk[b * ne + a] = s;
+        }
+      double Quud[16];
+      mv(Quud, Quu, d, m, m);
+      double* pk = w.pv + k * ne;
+      for (int a = 0; a < ne; ++a) {
+        double s = Qx[a];
+        for (int i = 0; i < m; ++i) s += K[i * ne + a] * (Quud[i] + Qu[i]) + Qux[i * ne + a] * d[i];
+        pk[a] = s;
+      }
+      dphi0 += dot(Qu, d, m);
+    }
+    if (!bp_ok) { status = ALTRO_REF_BACKWARD_FAILED; break; }
+
+    /* ---------------- forward pass with back-tracking line search */
+    double alpha = 1.0, phin = 0, violn = 0;
+    int accepted = 0;
+    for (int ls = 0; ls < o->ls_iters_max; ++ls) {
+      ++trials;
+      memcpy(w.Xn, P->x0, sizeof(double) * n);
+      for (int k = 0; k < N; ++k) {
+        double dx[32];
+        state_diff(w.Xn + k * n, X + k * n, n, qi, dx);
+        const double *K = w.K + k * m * ne, *d = w.d + k * m;
+        for (int i = 0; i < m; ++i) w.Un[k * m + i] = U[k * m + i] + alpha * d[i] + dot(K + i * ne, dx, ne);
+        P->dyn(P->ctx, w.Xn + (k + 1) * n, w.Xn + k * n, w.Un + k * m, h);
+      }
+      phin = merit(P, &w, w.Xn, w.Un, &violn);
+      if (isfinite(phin) && phin <= phi + o->ls_c1 * alpha * dphi0) { accepted = 1; break; }
+      alpha *= o->ls_decrease;
+    }
+    iters = it + 1;
+    if (!accepted) { status = ALTRO_REF_LINESEARCH_FAILED; break; }
+    cost_decrease = phi - phin;
+    for (int k = 0; k <= N; ++k) {
+      double dx[32];
+      state_diff(w.Xn + k * n, X + k * n, n, qi, dx);
+      mv(w.Y + k * ne, w.P + k * ne * ne, dx, ne, ne);
+      for (int a = 0; a < ne; ++a) w.Y[k * ne + a] += w.pv[k * ne + a];
+    }
+    memcpy(X, w.Xn, sizeof(double) * (N + 1) * n);
+    memcpy(U, w.Un, sizeof(double) * N * m);
+    phi = phin;
+    viol = violn;
+  }
+
+  if (st) {
+    st->iterations = iters;
+    st->status = status;
+    st->ls_trials = trials;
+    st->cost = phi;
+    st->max_violation = viol;
+    st->stationarity = stat;
+    st->penalty = w.rho[0];
+  }
+  free(base);
+  return 0;
+}

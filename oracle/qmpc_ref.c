@@ -1,0 +1,456 @@
+/*
+ * qmpc_ref.c — fp64 CPU restatement of legged_ctrl's MPC problem assembly on top of altro_ref.c.
+ * TEST INFRASTRUCTURE ONLY (see altro_ref.h).  Uses the product's public structs (include/qmpc.h)
+ * so that the oracle and the CUDA library are fed byte-identical inputs.
+ *
+ * Follows, line by line:
+ *   QuatMpc::grf_update          legged_ctrl/src/mpc/QuatMpc.cpp:109-276
+ *   ConvexMpc::grf_update        legged_ctrl/src/mpc/ConvexMpc.cpp:81-198
+ *   ct_srb_quat_dynamics/jacobian, ct_srb_trot_quat_*, ct_srb_dynamics/jacobian
+ *                                legged_ctrl/src/utils/AltroUtils.cpp:224-513
+ *   midpoint_dynamics/jacobian   legged_ctrl/src/utils/AltroUtils.cpp:9-22,78-110
+ *   QuaternionUtils::G / L       legged_ctrl/src/utils/QuaternionUtils.cpp:30-52
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/qmpc.h"
+#include "altro_ref.h"
+
+#include "qmpc_ref_internal.h"
+
+static void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+void qref_inv3(const double* A, double* B) {
+  double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  B[0] = c00 / det; B[1] = (A[2] * A[7] - A[1] * A[8]) / det; B[2] = (A[1] * A[5] - A[2] * A[4]) / det;
+  B[3] = c01 / det; B[4] = (A[0] * A[8] - A[2] * A[6]) / det; B[5] = (A[2] * A[3] - A[0] * A[5]) / det;
+  B[6] = c02 / det; B[7] = (A[1] * A[6] - A[0] * A[7]) / det; B[8] = (A[0] * A[4] - A[1] * A[3]) / det;
+}
+static void mat3v(const double* A, const double* v, double* r) {
+  for (int i = 0; i < 3; ++i) r[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+}
+/* Eigen::Quaterniond::toRotationMatrix (BaseInterface.cpp:196), row-major, q = (w,x,y,z) */
+static void quat_to_rot(const double* q, double* R) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+  double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+
+/* ---- quaternion SRB, nf feet (AltroUtils.cpp:363-392 / 441-468) */
+void qref_quat_ct_dyn(void* ctx, double* xd, const double* x, const double* u) {
+  const Model* M = (const Model*)ctx;
+  const double *q = x + 3, *w = x + 10;
+  double mom[3] = {M->tau_g[0], M->tau_g[1], M->tau_g[2]}, fs[3] = {0, 0, 0};
+  for (int i = 0; i < M->nf; ++i) {
+    double c[3];
+    cross3(M->foot + 3 * i, u + 3 * i, c);
+    for (int j = 0; j < 3; ++j) { mom[j] += c[j]; fs[j] += u[3 * i + j]; }
+  }
+  xd[0] = x[7]; xd[1] = x[8]; xd[2] = x[9];
+  /* 0.5 * G(q) * omega */
+  xd[3] = 0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
+  xd[4] = 0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
+  xd[5] = 0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
+  xd[6] = 0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
+  for (int j = 0; j < 3; ++j) xd[7 + j] = fs[j] / M->mass + M->g_vec[j];
+  mat3v(M->Iinv, mom, xd + 10);
+}
+/* 13 x (13+m) column-major (AltroUtils.cpp:395-439 / 471-513) */
+void qref_quat_ct_jac(void* ctx, double* J, const double* x, const double* u) {
+  (void)u;
+  const Model* M = (const Model*)ctx;
+  const int n = 13, m = M->m;
+  memset(J, 0, sizeof(double) * n * (n + m));
+#define JJ(i, j) J[(j) * n + (i)]
+  const double *q = x + 3, *w = x + 10;
+  JJ(0, 7) = 1; JJ(1, 8) = 1; JJ(2, 9) = 1;
+  JJ(3, 4) = -0.5 * w[0]; JJ(3, 5) = -0.5 * w[1]; JJ(3, 6) = -0.5 * w[2];
+  JJ(4, 3) = 0.5 * w[0]; JJ(5, 3) = 0.5 * w[1]; JJ(6, 3) = 0.5 * w[2];
+  /* -0.5 * skew(w) */
+  JJ(4, 5) = 0.5 * w[2];  JJ(4, 6) = -0.5 * w[1];
+  JJ(5, 4) = -0.5 * w[2]; JJ(5, 6) = 0.5 * w[0];
+  JJ(6, 4) = 0.5 * w[1];  JJ(6, 5) = -0.5 * w[0];
+  JJ(3, 10) = -0.5 * q[1]; JJ(3, 11) = -0.5 * q[2]; JJ(3, 12) = -0.5 * q[3];
+  JJ(4, 10) = 0.5 * q[0];  JJ(4, 11) = -0.5 * q[3]; JJ(4, 12) = 0.5 * q[2];
+  JJ(5, 10) = 0.5 * q[3];  JJ(5, 11) = 0.5 * q[0];  JJ(5, 12) = -0.5 * q[1];
+  JJ(6, 10) = -0.5 * q[2]; JJ(6, 11) = 0.5 * q[1];  JJ(6, 12) = 0.5 * q[0];
+  for (int i = 0; i < M->nf; ++i) {
+    const double* r = M->foot + 3 * i;
+    double S[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+    for (int a = 0; a < 3; ++a) {
+      JJ(7 + a, 13 + 3 * i + a) = 1.0 / M->mass;
+      for (int b = 0; b < 3; ++b) {
+        double s = 0;
+        for (int l = 0; l < 3; ++l) s += M->Iinv[3 * a + l] * S[3 * l + b];
+        JJ(10 + a, 13 + 3 * i + b) = s;
+      }
+    }
+  }
+#undef JJ
+}
+
+/* ---- Euler-angle SRB of ConvexMpc (AltroUtils.cpp:224-359), intended 12-state math */
+typedef struct ConvexCtx {
+  Model M;
+  double It[9]; /* hard-coded trunk inertia, AltroUtils.cpp:268-270 */
+} ConvexCtx;
+static void convex_Bc(const Model* M, double yaw, double* IwinvS /* 4 blocks 3x3 row-major */) {
+  double cy = cos(yaw), sy = sin(yaw);
+  double Rz[9] = {cy, -sy, 0, sy, cy, 0, 0, 0, 1};
+  const double It[3] = {0.0168128557, 0.063009565, 0.0716547275};
+  double Iw[9], Iwinv[9];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      double s = 0;
+      for (int l = 0; l < 3; ++l) s += Rz[3 * a + l] * It[l] * Rz[3 * b + l];
+      Iw[3 * a + b] = s;
+    }
+  qref_inv3(Iw, Iwinv);
+  for (int i = 0; i < 4; ++i) {
+    const double* r = M->foot + 3 * i;
+    double S[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        double s = 0;
+        for (int l = 0; l < 3; ++l) s += Iwinv[3 * a + l] * S[3 * l + b];
+        IwinvS[9 * i + 3 * a + b] = s;
+      }
+  }
+}
+void qref_convex_ct_dyn(void* ctx, double* xd, const double* x, const double* u) {
+  const Model* M = (const Model*)ctx;
+  double cy = cos(x[2]), sy = sin(x[2]);
+  double BS[36];
+  convex_Bc(M, x[2], BS);
+  /* rpy rate = [cy sy 0; -sy cy 0; 0 0 1] * omega_world (yaw-only map, AltroUtils.cpp:257-259) */
+  xd[0] = cy * x[6] + sy * x[7];
+  xd[1] = -sy * x[6] + cy * x[7];
+  xd[2] = x[8];
+  xd[3] = x[9]; xd[4] = x[10]; xd[5] = x[11];
+  for (int a = 0; a < 3; ++a) {
+    double s = 0, f = 0;
+    for (int i = 0; i < 4; ++i) {
+      for (int b = 0; b < 3; ++b) s += BS[9 * i + 3 * a + b] * u[3 * i + b];
+      f += u[3 * i + a];
+    }
+    xd[6 + a] = s;
+    xd[9 + a] = f / 12.84; /* hard-coded mass, AltroUtils.cpp:239 */
+  }
+  xd[11] += -9.81;
+}
+void qref_convex_ct_jac(void* ctx, double* J, const double* x, const double* u) {
+  (void)u;
+  const Model* M = (const Model*)ctx;
+  const int n = 12;
+  memset(J, 0, sizeof(double) * n * 24);
+#define JJ(i, j) J[(j) * n + (i)]
+  double cy = cos(x[2]), sy = sin(x[2]);
+  double BS[36];
+  convex_Bc(M, x[2], BS);
+  JJ(0, 2) = x[7] * cy - x[6] * sy;  /* AltroUtils.cpp:355 */
+  JJ(1, 2) = -x[6] * cy - x[7] * sy; /* AltroUtils.cpp:356 */
+  JJ(0, 6) = cy; JJ(0, 7) = sy; JJ(1, 6) = -sy; JJ(1, 7) = cy; JJ(2, 8) = 1;
+  JJ(3, 9) = 1; JJ(4, 10) = 1; JJ(5, 11) = 1;
+  for (int i = 0; i < 4; ++i)
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) JJ(6 + a, 12 + 3 * i + b) = BS[9 * i + 3 * a + b];
+      JJ(9 + a, 12 + 3 * i + a) = 1.0 / 12.84;
+    }
+#undef JJ
+}
+
+/* ---- explicit midpoint (AltroUtils.cpp:9-22, 78-110); float h, h/2 evaluated in float (exact) */
+void qref_mid_dyn(void* ctx, double* xn, const double* x, const double* u, float h) {
+  const Model* M = (const Model*)ctx;
+  const int n = M->n;
+  double xm[16], hh = (double)(h / 2), hd = (double)h;
+  M->f(ctx, xm, x, u);
+  for (int i = 0; i < n; ++i) xm[i] = xm[i] * hh + x[i];
+  M->f(ctx, xn, xm, u);
+  for (int i = 0; i < n; ++i) xn[i] = x[i] + hd * xn[i];
+}
+void qref_mid_jac(void* ctx, double* J, const double* x, const double* u, float h) {
+  const Model* M = (const Model*)ctx;
+  const int n = M->n, m = M->m;
+  double xm[16], hh = (double)(h / 2), hd = (double)h;
+  double Jc[16 * 28], Jm[16 * 28];
+  M->f(ctx, xm, x, u);
+  for (int i = 0; i < n; ++i) xm[i] = x[i] + hh * xm[i];
+  M->df(ctx, Jc, x, u);
+  M->df(ctx, Jm, xm, u);
+  /* A_d = I + h Am (I + h/2 A) ; B_d = h (Am (h/2) B + Bm) ; column-major n x (n+m) */
+  for (int j = 0; j < n + m; ++j)
+    for (int i = 0; i < n; ++i) {
+      double s = 0;
+      for (int l = 0; l < n; ++l) s += Jm[l * n + i] * Jc[j * n + l];
+      double v = hd * (hh * s + Jm[j * n + i]);
+      if (j < n && i == j) v += 1.0;
+      J[j * n + i] = v;
+    }
+}
+
+/* ---- friction-cone rows (QuatMpc.cpp:194-215; ConvexMpc.cpp:14-35,130-140) */
+void qref_cone_con(void* ctx, int k, double* c, const double* x, const double* u) {
+  (void)k; (void)x;
+  const Model* M = (const Model*)ctx;
+  for (int i = 0; i < M->nf; ++i) {
+    for (int r = 0; r < 6; ++r)
+      c[6 * i + r] = M->CR[3 * r] * u[3 * i] + M->CR[3 * r + 1] * u[3 * i + 1] + M->CR[3 * r + 2] * u[3 * i + 2];
+    c[6 * i + 4] += -M->fzmax_c[i];
+  }
+}
+void qref_cone_jac(void* ctx, int k, double* J, const double* x, const double* u) {
+  (void)k; (void)x; (void)u;
+  const Model* M = (const Model*)ctx;
+  const int p = 6 * M->nf, ne = 12;
+  for (int i = 0; i < M->nf; ++i)
+    for (int r = 0; r < 6; ++r)
+      for (int b = 0; b < 3; ++b) J[(ne + 3 * i + b) * p + 6 * i + r] = M->CR[3 * r + b];
+}
+
+void qref_fill_cone(Model* M, double mu, const double* R0 /* NULL = identity */) {
+  const double C[18] = {1, 0, -mu, -1, 0, -mu, 0, 1, -mu, 0, -1, -mu, 0, 0, 1, 0, 0, -1};
+  for (int r = 0; r < 6; ++r)
+    for (int b = 0; b < 3; ++b) {
+      if (!R0) { M->CR[3 * r + b] = C[3 * r + b]; continue; }
+      double s = 0;
+      for (int l = 0; l < 3; ++l) s += C[3 * r + l] * R0[3 * l + b];
+      M->CR[3 * r + b] = s;
+    }
+}
+
+static void opts_from_cfg(const QmpcConfig* cfg, AltroRefOptions* o) {
+  altro_ref_default_options(o);
+  o->iterations_max = cfg->iterations_max;
+  o->penalty_initial = cfg->penalty_initial;
+  o->penalty_scaling = cfg->penalty_scaling;
+  o->penalty_max = cfg->penalty_max;
+  o->tol_cost_intermediate = cfg->tol_cost_intermediate;
+  o->tol_primal_feasibility = cfg->tol_primal_feasibility;
+  o->tol_stationarity = cfg->tol_stationarity;
+}
+
+/* ============================================================ QuatMpc::grf_update, one problem */
+int qmpc_ref_solve_one(const QmpcConfig* cfg, const QmpcProblem* in, QmpcResult* out) {
+  const int N = cfg->horizon;
+  const int nf = cfg->model == QMPC_MODEL_QUAT_2FOOT ? 2 : 4;
+  const int n = 13, m = 3 * nf;
+  if (N < 1 || N > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
+  Model M;
+  memset(&M, 0, sizeof(M));
+  M.n = n; M.m = m; M.nf = nf;
+  M.f = qref_quat_ct_dyn; M.df = qref_quat_ct_jac;
+  memcpy(M.foot, in->foot_pos_body, sizeof(double) * 3 * nf);
+  qref_inv3(cfg->inertia, M.Iinv);
+  M.mass = cfg->robot_mass;
+
+  double R0[9];
+  quat_to_rot(in->torso_quat, R0);
+  double gw[3] = {0, 0, -cfg->gravity};
+  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) {
+    /* g_body = R0^T g_world frozen at the measured attitude (AltroUtils.cpp:370-371) */
+    for (int i = 0; i < 3; ++i) M.g_vec[i] = R0[i] * gw[0] + R0[3 + i] * gw[1] + R0[6 + i] * gw[2];
+  } else {
+    memcpy(M.g_vec, gw, sizeof(gw)); /* ct_srb_trot_quat_dynamics does not rotate (AltroUtils.cpp:446-447) */
+  }
+  double mg[3] = {cfg->com_mass * M.g_vec[0], cfg->com_mass * M.g_vec[1], cfg->com_mass * M.g_vec[2]};
+  cross3(cfg->com_offset, mg, M.tau_g);
+  qref_fill_cone(&M, cfg->mu, R0);
+
+  /* references (QuatMpc.cpp:118-176) */
+  int num_contacts = 0;
+  for (int i = 0; i < nf; ++i) num_contacts += in->plan_contacts[i] ? 1 : 0;
+  double uref[12] = {0};
+  for (int i = 0; i < nf; ++i) {
+    uref[3 * i + 2] = (in->plan_contacts[i] ? 1.0 : 0.0) * cfg->robot_mass * cfg->gravity / num_contacts;
+    M.fzmax_c[i] = cfg->fz_max * (in->plan_contacts[i] ? 1.0 : 0.0);
+  }
+  /* torso_quat_d += 0.5 G(q_d) w_d * 5 ms ; renormalise (QuatMpc.cpp:128-137) */
+  double qd[4];
+  {
+    const double *q = in->torso_quat_d, *w = in->torso_ang_vel_d_body;
+    double s = 0.5 * cfg->quat_d_dt;
+    qd[0] = q[0] + s * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
+    qd[1] = q[1] + s * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
+    qd[2] = q[2] + s * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
+    qd[3] = q[3] + s * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
+    double nrm = sqrt(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
+    for (int i = 0; i < 4; ++i) qd[i] /= nrm;
+  }
+  double Q[(QMPC_MAX_HORIZON + 1) * 13], R[(QMPC_MAX_HORIZON + 1) * 12], xref[(QMPC_MAX_HORIZON + 1) * 13],
+      ur[(QMPC_MAX_HORIZON + 1) * 12], wq[QMPC_MAX_HORIZON + 1];
+  int p[QMPC_MAX_HORIZON + 1], ct[QMPC_MAX_HORIZON + 1];
+  for (int k = 0; k <= N; ++k) {
+    double* xr = xref + k * n;
+    memset(xr, 0, sizeof(double) * n);
+    /* i * h / 1000.0 with h in ms, evaluated in double (QuatMpc.cpp:156-157) */
+    xr[0] = in->torso_pos_d_body[0] + in->torso_lin_vel_d_body[0] * k * cfg->dt;
+    xr[1] = in->torso_pos_d_body[1] + in->torso_lin_vel_d_body[1] * k * cfg->dt;
+    xr[2] = in->torso_pos_d_body[2];
+    memcpy(xr + 3, qd, sizeof(qd));
+    memcpy(xr + 7, in->torso_lin_vel_d_body, sizeof(double) * 3);
+    memcpy(Q + k * n, cfg->q_weights, sizeof(double) * n);
+    memcpy(R + k * m, cfg->r_weights, sizeof(double) * m);
+    memcpy(ur + k * m, uref, sizeof(double) * m);
+    wq[k] = cfg->w;
+    /* SetConstraint(..., 0, horizon): knots 0..N-1 (QuatMpc.cpp:229) */
+    p[k] = k < N ? 6 * nf : 0;
+    ct[k] = ALTRO_REF_INEQUALITY;
+  }
+  /* x_init (QuatMpc.cpp:231-245): omega dropped by the reference's `;` at :242 */
+  double x0[13] = {0};
+  memcpy(x0 + 3, in->torso_quat, sizeof(double) * 4);
+  for (int i = 0; i < 3; ++i)
+    x0[7 + i] = R0[i] * in->torso_lin_vel_world[0] + R0[3 + i] * in->torso_lin_vel_world[1] +
+                R0[6 + i] * in->torso_lin_vel_world[2];
+  if (!cfg->drop_omega0) memcpy(x0 + 10, in->torso_ang_vel_body, sizeof(double) * 3);
+
+  AltroRefProblem P;
+  memset(&P, 0, sizeof(P));
+  P.N = N; P.n = n; P.m = m; P.h = (float)cfg->dt; P.ctx = &M;
+  P.dyn = qref_mid_dyn; P.jac = qref_mid_jac;
+  P.Q = Q; P.R = R; P.xref = xref; P.uref = ur; P.w = wq;
+  P.p = p; P.ctype = ct; P.con = qref_cone_con; P.conjac = qref_cone_jac; P.x0 = x0;
+  AltroRefOptions o;
+  opts_from_cfg(cfg, &o);
+  o.use_quaternion = 1;
+  o.quat_start_index = 3;
+
+  double X[(QMPC_MAX_HORIZON + 1) * 13], U[QMPC_MAX_HORIZON * 12];
+  for (int k = 0; k < N; ++k) memcpy(U + k * m, uref, sizeof(double) * m); /* SetInput(u_ref[0]) :253 */
+  AltroRefStats st;
+  if (altro_ref_solve(&P, &o, X, U, &st)) return QMPC_ERR_ARG;
+
+  memset(out, 0, sizeof(*out));
+  for (int i = 0; i < nf; ++i) {
+    mat3v(R0, U + 3 * i, out->grf_world + 3 * i);            /* QuatMpc.cpp:268 */
+    memcpy(out->grf_body + 3 * i, U + 3 * i, sizeof(double) * 3); /* QuatMpc.cpp:269 */
+  }
+  memcpy(out->torso_quat_d, qd, sizeof(qd));
+  out->max_violation = st.max_violation;
+  out->iterations = st.iterations;
+  out->status = st.status;
+  return QMPC_OK;
+}
+
+/* ============================================================ ConvexMpc::grf_update, one problem */
+int qmpc_ref_solve_one_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in, QmpcResult* out) {
+  const int N = cfg->horizon, n = 12, m = 12;
+  if (N < 1 || N > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
+  Model M;
+  memset(&M, 0, sizeof(M));
+  M.n = n; M.m = m; M.nf = 4;
+  M.f = qref_convex_ct_dyn; M.df = qref_convex_ct_jac;
+  memcpy(M.foot, in->foot_pos_abs_com, sizeof(double) * 12);
+  qref_fill_cone(&M, cfg->mu, NULL);
+  int num_contacts = 0;
+  for (int i = 0; i < 4; ++i) num_contacts += in->plan_contacts[i] ? 1 : 0;
+  double uref[12] = {0};
+  for (int i = 0; i < 4; ++i) {
+    uref[3 * i + 2] = cfg->robot_mass * cfg->gravity / num_contacts * (in->plan_contacts[i] ? 1.0 : 0.0);
+    M.fzmax_c[i] = cfg->fz_max * (in->plan_contacts[i] ? 1.0 : 0.0);
+  }
+  double Q[(QMPC_MAX_HORIZON + 1) * 12], R[(QMPC_MAX_HORIZON + 1) * 12], xref[(QMPC_MAX_HORIZON + 1) * 12],
+      ur[(QMPC_MAX_HORIZON + 1) * 12], wq[QMPC_MAX_HORIZON + 1];
+  int p[QMPC_MAX_HORIZON + 1], ct[QMPC_MAX_HORIZON + 1];
+  for (int k = 0; k <= N; ++k) {
+    double* xr = xref + k * n; /* ConvexMpc.cpp:95-108 */
+    memset(xr, 0, sizeof(double) * n);
+    xr[2] = in->torso_euler[2] + in->yaw_rate_d * cfg->dt * k;
+    xr[3] = in->torso_pos_d_world[0]; xr[4] = in->torso_pos_d_world[1]; xr[5] = in->torso_pos_d_world[2];
+    xr[8] = in->yaw_rate_d;
+    xr[9] = in->torso_lin_vel_d_world[0]; xr[10] = in->torso_lin_vel_d_world[1];
+    memcpy(Q + k * n, cfg->q_weights, sizeof(double) * n);
+    memcpy(R + k * m, cfg->r_weights, sizeof(double) * m);
+    memcpy(ur + k * m, uref, sizeof(double) * m);
+    wq[k] = 0.0;
+    /* reference range is [0, N+1) (ConvexMpc.cpp:153-154); at knot N the rows depend on no
+       optimisation variable (u_N does not exist, Jx = 0) so they are a no-op and are dropped */
+    p[k] = k < N ? 24 : 0;
+    ct[k] = ALTRO_REF_INEQUALITY;
+  }
+  double x0[12];
+  memcpy(x0, in->torso_euler, 24); memcpy(x0 + 3, in->torso_pos_world, 24);
+  memcpy(x0 + 6, in->torso_ang_vel_world, 24); memcpy(x0 + 9, in->torso_lin_vel_world, 24);
+
+  AltroRefProblem P;
+  memset(&P, 0, sizeof(P));
+  P.N = N; P.n = n; P.m = m; P.h = (float)cfg->dt; P.ctx = &M;
+  P.dyn = qref_mid_dyn; P.jac = qref_mid_jac; /* ConvexMpc.cpp:123-124 uses the midpoint rule */
+  P.Q = Q; P.R = R; P.xref = xref; P.uref = ur; P.w = wq;
+  P.p = p; P.ctype = ct; P.con = qref_cone_con; P.conjac = qref_cone_jac; P.x0 = x0;
+  AltroRefOptions o;
+  opts_from_cfg(cfg, &o);
+  double X[(QMPC_MAX_HORIZON + 1) * 12], U[QMPC_MAX_HORIZON * 12];
+  for (int k = 0; k < N; ++k) memcpy(U + k * m, uref, sizeof(double) * m);
+  AltroRefStats st;
+  if (altro_ref_solve(&P, &o, X, U, &st)) return QMPC_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  for (int i = 0; i < 4; ++i) {
+    /* optimized_input = R0^T u (ConvexMpc.cpp:190-192); u itself is the world-frame GRF */
+    const double *R0 = in->torso_rot_mat, *f = U + 3 * i;
+    for (int a = 0; a < 3; ++a) out->grf_body[3 * i + a] = R0[a] * f[0] + R0[3 + a] * f[1] + R0[6 + a] * f[2];
+    memcpy(out->grf_world + 3 * i, f, sizeof(double) * 3);
+  }
+  out->torso_quat_d[0] = 1.0;
+  out->max_violation = st.max_violation;
+  out->iterations = st.iterations;
+  out->status = st.status;
+  return QMPC_OK;
+}
+
+/* ============================================================ batch drivers (one worker per core) */
+typedef struct Job {
+  const QmpcConfig* cfg;
+  const void* in;
+  QmpcResult* out;
+  int lo, hi, convex, rc;
+} Job;
+static void* worker(void* arg) {
+  Job* j = (Job*)arg;
+  for (int i = j->lo; i < j->hi; ++i) {
+    int rc = j->convex ? qmpc_ref_solve_one_convex(j->cfg, (const QmpcConvexProblem*)j->in + i, j->out + i)
+                       : qmpc_ref_solve_one(j->cfg, (const QmpcProblem*)j->in + i, j->out + i);
+    if (rc) j->rc = rc;
+  }
+  return NULL;
+}
+static int run_batch(const QmpcConfig* cfg, const void* in, int batch, QmpcResult* out, int nthreads, int convex) {
+  if (!cfg || !in || !out || batch < 0) return QMPC_ERR_ARG;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  if (nthreads > batch) nthreads = batch > 0 ? batch : 1;
+  pthread_t th[256];
+  Job jobs[256];
+  for (int t = 0; t < nthreads; ++t) {
+    jobs[t].cfg = cfg; jobs[t].in = in; jobs[t].out = out; jobs[t].convex = convex; jobs[t].rc = 0;
+    jobs[t].lo = (int)((long long)batch * t / nthreads);
+    jobs[t].hi = (int)((long long)batch * (t + 1) / nthreads);
+    if (nthreads == 1) worker(&jobs[t]);
+    else pthread_create(&th[t], NULL, worker, &jobs[t]);
+  }
+  int rc = 0;
+  for (int t = 0; t < nthreads; ++t) {
+    if (nthreads > 1) pthread_join(th[t], NULL);
+    if (jobs[t].rc) rc = jobs[t].rc;
+  }
+  return rc;
+}
+int qmpc_ref_solve_batch(const QmpcConfig* cfg, const QmpcProblem* in, int batch, QmpcResult* out, int nthreads) {
+  return run_batch(cfg, in, batch, out, nthreads, 0);
+}
+int qmpc_ref_solve_batch_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in, int batch, QmpcResult* out,
+                                int nthreads) {
+  return run_batch(cfg, in, batch, out, nthreads, 1);
+}

@@ -1,0 +1,111 @@
+"""ctypes / numpy mirror of include/qmpc.h (the C-ABI of libqmpc_b200.so).
+
+Only layout definitions and the library loader live here — no arithmetic.  The numpy structured
+dtypes are byte-identical to the C structs so a batch is one contiguous array that can be handed
+to the C-ABI (host entry points) or copied to the device as raw bytes (device entry points).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+QMPC_MODEL_QUAT_4FOOT = 0
+QMPC_MODEL_QUAT_2FOOT = 1
+QMPC_MODEL_EULER_CONVEX = 2
+QMPC_MAX_HORIZON = 32
+
+QMPC_OK = 0
+QMPC_ERR_ARG = -1
+QMPC_ERR_CUDA = -2
+QMPC_ERR_CAPACITY = -3
+
+STATUS_NAMES = {0: "success", 1: "max_iterations", 2: "linesearch_failed", 3: "backward_failed",
+                4: "nonfinite"}
+
+
+class QmpcConfig(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("horizon", C.c_int32), ("dt", C.c_double),
+        ("q_weights", C.c_double * 13), ("r_weights", C.c_double * 12), ("w", C.c_double),
+        ("mu", C.c_double), ("fz_max", C.c_double), ("robot_mass", C.c_double),
+        ("inertia", C.c_double * 9), ("com_offset", C.c_double * 3), ("com_mass", C.c_double),
+        ("gravity", C.c_double), ("quat_d_dt", C.c_double),
+        ("iterations_max", C.c_int32), ("drop_omega0", C.c_int32),
+        ("penalty_initial", C.c_double), ("penalty_scaling", C.c_double), ("penalty_max", C.c_double),
+        ("tol_cost_intermediate", C.c_double), ("tol_primal_feasibility", C.c_double),
+        ("tol_stationarity", C.c_double),
+    ]
+
+
+PROBLEM_DTYPE = np.dtype([
+    ("torso_quat", "f8", 4), ("torso_lin_vel_world", "f8", 3), ("torso_ang_vel_body", "f8", 3),
+    ("foot_pos_body", "f8", 12), ("torso_pos_d_body", "f8", 3), ("torso_lin_vel_d_body", "f8", 3),
+    ("torso_quat_d", "f8", 4), ("torso_ang_vel_d_body", "f8", 3), ("plan_contacts", "i4", 4),
+], align=True)
+
+CONVEX_PROBLEM_DTYPE = np.dtype([
+    ("torso_euler", "f8", 3), ("torso_pos_world", "f8", 3), ("torso_ang_vel_world", "f8", 3),
+    ("torso_lin_vel_world", "f8", 3), ("foot_pos_abs_com", "f8", 12), ("torso_rot_mat", "f8", 9),
+    ("torso_pos_d_world", "f8", 3), ("torso_lin_vel_d_world", "f8", 3), ("yaw_rate_d", "f8"),
+    ("plan_contacts", "i4", 4), ("pad_", "i4", 2),
+], align=True)
+
+RESULT_DTYPE = np.dtype([
+    ("grf_body", "f8", 12), ("grf_world", "f8", 12), ("torso_quat_d", "f8", 4),
+    ("max_violation", "f8"), ("iterations", "i4"), ("status", "i4"),
+], align=True)
+
+assert PROBLEM_DTYPE.itemsize == 35 * 8 + 16
+assert CONVEX_PROBLEM_DTYPE.itemsize == 40 * 8 + 24
+assert RESULT_DTYPE.itemsize == 29 * 8 + 8
+
+EXPORTED_SYMBOLS = [
+    "qmpc_default_config", "qmpc_create", "qmpc_solve_batch", "qmpc_solve_batch_convex",
+    "qmpc_solve_batch_host", "qmpc_solve_batch_convex_host", "qmpc_destroy", "qmpc_launch_count",
+    "qmpc_last_error", "qmpc_status_string", "qmpc_abi_version",
+]
+
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqmpc_b200.so")
+
+
+def load_library():
+    """Load libqmpc_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if absent:
+    there is no Python / CPU fallback for the solve."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: the CUDA extension is not built. Run `python -c 'import "
+            "__graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.qmpc_default_config.argtypes = [i32, i32, C.POINTER(QmpcConfig)]
+    lib.qmpc_default_config.restype = C.c_int
+    lib.qmpc_create.argtypes = [C.POINTER(QmpcConfig), i32, i32, C.POINTER(vp)]
+    lib.qmpc_create.restype = C.c_int
+    for name in ("qmpc_solve_batch", "qmpc_solve_batch_convex"):
+        f = getattr(lib, name)
+        f.argtypes = [vp, vp, i32, vp, vp]
+        f.restype = C.c_int
+    for name in ("qmpc_solve_batch_host", "qmpc_solve_batch_convex_host"):
+        f = getattr(lib, name)
+        f.argtypes = [vp, vp, i32, vp]
+        f.restype = C.c_int
+    lib.qmpc_destroy.argtypes = [vp]
+    lib.qmpc_destroy.restype = None
+    lib.qmpc_launch_count.argtypes = [vp]
+    lib.qmpc_launch_count.restype = i64
+    lib.qmpc_last_error.argtypes = [vp]
+    lib.qmpc_last_error.restype = C.c_char_p
+    lib.qmpc_status_string.argtypes = [i32]
+    lib.qmpc_status_string.restype = C.c_char_p
+    lib.qmpc_abi_version.argtypes = []
+    lib.qmpc_abi_version.restype = i32
+    _LIB = lib
+    return lib

@@ -1,0 +1,149 @@
+"""Pins the CPU oracle (oracle/altro_ref.c + qmpc_ref.c) against every known-answer test and golden
+vector the reference holds for the solve path.  CPU only."""
+import json
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- TestDoubleIntegrator.cpp ---------------------------------------------------------------
+def test_double_integrator_dynamics_kat(oracle):
+    # TestDoubleIntegrator.cpp:37-66
+    xn, J = oracle.kat_di_dynamics([0.1, 0.2, 0.3, 0.4], [10.1, -20.4], 0.01)
+    exp = np.array([0.10350500000000001, 0.20298000000000002, 0.40099999999999997, 0.19600000000000004])
+    assert np.linalg.norm(xn - exp) < 1e-8
+    h = float(np.float32(0.01)); b = h * h / 2
+    Jexp = np.array([[1, 0, h, 0, b, 0], [0, 1, 0, h, 0, b], [0, 0, 1, 0, h, 0], [0, 0, 0, 1, 0, h]])
+    assert np.linalg.norm(J - Jexp) < 1e-8
+
+
+def test_double_integrator_unconstrained(oracle):
+    # TestDoubleIntegrator.cpp:69-168: moves closer to the goal but not to it within 3 iterations
+    X, U, st = oracle.kat_double_integrator(0, iterations_max=3)
+    d = np.linalg.norm(X[-1])
+    assert st.status == 0
+    assert 1e-3 < d < np.linalg.norm(X[0])
+
+
+def test_double_integrator_goal_constraint_3_iterations(oracle):
+    # TestDoubleIntegrator.cpp:170-256: penalty_scaling=100 -> dist < 1e-4 and GetIterations()==3
+    X, U, st = oracle.kat_double_integrator(1, penalty_scaling=100.0)
+    assert st.status == 0
+    assert np.linalg.norm(X[-1]) < 1e-4
+    assert st.iterations == 3
+
+
+def test_double_integrator_control_bounds_5_iterations(oracle):
+    # TestDoubleIntegrator.cpp:258-375: penalty_initial=100, scaling=100 -> u0 saturates at -1 (1e-4), 5 iters
+    X, U, st = oracle.kat_double_integrator(2, penalty_initial=100.0, penalty_scaling=100.0)
+    assert st.status == 0
+    assert np.linalg.norm(X[-1]) < 1e-4
+    assert np.allclose(U[0], -1.0, atol=1e-4)
+    assert st.iterations == 5
+
+
+# ---- TestPendulum.cpp -----------------------------------------------------------------------
+def test_pendulum_midpoint_kats(oracle):
+    # TestPendulum.cpp:15-43 (tolerance 1e-6 as in the reference test)
+    xn, J = oracle.kat_pendulum_midpoint([0.1, -0.4], [1.34], 0.05)
+    assert np.linalg.norm(xn - [0.08445158545673655, -0.21395149094594346]) < 1e-6
+    Jexp = np.array([[0.9755975228465564, 0.0495, 0.005000000000000001],
+                     [-0.967268640223389, 0.9557742592228808, 0.198]])
+    assert np.linalg.norm(J - Jexp) < 1e-6
+
+
+def test_pendulum_unconstrained_swingup(oracle):
+    # TestPendulum.cpp:45-115: Success, <= 10 iterations, xN = expected.  The reference run used
+    # ALTRO's default cubic line search (opts.use_backtracking_linesearch not set there) and checks
+    # 1e-5; the MPC path (and this oracle) uses back-tracking, stops on the same stationarity
+    # tolerance after 9 iterations and lands 2.9e-5 from that optimum -> checked to 1e-4.
+    X, U, st = oracle.kat_pendulum(0)
+    assert st.status == 0
+    assert st.iterations <= 10
+    assert np.linalg.norm(X[-1] - [3.12099917161669, 0.0011966258762942175]) < 1e-4
+
+
+def test_pendulum_goal_constrained(oracle):
+    # TestPendulum.cpp:117-203: Success, dist to goal < 1e-4, <= 10 iterations
+    X, U, st = oracle.kat_pendulum(1)
+    assert st.status == 0
+    assert np.linalg.norm(X[-1] - [np.pi, 0.0]) < 1e-4
+    assert st.iterations <= 10
+
+
+# ---- golden quaternion-MPC trajectories ------------------------------------------------------
+def _gold(name):
+    with open(os.path.join(GOLD, name)) as f:
+        d = json.load(f)
+    return np.array(d["state_trajectory"]), np.array(d["input_trajectory"])
+
+
+def test_golden_rollouts_reproduce_states(oracle):
+    # the restated SRB dynamics + float-h midpoint rule reproduce the
+    # golden states from the golden inputs
+    for which, name, tol in ((0, "quat_mpc_test.json", 5e-12), (1, "trot_quat_mpc_test.json", 1e-14)):
+        Xg, Ug = _gold(name)
+        assert np.abs(oracle.kat_quat_rollout(which, Ug) - Xg).max() < tol
+
+
+def test_golden_quat_mpc_stand(oracle):
+    # TestAltroQuatMpc.cpp -> quat_mpc_test.json (4 feet, N=20, 10 iterations allowed)
+    Xg, Ug = _gold("quat_mpc_test.json")
+    X, U, st = oracle.kat_quat_golden(0)
+    assert st.status == 0
+    assert np.abs(U[0] - Ug[0]).max() < 2e-6     # first-step GRFs, the quantity the MPC returns
+    assert np.abs(U - Ug).max() < 1e-5
+    assert np.abs(X - Xg).max() < 5e-6
+
+
+def test_golden_quat_mpc_trot_two_feet(oracle):
+    # TestAltroTrotQuatMpc.cpp -> trot_quat_mpc_test.json (2 feet, m=6, w=10)
+    Xg, Ug = _gold("trot_quat_mpc_test.json")
+    X, U, st = oracle.kat_quat_golden(1)
+    assert st.status == 0
+    assert np.abs(U - Ug).max() < 5e-6
+    assert np.abs(X - Xg).max() < 1e-6
+
+
+# ---- numpy restatement cross-check -----------------------------------------------------------
+def test_c_oracle_matches_numpy_restatement(oracle):
+    from oracle import altro_np as A
+    from quaternion_mpc_b200.config import default_config
+    from quaternion_mpc_b200.workloads import random_batch
+    cfg = default_config(0, 6)
+    cfg.iterations_max = 4
+    probs = random_batch(3, seed=5, gait="mixed")
+    out = oracle.solve_batch(cfg, probs)
+    for i in range(3):
+        pr = probs[i]
+        q0 = pr["torso_quat"]; R0 = A.quat_to_rot(q0)
+        feet = pr["foot_pos_body"].reshape(4, 3).T
+        con = pr["plan_contacts"]
+        I_b = np.array(cfg.inertia[:]).reshape(3, 3)
+        f, df = A.srb_quat_model(feet, I_b, cfg.robot_mass, R0.T @ np.array([0, 0, -9.81]))
+        dyn, jac = A.midpoint_dynamics(f), A.midpoint_jacobian(f, df, 13)
+        x0 = np.zeros(13); x0[3:7] = q0; x0[7:10] = R0.T @ pr["torso_lin_vel_world"]
+        N = cfg.horizon
+        P = A.Problem(N, 13, 12, cfg.dt, dyn, jac, x0, qidx=3)
+        uref = np.zeros(12); uref[2::3] = con * cfg.robot_mass * 9.81 / con.sum()
+        for k in range(N + 1):
+            xr = np.zeros(13)
+            xr[0:2] = pr["torso_pos_d_body"][:2] + pr["torso_lin_vel_d_body"][:2] * k * cfg.dt
+            xr[2] = pr["torso_pos_d_body"][2]; xr[3:7] = pr["torso_quat_d"]; xr[7:10] = pr["torso_lin_vel_d_body"]
+            P.set_quat_cost(np.array(cfg.q_weights[:]), np.array(cfg.r_weights[:]), cfg.w, xr, uref, k, 0)
+        Cm = np.array([[1, 0, -cfg.mu], [-1, 0, -cfg.mu], [0, 1, -cfg.mu], [0, -1, -cfg.mu], [0, 0, 1], [0, 0, -1.]])
+        CR = Cm @ R0
+        def c(x, u):
+            o = np.zeros(24)
+            for j in range(4):
+                o[6 * j:6 * j + 6] = CR @ u[3 * j:3 * j + 3] + np.array([0, 0, 0, 0, -cfg.fz_max * con[j], 0])
+            return o
+        Jc = np.zeros((24, 24))
+        for j in range(4):
+            Jc[6 * j:6 * j + 6, 12 + 3 * j:15 + 3 * j] = CR
+        P.set_constraint(c, lambda x, u: Jc, 24, A.INEQUALITY, 0, N)
+        r = A.solve(P, [uref] * N, dict(iterations_max=4, penalty_scaling=20.0, stat_mode="riccati"))
+        assert r["iters"] == out["iterations"][i]
+        assert np.abs(np.array(r["U"][0]) - out["grf_body"][i]).max() < 1e-8
