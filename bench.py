@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py — Go1 quaternion-MPC solves/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            # CPU arm: the fp64 oracle port on all host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, batch sharded, no collective
+                                                           # on the data path (one NCCL gather of the GRFs)
+
+A "step" is one batched solve of the workload (default: BASELINE configs[1] = batch 4096 per GPU,
+Go1, horizon 10, trot masks {1001,0110}, random states, seed 0).  `value` = solves/s with the
+problem batch already resident in HBM (CUDA events, L2 flushed between steps); `e2e` = the same
+through the host-buffer C-ABI call (pinned host memory, H2D + solve + D2H inside the timed region).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_KNOT_ITER = 65.8e3   # dense reference-equivalent AL-iLQR, ne=12, m=12, p=24
+IN_BYTES, OUT_BYTES = 296, 240  # sizeof(QmpcProblem), sizeof(QmpcResult)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="problems per GPU per step")
+    ap.add_argument("--horizon", type=int, default=10)
+    ap.add_argument("--gait", default="trot")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(cfg, probs, threads):
+    """Times the fp64 oracle port (oracle/, test infrastructure) on the host cores."""
+    from oracle import binding as oracle
+    oracle.solve_batch(cfg, probs[:min(64, len(probs))], nthreads=threads)  # warm the caches / pages
+    t0 = time.perf_counter()
+    out = oracle.solve_batch(cfg, probs, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return len(probs) / dt, dt, out
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    from quaternion_mpc_b200 import abi
+    from quaternion_mpc_b200.config import default_config
+    from quaternion_mpc_b200.workloads import random_batch
+
+    cfg = default_config(abi.QMPC_MODEL_QUAT_4FOOT, a.horizon)
+    workload = f"go1_quat_mpc_N{a.horizon}_{a.gait}_batch{a.batch}_per_gpu_seed0"
+    threads = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference (CPU) arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        n = a.cpu_sample or max(threads * 16, 512)
+        probs = random_batch(n, seed=0, gait=a.gait)
+        vals = []
+        for i in range(a.warmup + a.steps):
+            v, dt, _ = cpu_arm(cfg, probs, threads)
+            if i >= a.warmup:
+                vals.append((v, dt))
+        v = float(np.mean([x[0] for x in vals]))
+        line = {
+            "impl": "reference", "metric": "go1_quat_mpc_solves_per_sec", "value": v, "unit": "solves/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": float(np.mean([x[1] for x in vals]) * 1e3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "horizon": a.horizon, "gait": a.gait,
+                       "note": "reference CPU solver = fp64 oracle port (ALTRO/Eigen/ROS absent: reference unbuildable here)"},
+            "cpu_baseline": {"value": v, "unit": "solves/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} problems of the workload per step, {threads} pthreads"},
+            "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from quaternion_mpc_b200 import QuatMpc
+
+    B = a.batch
+    probs = random_batch(B, seed=0 + rank, gait=a.gait)   # each rank owns its shard of the global batch
+    mpc = QuatMpc(max_batch=B, device=local, cfg=cfg)
+    d_in = mpc.to_device(probs)
+    d_out = mpc.alloc_results(B)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        flush.fill_(1)
+        mpc.grf_update_device(d_in, d_out)
+    barrier()
+    launches0 = mpc.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    for _ in range(a.steps):
+        flush.fill_(1)                        # L2 flush between timed iterations (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        mpc.grf_update_device(d_in, d_out)
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = float(sum(kernel_ms))
+    launches = mpc.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers through the C-ABI host entry point (H2D + solve + D2H per step)
+    h_in = torch.from_numpy(probs.view(np.uint8).reshape(B, -1).copy()).pin_memory()
+    h_out = torch.empty((B, OUT_BYTES), dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        mpc.grf_update_host_ptr(h_in.data_ptr(), B, h_out.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        mpc.grf_update_host_ptr(h_in.data_ptr(), B, h_out.data_ptr())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    res = h_out.numpy().reshape(-1).view(abi.RESULT_DTYPE)
+    mean_iters = float(res["iterations"].mean())
+
+    # ---- max over ranks
+    t = torch.tensor([total_ms, e2e_s * 1e3, mean_iters], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        mean_iters = float(tsum[2]) / world
+        # the one collective of the path: gather every rank's GRFs on rank 0
+        grf = torch.from_numpy(np.ascontiguousarray(res["grf_body"])).to(f"cuda:{local}")
+        gathered = [torch.empty_like(grf) for _ in range(world)] if rank == 0 else None
+        dist.gather(grf, gathered, dst=0)
+    else:
+        e2e_ms = e2e_s * 1e3
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    solves = B * world * a.steps
+    value = solves / (total_ms * 1e-3)
+    e2e_value = solves / (e2e_ms * 1e-3)
+
+    # ---- roofline: this path is bound by the vector-FMA pipe, not HBM/tensor
+    f64, f32 = C.c_double(), C.c_double()
+    mpc.lib.qmpc_measure_fma_peak(local, C.byref(f64), C.byref(f32))
+    flops_per_solve = mean_iters * a.horizon * FLOPS_PER_KNOT_ITER
+    avg_launch_s = (total_ms * 1e-3) / max(launches, 1)
+    achieved_tflops = B * flops_per_solve / avg_launch_s / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_achieved = B * (IN_BYTES + OUT_BYTES) / avg_launch_s / 1e9
+    roofline = {
+        "bound": "fp64_fma", "achieved": achieved_tflops, "peak": f64.value, "unit": "TFLOP/s",
+        "frac": achieved_tflops / f64.value if f64.value > 0 else None, "traffic": None,
+        "peak_source": "measured live by qmpc_measure_fma_peak (FP64 vector FMA; FP32 = %.1f TFLOP/s)" % f32.value,
+        "algorithmic_flops_per_solve": flops_per_solve, "mean_iterations": mean_iters,
+        "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak, "frac": hbm_achieved / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_solve": IN_BYTES + OUT_BYTES},
+    }
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        n = a.cpu_sample or min(B, max(threads * 16, 512))
+        v, dt, ref = cpu_arm(cfg, probs[:n], threads)
+        err = float(np.abs(ref["grf_body"] - res["grf_body"][:n]).max())
+        cpu = {"value": v, "unit": "solves/s", "cores": threads, "kind": "port",
+               "sample": f"first {n} problems of rank 0's batch, {threads} pthreads, {dt:.2f} s",
+               "grf_max_abs_err_vs_gpu": err}
+
+    line = {
+        "metric": "go1_quat_mpc_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "horizon": a.horizon, "gait": a.gait, "batch_per_gpu": B,
+                   "global_batch": B * world, "iterations_max": cfg.iterations_max,
+                   "l2": "256 MiB flush between timed steps", "parallelism": f"batch-sharded x{world}"},
+        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": B * IN_BYTES,
+                "d2h_bytes_per_step": B * OUT_BYTES},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

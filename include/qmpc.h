@@ -154,6 +154,10 @@ const char* qmpc_last_error(const QmpcHandle* h);
 const char* qmpc_status_string(int32_t status);
 int32_t     qmpc_abi_version(void);
 
+/* Measurement utility (not on the solve path): sustained FP64 / FP32 vector-FMA throughput of
+ * `device` in TFLOP/s — the roofline denominator of this FMA-bound path (bench.py). */
+int qmpc_measure_fma_peak(int32_t device, double* fp64_tflops, double* fp32_tflops);
+
 #ifdef __cplusplus
 }
 #endif

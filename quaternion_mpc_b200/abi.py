@@ -62,7 +62,7 @@ assert RESULT_DTYPE.itemsize == 29 * 8 + 8
 EXPORTED_SYMBOLS = [
     "qmpc_default_config", "qmpc_create", "qmpc_solve_batch", "qmpc_solve_batch_convex",
     "qmpc_solve_batch_host", "qmpc_solve_batch_convex_host", "qmpc_destroy", "qmpc_launch_count",
-    "qmpc_last_error", "qmpc_status_string", "qmpc_abi_version",
+    "qmpc_last_error", "qmpc_status_string", "qmpc_abi_version", "qmpc_measure_fma_peak",
 ]
 
 _LIB = None
@@ -105,6 +105,8 @@ def load_library():
     lib.qmpc_last_error.restype = C.c_char_p
     lib.qmpc_status_string.argtypes = [i32]
     lib.qmpc_status_string.restype = C.c_char_p
+    lib.qmpc_measure_fma_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.qmpc_measure_fma_peak.restype = C.c_int
     lib.qmpc_abi_version.argtypes = []
     lib.qmpc_abi_version.restype = i32
     _LIB = lib

@@ -1,0 +1,211 @@
+// qmpc_api.cu — the C-ABI of libqmpc_b200.so (declared in include/qmpc.h).
+//
+// Host side only: configuration defaults, handle life-cycle (device workspace allocated once),
+// kernel selection and launch.  No solver arithmetic happens on the host and there is no CPU
+// fallback: every solve entry point ends in a CUDA kernel launch or returns QMPC_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/qmpc.h"
+#include "qmpc_dense.cuh"
+
+using namespace qmpc;
+
+struct QmpcHandle {
+  QmpcConfig cfg;
+  SolverOpts opts;
+  int device;
+  int max_batch;
+  size_t stride;       // workspace problem stride (max_batch rounded up to 32)
+  double* ws;          // device workspace
+  size_t ws_bytes;
+  void* d_in;          // staging for the *_host entry points
+  QmpcResult* d_out;
+  cudaStream_t stream; // stream used by the *_host entry points
+  int64_t launches;
+  int kernel;          // 0 = dense
+  char err[256];
+};
+
+static int set_err(QmpcHandle* h, cudaError_t e, const char* where) {
+  if (h) snprintf(h->err, sizeof(h->err), "%s: %s", where, cudaGetErrorString(e));
+  return QMPC_ERR_CUDA;
+}
+#define CU(call)                                       \
+  do {                                                 \
+    cudaError_t e_ = (call);                           \
+    if (e_ != cudaSuccess) return set_err(h, e_, #call); \
+  } while (0)
+
+extern "C" int32_t qmpc_abi_version(void) { return QMPC_ABI_VERSION; }
+
+extern "C" const char* qmpc_status_string(int32_t s) {
+  switch (s) {
+    case QMPC_STATUS_SUCCESS: return "success";
+    case QMPC_STATUS_MAX_ITERATIONS: return "max_iterations";
+    case QMPC_STATUS_LINESEARCH_FAILED: return "linesearch_failed";
+    case QMPC_STATUS_BACKWARD_FAILED: return "backward_failed";
+    case QMPC_STATUS_NONFINITE: return "nonfinite";
+  }
+  return "unknown";
+}
+
+extern "C" int qmpc_default_config(int32_t model, int32_t horizon, QmpcConfig* c) {
+  if (!c) return QMPC_ERR_ARG;
+  if (model != QMPC_MODEL_QUAT_4FOOT && model != QMPC_MODEL_QUAT_2FOOT && model != QMPC_MODEL_EULER_CONVEX)
+    return QMPC_ERR_ARG;
+  if (horizon < 1 || horizon > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
+  memset(c, 0, sizeof(*c));
+  c->model = model;
+  c->horizon = horizon;
+  c->robot_mass = 12.84;  // gazebo_go1_quat_mpc.yaml:115
+  c->gravity = 9.81;
+  c->quat_d_dt = 5.0 / 1000.0;  // QuatMpc.cpp:132
+  c->com_offset[0] = 0.0223; c->com_offset[1] = 0.002; c->com_offset[2] = -0.0005;  // AltroUtils.cpp:373
+  c->com_mass = 5.204;
+  for (int i = 0; i < 12; ++i) c->r_weights[i] = 1e-6;  // yaml:58-72
+  c->penalty_initial = 1.0;
+  c->penalty_max = 1e8;
+  c->tol_cost_intermediate = c->tol_primal_feasibility = c->tol_stationarity = 1e-4;
+  c->drop_omega0 = 1;
+  const double It[3] = {0.0168128557, 0.063009565, 0.0716547275};  // yaml:117-122
+  double scale;
+  if (model == QMPC_MODEL_EULER_CONVEX) {
+    c->dt = 5.0 / 1000.0;  // gazebo_go1_convex_mpc.yaml:36
+    const double q[13] = {3.0, 3.0, 3.0, 1.0, 1.0, 20.0, 0.0, 0.0, 3.0, 2.0, 3.0, 2.0, 0.0};
+    memcpy(c->q_weights, q, sizeof(q));
+    c->w = 0.0; c->mu = 0.6; c->fz_max = 200.0;
+    scale = 1.0;
+    c->iterations_max = 5;      // ConvexMpc.cpp:37
+    c->penalty_scaling = 10.0;  // ALTRO default
+  } else {
+    c->dt = 10.0 / 1000.0;  // gazebo_go1_quat_mpc.yaml:36
+    const double q[13] = {2.5, 2.5, 10.0, 0, 0, 0, 0, 0.1, 0.1, 0.1, 0.15, 0.15, 0.15};
+    memcpy(c->q_weights, q, sizeof(q));
+    c->w = 50.0; c->mu = 0.7; c->fz_max = 100.0;
+    scale = 1.2;                // QuatMpc.cpp:182
+    c->iterations_max = 10;     // QuatMpc.cpp:22
+    c->penalty_scaling = 20.0;  // QuatMpc.cpp:26
+  }
+  for (int i = 0; i < 3; ++i) c->inertia[4 * i] = scale * It[i];
+  return QMPC_OK;
+}
+
+static size_t ws_elems(const QmpcConfig& c) {
+  switch (c.model) {
+    case QMPC_MODEL_QUAT_4FOOT: return DenseLayout<QuatModel<4>>::total(c.horizon);
+    case QMPC_MODEL_QUAT_2FOOT: return DenseLayout<QuatModel<2>>::total(c.horizon);
+    default: return DenseLayout<ConvexModel>::total(c.horizon);
+  }
+}
+
+extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t device, QmpcHandle** out) {
+  if (!cfg || !out || max_batch < 1) return QMPC_ERR_ARG;
+  if (cfg->horizon < 1 || cfg->horizon > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
+  if (cfg->model < 0 || cfg->model > QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;
+  if (cfg->iterations_max < 0 || !(cfg->penalty_initial > 0) || !(cfg->dt > 0)) return QMPC_ERR_ARG;
+  QmpcHandle* h = new (std::nothrow) QmpcHandle();
+  if (!h) return QMPC_ERR_ARG;
+  memset(h, 0, sizeof(*h));
+  *out = h;  // returned even on CUDA failure so the caller can read qmpc_last_error(); destroy is safe
+  h->cfg = *cfg;
+  h->device = device;
+  h->max_batch = max_batch;
+  h->stride = ((size_t)max_batch + 31) / 32 * 32;
+  SolverOpts& o = h->opts;
+  o.N = cfg->horizon;
+  o.iterations_max = cfg->iterations_max;
+  o.h = (float)cfg->dt;  // ALTRO takes the step as float (AltroUtils.cpp:10)
+  o.penalty_initial = cfg->penalty_initial;
+  o.penalty_scaling = cfg->penalty_scaling;
+  o.penalty_max = cfg->penalty_max;
+  o.tol_cost_intermediate = cfg->tol_cost_intermediate;
+  o.tol_primal_feasibility = cfg->tol_primal_feasibility;
+  o.tol_stationarity = cfg->tol_stationarity;
+  o.ls_c1 = 1e-4;
+  o.ls_decrease = 0.5;
+  o.ls_iters_max = 25;
+  CU(cudaSetDevice(device));
+  h->ws_bytes = ws_elems(*cfg) * h->stride * sizeof(double);
+  CU(cudaMalloc(&h->ws, h->ws_bytes));
+  size_t in_sz = cfg->model == QMPC_MODEL_EULER_CONVEX ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
+  CU(cudaMalloc(&h->d_in, in_sz * (size_t)max_batch));
+  CU(cudaMalloc(&h->d_out, sizeof(QmpcResult) * (size_t)max_batch));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  return QMPC_OK;
+}
+
+extern "C" void qmpc_destroy(QmpcHandle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->ws) cudaFree(h->ws);
+  if (h->d_in) cudaFree(h->d_in);
+  if (h->d_out) cudaFree(h->d_out);
+  delete h;
+}
+
+extern "C" int64_t qmpc_launch_count(const QmpcHandle* h) { return h ? h->launches : 0; }
+extern "C" const char* qmpc_last_error(const QmpcHandle* h) { return h ? h->err : "null handle"; }
+
+template <class M>
+static int launch_dense(QmpcHandle* h, const typename M::Problem* d_in, int batch, QmpcResult* d_out,
+                        cudaStream_t s) {
+  const int block = 64;
+  const int grid = (batch + block - 1) / block;
+  qmpc_dense_kernel<M><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, d_out, h->ws, batch, h->stride);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
+static int solve_any(QmpcHandle* h, const void* d_in, int32_t batch, QmpcResult* d_out, void* stream, bool convex) {
+  if (!h || !h->ws) return h ? QMPC_ERR_CUDA : QMPC_ERR_ARG;
+  if (!d_in || !d_out || batch < 0) return QMPC_ERR_ARG;
+  if (convex != (h->cfg.model == QMPC_MODEL_EULER_CONVEX)) return QMPC_ERR_ARG;
+  if (batch > h->max_batch) return QMPC_ERR_CAPACITY;
+  if (batch == 0) return QMPC_OK;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (h->cfg.model) {
+    case QMPC_MODEL_QUAT_4FOOT: return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
+    case QMPC_MODEL_QUAT_2FOOT: return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
+    default: return launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, batch, d_out, s);
+  }
+}
+
+extern "C" int qmpc_solve_batch(QmpcHandle* h, const QmpcProblem* d_in, int32_t batch, QmpcResult* d_out,
+                                void* cuda_stream) {
+  return solve_any(h, d_in, batch, d_out, cuda_stream, false);
+}
+extern "C" int qmpc_solve_batch_convex(QmpcHandle* h, const QmpcConvexProblem* d_in, int32_t batch,
+                                       QmpcResult* d_out, void* cuda_stream) {
+  return solve_any(h, d_in, batch, d_out, cuda_stream, true);
+}
+
+static int solve_host_any(QmpcHandle* h, const void* in, int32_t batch, QmpcResult* out, bool convex) {
+  if (!h || !h->ws) return h ? QMPC_ERR_CUDA : QMPC_ERR_ARG;
+  if (!in || !out || batch < 0) return QMPC_ERR_ARG;
+  if (batch > h->max_batch) return QMPC_ERR_CAPACITY;
+  if (batch == 0) return QMPC_OK;
+  CU(cudaSetDevice(h->device));
+  size_t in_sz = convex ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
+  CU(cudaMemcpyAsync(h->d_in, in, in_sz * batch, cudaMemcpyHostToDevice, h->stream));
+  int rc = solve_any(h, h->d_in, batch, h->d_out, h->stream, convex);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, h->d_out, sizeof(QmpcResult) * batch, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_solve_batch_host(QmpcHandle* h, const QmpcProblem* in, int32_t batch, QmpcResult* out) {
+  return solve_host_any(h, in, batch, out, false);
+}
+extern "C" int qmpc_solve_batch_convex_host(QmpcHandle* h, const QmpcConvexProblem* in, int32_t batch,
+                                            QmpcResult* out) {
+  return solve_host_any(h, in, batch, out, true);
+}

@@ -1,0 +1,320 @@
+// qmpc_models.cuh — device-side single-rigid-body models and per-problem set-up.
+//
+// What the reference computes here (all fp64):
+//   QuadrupedModel::ct_srb_quat_dynamics / ct_srb_quat_jacobian   legged_ctrl/src/utils/AltroUtils.cpp:363-439
+//   QuadrupedModel::ct_srb_trot_quat_*  (2 feet)                  AltroUtils.cpp:441-513
+//   QuadrupedModel::ct_srb_dynamics / ct_srb_jacobian (Euler)     AltroUtils.cpp:224-359
+//   QuaternionUtils::L / G                                        legged_ctrl/src/utils/QuaternionUtils.cpp:30-52
+//   problem assembly of QuatMpc::grf_update                       legged_ctrl/src/mpc/QuatMpc.cpp:109-253
+//   problem assembly of ConvexMpc::grf_update                     legged_ctrl/src/mpc/ConvexMpc.cpp:81-175
+// Written from the mathematical statement in SURVEY.md appendix A; one thread owns one problem.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/qmpc.h"
+
+namespace qmpc {
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__device__ __forceinline__ void inv3(const double* A, double* B) {
+  double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  B[0] = c00 / det; B[1] = (A[2] * A[7] - A[1] * A[8]) / det; B[2] = (A[1] * A[5] - A[2] * A[4]) / det;
+  B[3] = c01 / det; B[4] = (A[0] * A[8] - A[2] * A[6]) / det; B[5] = (A[2] * A[3] - A[0] * A[5]) / det;
+  B[6] = c02 / det; B[7] = (A[1] * A[6] - A[0] * A[7]) / det; B[8] = (A[0] * A[4] - A[1] * A[3]) / det;
+}
+
+// Eigen::Quaterniond::toRotationMatrix (BaseInterface.cpp:196), row-major, q = (w,x,y,z)
+__device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+  double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+
+// G(q) = L(q) H, 4x3 row-major
+__device__ __forceinline__ void quat_G(const double* q, double* G) {
+  G[0] = -q[1]; G[1] = -q[2]; G[2] = -q[3];
+  G[3] = q[0];  G[4] = -q[3]; G[5] = q[2];
+  G[6] = q[3];  G[7] = q[0];  G[8] = -q[1];
+  G[9] = -q[2]; G[10] = q[1]; G[11] = q[0];
+}
+
+// Friction-cone rows per foot: C_mat * Rc with C_mat from QuatMpc.cpp:47-52
+__device__ __forceinline__ void fill_cone(double mu, const double* Rc /* nullptr = identity */, double* CR) {
+  const double C[18] = {1, 0, -mu, -1, 0, -mu, 0, 1, -mu, 0, -1, -mu, 0, 0, 1, 0, 0, -1};
+  for (int r = 0; r < 6; ++r)
+    for (int b = 0; b < 3; ++b) {
+      if (!Rc) { CR[3 * r + b] = C[3 * r + b]; continue; }
+      double s = 0;
+      for (int l = 0; l < 3; ++l) s += C[3 * r + l] * Rc[3 * l + b];
+      CR[3 * r + b] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Quaternion SRB with NF feet (QuatMpc: NF = 4; 2-contact model: NF = 2)
+template <int NF>
+struct QuatModel {
+  static constexpr int NX = 13, NE = 12, NU = 3 * NF, NC = 6 * NF, QI = 3;
+  static constexpr bool kQuat = true;
+  using Problem = QmpcProblem;
+
+  double foot[3 * NF];
+  double IS[9 * NF];  // Iinv * skew(r_i), 3x3 row-major per foot  (AltroUtils.cpp:433)
+  double Iinv[9];
+  double inv_mass, g[3], tau_g[3];
+  double CR[18], fzc[NF];
+  double uref[NU];
+  double qd[4], pd[3], vd[3];
+  double R0[9];
+  double dtk;  // reference time step for x_ref (double, QuatMpc.cpp:156)
+
+  __device__ void setup(const QmpcConfig& cfg, const QmpcProblem& in, double* x0) {
+    for (int i = 0; i < 3 * NF; ++i) foot[i] = in.foot_pos_body[i];
+    inv3(cfg.inertia, Iinv);
+    inv_mass = 1.0 / cfg.robot_mass;
+    quat_to_rot(in.torso_quat, R0);
+    const double gw[3] = {0, 0, -cfg.gravity};
+    if (NF == 4) {
+      for (int i = 0; i < 3; ++i) g[i] = R0[i] * gw[0] + R0[3 + i] * gw[1] + R0[6 + i] * gw[2];
+    } else {
+      for (int i = 0; i < 3; ++i) g[i] = gw[i];
+    }
+    double mg[3] = {cfg.com_mass * g[0], cfg.com_mass * g[1], cfg.com_mass * g[2]};
+    cross3(cfg.com_offset, mg, tau_g);
+    fill_cone(cfg.mu, R0, CR);
+    for (int i = 0; i < NF; ++i) {
+      const double* r = foot + 3 * i;
+      const double S[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          double s = 0;
+          for (int l = 0; l < 3; ++l) s += Iinv[3 * a + l] * S[3 * l + b];
+          IS[9 * i + 3 * a + b] = s;
+        }
+    }
+    int nc = 0;
+    for (int i = 0; i < NF; ++i) nc += in.plan_contacts[i] ? 1 : 0;
+    for (int i = 0; i < NU; ++i) uref[i] = 0;
+    for (int i = 0; i < NF; ++i) {
+      double c = in.plan_contacts[i] ? 1.0 : 0.0;
+      uref[3 * i + 2] = c * cfg.robot_mass * cfg.gravity / nc;
+      fzc[i] = cfg.fz_max * c;
+    }
+    {
+      const double *q = in.torso_quat_d, *w = in.torso_ang_vel_d_body;
+      double s = 0.5 * cfg.quat_d_dt;
+      qd[0] = q[0] + s * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
+      qd[1] = q[1] + s * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
+      qd[2] = q[2] + s * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
+      qd[3] = q[3] + s * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
+      double nrm = sqrt(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
+      for (int i = 0; i < 4; ++i) qd[i] /= nrm;
+    }
+    for (int i = 0; i < 3; ++i) { pd[i] = in.torso_pos_d_body[i]; vd[i] = in.torso_lin_vel_d_body[i]; }
+    dtk = cfg.dt;
+    for (int i = 0; i < NX; ++i) x0[i] = 0;
+    for (int i = 0; i < 4; ++i) x0[3 + i] = in.torso_quat[i];
+    for (int i = 0; i < 3; ++i)
+      x0[7 + i] = R0[i] * in.torso_lin_vel_world[0] + R0[3 + i] * in.torso_lin_vel_world[1] +
+                  R0[6 + i] * in.torso_lin_vel_world[2];
+    if (!cfg.drop_omega0)
+      for (int i = 0; i < 3; ++i) x0[10 + i] = in.torso_ang_vel_body[i];
+  }
+
+  __device__ void xref(int k, double* xr) const {
+    xr[0] = pd[0] + vd[0] * k * dtk;
+    xr[1] = pd[1] + vd[1] * k * dtk;
+    xr[2] = pd[2];
+    for (int i = 0; i < 4; ++i) xr[3 + i] = qd[i];
+    for (int i = 0; i < 3; ++i) { xr[7 + i] = vd[i]; xr[10 + i] = 0; }
+  }
+
+  __device__ void ct_dyn(const double* x, const double* u, double* xd) const {
+    const double *q = x + 3, *w = x + 10;
+    double mom[3] = {0, 0, 0}, fs[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      double c[3];
+      cross3(foot + 3 * i, u + 3 * i, c);
+      for (int j = 0; j < 3; ++j) { mom[j] += c[j]; fs[j] += u[3 * i + j]; }
+    }
+    for (int j = 0; j < 3; ++j) mom[j] += tau_g[j];
+    xd[0] = x[7]; xd[1] = x[8]; xd[2] = x[9];
+    xd[3] = 0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
+    xd[4] = 0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
+    xd[5] = 0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
+    xd[6] = 0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
+    for (int j = 0; j < 3; ++j) xd[7 + j] = fs[j] * inv_mass + g[j];
+    for (int a = 0; a < 3; ++a) xd[10 + a] = Iinv[3 * a] * mom[0] + Iinv[3 * a + 1] * mom[1] + Iinv[3 * a + 2] * mom[2];
+  }
+
+  // dense column-major NX x (NX+NU)
+  __device__ void ct_jac(const double* x, const double* u, double* J) const {
+    (void)u;
+    for (int i = 0; i < NX * (NX + NU); ++i) J[i] = 0;
+#define JJ(i, j) J[(j) * NX + (i)]
+    const double *q = x + 3, *w = x + 10;
+    JJ(0, 7) = 1; JJ(1, 8) = 1; JJ(2, 9) = 1;
+    JJ(3, 4) = -0.5 * w[0]; JJ(3, 5) = -0.5 * w[1]; JJ(3, 6) = -0.5 * w[2];
+    JJ(4, 3) = 0.5 * w[0]; JJ(5, 3) = 0.5 * w[1]; JJ(6, 3) = 0.5 * w[2];
+    JJ(4, 5) = 0.5 * w[2];  JJ(4, 6) = -0.5 * w[1];
+    JJ(5, 4) = -0.5 * w[2]; JJ(5, 6) = 0.5 * w[0];
+    JJ(6, 4) = 0.5 * w[1];  JJ(6, 5) = -0.5 * w[0];
+    JJ(3, 10) = -0.5 * q[1]; JJ(3, 11) = -0.5 * q[2]; JJ(3, 12) = -0.5 * q[3];
+    JJ(4, 10) = 0.5 * q[0];  JJ(4, 11) = -0.5 * q[3]; JJ(4, 12) = 0.5 * q[2];
+    JJ(5, 10) = 0.5 * q[3];  JJ(5, 11) = 0.5 * q[0];  JJ(5, 12) = -0.5 * q[1];
+    JJ(6, 10) = -0.5 * q[2]; JJ(6, 11) = 0.5 * q[1];  JJ(6, 12) = 0.5 * q[0];
+    for (int i = 0; i < NF; ++i)
+      for (int a = 0; a < 3; ++a) {
+        JJ(7 + a, 13 + 3 * i + a) = inv_mass;
+        for (int b = 0; b < 3; ++b) JJ(10 + a, 13 + 3 * i + b) = IS[9 * i + 3 * a + b];
+      }
+#undef JJ
+  }
+
+  __device__ void write_result(const double* u0, QmpcResult& out) const {
+    for (int i = 0; i < 12; ++i) { out.grf_body[i] = 0; out.grf_world[i] = 0; }
+    for (int i = 0; i < NF; ++i) {
+      const double* f = u0 + 3 * i;
+      for (int a = 0; a < 3; ++a) {
+        out.grf_world[3 * i + a] = R0[3 * a] * f[0] + R0[3 * a + 1] * f[1] + R0[3 * a + 2] * f[2];
+        out.grf_body[3 * i + a] = f[a];
+      }
+    }
+    for (int i = 0; i < 4; ++i) out.torso_quat_d[i] = qd[i];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Euler-angle SRB of ConvexMpc: x = [rpy, p_w, omega_w, v_w]
+struct ConvexModel {
+  static constexpr int NX = 12, NE = 12, NU = 12, NC = 24, QI = -1;
+  static constexpr bool kQuat = false;
+  using Problem = QmpcConvexProblem;
+
+  double foot[12];
+  double CR[18], fzc[4];
+  double uref[12];
+  double xr0[12], yaw_rate, dtk;
+  double R0[9];
+
+  __device__ void setup(const QmpcConfig& cfg, const QmpcConvexProblem& in, double* x0) {
+    for (int i = 0; i < 12; ++i) foot[i] = in.foot_pos_abs_com[i];
+    for (int i = 0; i < 9; ++i) R0[i] = in.torso_rot_mat[i];
+    fill_cone(cfg.mu, nullptr, CR);
+    int nc = 0;
+    for (int i = 0; i < 4; ++i) nc += in.plan_contacts[i] ? 1 : 0;
+    for (int i = 0; i < 12; ++i) uref[i] = 0;
+    for (int i = 0; i < 4; ++i) {
+      double c = in.plan_contacts[i] ? 1.0 : 0.0;
+      uref[3 * i + 2] = cfg.robot_mass * cfg.gravity / nc * c;
+      fzc[i] = cfg.fz_max * c;
+    }
+    for (int i = 0; i < 12; ++i) xr0[i] = 0;
+    xr0[2] = in.torso_euler[2];
+    for (int i = 0; i < 3; ++i) xr0[3 + i] = in.torso_pos_d_world[i];
+    xr0[8] = in.yaw_rate_d;
+    xr0[9] = in.torso_lin_vel_d_world[0];
+    xr0[10] = in.torso_lin_vel_d_world[1];
+    yaw_rate = in.yaw_rate_d;
+    dtk = cfg.dt;
+    for (int i = 0; i < 3; ++i) {
+      x0[i] = in.torso_euler[i]; x0[3 + i] = in.torso_pos_world[i];
+      x0[6 + i] = in.torso_ang_vel_world[i]; x0[9 + i] = in.torso_lin_vel_world[i];
+    }
+  }
+
+  __device__ void xref(int k, double* xr) const {
+    for (int i = 0; i < 12; ++i) xr[i] = xr0[i];
+    xr[2] = xr0[2] + yaw_rate * dtk * k;
+  }
+
+  // (Rz I_t Rz^T)^-1 skew(r_i), 4 blocks 3x3 row-major (AltroUtils.cpp:268-288)
+  __device__ void Bc(double yaw, double* BS) const {
+    double sy, cy;
+    sincos(yaw, &sy, &cy);
+    const double Rz[9] = {cy, -sy, 0, sy, cy, 0, 0, 0, 1};
+    const double It[3] = {0.0168128557, 0.063009565, 0.0716547275};
+    double Iw[9], Iwinv[9];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        double s = 0;
+        for (int l = 0; l < 3; ++l) s += Rz[3 * a + l] * It[l] * Rz[3 * b + l];
+        Iw[3 * a + b] = s;
+      }
+    inv3(Iw, Iwinv);
+    for (int i = 0; i < 4; ++i) {
+      const double* r = foot + 3 * i;
+      const double S[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          double s = 0;
+          for (int l = 0; l < 3; ++l) s += Iwinv[3 * a + l] * S[3 * l + b];
+          BS[9 * i + 3 * a + b] = s;
+        }
+    }
+  }
+
+  __device__ void ct_dyn(const double* x, const double* u, double* xd) const {
+    double sy, cy, BS[36];
+    sincos(x[2], &sy, &cy);
+    Bc(x[2], BS);
+    xd[0] = cy * x[6] + sy * x[7];
+    xd[1] = -sy * x[6] + cy * x[7];
+    xd[2] = x[8];
+    xd[3] = x[9]; xd[4] = x[10]; xd[5] = x[11];
+    for (int a = 0; a < 3; ++a) {
+      double s = 0, f = 0;
+      for (int i = 0; i < 4; ++i) {
+        for (int b = 0; b < 3; ++b) s += BS[9 * i + 3 * a + b] * u[3 * i + b];
+        f += u[3 * i + a];
+      }
+      xd[6 + a] = s;
+      xd[9 + a] = f / 12.84;
+    }
+    xd[11] += -9.81;
+  }
+
+  __device__ void ct_jac(const double* x, const double* u, double* J) const {
+    (void)u;
+    for (int i = 0; i < NX * (NX + NU); ++i) J[i] = 0;
+#define JJ(i, j) J[(j) * NX + (i)]
+    double sy, cy, BS[36];
+    sincos(x[2], &sy, &cy);
+    Bc(x[2], BS);
+    JJ(0, 2) = x[7] * cy - x[6] * sy;
+    JJ(1, 2) = -x[6] * cy - x[7] * sy;
+    JJ(0, 6) = cy; JJ(0, 7) = sy; JJ(1, 6) = -sy; JJ(1, 7) = cy; JJ(2, 8) = 1;
+    JJ(3, 9) = 1; JJ(4, 10) = 1; JJ(5, 11) = 1;
+    for (int i = 0; i < 4; ++i)
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) JJ(6 + a, 12 + 3 * i + b) = BS[9 * i + 3 * a + b];
+        JJ(9 + a, 12 + 3 * i + a) = 1.0 / 12.84;
+      }
+#undef JJ
+  }
+
+  __device__ void write_result(const double* u0, QmpcResult& out) const {
+    for (int i = 0; i < 4; ++i) {
+      const double* f = u0 + 3 * i;
+      for (int a = 0; a < 3; ++a) {
+        out.grf_body[3 * i + a] = R0[a] * f[0] + R0[3 + a] * f[1] + R0[6 + a] * f[2];  // R0^T u
+        out.grf_world[3 * i + a] = f[a];
+      }
+    }
+    out.torso_quat_d[0] = 1; out.torso_quat_d[1] = 0; out.torso_quat_d[2] = 0; out.torso_quat_d[3] = 0;
+  }
+};
+
+}  // namespace qmpc

