@@ -12,6 +12,7 @@
 
 #include "../../include/qmpc.h"
 #include "qmpc_dense.cuh"
+#include "qmpc_srb.cuh"
 
 using namespace qmpc;
 
@@ -27,7 +28,7 @@ struct QmpcHandle {
   QmpcResult* d_out;
   cudaStream_t stream; // stream used by the *_host entry points
   int64_t launches;
-  int kernel;          // 0 = dense
+  int kernel;          // 0 = dense (generic), 1 = srb (structure-exploiting, QUAT models only)
   char err[256];
 };
 
@@ -95,10 +96,12 @@ extern "C" int qmpc_default_config(int32_t model, int32_t horizon, QmpcConfig* c
   return QMPC_OK;
 }
 
-static size_t ws_elems(const QmpcConfig& c) {
+static size_t ws_elems(const QmpcConfig& c, int kernel) {
   switch (c.model) {
-    case QMPC_MODEL_QUAT_4FOOT: return DenseLayout<QuatModel<4>>::total(c.horizon);
-    case QMPC_MODEL_QUAT_2FOOT: return DenseLayout<QuatModel<2>>::total(c.horizon);
+    case QMPC_MODEL_QUAT_4FOOT:
+      return kernel == 1 ? SrbLayout<4>::total(c.horizon) : DenseLayout<QuatModel<4>>::total(c.horizon);
+    case QMPC_MODEL_QUAT_2FOOT:
+      return kernel == 1 ? SrbLayout<2>::total(c.horizon) : DenseLayout<QuatModel<2>>::total(c.horizon);
     default: return DenseLayout<ConvexModel>::total(c.horizon);
   }
 }
@@ -129,8 +132,14 @@ extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t dev
   o.ls_c1 = 1e-4;
   o.ls_decrease = 0.5;
   o.ls_iters_max = 25;
+  // kernel selection: the structured SRB kernel for the quaternion models; QMPC_KERNEL=dense forces
+  // the generic dense kernel (kept as the on-device cross-check and for the Euler/ConvexMpc model)
+  h->kernel = cfg->model == QMPC_MODEL_EULER_CONVEX ? 0 : 1;
+  if (const char* k = getenv("QMPC_KERNEL")) {
+    if (!strcmp(k, "dense")) h->kernel = 0;
+  }
   CU(cudaSetDevice(device));
-  h->ws_bytes = ws_elems(*cfg) * h->stride * sizeof(double);
+  h->ws_bytes = ws_elems(*cfg, h->kernel) * h->stride * sizeof(double);
   CU(cudaMalloc(&h->ws, h->ws_bytes));
   size_t in_sz = cfg->model == QMPC_MODEL_EULER_CONVEX ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
   CU(cudaMalloc(&h->d_in, in_sz * (size_t)max_batch));
@@ -163,6 +172,16 @@ static int launch_dense(QmpcHandle* h, const typename M::Problem* d_in, int batc
   return QMPC_OK;
 }
 
+template <int NF>
+static int launch_srb(QmpcHandle* h, const QmpcProblem* d_in, int batch, QmpcResult* d_out, cudaStream_t s) {
+  const int block = 64;
+  const int grid = (batch + block - 1) / block;
+  qmpc_srb_kernel<NF><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, d_out, h->ws, batch, h->stride);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
 static int solve_any(QmpcHandle* h, const void* d_in, int32_t batch, QmpcResult* d_out, void* stream, bool convex) {
   if (!h || !h->ws) return h ? QMPC_ERR_CUDA : QMPC_ERR_ARG;
   if (!d_in || !d_out || batch < 0) return QMPC_ERR_ARG;
@@ -172,8 +191,12 @@ static int solve_any(QmpcHandle* h, const void* d_in, int32_t batch, QmpcResult*
   CU(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   switch (h->cfg.model) {
-    case QMPC_MODEL_QUAT_4FOOT: return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
-    case QMPC_MODEL_QUAT_2FOOT: return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
+    case QMPC_MODEL_QUAT_4FOOT:
+      if (h->kernel == 1) return launch_srb<4>(h, (const QmpcProblem*)d_in, batch, d_out, s);
+      return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
+    case QMPC_MODEL_QUAT_2FOOT:
+      if (h->kernel == 1) return launch_srb<2>(h, (const QmpcProblem*)d_in, batch, d_out, s);
+      return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
     default: return launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, batch, d_out, s);
   }
 }

@@ -9,20 +9,27 @@
 //   problem assembly of ConvexMpc::grf_update                     legged_ctrl/src/mpc/ConvexMpc.cpp:81-175
 // Written from the mathematical statement in SURVEY.md appendix A; one thread owns one problem.
 #pragma once
-#include <cuda_runtime.h>
 #include <math.h>
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define QMPC_HD __host__ __device__
+#else
+// host-only translation units (tests/emul: runs the very same solver bodies on the CPU so they can
+// be debugged in a GPU-less container; never part of libqmpc_b200.so)
+#define QMPC_HD
+#endif
 
 #include "../../include/qmpc.h"
 
 namespace qmpc {
 
-__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+QMPC_HD inline void cross3(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1];
   c[1] = a[2] * b[0] - a[0] * b[2];
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-__device__ __forceinline__ void inv3(const double* A, double* B) {
+QMPC_HD inline void inv3(const double* A, double* B) {
   double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
   double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
   B[0] = c00 / det; B[1] = (A[2] * A[7] - A[1] * A[8]) / det; B[2] = (A[1] * A[5] - A[2] * A[4]) / det;
@@ -31,7 +38,7 @@ __device__ __forceinline__ void inv3(const double* A, double* B) {
 }
 
 // Eigen::Quaterniond::toRotationMatrix (BaseInterface.cpp:196), row-major, q = (w,x,y,z)
-__device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
+QMPC_HD inline void quat_to_rot(const double* q, double* R) {
   double w = q[0], x = q[1], y = q[2], z = q[3];
   double tx = 2 * x, ty = 2 * y, tz = 2 * z;
   double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
@@ -42,7 +49,7 @@ __device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
 }
 
 // G(q) = L(q) H, 4x3 row-major
-__device__ __forceinline__ void quat_G(const double* q, double* G) {
+QMPC_HD inline void quat_G(const double* q, double* G) {
   G[0] = -q[1]; G[1] = -q[2]; G[2] = -q[3];
   G[3] = q[0];  G[4] = -q[3]; G[5] = q[2];
   G[6] = q[3];  G[7] = q[0];  G[8] = -q[1];
@@ -50,7 +57,7 @@ __device__ __forceinline__ void quat_G(const double* q, double* G) {
 }
 
 // Friction-cone rows per foot: C_mat * Rc with C_mat from QuatMpc.cpp:47-52
-__device__ __forceinline__ void fill_cone(double mu, const double* Rc /* nullptr = identity */, double* CR) {
+QMPC_HD inline void fill_cone(double mu, const double* Rc /* nullptr = identity */, double* CR) {
   const double C[18] = {1, 0, -mu, -1, 0, -mu, 0, 1, -mu, 0, -1, -mu, 0, 0, 1, 0, 0, -1};
   for (int r = 0; r < 6; ++r)
     for (int b = 0; b < 3; ++b) {
@@ -79,7 +86,7 @@ struct QuatModel {
   double R0[9];
   double dtk;  // reference time step for x_ref (double, QuatMpc.cpp:156)
 
-  __device__ void setup(const QmpcConfig& cfg, const QmpcProblem& in, double* x0) {
+  QMPC_HD void setup(const QmpcConfig& cfg, const QmpcProblem& in, double* x0) {
     for (int i = 0; i < 3 * NF; ++i) foot[i] = in.foot_pos_body[i];
     inv3(cfg.inertia, Iinv);
     inv_mass = 1.0 / cfg.robot_mass;
@@ -132,7 +139,7 @@ struct QuatModel {
       for (int i = 0; i < 3; ++i) x0[10 + i] = in.torso_ang_vel_body[i];
   }
 
-  __device__ void xref(int k, double* xr) const {
+  QMPC_HD void xref(int k, double* xr) const {
     xr[0] = pd[0] + vd[0] * k * dtk;
     xr[1] = pd[1] + vd[1] * k * dtk;
     xr[2] = pd[2];
@@ -140,7 +147,7 @@ struct QuatModel {
     for (int i = 0; i < 3; ++i) { xr[7 + i] = vd[i]; xr[10 + i] = 0; }
   }
 
-  __device__ void ct_dyn(const double* x, const double* u, double* xd) const {
+  QMPC_HD void ct_dyn(const double* x, const double* u, double* xd) const {
     const double *q = x + 3, *w = x + 10;
     double mom[3] = {0, 0, 0}, fs[3] = {0, 0, 0};
 #pragma unroll
@@ -160,7 +167,7 @@ struct QuatModel {
   }
 
   // dense column-major NX x (NX+NU)
-  __device__ void ct_jac(const double* x, const double* u, double* J) const {
+  QMPC_HD void ct_jac(const double* x, const double* u, double* J) const {
     (void)u;
     for (int i = 0; i < NX * (NX + NU); ++i) J[i] = 0;
 #define JJ(i, j) J[(j) * NX + (i)]
@@ -183,7 +190,7 @@ struct QuatModel {
 #undef JJ
   }
 
-  __device__ void write_result(const double* u0, QmpcResult& out) const {
+  QMPC_HD void write_result(const double* u0, QmpcResult& out) const {
     for (int i = 0; i < 12; ++i) { out.grf_body[i] = 0; out.grf_world[i] = 0; }
     for (int i = 0; i < NF; ++i) {
       const double* f = u0 + 3 * i;
@@ -209,7 +216,7 @@ struct ConvexModel {
   double xr0[12], yaw_rate, dtk;
   double R0[9];
 
-  __device__ void setup(const QmpcConfig& cfg, const QmpcConvexProblem& in, double* x0) {
+  QMPC_HD void setup(const QmpcConfig& cfg, const QmpcConvexProblem& in, double* x0) {
     for (int i = 0; i < 12; ++i) foot[i] = in.foot_pos_abs_com[i];
     for (int i = 0; i < 9; ++i) R0[i] = in.torso_rot_mat[i];
     fill_cone(cfg.mu, nullptr, CR);
@@ -235,15 +242,15 @@ struct ConvexModel {
     }
   }
 
-  __device__ void xref(int k, double* xr) const {
+  QMPC_HD void xref(int k, double* xr) const {
     for (int i = 0; i < 12; ++i) xr[i] = xr0[i];
     xr[2] = xr0[2] + yaw_rate * dtk * k;
   }
 
   // (Rz I_t Rz^T)^-1 skew(r_i), 4 blocks 3x3 row-major (AltroUtils.cpp:268-288)
-  __device__ void Bc(double yaw, double* BS) const {
+  QMPC_HD void Bc(double yaw, double* BS) const {
     double sy, cy;
-    sincos(yaw, &sy, &cy);
+    sy = sin(yaw); cy = cos(yaw);
     const double Rz[9] = {cy, -sy, 0, sy, cy, 0, 0, 0, 1};
     const double It[3] = {0.0168128557, 0.063009565, 0.0716547275};
     double Iw[9], Iwinv[9];
@@ -266,9 +273,9 @@ struct ConvexModel {
     }
   }
 
-  __device__ void ct_dyn(const double* x, const double* u, double* xd) const {
+  QMPC_HD void ct_dyn(const double* x, const double* u, double* xd) const {
     double sy, cy, BS[36];
-    sincos(x[2], &sy, &cy);
+    sy = sin(x[2]); cy = cos(x[2]);
     Bc(x[2], BS);
     xd[0] = cy * x[6] + sy * x[7];
     xd[1] = -sy * x[6] + cy * x[7];
@@ -286,12 +293,12 @@ struct ConvexModel {
     xd[11] += -9.81;
   }
 
-  __device__ void ct_jac(const double* x, const double* u, double* J) const {
+  QMPC_HD void ct_jac(const double* x, const double* u, double* J) const {
     (void)u;
     for (int i = 0; i < NX * (NX + NU); ++i) J[i] = 0;
 #define JJ(i, j) J[(j) * NX + (i)]
     double sy, cy, BS[36];
-    sincos(x[2], &sy, &cy);
+    sy = sin(x[2]); cy = cos(x[2]);
     Bc(x[2], BS);
     JJ(0, 2) = x[7] * cy - x[6] * sy;
     JJ(1, 2) = -x[6] * cy - x[7] * sy;
@@ -305,7 +312,7 @@ struct ConvexModel {
 #undef JJ
   }
 
-  __device__ void write_result(const double* u0, QmpcResult& out) const {
+  QMPC_HD void write_result(const double* u0, QmpcResult& out) const {
     for (int i = 0; i < 4; ++i) {
       const double* f = u0 + 3 * i;
       for (int a = 0; a < 3; ++a) {
