@@ -13,6 +13,7 @@
 #include "../../include/qmpc.h"
 #include "qmpc_dense.cuh"
 #include "qmpc_srb.cuh"
+#include "qmpc_coop.cuh"
 
 using namespace qmpc;
 
@@ -28,7 +29,10 @@ struct QmpcHandle {
   QmpcResult* d_out;
   cudaStream_t stream; // stream used by the *_host entry points
   int64_t launches;
-  int kernel;          // 0 = dense (generic), 1 = srb (structure-exploiting, QUAT models only)
+  int kernel;          // 0 = dense (generic), 1 = srb (structured, thread per problem), 2 = coop (structured,
+                       //     16 lanes per problem, shared-memory resident; default for the QUAT models)
+  int coop_grid, coop_smem_doubles;   // persistent launch geometry of the coop kernel
+  size_t coop_scratch_doubles;
   char err[256];
 };
 
@@ -106,6 +110,32 @@ static size_t ws_elems(const QmpcConfig& c, int kernel) {
   }
 }
 
+constexpr int kCoopG = 16, kCoopBlock = 64;
+
+// persistent-kernel geometry: as many resident blocks as the device holds (or the batch needs)
+template <int NF>
+static int coop_prepare_t(QmpcHandle* h) {
+  using L = CoopLayout<NF, kCoopG>;
+  const int N = h->cfg.horizon;
+  h->coop_smem_doubles = L::smem_doubles(N);
+  h->coop_scratch_doubles = L::scratch_doubles(N);
+  const int groups = kCoopBlock / kCoopG;
+  const size_t smem_bytes = (size_t)groups * h->coop_smem_doubles * sizeof(double);
+  CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  int per_sm = 0, sms = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_coop_kernel<NF, kCoopG>, kCoopBlock, smem_bytes));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  if (per_sm < 1) { snprintf(h->err, sizeof(h->err), "coop kernel does not fit on an SM"); return QMPC_ERR_CUDA; }
+  const int need = (h->max_batch + groups - 1) / groups;
+  const int resident = per_sm * sms;
+  h->coop_grid = need < resident ? need : resident;
+  h->ws_bytes = (size_t)h->coop_grid * groups * h->coop_scratch_doubles * sizeof(double);
+  return QMPC_OK;
+}
+static int coop_prepare(QmpcHandle* h) {
+  return h->cfg.model == QMPC_MODEL_QUAT_4FOOT ? coop_prepare_t<4>(h) : coop_prepare_t<2>(h);
+}
+
 extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t device, QmpcHandle** out) {
   if (!cfg || !out || max_batch < 1) return QMPC_ERR_ARG;
   if (cfg->horizon < 1 || cfg->horizon > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
@@ -134,12 +164,18 @@ extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t dev
   o.ls_iters_max = 25;
   // kernel selection: the structured SRB kernel for the quaternion models; QMPC_KERNEL=dense forces
   // the generic dense kernel (kept as the on-device cross-check and for the Euler/ConvexMpc model)
-  h->kernel = cfg->model == QMPC_MODEL_EULER_CONVEX ? 0 : 1;
+  h->kernel = cfg->model == QMPC_MODEL_EULER_CONVEX ? 0 : 2;
   if (const char* k = getenv("QMPC_KERNEL")) {
     if (!strcmp(k, "dense")) h->kernel = 0;
+    else if (!strcmp(k, "srb") && cfg->model != QMPC_MODEL_EULER_CONVEX) h->kernel = 1;
   }
   CU(cudaSetDevice(device));
-  h->ws_bytes = ws_elems(*cfg, h->kernel) * h->stride * sizeof(double);
+  if (h->kernel == 2) {
+    int rc = coop_prepare(h);
+    if (rc) return rc;
+  } else {
+    h->ws_bytes = ws_elems(*cfg, h->kernel) * h->stride * sizeof(double);
+  }
   CU(cudaMalloc(&h->ws, h->ws_bytes));
   size_t in_sz = cfg->model == QMPC_MODEL_EULER_CONVEX ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
   CU(cudaMalloc(&h->d_in, in_sz * (size_t)max_batch));
@@ -182,6 +218,19 @@ static int launch_srb(QmpcHandle* h, const QmpcProblem* d_in, int batch, QmpcRes
   return QMPC_OK;
 }
 
+template <int NF>
+static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, int batch, QmpcResult* d_out, cudaStream_t s) {
+  const int groups = kCoopBlock / kCoopG;
+  const int need = (batch + groups - 1) / groups;
+  const int grid = need < h->coop_grid ? need : h->coop_grid;
+  const size_t smem_bytes = (size_t)groups * h->coop_smem_doubles * sizeof(double);
+  qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, d_out, h->ws, batch,
+                                                                   h->coop_smem_doubles, h->coop_scratch_doubles);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
 static int solve_any(QmpcHandle* h, const void* d_in, int32_t batch, QmpcResult* d_out, void* stream, bool convex) {
   if (!h || !h->ws) return h ? QMPC_ERR_CUDA : QMPC_ERR_ARG;
   if (!d_in || !d_out || batch < 0) return QMPC_ERR_ARG;
@@ -192,9 +241,11 @@ static int solve_any(QmpcHandle* h, const void* d_in, int32_t batch, QmpcResult*
   cudaStream_t s = (cudaStream_t)stream;
   switch (h->cfg.model) {
     case QMPC_MODEL_QUAT_4FOOT:
+      if (h->kernel == 2) return launch_coop<4>(h, (const QmpcProblem*)d_in, batch, d_out, s);
       if (h->kernel == 1) return launch_srb<4>(h, (const QmpcProblem*)d_in, batch, d_out, s);
       return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
     case QMPC_MODEL_QUAT_2FOOT:
+      if (h->kernel == 2) return launch_coop<2>(h, (const QmpcProblem*)d_in, batch, d_out, s);
       if (h->kernel == 1) return launch_srb<2>(h, (const QmpcProblem*)d_in, batch, d_out, s);
       return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
     default: return launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, batch, d_out, s);

@@ -1,0 +1,641 @@
+// qmpc_coop.cuh — kernel "coop": G (=16) lanes of a warp own one MPC problem; every per-problem
+// matrix lives in shared memory, the gains / value functions / duals in an L2-resident per-slot
+// scratch.  Same algorithm, decisions and (where it matters) operation order as the structured
+// one-thread-per-problem kernel (qmpc_srb.cuh) and the CPU oracle.
+//
+// Why (profiles/r01_ncu_srb_thread_per_problem_B16384.txt): with one thread per problem the fp64
+// working set (~13 KB of 12x12 temporaries per thread) spills to local memory, misses L1/L2 and the
+// kernel runs at 3 % fp64-pipe utilisation on DRAM latency.  Here the working set per problem is
+// ~10 KB of shared memory, shared by 16 lanes:
+//   * the Riccati step is a sequence of "phases"; in each phase the lanes split the output
+//     elements of one small block product (operands read from shared memory, mostly broadcast or
+//     conflict-free), separated by __syncwarp on the half-warp;
+//   * the back-tracking line search is evaluated speculatively: lane l rolls out step length
+//     2^-l (all 16 trial steps at once, K_k/d_k read as broadcasts), the first lane that passes the
+//     Armijo test wins — identical result to the sequential search, ~1 roll-out of latency instead
+//     of ~5;
+//   * linearisation, stationarity residuals, dual update, Riccati duals are parallel over knots.
+// The kernel is persistent: grid = resident slots, each slot strides over the batch.
+//
+// The body is written with COOP_PHASE / COOP_SYNC so that the very same source runs on the host
+// (tests/emul, lanes executed one after another) for GPU-less debugging.
+#pragma once
+#include "qmpc_srb.cuh"
+
+#ifdef __CUDA_ARCH__
+#define COOP_PHASE for (int lane = lane_id, once_ = 1; once_; once_ = 0)
+#define COOP_SYNC() __syncwarp(lane_mask)
+#else
+#define COOP_PHASE for (int lane = 0; lane < G; ++lane)
+#define COOP_SYNC() ((void)0)
+#endif
+
+namespace qmpc {
+
+template <int NF, int G>
+struct CoopLayout {
+  static constexpr int NU = 3 * NF, NC = 6 * NF;
+  static constexpr int kModel = (int)((sizeof(QuatModel<NF>) + 7) / 8);
+  // ---- shared memory (doubles) per problem
+  static constexpr int kVec = 160;
+  QMPC_HD static int sX(int N) { return kModel; }
+  QMPC_HD static int sU(int N) { return sX(N) + (N + 1) * 13; }
+  QMPC_HD static int sDX(int N) { return sU(N) + N * NU; }
+  QMPC_HD static int sP(int N) { return sDX(N) + (N + 1) * 12; }
+  QMPC_HD static int sPA(int N) { return sP(N) + 144; }    // PA, later Quu / its Cholesky factor
+  QMPC_HD static int sT(int N) { return sPA(N) + 144; }
+  QMPC_HD static int sPM(int N) { return sT(N) + 72; }     // PM, later SW
+  QMPC_HD static int sS(int N) { return sPM(N) + 72; }
+  QMPC_HD static int sQux(int N) { return sS(N) + 36; }    // Qux, later V = L^-1 Qux
+  QMPC_HD static int sVec(int N) { return sQux(N) + NU * 12; }
+  QMPC_HD static int sRed(int N) { return sVec(N) + kVec; }
+  QMPC_HD static int sLin(int N) { return sRed(N) + 2 * G; }
+  QMPC_HD static int smem_doubles(int N) { return (sLin(N) + 27 + 1) / 2 * 2; }
+  // ---- global scratch (doubles) per slot
+  QMPC_HD static size_t gK(int N) { return 0; }
+  QMPC_HD static size_t gd(int N) { return gK(N) + (size_t)N * NU * 12; }
+  QMPC_HD static size_t gP(int N) { return gd(N) + (size_t)N * NU; }
+  QMPC_HD static size_t gpv(int N) { return gP(N) + (size_t)(N + 1) * 78; }
+  QMPC_HD static size_t gmu(int N) { return gpv(N) + (size_t)(N + 1) * 12; }
+  QMPC_HD static size_t glin(int N) { return gmu(N) + (size_t)N * NC; }
+  QMPC_HD static size_t scratch_doubles(int N) { return (glin(N) + (size_t)N * 27 + 15) / 16 * 16; }
+};
+
+// offsets inside the shared "vec" block
+namespace cv {
+constexpr int lx = 0, Qx = 12, Qu = 24, s = 36, Atp = 42, g = 54, Dblk = 66, Hphi = 102, vu = 111, tcol = 123,
+              pv = 135, scal = 147;  // scal[0]=dphi0 [1]=hphi [2]=phi [3]=viol
+}
+
+// stage cost + AL terms of one knot (same accumulation order as merit() in qmpc_dense.cuh)
+template <class M>
+QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, int k, int N, const double* x, const double* u,
+                               const double* mu_k, double rho, double& J, double& viol) {
+  J += stage_cost(m, cfg, k, N, x, u);
+  if (k < N) {
+    double c[M::NC];
+    cone_eval(m, u, c);
+    double acc = 0;
+#pragma unroll
+    for (int i = 0; i < M::NC; ++i) {
+      const double mui = mu_k[i];
+      const double est = mui + rho * c[i];
+      const double lh = est > 0 ? est : 0;
+      if (c[i] > viol) viol = c[i];
+      acc += lh * lh - mui * mui;
+    }
+    J += acc / (2 * rho);
+  }
+}
+
+// cost Hessian entry (a,b) in error coordinates given the attitude block Hphi (3x3)
+QMPC_HD inline double lxx_entry(const QmpcConfig& cfg, const double* Hphi, int a, int b) {
+  const int ab = a / 3, bb = b / 3;
+  if (ab == 1 && bb == 1) return Hphi[3 * (a - 3) + (b - 3)];
+  if (a != b) return 0.0;
+  return a < 3 ? cfg.q_weights[a] : cfg.q_weights[a + 1];
+}
+
+// attitude block of the cost Hessian: G^T diag(Qq) G + hphi I
+QMPC_HD inline void hphi_block(const QmpcConfig& cfg, const double* x, double hphi, double* H) {
+  double Gq[12];
+  quat_G(x + 3, Gq);
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      double s = 0;
+      for (int i = 0; i < 4; ++i) s += Gq[3 * i + a] * cfg.q_weights[3 + i] * Gq[3 * i + b];
+      H[3 * a + b] = s + (a == b ? hphi : 0.0);
+    }
+}
+
+template <int NF, int G>
+QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in, QmpcResult* out,
+                            int pid, double* sm, double* gs, int lane_id, unsigned lane_mask) {
+  using M = QuatModel<NF>;
+  using L = CoopLayout<NF, G>;
+  constexpr int NX = 13, NE = 12, NU = M::NU, NC = M::NC;
+  (void)lane_id; (void)lane_mask;
+  const int N = o.N;
+  const float h = o.h;
+  const double hd = (double)h, hh = (double)(h / 2), c1 = hd * hh;
+
+  M& m = *reinterpret_cast<M*>(sm);
+  double* X = sm + L::sX(N);
+  double* U = sm + L::sU(N);
+  double* DX = sm + L::sDX(N);
+  double* P = sm + L::sP(N);
+  double* PA = sm + L::sPA(N);
+  double* Quu = PA;
+  double* T = sm + L::sT(N);
+  double* PM = sm + L::sPM(N);
+  double* SW = PM;
+  double* S = sm + L::sS(N);
+  double* Qux = sm + L::sQux(N);
+  double* vec = sm + L::sVec(N);
+  double* red = sm + L::sRed(N);
+  double* lin = sm + L::sLin(N);
+  double* gK = gs + L::gK(N);
+  double* gd = gs + L::gd(N);
+  double* gP = gs + L::gP(N);
+  double* gpv = gs + L::gpv(N);
+  double* gmu = gs + L::gmu(N);
+  double* glin = gs + L::glin(N);
+  double* scal = vec + cv::scal;
+
+  // ------------------------------------------------------------------ set-up + nominal roll-out
+  COOP_PHASE {
+    for (int i = lane; i < N * NC; i += G) gmu[i] = 0.0;
+    if (lane == 0) {
+      QmpcProblem prob = in[pid];
+      m.setup(cfg, prob, X);
+    }
+  }
+  COOP_SYNC();
+  double rho = o.penalty_initial;
+  COOP_PHASE {
+    if (lane == 0) {
+      double x[NX], xn[NX], J = 0, vl = 0;
+      for (int i = 0; i < NX; ++i) x[i] = X[i];
+#pragma unroll 1
+      for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < NU; ++i) U[k * NU + i] = m.uref[i];
+        knot_merit(m, cfg, k, N, x, m.uref, gmu + k * NC, rho, J, vl);
+        mid_dyn(m, x, m.uref, h, xn);
+        for (int i = 0; i < NX; ++i) { x[i] = xn[i]; X[(k + 1) * NX + i] = xn[i]; }
+      }
+      knot_merit(m, cfg, N, N, x, m.uref, gmu, rho, J, vl);
+      scal[2] = J;
+      scal[3] = vl;
+    }
+  }
+  COOP_SYNC();
+  double phi = scal[2], viol = scal[3];
+  int status = QMPC_STATUS_MAX_ITERATIONS, iters = 0;
+  double cost_decrease = INFINITY;
+  if (!isfinite(phi)) status = QMPC_STATUS_NONFINITE;
+
+#pragma unroll 1
+  for (int it = 0; it < o.iterations_max && status == QMPC_STATUS_MAX_ITERATIONS; ++it) {
+    // ---------------- linearise: lane k <- knot k (27 doubles to the scratch)
+    COOP_PHASE {
+      for (int k = lane; k < N; k += G) {
+        KnotLin Lk;
+        srb_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
+        for (int i = 0; i < 9; ++i) {
+          glin[k * 27 + i] = Lk.Aff[i];
+          glin[k * 27 + 9 + i] = Lk.Afw[i];
+          glin[k * 27 + 18 + i] = Lk.Cf[i];
+        }
+      }
+    }
+    COOP_SYNC();
+
+    if (it > 0) {
+      // ---------------- stationarity with the Riccati duals of the accepted step (DX holds y_k)
+      COOP_PHASE {
+        double rx = 0, ru = 0;
+        for (int k = lane; k <= N; k += G) {
+          double lx[NE], hphi;
+          cost_expand(m, cfg, k, X + k * NX, lx, &hphi);
+          if (k == N) {
+            for (int a = 0; a < NE; ++a) {
+              double v = fabs(lx[a] - DX[N * NE + a]);
+              if (v > rx) rx = v;
+            }
+          } else {
+            KnotLin Lk;
+            for (int i = 0; i < 9; ++i) {
+              Lk.Aff[i] = glin[k * 27 + i];
+              Lk.Afw[i] = glin[k * 27 + 9 + i];
+              Lk.Cf[i] = glin[k * 27 + 18 + i];
+            }
+            const double* u = U + k * NU;
+            const double* yn = DX + (k + 1) * NE;
+            double gu[NU], Hb[9 * NF], Aty[NE], t6[6], Bty[NU];
+            al_terms(m, u, GVec{gmu + k * NC, 1}, rho, gu, Hb);
+            srb_At_vec(Lk, hd, yn, Aty);
+            srb_Mt_vec(Lk, hd, hh, yn, t6);
+            srb_Wt_vec(m, t6, Bty);
+            for (int a = 0; a < NE; ++a) {
+              double v = fabs(lx[a] + Aty[a] - DX[k * NE + a]);
+              if (v > rx) rx = v;
+            }
+            for (int a = 0; a < NU; ++a) {
+              double v = fabs(cfg.r_weights[a] * (u[a] - m.uref[a]) + gu[a] + Bty[a]);
+              if (v > ru) ru = v;
+            }
+          }
+        }
+        red[lane] = rx > ru ? rx : ru;
+      }
+      COOP_SYNC();
+      double stat = 0;
+      for (int l = 0; l < G; ++l) stat = red[l] > stat ? red[l] : stat;
+      COOP_SYNC();
+      if (stat < o.tol_stationarity && viol < o.tol_primal_feasibility) {
+        status = QMPC_STATUS_SUCCESS;
+        break;
+      }
+      if (fabs(cost_decrease) < o.tol_cost_intermediate || stat < o.tol_stationarity) {
+        // dual update (row-parallel), penalty update, merit refresh (knot-parallel)
+        COOP_PHASE {
+          for (int idx = lane; idx < N * NC; idx += G) {
+            const int k = idx / NC, r = idx % NC, f = r / 6, rr = r % 6;
+            const double* u = U + k * NU + 3 * f;
+            double c = m.CR[3 * rr] * u[0] + m.CR[3 * rr + 1] * u[1] + m.CR[3 * rr + 2] * u[2];
+            if (rr == 4) c += -m.fzc[f];
+            const double est = gmu[idx] + rho * c;
+            gmu[idx] = est > 0 ? est : 0;
+          }
+        }
+        COOP_SYNC();
+        {
+          const double r = rho * o.penalty_scaling;
+          rho = r < o.penalty_max ? r : o.penalty_max;
+        }
+        COOP_PHASE {
+          double J = 0, vl = 0;
+          for (int k = lane; k <= N; k += G) knot_merit(m, cfg, k, N, X + k * NX, U + k * NU, gmu + k * NC, rho, J, vl);
+          red[lane] = J;
+          red[G + lane] = vl;
+        }
+        COOP_SYNC();
+        phi = 0;
+        viol = 0;
+        for (int l = 0; l < G; ++l) {
+          phi += red[l];
+          viol = red[G + l] > viol ? red[G + l] : viol;
+        }
+        COOP_SYNC();
+      }
+    }
+
+    // ---------------- Riccati backward pass
+    bool bp_ok = true;
+    COOP_PHASE {
+      if (lane == 0) {
+        double hphi;
+        cost_expand(m, cfg, N, X + N * NX, vec + cv::pv, &hphi);
+        hphi_block(cfg, X + N * NX, hphi, vec + cv::Hphi);
+        scal[0] = 0.0;
+      }
+    }
+    COOP_SYNC();
+    COOP_PHASE {
+      for (int e = lane; e < 144; e += G) P[e] = lxx_entry(cfg, vec + cv::Hphi, e / 12, e % 12);
+      for (int e = lane; e < 12; e += G) gpv[N * 12 + e] = vec[cv::pv + e];
+      for (int idx = lane; idx < 78; idx += G) {
+        // packed upper-triangle index -> (a,b)
+        int a = 0, rem = idx;
+        while (rem >= 12 - a) { rem -= 12 - a; ++a; }
+        const int b = a + rem;
+        gP[N * 78 + idx] = lxx_entry(cfg, vec + cv::Hphi, a, b);
+      }
+    }
+    COOP_SYNC();
+
+#pragma unroll 1
+    for (int k = N - 1; k >= 0 && bp_ok; --k) {
+      // ---- phase A: stage the knot's 3x3 blocks; per-foot AL terms; cost expansion
+      COOP_PHASE {
+        for (int e = lane; e < 27; e += G) lin[e] = glin[k * 27 + e];
+        if (lane < NF) {
+          const int f = lane;
+          const double* u = U + k * NU + 3 * f;
+          double g0 = 0, g1 = 0, g2 = 0, hb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          for (int r = 0; r < 6; ++r) {
+            double c = m.CR[3 * r] * u[0] + m.CR[3 * r + 1] * u[1] + m.CR[3 * r + 2] * u[2];
+            if (r == 4) c += -m.fzc[f];
+            const double est = gmu[k * NC + 6 * f + r] + rho * c;
+            if (est > 0) {
+              const double j0 = m.CR[3 * r], j1 = m.CR[3 * r + 1], j2 = m.CR[3 * r + 2];
+              g0 += j0 * est; g1 += j1 * est; g2 += j2 * est;
+              hb[0] += rho * j0 * j0; hb[1] += rho * j0 * j1; hb[2] += rho * j0 * j2;
+              hb[3] += rho * j1 * j0; hb[4] += rho * j1 * j1; hb[5] += rho * j1 * j2;
+              hb[6] += rho * j2 * j0; hb[7] += rho * j2 * j1; hb[8] += rho * j2 * j2;
+            }
+          }
+          hb[0] += cfg.r_weights[3 * f]; hb[4] += cfg.r_weights[3 * f + 1]; hb[8] += cfg.r_weights[3 * f + 2];
+          for (int a = 0; a < 9; ++a) vec[cv::Dblk + 9 * f + a] = hb[a];
+          vec[cv::g + 3 * f] = cfg.r_weights[3 * f] * (u[0] - m.uref[3 * f]) + g0;
+          vec[cv::g + 3 * f + 1] = cfg.r_weights[3 * f + 1] * (u[1] - m.uref[3 * f + 1]) + g1;
+          vec[cv::g + 3 * f + 2] = cfg.r_weights[3 * f + 2] * (u[2] - m.uref[3 * f + 2]) + g2;
+        }
+        if (lane == NF) {
+          double hphi;
+          cost_expand(m, cfg, k, X + k * NX, vec + cv::lx, &hphi);
+          hphi_block(cfg, X + k * NX, hphi, vec + cv::Hphi);
+        }
+      }
+      COOP_SYNC();
+      const double* Aff = lin;
+      const double* Afw = lin + 9;
+      const double* Cf = lin + 18;
+      const double* pv = vec + cv::pv;
+      // ---- phase B: PA = P A, PM = P M, s = M^T p, Atp = A^T p
+      COOP_PHASE {
+        for (int e = lane; e < 144; e += G) {
+          const int i = e / 12, j = e % 12, jb = j / 3, jj = j % 3;
+          const double* Pi = P + 12 * i;
+          double v;
+          if (jb == 0) v = Pi[j];
+          else if (jb == 1) v = Pi[3] * Aff[jj] + Pi[4] * Aff[3 + jj] + Pi[5] * Aff[6 + jj];
+          else if (jb == 2) v = hd * Pi[jj] + Pi[6 + jj];
+          else v = Pi[3] * Afw[jj] + Pi[4] * Afw[3 + jj] + Pi[5] * Afw[6 + jj] + Pi[9 + jj];
+          PA[e] = v;
+        }
+        for (int e = lane; e < 72; e += G) {
+          const int i = e / 6, c = e % 6;
+          const double* Pi = P + 12 * i;
+          PM[e] = c < 3 ? c1 * Pi[c] + hd * Pi[6 + c]
+                        : Pi[3] * Cf[c - 3] + Pi[4] * Cf[c] + Pi[5] * Cf[3 + c] + hd * Pi[6 + c];
+        }
+        for (int e = lane; e < 18; e += G) {
+          if (e < 6) {
+            vec[cv::s + e] = e < 3 ? hd * hh * pv[e] + hd * pv[6 + e]
+                                   : Cf[e - 3] * pv[3] + Cf[e] * pv[4] + Cf[3 + e] * pv[5] + hd * pv[6 + e];
+          } else {
+            const int a = e - 6, ab = a / 3, aa = a % 3;
+            double v;
+            if (ab == 0) v = pv[a];
+            else if (ab == 1) v = Aff[aa] * pv[3] + Aff[3 + aa] * pv[4] + Aff[6 + aa] * pv[5];
+            else if (ab == 2) v = hd * pv[aa] + pv[6 + aa];
+            else v = Afw[aa] * pv[3] + Afw[3 + aa] * pv[4] + Afw[6 + aa] * pv[5] + pv[9 + aa];
+            vec[cv::Atp + a] = v;
+          }
+        }
+      }
+      COOP_SYNC();
+      // ---- phase C: T = M^T PA, S = M^T PM, P <- A^T PA + lxx, Qx = lx + Atp
+      COOP_PHASE {
+        for (int e = lane; e < 72; e += G) {
+          const int i = e / 12, j = e % 12;
+          T[e] = i < 3 ? c1 * PA[12 * i + j] + hd * PA[12 * (6 + i) + j]
+                       : Cf[i - 3] * PA[36 + j] + Cf[i] * PA[48 + j] + Cf[3 + i] * PA[60 + j] + hd * PA[12 * (6 + i) + j];
+        }
+        for (int e = lane; e < 36; e += G) {
+          const int i = e / 6, c = e % 6;
+          S[e] = i < 3 ? c1 * PM[6 * i + c] + hd * PM[6 * (6 + i) + c]
+                       : Cf[i - 3] * PM[18 + c] + Cf[i] * PM[24 + c] + Cf[3 + i] * PM[30 + c] + hd * PM[6 * (6 + i) + c];
+        }
+        for (int e = lane; e < 144; e += G) {
+          const int a = e / 12, b = e % 12, ab = a / 3, aa = a % 3;
+          double v;
+          if (ab == 0) v = PA[12 * a + b];
+          else if (ab == 1) v = Aff[aa] * PA[36 + b] + Aff[3 + aa] * PA[48 + b] + Aff[6 + aa] * PA[60 + b];
+          else if (ab == 2) v = hd * PA[12 * aa + b] + PA[12 * (6 + aa) + b];
+          else v = Afw[aa] * PA[36 + b] + Afw[3 + aa] * PA[48 + b] + Afw[6 + aa] * PA[60 + b] + PA[12 * (9 + aa) + b];
+          P[e] = v + lxx_entry(cfg, vec + cv::Hphi, a, b);
+        }
+        for (int e = lane; e < 12; e += G) vec[cv::Qx + e] = vec[cv::Atp + e] + vec[cv::lx + e];
+      }
+      COOP_SYNC();
+      // ---- phase D: Qux = W^T T, SW = S W, Qu = g + W^T s
+      COOP_PHASE {
+        for (int e = lane; e < NU * 12; e += G) {
+          const int i = e / 12, j = e % 12, f = i / 3, a = i % 3;
+          const double* IS = m.IS + 9 * f;
+          Qux[e] = m.inv_mass * T[12 * a + j] + IS[a] * T[36 + j] + IS[3 + a] * T[48 + j] + IS[6 + a] * T[60 + j];
+        }
+        for (int e = lane; e < 6 * NU; e += G) {
+          const int r = e / NU, col = e % NU, f = col / 3, b = col % 3;
+          const double* IS = m.IS + 9 * f;
+          SW[e] = m.inv_mass * S[6 * r + b] + S[6 * r + 3] * IS[b] + S[6 * r + 4] * IS[3 + b] + S[6 * r + 5] * IS[6 + b];
+        }
+        for (int e = lane; e < NU; e += G) {
+          const int f = e / 3, a = e % 3;
+          const double* IS = m.IS + 9 * f;
+          const double* s = vec + cv::s;
+          vec[cv::Qu + e] = (m.inv_mass * s[a] + IS[a] * s[3] + IS[3 + a] * s[4] + IS[6 + a] * s[5]) + vec[cv::g + e];
+        }
+      }
+      COOP_SYNC();
+      // ---- phase E: Quu = D + W^T (S W)   (into the PA buffer)
+      COOP_PHASE {
+        for (int e = lane; e < NU * NU; e += G) {
+          const int i = e / NU, j = e % NU, f = i / 3, a = i % 3;
+          const double* IS = m.IS + 9 * f;
+          double v = m.inv_mass * SW[NU * a + j] + IS[a] * SW[NU * 3 + j] + IS[3 + a] * SW[NU * 4 + j] +
+                     IS[6 + a] * SW[NU * 5 + j];
+          if (j / 3 == f) v += vec[cv::Dblk + 9 * f + 3 * a + (j % 3)];
+          Quu[e] = v;
+        }
+      }
+      COOP_SYNC();
+      // ---- Cholesky of Quu (left-looking, one row per lane), same arithmetic as chol<NU>()
+#pragma unroll 1
+      for (int j = 0; j < NU && bp_ok; ++j) {
+        COOP_PHASE {
+          for (int i = j + lane; i < NU; i += G) {
+            double t = Quu[NU * i + j];
+            for (int l = 0; l < j; ++l) t -= Quu[NU * i + l] * Quu[NU * j + l];
+            vec[cv::tcol + i] = t;
+          }
+        }
+        COOP_SYNC();
+        const double sjj = vec[cv::tcol + j];
+        if (!(sjj > 0.0)) {
+          bp_ok = false;
+        } else {
+          const double dg = sqrt(sjj);
+          COOP_PHASE {
+            for (int i = j + lane; i < NU; i += G) Quu[NU * i + j] = (i == j) ? dg : vec[cv::tcol + i] / dg;
+          }
+        }
+        COOP_SYNC();
+      }
+      if (!bp_ok) break;
+      // ---- solves: lane c <- right-hand side c (12 columns of Qux, then Qu)
+      COOP_PHASE {
+        for (int c = lane; c <= 12; c += G) {
+          double rhs[NU];
+          for (int i = 0; i < NU; ++i) rhs[i] = c < 12 ? Qux[12 * i + c] : vec[cv::Qu + i];
+          for (int i = 0; i < NU; ++i) {
+            double t = rhs[i];
+            for (int l = 0; l < i; ++l) t -= Quu[NU * i + l] * rhs[l];
+            rhs[i] = t / Quu[NU * i + i];
+          }
+          if (c < 12) { for (int i = 0; i < NU; ++i) Qux[12 * i + c] = rhs[i]; }   // V = L^-1 Qux
+          else { for (int i = 0; i < NU; ++i) vec[cv::vu + i] = rhs[i]; }
+          for (int i = NU - 1; i >= 0; --i) {
+            double t = rhs[i];
+            for (int l = i + 1; l < NU; ++l) t -= Quu[NU * l + i] * rhs[l];
+            rhs[i] = t / Quu[NU * i + i];
+          }
+          if (c < 12) {
+            for (int i = 0; i < NU; ++i) gK[((size_t)k * NU + i) * 12 + c] = -rhs[i];
+          } else {
+            double t = 0;
+            for (int i = 0; i < NU; ++i) {
+              gd[k * NU + i] = -rhs[i];
+              t += vec[cv::Qu + i] * (-rhs[i]);
+            }
+            scal[0] += t;
+          }
+        }
+      }
+      COOP_SYNC();
+      // ---- phase F: P <- sym(P) - V^T V (packed upper triangle, mirrored) ; pv <- Qx - V^T vu
+      COOP_PHASE {
+        for (int idx = lane; idx < 78; idx += G) {
+          int a = 0, rem = idx;
+          while (rem >= 12 - a) { rem -= 12 - a; ++a; }
+          const int b = a + rem;
+          double t = 0;
+          for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * Qux[12 * l + b];
+          const double v = 0.5 * (P[12 * a + b] + P[12 * b + a]) - t;
+          P[12 * a + b] = v;
+          P[12 * b + a] = v;
+          gP[(size_t)k * 78 + idx] = v;
+        }
+        for (int a = lane; a < 12; a += G) {
+          double t = 0;
+          for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * vec[cv::vu + l];
+          const double v = vec[cv::Qx + a] - t;
+          vec[cv::pv + a] = v;
+          gpv[k * 12 + a] = v;
+        }
+      }
+      COOP_SYNC();
+    }
+    if (!bp_ok) { status = QMPC_STATUS_BACKWARD_FAILED; break; }
+    const double dphi0 = scal[0];
+
+    // ---------------- forward pass: speculative back-tracking line search, lane l <- alpha = 2^-(l + G*round)
+    int acc_j = -1;
+    double phin = 0, violn = 0, alpha_acc = 0;
+#pragma unroll 1
+    for (int round = 0; round * G < o.ls_iters_max && acc_j < 0; ++round) {
+      COOP_PHASE {
+        const int j = round * G + lane;
+        double J = NAN, vl = 0;
+        if (j < o.ls_iters_max) {
+          double alpha = 1.0;
+          for (int q = 0; q < j; ++q) alpha *= o.ls_decrease;
+          double x[NX], xn[NX];
+          for (int i = 0; i < NX; ++i) x[i] = X[i];
+          J = 0;
+#pragma unroll 1
+          for (int k = 0; k < N; ++k) {
+            double dx[NE], u[NU];
+            state_diff<M>(x, X + k * NX, dx);
+            const double* Kk = gK + (size_t)k * NU * 12;
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+              double t = 0;
+#pragma unroll
+              for (int l = 0; l < NE; ++l) t += Kk[i * 12 + l] * dx[l];
+              u[i] = U[k * NU + i] + alpha * gd[k * NU + i] + t;
+            }
+            knot_merit(m, cfg, k, N, x, u, gmu + k * NC, rho, J, vl);
+            mid_dyn(m, x, u, h, xn);
+            for (int i = 0; i < NX; ++i) x[i] = xn[i];
+          }
+          knot_merit(m, cfg, N, N, x, x, gmu, rho, J, vl);
+        }
+        red[lane] = J;
+        red[G + lane] = vl;
+      }
+      COOP_SYNC();
+      {
+        double alpha = 1.0;
+        for (int q = 0; q < round * G; ++q) alpha *= o.ls_decrease;
+        for (int l = 0; l < G && acc_j < 0; ++l) {
+          const double pl = red[l];
+          if (round * G + l < o.ls_iters_max && isfinite(pl) && pl <= phi + o.ls_c1 * alpha * dphi0) {
+            acc_j = round * G + l;
+            phin = pl;
+            violn = red[G + l];
+            alpha_acc = alpha;
+          }
+          alpha *= o.ls_decrease;
+        }
+      }
+      COOP_SYNC();
+    }
+    iters = it + 1;
+    if (acc_j < 0) { status = QMPC_STATUS_LINESEARCH_FAILED; break; }
+    // ---------------- accepted step: redo its roll-out in place (X,U <- new; DX <- dx_k)
+    COOP_PHASE {
+      if (lane == 0) {
+        double x[NX], xn[NX];
+        for (int i = 0; i < NX; ++i) x[i] = X[i];
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+          double dx[NE], u[NU];
+          state_diff<M>(x, X + k * NX, dx);
+          const double* Kk = gK + (size_t)k * NU * 12;
+          for (int i = 0; i < NU; ++i) {
+            double t = 0;
+            for (int l = 0; l < NE; ++l) t += Kk[i * 12 + l] * dx[l];
+            u[i] = U[k * NU + i] + alpha_acc * gd[k * NU + i] + t;
+          }
+          for (int i = 0; i < NE; ++i) DX[k * NE + i] = dx[i];
+          for (int i = 0; i < NU; ++i) U[k * NU + i] = u[i];
+          for (int i = 0; i < NX; ++i) X[k * NX + i] = x[i];
+          mid_dyn(m, x, u, h, xn);
+          for (int i = 0; i < NX; ++i) x[i] = xn[i];
+        }
+        double dx[NE];
+        state_diff<M>(x, X + N * NX, dx);
+        for (int i = 0; i < NE; ++i) DX[N * NE + i] = dx[i];
+        for (int i = 0; i < NX; ++i) X[N * NX + i] = x[i];
+      }
+    }
+    COOP_SYNC();
+    // ---------------- Riccati duals of the accepted step: y_k = P_k dx_k + p_k  (lane k <- knot k)
+    COOP_PHASE {
+      for (int k = lane; k <= N; k += G) {
+        double dx[NE], y[NE];
+        for (int i = 0; i < NE; ++i) { dx[i] = DX[k * NE + i]; y[i] = gpv[k * 12 + i]; }
+        int idx = 0;
+        for (int a = 0; a < NE; ++a)
+          for (int b = a; b < NE; ++b) {
+            const double v = gP[(size_t)k * 78 + idx++];
+            y[a] += v * dx[b];
+            if (b != a) y[b] += v * dx[a];
+          }
+        for (int i = 0; i < NE; ++i) DX[k * NE + i] = y[i];
+      }
+    }
+    COOP_SYNC();
+    cost_decrease = phi - phin;
+    phi = phin;
+    viol = violn;
+  }
+
+  COOP_PHASE {
+    if (lane == 0) {
+      QmpcResult r;
+      m.write_result(U, r);
+      r.max_violation = viol;
+      r.iterations = iters;
+      r.status = status;
+      out[pid] = r;
+    }
+  }
+  COOP_SYNC();
+}
+
+#ifdef __CUDACC__
+// persistent launch: every group of G lanes is a "slot" that strides over the batch
+template <int NF, int G>
+__global__ void __launch_bounds__(64)
+qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in, QmpcResult* __restrict__ out,
+                 double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot) {
+  extern __shared__ double smem_pool[];
+  const int groups_per_block = blockDim.x / G;
+  const int group = threadIdx.x / G;
+  const int lane_id = threadIdx.x % G;
+  const int slot = blockIdx.x * groups_per_block + group;
+  const int nslots = gridDim.x * groups_per_block;
+  const unsigned lane_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
+  double* sm = smem_pool + (size_t)group * smem_per_problem;
+  double* gs = scratch + (size_t)slot * scratch_per_slot;
+  for (int pid = slot; pid < batch; pid += nslots) {
+    coop_solve_one<NF, G>(cfg, o, in, out, pid, sm, gs, lane_id, lane_mask);
+  }
+}
+#endif
+
+}  // namespace qmpc

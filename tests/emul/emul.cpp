@@ -11,6 +11,7 @@
 #include "../../quaternion_mpc_b200/csrc/qmpc_dense.cuh"
 #ifdef QMPC_EMUL_SRB
 #include "../../quaternion_mpc_b200/csrc/qmpc_srb.cuh"
+#include "../../quaternion_mpc_b200/csrc/qmpc_coop.cuh"
 #endif
 
 using namespace qmpc;
@@ -56,5 +57,22 @@ extern "C" int emul_solve_srb(const QmpcConfig* cfg, const QmpcProblem* in, int 
   if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_srb<4>(*cfg, in, batch, out);
   if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_srb<2>(*cfg, in, batch, out);
   return -1;
+}
+
+template <int NF, int G>
+static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, int batch, QmpcResult* out) {
+  SolverOpts o = make_opts(cfg);
+  using L = CoopLayout<NF, G>;
+  std::vector<double> sm(L::smem_doubles(cfg.horizon)), gs(L::scratch_doubles(cfg.horizon));
+  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, out, i, sm.data(), gs.data(), 0, 0u);
+  return 0;
+}
+extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, int batch, QmpcResult* out) {
+  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_coop<4, 16>(*cfg, in, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_coop<2, 16>(*cfg, in, batch, out);
+  return -1;
+}
+extern "C" int emul_coop_smem_bytes(int nf, int horizon) {
+  return 8 * (nf == 4 ? CoopLayout<4, 16>::smem_doubles(horizon) : CoopLayout<2, 16>::smem_doubles(horizon));
 }
 #endif
