@@ -206,10 +206,11 @@ def main():
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         total_ms, e2e_ms = float(tmax[0]), float(tmax[1])
         mean_iters = float(tsum[2]) / world
-        # the one collective of the path: gather every rank's GRFs on rank 0
-        grf = torch.from_numpy(np.ascontiguousarray(res["grf_body"])).to(f"cuda:{local}")
-        gathered = [torch.empty_like(grf) for _ in range(world)] if rank == 0 else None
-        dist.gather(grf, gathered, dst=0)
+        # the one collective of the path: gather every rank's results on rank 0
+        from quaternion_mpc_b200.sharding import gather_results
+        allres = gather_results(res, B * world, device=f"cuda:{local}")
+        if rank == 0:
+            assert allres.shape[0] == B * world and np.isfinite(allres["grf_body"]).all()
     else:
         e2e_ms = e2e_s * 1e3
     if rank != 0:

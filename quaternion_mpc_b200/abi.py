@@ -69,7 +69,8 @@ _LIB = None
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqmpc_b200.so")
+    # QMPC_LIB lets an experiment point at an alternative build of the same library
+    return os.environ.get("QMPC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqmpc_b200.so")
 
 
 def load_library():

@@ -122,6 +122,8 @@ static int coop_prepare_t(QmpcHandle* h) {
   const int groups = kCoopBlock / kCoopG;
   const size_t smem_bytes = (size_t)groups * h->coop_smem_doubles * sizeof(double);
   CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          (int)cudaSharedmemCarveoutMaxShared));
   int per_sm = 0, sms = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_coop_kernel<NF, kCoopG>, kCoopBlock, smem_bytes));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));

@@ -37,7 +37,7 @@ struct CoopLayout {
   static constexpr int NU = 3 * NF, NC = 6 * NF;
   static constexpr int kModel = (int)((sizeof(QuatModel<NF>) + 7) / 8);
   // ---- shared memory (doubles) per problem
-  static constexpr int kVec = 160;
+  static constexpr int kVec = 172;
   QMPC_HD static int sX(int N) { return kModel; }
   QMPC_HD static int sU(int N) { return sX(N) + (N + 1) * 13; }
   QMPC_HD static int sDX(int N) { return sU(N) + N * NU; }
@@ -64,7 +64,7 @@ struct CoopLayout {
 // offsets inside the shared "vec" block
 namespace cv {
 constexpr int lx = 0, Qx = 12, Qu = 24, s = 36, Atp = 42, g = 54, Dblk = 66, Hphi = 102, vu = 111, tcol = 123,
-              pv = 135, scal = 147;  // scal[0]=dphi0 [1]=hphi [2]=phi [3]=viol
+              pv = 135, scal = 147, rdiag = 148 + 8;  // scal[0]=dphi0 [1]=hphi [2]=phi [3]=viol
 }
 
 // stage cost + AL terms of one knot (same accumulation order as merit() in qmpc_dense.cuh)
@@ -428,6 +428,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         COOP_PHASE {
           for (int i = j + lane; i < NU; i += G) {
             double t = Quu[NU * i + j];
+#pragma unroll 4
             for (int l = 0; l < j; ++l) t -= Quu[NU * i + l] * Quu[NU * j + l];
             vec[cv::tcol + i] = t;
           }
@@ -438,8 +439,12 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           bp_ok = false;
         } else {
           const double dg = sqrt(sjj);
+          const double rdg = 1.0 / dg;
           COOP_PHASE {
-            for (int i = j + lane; i < NU; i += G) Quu[NU * i + j] = (i == j) ? dg : vec[cv::tcol + i] / dg;
+            for (int i = j + lane; i < NU; i += G) {
+              if (i == j) { Quu[NU * i + j] = dg; vec[cv::rdiag + j] = rdg; }
+              else Quu[NU * i + j] = vec[cv::tcol + i] * rdg;
+            }
           }
         }
         COOP_SYNC();
@@ -449,23 +454,35 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       COOP_PHASE {
         for (int c = lane; c <= 12; c += G) {
           double rhs[NU];
+#pragma unroll
           for (int i = 0; i < NU; ++i) rhs[i] = c < 12 ? Qux[12 * i + c] : vec[cv::Qu + i];
+#pragma unroll
           for (int i = 0; i < NU; ++i) {
             double t = rhs[i];
+#pragma unroll
             for (int l = 0; l < i; ++l) t -= Quu[NU * i + l] * rhs[l];
-            rhs[i] = t / Quu[NU * i + i];
-          }
-          if (c < 12) { for (int i = 0; i < NU; ++i) Qux[12 * i + c] = rhs[i]; }   // V = L^-1 Qux
-          else { for (int i = 0; i < NU; ++i) vec[cv::vu + i] = rhs[i]; }
-          for (int i = NU - 1; i >= 0; --i) {
-            double t = rhs[i];
-            for (int l = i + 1; l < NU; ++l) t -= Quu[NU * l + i] * rhs[l];
-            rhs[i] = t / Quu[NU * i + i];
+            rhs[i] = t * vec[cv::rdiag + i];
           }
           if (c < 12) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) Qux[12 * i + c] = rhs[i];   // V = L^-1 Qux
+          } else {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) vec[cv::vu + i] = rhs[i];
+          }
+#pragma unroll
+          for (int i = NU - 1; i >= 0; --i) {
+            double t = rhs[i];
+#pragma unroll
+            for (int l = i + 1; l < NU; ++l) t -= Quu[NU * l + i] * rhs[l];
+            rhs[i] = t * vec[cv::rdiag + i];
+          }
+          if (c < 12) {
+#pragma unroll
             for (int i = 0; i < NU; ++i) gK[((size_t)k * NU + i) * 12 + c] = -rhs[i];
           } else {
             double t = 0;
+#pragma unroll
             for (int i = 0; i < NU; ++i) {
               gd[k * NU + i] = -rhs[i];
               t += vec[cv::Qu + i] * (-rhs[i]);
@@ -619,8 +636,11 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 
 #ifdef __CUDACC__
 // persistent launch: every group of G lanes is a "slot" that strides over the batch
+#ifndef QMPC_COOP_MIN_BLOCKS
+#define QMPC_COOP_MIN_BLOCKS 4
+#endif
 template <int NF, int G>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, QMPC_COOP_MIN_BLOCKS)
 qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in, QmpcResult* __restrict__ out,
                  double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot) {
   extern __shared__ double smem_pool[];
