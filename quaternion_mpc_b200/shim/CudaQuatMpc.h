@@ -1,0 +1,58 @@
+// CudaQuatMpc.h — drop-in replacement for legged::QuatMpc behind the reference's own boundary,
+// the abstract class legged::LeggedMpc (legged_ctrl/include/mpc/LeggedMpc.h:21-49).
+//
+// Main.cpp:94-95 would construct this instead of QuatMpc; the 200 Hz
+// mpc_thread keeps calling mpc_ptr->update(state) (Main.cpp:107) unchanged.  goal_update and
+// foot_update stay host-side (stateful joystick filters and gait FSM, QuatMpc.cpp:68-107, 278-305);
+// only grf_update — the solve — goes through the C-ABI (include/qmpc.h) to the B200.
+//
+// The class only uses the LeggedState fields QuatMpc itself touches, through accessors that both
+// Eigen (real build) and tests/stubs (stand-alone test build) provide: operator[], operator()(i,j),
+// w()/x()/y()/z().
+#pragma once
+
+#include <deque>
+
+#include "mpc/LeggedMpc.h"
+#include "qmpc.h"
+
+namespace legged {
+
+class CudaQuatMpc : public LeggedMpc {
+ public:
+  // device: CUDA device ordinal.  Throws std::runtime_error if the CUDA library cannot create a
+  // handle (there is no CPU fallback).
+  explicit CudaQuatMpc(LeggedState& state, int device = 0);
+  ~CudaQuatMpc();
+  CudaQuatMpc(const CudaQuatMpc&) = delete;
+  CudaQuatMpc& operator=(const CudaQuatMpc&) = delete;
+
+  bool update(LeggedState& state) override;       // QuatMpc.cpp:57-66
+  bool goal_update(LeggedState& state) override;  // QuatMpc.cpp:68-107
+  bool grf_update(LeggedState& state) override;   // QuatMpc.cpp:109-276  -> qmpc_solve_batch_host
+  bool foot_update(LeggedState& state) override;  // QuatMpc.cpp:278-305
+  bool terrain_update(LeggedState&) override { return true; }
+
+  // last solve's status / iteration count (the reference discards ALTRO's SolveStatus)
+  int last_status() const { return last_.status; }
+  int last_iterations() const { return last_.iterations; }
+  const QmpcProblem& last_problem() const { return prob_; }
+
+ private:
+  // 100-sample moving average with Neumaier-compensated running sum, same arithmetic as
+  // utils/MovingWindowFilter.hpp:26-62 (kept local so the shim has no dependency on that header)
+  struct Avg100 {
+    std::deque<double> q;
+    double sum = 0.0, corr = 0.0;
+    double push(double v);
+  };
+  Avg100 vel_filt_[3], pos_filt_[3];
+  double vel_d_body_filt_[3] = {0, 0, 0}, pos_d_body_filt_[3] = {0, 0, 0};
+  bool pos_d_world_init_ = false;
+  QmpcHandle* handle_ = nullptr;
+  QmpcConfig cfg_;
+  QmpcProblem prob_;
+  QmpcResult last_;
+};
+
+}  // namespace legged

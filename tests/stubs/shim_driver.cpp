@@ -1,0 +1,71 @@
+// Test driver: builds a LeggedState from a QmpcProblem-like description, runs CudaQuatMpc::update
+// through the LeggedMpc base pointer (as Main.cpp:107 does) and returns what it wrote.
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+
+#include "CudaQuatMpc.h"
+
+extern "C" int shim_construct_only(int device, char* err, int errlen) {
+  legged::LeggedState st;
+  try {
+    legged::CudaQuatMpc mpc(st, device);
+  } catch (const std::exception& e) {
+    std::strncpy(err, e.what(), errlen - 1);
+    err[errlen - 1] = 0;
+    return 1;
+  }
+  return 0;
+}
+
+// in: QmpcProblem (desired quantities are fed through joystick-free state: see below); ticks >= 1
+// out_problem: the QmpcProblem the shim packed on the last tick; out_grf_body/out_grf_world: 12 each
+extern "C" int shim_run(const QmpcProblem* in, int horizon, int ticks, QmpcProblem* out_problem,
+                        double* out_grf_body, double* out_grf_world, int* status_iters) {
+  using namespace legged;
+  LeggedState st;
+  st.param.mpc_horizon = horizon;
+  const double Q[13] = {2.5, 2.5, 10.0, 0, 0, 0, 0, 0.1, 0.1, 0.1, 0.15, 0.15, 0.15};
+  for (int i = 0; i < 13; ++i) st.param.q_weights[i] = Q[i];
+  for (int i = 0; i < 12; ++i) st.param.r_weights[i] = 1e-6;
+  st.param.trunk_inertia(0, 0) = 0.0168128557;
+  st.param.trunk_inertia(1, 1) = 0.063009565;
+  st.param.trunk_inertia(2, 2) = 0.0716547275;
+  st.fbk.torso_quat.w() = in->torso_quat[0]; st.fbk.torso_quat.x() = in->torso_quat[1];
+  st.fbk.torso_quat.y() = in->torso_quat[2]; st.fbk.torso_quat.z() = in->torso_quat[3];
+  {  // toRotationMatrix (BaseInterface.cpp:196)
+    double w = in->torso_quat[0], x = in->torso_quat[1], y = in->torso_quat[2], z = in->torso_quat[3];
+    auto& R = st.fbk.torso_rot_mat;
+    R(0, 0) = 1 - 2 * (y * y + z * z); R(0, 1) = 2 * (x * y - w * z); R(0, 2) = 2 * (x * z + w * y);
+    R(1, 0) = 2 * (x * y + w * z); R(1, 1) = 1 - 2 * (x * x + z * z); R(1, 2) = 2 * (y * z - w * x);
+    R(2, 0) = 2 * (x * z - w * y); R(2, 1) = 2 * (y * z + w * x); R(2, 2) = 1 - 2 * (x * x + y * y);
+    for (int i = 0; i < 3; ++i) st.fbk.torso_rot_mat_z(i, i) = 1.0;
+  }
+  st.fbk.torso_pos_world[2] = 0.3;
+  for (int i = 0; i < 3; ++i) {
+    st.fbk.torso_lin_vel_world[i] = in->torso_lin_vel_world[i];
+    st.fbk.torso_ang_vel_body[i] = in->torso_ang_vel_body[i];
+  }
+  for (int leg = 0; leg < 4; ++leg)
+    for (int i = 0; i < 3; ++i) st.fbk.foot_pos_body(i, leg) = in->foot_pos_body[3 * leg + i];
+  st.ctrl.torso_quat_d.w() = in->torso_quat_d[0]; st.ctrl.torso_quat_d.x() = in->torso_quat_d[1];
+  st.ctrl.torso_quat_d.y() = in->torso_quat_d[2]; st.ctrl.torso_quat_d.z() = in->torso_quat_d[3];
+  st.joy.velx = 0.3; st.joy.vely = -0.05; st.joy.yaw_rate = 0.2; st.joy.body_height = 0.31;
+  st.ctrl.movement_mode = 0;  // stand: foot_update sets all plan_contacts
+  std::unique_ptr<LeggedMpc> mpc_ptr;
+  try {
+    mpc_ptr = std::make_unique<CudaQuatMpc>(st, 0);
+  } catch (const std::exception&) {
+    return 1;
+  }
+  for (int t = 0; t < ticks; ++t) mpc_ptr->update(st);
+  auto* q = static_cast<CudaQuatMpc*>(mpc_ptr.get());
+  *out_problem = q->last_problem();
+  for (int i = 0; i < 12; ++i) {
+    out_grf_body[i] = st.ctrl.optimized_input[i];
+    out_grf_world[i] = st.ctrl.mpc_grf_world[i];
+  }
+  status_iters[0] = q->last_status();
+  status_iters[1] = q->last_iterations();
+  return 0;
+}

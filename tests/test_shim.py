@@ -1,0 +1,55 @@
+"""The C++ host shim (CudaQuatMpc : LeggedMpc) compiled against stub reference headers."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from quaternion_mpc_b200 import abi
+from quaternion_mpc_b200.config import default_config
+from quaternion_mpc_b200.workloads import random_batch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "tests", "stubs", "libshim_test.so")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    import __graft_entry__ as g
+    g.build()
+    pkg = os.path.join(ROOT, "quaternion_mpc_b200")
+    srcs = [os.path.join(pkg, "shim", "CudaQuatMpc.cpp"), os.path.join(ROOT, "tests", "stubs", "shim_driver.cpp")]
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + srcs + [
+            "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"),
+            "-I", os.path.join(pkg, "shim"), "-L", pkg, "-lqmpc_b200", f"-Wl,-rpath,{pkg}"])
+    return C.CDLL(SO)
+
+
+def test_shim_builds_and_fails_loudly_without_gpu(shim):
+    import torch
+    err = C.create_string_buffer(256)
+    rc = shim.shim_construct_only(0, err, 256)
+    if torch.cuda.is_available():
+        assert rc == 0
+    else:
+        assert rc == 1 and b"qmpc_create failed" in err.value
+
+
+@pytest.mark.gpu
+def test_shim_tick_matches_oracle(shim, oracle):
+    p = random_batch(1, seed=21, gait="stand")
+    out_p = np.zeros(1, dtype=abi.PROBLEM_DTYPE)
+    gb, gw, si = np.zeros(12), np.zeros(12), np.zeros(2, dtype=np.int32)
+    rc = shim.shim_run(C.c_void_p(p.ctypes.data), 10, 3, C.c_void_p(out_p.ctypes.data),
+                       C.c_void_p(gb.ctypes.data), C.c_void_p(gw.ctypes.data), C.c_void_p(si.ctypes.data))
+    assert rc == 0
+    # the shim packed: measured state from the input, desired quantities from its own filters
+    assert np.allclose(out_p["torso_quat"], p["torso_quat"])
+    assert (out_p["plan_contacts"] == 1).all()
+    assert abs(out_p["torso_lin_vel_d_body"][0, 0]) > 0          # joystick velocity went through the filter
+    ref = oracle.solve_batch(default_config(0, 10), out_p)
+    assert np.abs(ref["grf_body"][0] - gb).max() < 1e-4
+    assert np.abs(ref["grf_world"][0] - gw).max() < 1e-4
+    assert si[1] == ref["iterations"][0]
