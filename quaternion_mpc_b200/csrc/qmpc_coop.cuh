@@ -30,7 +30,53 @@
 #define COOP_SYNC() ((void)0)
 #endif
 
+#ifdef __CUDACC__
+#define QMPC_NOINLINE __noinline__
+#else
+#define QMPC_NOINLINE
+#endif
+
 namespace qmpc {
+
+// ---- 3x3 block kernels used by the block-per-lane phases (lane = (block row, block col)) --------
+// out = X(:, 3:6) * Mt + beta * X(:, 9:12)      X: 3 rows of a row-major matrix with leading dim ld
+QMPC_HD inline void blk_right(const double* X, int ld, const double* Mt, double beta, double* out) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      out[3 * a + b] = X[ld * a + 3] * Mt[b] + X[ld * a + 4] * Mt[3 + b] + X[ld * a + 5] * Mt[6 + b] +
+                       beta * X[ld * a + 9 + b];
+}
+// out = alpha * X(:, 0:3) + beta * X(:, 6:9)
+QMPC_HD inline void blk_even(const double* X, int ld, double alpha, double beta, double* out) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) out[3 * a + b] = alpha * X[ld * a + b] + beta * X[ld * a + 6 + b];
+}
+// out = Mt^T * Y(3:6, :) + beta * Y(9:12, :)     Y: 3 columns (starting at Y) of a row-major matrix
+QMPC_HD inline void blk_left(const double* Y, int ld, const double* Mt, double beta, double* out) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      out[3 * a + b] = Mt[a] * Y[ld * 3 + b] + Mt[3 + a] * Y[ld * 4 + b] + Mt[6 + a] * Y[ld * 5 + b] +
+                       beta * Y[ld * (9 + a) + b];
+}
+// out = alpha * Y(0:3, :) + beta * Y(6:9, :)
+QMPC_HD inline void blk_evenT(const double* Y, int ld, double alpha, double beta, double* out) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) out[3 * a + b] = alpha * Y[ld * a + b] + beta * Y[ld * (6 + a) + b];
+}
+QMPC_HD inline void blk_store(double* dst, int ld, const double* v) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) dst[ld * a + b] = v[3 * a + b];
+}
 
 template <int NF, int G>
 struct CoopLayout {
@@ -55,7 +101,7 @@ struct CoopLayout {
   QMPC_HD static size_t gK(int N) { return 0; }
   QMPC_HD static size_t gd(int N) { return gK(N) + (size_t)N * NU * 12; }
   QMPC_HD static size_t gP(int N) { return gd(N) + (size_t)N * NU; }
-  QMPC_HD static size_t gpv(int N) { return gP(N) + (size_t)(N + 1) * 78; }
+  QMPC_HD static size_t gpv(int N) { return gP(N) + (size_t)(N + 1) * 144; }
   QMPC_HD static size_t gmu(int N) { return gpv(N) + (size_t)(N + 1) * 12; }
   QMPC_HD static size_t glin(int N) { return gmu(N) + (size_t)N * NC; }
   QMPC_HD static size_t scratch_doubles(int N) { return (glin(N) + (size_t)N * 27 + 15) / 16 * 16; }
@@ -108,6 +154,85 @@ QMPC_HD inline void hphi_block(const QmpcConfig& cfg, const double* x, double hp
     }
 }
 
+// 3x3 block (br, bc) of the cost Hessian in error coordinates
+QMPC_HD inline void lxx_block(const QmpcConfig& cfg, const double* Hphi, int br, int bc, double* out) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[i] = 0.0;
+  if (br != bc) return;
+  if (br == 1) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out[i] = Hphi[i];
+  } else {
+    const int q0 = br == 0 ? 0 : (br == 2 ? 7 : 10);
+    out[0] = cfg.q_weights[q0]; out[4] = cfg.q_weights[q0 + 1]; out[8] = cfg.q_weights[q0 + 2];
+  }
+}
+
+// One roll-out of the whole horizon by ONE lane (kept out of line: it is used by the nominal
+// roll-out, by the 16 speculative line-search lanes and by the accepted step, and inlining it three
+// times is what pushed the SASS far past the instruction cache).
+//   mode 0: open loop, u = u_ref: writes the nominal X, U; returns merit / violation
+//   mode 1: trial step `alpha` around (X, U) with gains (gK, gd): writes nothing, returns merit / violation
+//   mode 2: accepted step `alpha`: X, U updated in place, DX <- dx_k (error-state step per knot)
+template <int NF>
+QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig& cfg, int N, float h, double* X,
+                                        double* U, double* DX, const double* gK, const double* gd,
+                                        const double* gmu, double rho, double alpha, int mode, double* Jout,
+                                        double* violout) {
+  using M = QuatModel<NF>;
+  constexpr int NX = 13, NE = 12, NU = M::NU, NC = M::NC;
+  double x[NX], xn[NX], J = 0, vl = 0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = X[i];
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    double u[NU];
+    if (mode == 0) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) { u[i] = m.uref[i]; U[k * NU + i] = u[i]; }
+    } else {
+      double dx[NE];
+      state_diff<M>(x, X + k * NX, dx);
+      const double* Kk = gK + (size_t)k * NU * 12;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        double t = 0;
+#pragma unroll
+        for (int l = 0; l < NE; ++l) t += Kk[i * 12 + l] * dx[l];
+        u[i] = U[k * NU + i] + alpha * gd[k * NU + i] + t;
+      }
+      if (mode == 2) {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) DX[k * NE + i] = dx[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) U[k * NU + i] = u[i];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) X[k * NX + i] = x[i];
+      }
+    }
+    if (mode != 2) knot_merit(m, cfg, k, N, x, u, gmu + k * NC, rho, J, vl);
+    mid_dyn(m, x, u, h, xn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = xn[i];
+    if (mode == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) X[(k + 1) * NX + i] = xn[i];
+    }
+  }
+  if (mode == 2) {
+    double dx[NE];
+    state_diff<M>(x, X + N * NX, dx);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) DX[N * NE + i] = dx[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) X[N * NX + i] = x[i];
+  } else {
+    knot_merit(m, cfg, N, N, x, x, gmu, rho, J, vl);
+  }
+  *Jout = J;
+  *violout = vl;
+}
+
 template <int NF, int G>
 QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in, QmpcResult* out,
                             int pid, double* sm, double* gs, int lane_id, unsigned lane_mask) {
@@ -125,8 +250,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   double* DX = sm + L::sDX(N);
   double* P = sm + L::sP(N);
   double* PA = sm + L::sPA(N);
-  double* Quu = PA;
-  double* T = sm + L::sT(N);
+    double* T = sm + L::sT(N);
   double* PM = sm + L::sPM(N);
   double* SW = PM;
   double* S = sm + L::sS(N);
@@ -153,20 +277,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   COOP_SYNC();
   double rho = o.penalty_initial;
   COOP_PHASE {
-    if (lane == 0) {
-      double x[NX], xn[NX], J = 0, vl = 0;
-      for (int i = 0; i < NX; ++i) x[i] = X[i];
-#pragma unroll 1
-      for (int k = 0; k < N; ++k) {
-        for (int i = 0; i < NU; ++i) U[k * NU + i] = m.uref[i];
-        knot_merit(m, cfg, k, N, x, m.uref, gmu + k * NC, rho, J, vl);
-        mid_dyn(m, x, m.uref, h, xn);
-        for (int i = 0; i < NX; ++i) { x[i] = xn[i]; X[(k + 1) * NX + i] = xn[i]; }
-      }
-      knot_merit(m, cfg, N, N, x, m.uref, gmu, rho, J, vl);
-      scal[2] = J;
-      scal[3] = vl;
-    }
+    if (lane == 0) coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3]);
   }
   COOP_SYNC();
   double phi = scal[2], viol = scal[3];
@@ -270,8 +381,12 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       }
     }
 
-    // ---------------- Riccati backward pass
+    // ---------------- Riccati backward pass.  Lane (br, bc) = (lane / 4, lane % 4) owns the 3x3 block
+    // (br, bc) of every 12x12 quantity; all inner indices are compile-time.
+    static_assert(G == 16, "block-per-lane mapping assumes 16 lanes per problem");
     bool bp_ok = true;
+    double* Pc = P;   // value-function Hessian of knot k+1 (then the not-yet-corrected one of knot k)
+    double* Pw = PA;  // work buffer: P A, then Quu and its Cholesky factor, then the new P (ping-pong)
     COOP_PHASE {
       if (lane == 0) {
         double hphi;
@@ -282,15 +397,12 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     }
     COOP_SYNC();
     COOP_PHASE {
-      for (int e = lane; e < 144; e += G) P[e] = lxx_entry(cfg, vec + cv::Hphi, e / 12, e % 12);
-      for (int e = lane; e < 12; e += G) gpv[N * 12 + e] = vec[cv::pv + e];
-      for (int idx = lane; idx < 78; idx += G) {
-        // packed upper-triangle index -> (a,b)
-        int a = 0, rem = idx;
-        while (rem >= 12 - a) { rem -= 12 - a; ++a; }
-        const int b = a + rem;
-        gP[N * 78 + idx] = lxx_entry(cfg, vec + cv::Hphi, a, b);
-      }
+      const int br = lane >> 2, bc = lane & 3;
+      double o[9];
+      lxx_block(cfg, vec + cv::Hphi, br, bc, o);
+      blk_store(Pc + 36 * br + 3 * bc, 12, o);
+      blk_store(gP + (size_t)N * 144 + 36 * br + 3 * bc, 12, o);
+      if (lane < 12) gpv[N * 12 + lane] = vec[cv::pv + lane];
     }
     COOP_SYNC();
 
@@ -303,6 +415,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           const int f = lane;
           const double* u = U + k * NU + 3 * f;
           double g0 = 0, g1 = 0, g2 = 0, hb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
           for (int r = 0; r < 6; ++r) {
             double c = m.CR[3 * r] * u[0] + m.CR[3 * r + 1] * u[1] + m.CR[3 * r + 2] * u[2];
             if (r == 4) c += -m.fzc[f];
@@ -316,6 +429,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
             }
           }
           hb[0] += cfg.r_weights[3 * f]; hb[4] += cfg.r_weights[3 * f + 1]; hb[8] += cfg.r_weights[3 * f + 2];
+#pragma unroll
           for (int a = 0; a < 9; ++a) vec[cv::Dblk + 9 * f + a] = hb[a];
           vec[cv::g + 3 * f] = cfg.r_weights[3 * f] * (u[0] - m.uref[3 * f]) + g0;
           vec[cv::g + 3 * f + 1] = cfg.r_weights[3 * f + 1] * (u[1] - m.uref[3 * f + 1]) + g1;
@@ -332,93 +446,110 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       const double* Afw = lin + 9;
       const double* Cf = lin + 18;
       const double* pv = vec + cv::pv;
-      // ---- phase B: PA = P A, PM = P M, s = M^T p, Atp = A^T p
+      // ---- phase B: PA = P A (16 blocks), PM = P M (8 blocks), s = M^T p, Atp = A^T p
       COOP_PHASE {
-        for (int e = lane; e < 144; e += G) {
-          const int i = e / 12, j = e % 12, jb = j / 3, jj = j % 3;
-          const double* Pi = P + 12 * i;
+        const int br = lane >> 2, bc = lane & 3;
+        const double* Pr = Pc + 36 * br;
+        double o[9];
+        if (bc & 1) blk_right(Pr, 12, bc == 1 ? Aff : Afw, bc == 1 ? 0.0 : 1.0, o);
+        else blk_even(Pr, 12, bc == 0 ? 1.0 : hd, bc == 0 ? 0.0 : 1.0, o);
+        blk_store(Pw + 36 * br + 3 * bc, 12, o);
+        if (bc < 2) {
+          if (bc == 1) blk_right(Pr, 12, Cf, hd, o);
+          else blk_even(Pr, 12, c1, hd, o);
+          blk_store(PM + 18 * br + 3 * bc, 6, o);
+        }
+        if (lane < 6) {
+          const int e = lane;
+          vec[cv::s + e] = e < 3 ? hd * hh * pv[e] + hd * pv[6 + e]
+                                 : Cf[e - 3] * pv[3] + Cf[e] * pv[4] + Cf[3 + e] * pv[5] + hd * pv[6 + e];
+        }
+        if (lane < 12) {
+          const int a = lane, ab = a / 3, aa = a % 3;
           double v;
-          if (jb == 0) v = Pi[j];
-          else if (jb == 1) v = Pi[3] * Aff[jj] + Pi[4] * Aff[3 + jj] + Pi[5] * Aff[6 + jj];
-          else if (jb == 2) v = hd * Pi[jj] + Pi[6 + jj];
-          else v = Pi[3] * Afw[jj] + Pi[4] * Afw[3 + jj] + Pi[5] * Afw[6 + jj] + Pi[9 + jj];
-          PA[e] = v;
-        }
-        for (int e = lane; e < 72; e += G) {
-          const int i = e / 6, c = e % 6;
-          const double* Pi = P + 12 * i;
-          PM[e] = c < 3 ? c1 * Pi[c] + hd * Pi[6 + c]
-                        : Pi[3] * Cf[c - 3] + Pi[4] * Cf[c] + Pi[5] * Cf[3 + c] + hd * Pi[6 + c];
-        }
-        for (int e = lane; e < 18; e += G) {
-          if (e < 6) {
-            vec[cv::s + e] = e < 3 ? hd * hh * pv[e] + hd * pv[6 + e]
-                                   : Cf[e - 3] * pv[3] + Cf[e] * pv[4] + Cf[3 + e] * pv[5] + hd * pv[6 + e];
-          } else {
-            const int a = e - 6, ab = a / 3, aa = a % 3;
-            double v;
-            if (ab == 0) v = pv[a];
-            else if (ab == 1) v = Aff[aa] * pv[3] + Aff[3 + aa] * pv[4] + Aff[6 + aa] * pv[5];
-            else if (ab == 2) v = hd * pv[aa] + pv[6 + aa];
-            else v = Afw[aa] * pv[3] + Afw[3 + aa] * pv[4] + Afw[6 + aa] * pv[5] + pv[9 + aa];
-            vec[cv::Atp + a] = v;
-          }
+          if (ab == 0) v = pv[a];
+          else if (ab == 1) v = Aff[aa] * pv[3] + Aff[3 + aa] * pv[4] + Aff[6 + aa] * pv[5];
+          else if (ab == 2) v = hd * pv[aa] + pv[6 + aa];
+          else v = Afw[aa] * pv[3] + Afw[3 + aa] * pv[4] + Afw[6 + aa] * pv[5] + pv[9 + aa];
+          vec[cv::Atp + a] = v;
         }
       }
       COOP_SYNC();
-      // ---- phase C: T = M^T PA, S = M^T PM, P <- A^T PA + lxx, Qx = lx + Atp
+      // ---- phase C: P <- A^T PA + lxx (16 blocks), T = M^T PA (8 blocks), S = M^T PM (4 blocks), Qx
       COOP_PHASE {
-        for (int e = lane; e < 72; e += G) {
-          const int i = e / 12, j = e % 12;
-          T[e] = i < 3 ? c1 * PA[12 * i + j] + hd * PA[12 * (6 + i) + j]
-                       : Cf[i - 3] * PA[36 + j] + Cf[i] * PA[48 + j] + Cf[3 + i] * PA[60 + j] + hd * PA[12 * (6 + i) + j];
+        const int br = lane >> 2, bc = lane & 3;
+        const double* Yc = Pw + 3 * bc;
+        double o[9], lb[9];
+        if (br & 1) blk_left(Yc, 12, br == 1 ? Aff : Afw, br == 1 ? 0.0 : 1.0, o);
+        else blk_evenT(Yc, 12, br == 0 ? 1.0 : hd, br == 0 ? 0.0 : 1.0, o);
+        lxx_block(cfg, vec + cv::Hphi, br, bc, lb);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] += lb[i];
+        blk_store(Pc + 36 * br + 3 * bc, 12, o);
+        if (br < 2) {
+          if (br == 1) blk_left(Yc, 12, Cf, hd, o);
+          else blk_evenT(Yc, 12, c1, hd, o);
+          blk_store(T + 36 * br + 3 * bc, 12, o);
         }
-        for (int e = lane; e < 36; e += G) {
-          const int i = e / 6, c = e % 6;
-          S[e] = i < 3 ? c1 * PM[6 * i + c] + hd * PM[6 * (6 + i) + c]
-                       : Cf[i - 3] * PM[18 + c] + Cf[i] * PM[24 + c] + Cf[3 + i] * PM[30 + c] + hd * PM[6 * (6 + i) + c];
+        if (lane >= 8 && lane < 12) {
+          const int r = (lane >> 1) & 1, c = lane & 1;
+          const double* Ym = PM + 3 * c;
+          if (r == 1) blk_left(Ym, 6, Cf, hd, o);
+          else blk_evenT(Ym, 6, c1, hd, o);
+          blk_store(S + 18 * r + 3 * c, 6, o);
         }
-        for (int e = lane; e < 144; e += G) {
-          const int a = e / 12, b = e % 12, ab = a / 3, aa = a % 3;
-          double v;
-          if (ab == 0) v = PA[12 * a + b];
-          else if (ab == 1) v = Aff[aa] * PA[36 + b] + Aff[3 + aa] * PA[48 + b] + Aff[6 + aa] * PA[60 + b];
-          else if (ab == 2) v = hd * PA[12 * aa + b] + PA[12 * (6 + aa) + b];
-          else v = Afw[aa] * PA[36 + b] + Afw[3 + aa] * PA[48 + b] + Afw[6 + aa] * PA[60 + b] + PA[12 * (9 + aa) + b];
-          P[e] = v + lxx_entry(cfg, vec + cv::Hphi, a, b);
-        }
-        for (int e = lane; e < 12; e += G) vec[cv::Qx + e] = vec[cv::Atp + e] + vec[cv::lx + e];
+        if (lane < 12) vec[cv::Qx + lane] = vec[cv::Atp + lane] + vec[cv::lx + lane];
       }
       COOP_SYNC();
-      // ---- phase D: Qux = W^T T, SW = S W, Qu = g + W^T s
+      // ---- phase D: Qux = W^T T (NF x 4 blocks), SW = S W (2 x NF blocks), Qu = g + W^T s
       COOP_PHASE {
-        for (int e = lane; e < NU * 12; e += G) {
-          const int i = e / 12, j = e % 12, f = i / 3, a = i % 3;
-          const double* IS = m.IS + 9 * f;
-          Qux[e] = m.inv_mass * T[12 * a + j] + IS[a] * T[36 + j] + IS[3 + a] * T[48 + j] + IS[6 + a] * T[60 + j];
+        const int br = lane >> 2, bc = lane & 3;
+        double o[9];
+        if (br < NF) {
+          const double* IS = m.IS + 9 * br;
+          const double* Tc = T + 3 * bc;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+              o[3 * a + b] = m.inv_mass * Tc[12 * a + b] + IS[a] * Tc[36 + b] + IS[3 + a] * Tc[48 + b] + IS[6 + a] * Tc[60 + b];
+          blk_store(Qux + 36 * br + 3 * bc, 12, o);
         }
-        for (int e = lane; e < 6 * NU; e += G) {
-          const int r = e / NU, col = e % NU, f = col / 3, b = col % 3;
-          const double* IS = m.IS + 9 * f;
-          SW[e] = m.inv_mass * S[6 * r + b] + S[6 * r + 3] * IS[b] + S[6 * r + 4] * IS[3 + b] + S[6 * r + 5] * IS[6 + b];
+        if (br < 2 && bc < NF) {
+          const double* IS = m.IS + 9 * bc;
+          const double* Sr = S + 18 * br;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+              o[3 * i + b] = m.inv_mass * Sr[6 * i + b] + Sr[6 * i + 3] * IS[b] + Sr[6 * i + 4] * IS[3 + b] + Sr[6 * i + 5] * IS[6 + b];
+          blk_store(SW + 3 * NU * br + 3 * bc, NU, o);
         }
-        for (int e = lane; e < NU; e += G) {
-          const int f = e / 3, a = e % 3;
+        if (lane < NU) {
+          const int f = lane / 3, a = lane % 3;
           const double* IS = m.IS + 9 * f;
           const double* s = vec + cv::s;
-          vec[cv::Qu + e] = (m.inv_mass * s[a] + IS[a] * s[3] + IS[3 + a] * s[4] + IS[6 + a] * s[5]) + vec[cv::g + e];
+          vec[cv::Qu + lane] = (m.inv_mass * s[a] + IS[a] * s[3] + IS[3 + a] * s[4] + IS[6 + a] * s[5]) + vec[cv::g + lane];
         }
       }
       COOP_SYNC();
-      // ---- phase E: Quu = D + W^T (S W)   (into the PA buffer)
+      // ---- phase E: Quu = D + W^T (S W)  (NF x NF blocks, into the work buffer)
+      double* Quu = Pw;
       COOP_PHASE {
-        for (int e = lane; e < NU * NU; e += G) {
-          const int i = e / NU, j = e % NU, f = i / 3, a = i % 3;
-          const double* IS = m.IS + 9 * f;
-          double v = m.inv_mass * SW[NU * a + j] + IS[a] * SW[NU * 3 + j] + IS[3 + a] * SW[NU * 4 + j] +
-                     IS[6 + a] * SW[NU * 5 + j];
-          if (j / 3 == f) v += vec[cv::Dblk + 9 * f + 3 * a + (j % 3)];
-          Quu[e] = v;
+        const int br = lane >> 2, bc = lane & 3;
+        if (br < NF && bc < NF) {
+          const double* IS = m.IS + 9 * br;
+          const double* Wc = SW + 3 * bc;
+          double o[9];
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              double v = m.inv_mass * Wc[NU * a + j] + IS[a] * Wc[NU * 3 + j] + IS[3 + a] * Wc[NU * 4 + j] + IS[6 + a] * Wc[NU * 5 + j];
+              if (br == bc) v += vec[cv::Dblk + 9 * br + 3 * a + j];
+              o[3 * a + j] = v;
+            }
+          blk_store(Quu + 3 * NU * br + 3 * bc, NU, o);
         }
       }
       COOP_SYNC();
@@ -492,21 +623,26 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         }
       }
       COOP_SYNC();
-      // ---- phase F: P <- sym(P) - V^T V (packed upper triangle, mirrored) ; pv <- Qx - V^T vu
+      // ---- phase F: new P = sym(P) - V^T V (16 blocks, written to the work buffer: no race with the
+      //      transposed reads of Pc), pv <- Qx - V^T vu ; then swap the two buffers
       COOP_PHASE {
-        for (int idx = lane; idx < 78; idx += G) {
-          int a = 0, rem = idx;
-          while (rem >= 12 - a) { rem -= 12 - a; ++a; }
-          const int b = a + rem;
+        const int br = lane >> 2, bc = lane & 3;
+        double o[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            double t = 0;
+#pragma unroll
+            for (int l = 0; l < NU; ++l) t += Qux[12 * l + 3 * br + a] * Qux[12 * l + 3 * bc + b];
+            o[3 * a + b] = 0.5 * (Pc[12 * (3 * br + a) + 3 * bc + b] + Pc[12 * (3 * bc + b) + 3 * br + a]) - t;
+          }
+        blk_store(Pw + 36 * br + 3 * bc, 12, o);
+        blk_store(gP + (size_t)k * 144 + 36 * br + 3 * bc, 12, o);
+        if (lane < 12) {
+          const int a = lane;
           double t = 0;
-          for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * Qux[12 * l + b];
-          const double v = 0.5 * (P[12 * a + b] + P[12 * b + a]) - t;
-          P[12 * a + b] = v;
-          P[12 * b + a] = v;
-          gP[(size_t)k * 78 + idx] = v;
-        }
-        for (int a = lane; a < 12; a += G) {
-          double t = 0;
+#pragma unroll
           for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * vec[cv::vu + l];
           const double v = vec[cv::Qx + a] - t;
           vec[cv::pv + a] = v;
@@ -514,6 +650,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         }
       }
       COOP_SYNC();
+      { double* t = Pc; Pc = Pw; Pw = t; }
     }
     if (!bp_ok) { status = QMPC_STATUS_BACKWARD_FAILED; break; }
     const double dphi0 = scal[0];
@@ -529,26 +666,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         if (j < o.ls_iters_max) {
           double alpha = 1.0;
           for (int q = 0; q < j; ++q) alpha *= o.ls_decrease;
-          double x[NX], xn[NX];
-          for (int i = 0; i < NX; ++i) x[i] = X[i];
-          J = 0;
-#pragma unroll 1
-          for (int k = 0; k < N; ++k) {
-            double dx[NE], u[NU];
-            state_diff<M>(x, X + k * NX, dx);
-            const double* Kk = gK + (size_t)k * NU * 12;
-#pragma unroll
-            for (int i = 0; i < NU; ++i) {
-              double t = 0;
-#pragma unroll
-              for (int l = 0; l < NE; ++l) t += Kk[i * 12 + l] * dx[l];
-              u[i] = U[k * NU + i] + alpha * gd[k * NU + i] + t;
-            }
-            knot_merit(m, cfg, k, N, x, u, gmu + k * NC, rho, J, vl);
-            mid_dyn(m, x, u, h, xn);
-            for (int i = 0; i < NX; ++i) x[i] = xn[i];
-          }
-          knot_merit(m, cfg, N, N, x, x, gmu, rho, J, vl);
+          coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, alpha, 1, &J, &vl);
         }
         red[lane] = J;
         red[G + lane] = vl;
@@ -575,28 +693,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     // ---------------- accepted step: redo its roll-out in place (X,U <- new; DX <- dx_k)
     COOP_PHASE {
       if (lane == 0) {
-        double x[NX], xn[NX];
-        for (int i = 0; i < NX; ++i) x[i] = X[i];
-#pragma unroll 1
-        for (int k = 0; k < N; ++k) {
-          double dx[NE], u[NU];
-          state_diff<M>(x, X + k * NX, dx);
-          const double* Kk = gK + (size_t)k * NU * 12;
-          for (int i = 0; i < NU; ++i) {
-            double t = 0;
-            for (int l = 0; l < NE; ++l) t += Kk[i * 12 + l] * dx[l];
-            u[i] = U[k * NU + i] + alpha_acc * gd[k * NU + i] + t;
-          }
-          for (int i = 0; i < NE; ++i) DX[k * NE + i] = dx[i];
-          for (int i = 0; i < NU; ++i) U[k * NU + i] = u[i];
-          for (int i = 0; i < NX; ++i) X[k * NX + i] = x[i];
-          mid_dyn(m, x, u, h, xn);
-          for (int i = 0; i < NX; ++i) x[i] = xn[i];
-        }
-        double dx[NE];
-        state_diff<M>(x, X + N * NX, dx);
-        for (int i = 0; i < NE; ++i) DX[N * NE + i] = dx[i];
-        for (int i = 0; i < NX; ++i) X[N * NX + i] = x[i];
+        double Jd, vd;
+        coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, alpha_acc, 2, &Jd, &vd);
       }
     }
     COOP_SYNC();
@@ -605,13 +703,14 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       for (int k = lane; k <= N; k += G) {
         double dx[NE], y[NE];
         for (int i = 0; i < NE; ++i) { dx[i] = DX[k * NE + i]; y[i] = gpv[k * 12 + i]; }
-        int idx = 0;
-        for (int a = 0; a < NE; ++a)
-          for (int b = a; b < NE; ++b) {
-            const double v = gP[(size_t)k * 78 + idx++];
-            y[a] += v * dx[b];
-            if (b != a) y[b] += v * dx[a];
-          }
+        const double* Pk = gP + (size_t)k * 144;
+#pragma unroll
+        for (int a = 0; a < NE; ++a) {
+          double t = y[a];
+#pragma unroll
+          for (int b = 0; b < NE; ++b) t += Pk[12 * a + b] * dx[b];
+          y[a] = t;
+        }
         for (int i = 0; i < NE; ++i) DX[k * NE + i] = y[i];
       }
     }

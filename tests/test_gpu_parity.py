@@ -82,7 +82,7 @@ def test_dense_and_structured_kernels_agree(oracle, monkeypatch):
     ref = oracle.solve_batch(srb.cfg, probs, nthreads=NT)
     ea, eb = _check(a, ref), _check(b, ref)
     print(f"structured max|dGRF| = {ea:.3e} N, dense max|dGRF| = {eb:.3e} N")
-    assert np.abs(a["grf_body"] - b["grf_body"]).max() < TOL
+    _check(a, b)   # the two device implementations against each other, same policy
 
 
 def test_host_and_device_entry_points_agree(oracle):
