@@ -39,37 +39,43 @@
 namespace qmpc {
 
 // ---- 3x3 block kernels used by the block-per-lane phases (lane = (block row, block col)) --------
-// out = X(:, 3:6) * Mt + beta * X(:, 9:12)      X: 3 rows of a row-major matrix with leading dim ld
-QMPC_HD inline void blk_right(const double* X, int ld, const double* Mt, double beta, double* out) {
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b)
-      out[3 * a + b] = X[ld * a + 3] * Mt[b] + X[ld * a + 4] * Mt[3 + b] + X[ld * a + 5] * Mt[6 + b] +
-                       beta * X[ld * a + 9 + b];
-}
-// out = alpha * X(:, 0:3) + beta * X(:, 6:9)
-QMPC_HD inline void blk_even(const double* X, int ld, double alpha, double beta, double* out) {
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) out[3 * a + b] = alpha * X[ld * a + b] + beta * X[ld * a + 6 + b];
-}
-// out = Mt^T * Y(3:6, :) + beta * Y(9:12, :)     Y: 3 columns (starting at Y) of a row-major matrix
-QMPC_HD inline void blk_left(const double* Y, int ld, const double* Mt, double beta, double* out) {
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
+// The row loop is deliberately NOT unrolled: the kernel is instruction-fetch bound, compact code wins.
+// dst = X(:, 3:6) * Mt + beta * X(:, 9:12)   X: 3 rows of a row-major matrix with leading dim ld
+QMPC_HD inline void blk_right(const double* X, int ld, const double* Mt, double beta, double* dst, int ldd) {
+#pragma unroll 1
+  for (int a = 0; a < 3; ++a) {
+    const double* Xa = X + ld * a;
 #pragma unroll
     for (int b = 0; b < 3; ++b)
-      out[3 * a + b] = Mt[a] * Y[ld * 3 + b] + Mt[3 + a] * Y[ld * 4 + b] + Mt[6 + a] * Y[ld * 5 + b] +
-                       beta * Y[ld * (9 + a) + b];
+      dst[ldd * a + b] = Xa[3] * Mt[b] + Xa[4] * Mt[3 + b] + Xa[5] * Mt[6 + b] + beta * Xa[9 + b];
+  }
 }
-// out = alpha * Y(0:3, :) + beta * Y(6:9, :)
-QMPC_HD inline void blk_evenT(const double* Y, int ld, double alpha, double beta, double* out) {
+// dst = alpha * X(:, 0:3) + beta * X(:, 6:9)
+QMPC_HD inline void blk_even(const double* X, int ld, double alpha, double beta, double* dst, int ldd) {
+#pragma unroll 1
+  for (int a = 0; a < 3; ++a) {
+    const double* Xa = X + ld * a;
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) dst[ldd * a + b] = alpha * Xa[b] + beta * Xa[6 + b];
+  }
+}
+// dst = Mt^T * Y(3:6, :) + beta * Y(9:12, :)   Y: 3 columns (starting at Y) of a row-major matrix
+QMPC_HD inline void blk_left(const double* Y, int ld, const double* Mt, double beta, double* dst, int ldd) {
+#pragma unroll 1
+  for (int a = 0; a < 3; ++a) {
 #pragma unroll
-    for (int b = 0; b < 3; ++b) out[3 * a + b] = alpha * Y[ld * a + b] + beta * Y[ld * (6 + a) + b];
+    for (int b = 0; b < 3; ++b)
+      dst[ldd * a + b] = Mt[a] * Y[ld * 3 + b] + Mt[3 + a] * Y[ld * 4 + b] + Mt[6 + a] * Y[ld * 5 + b] +
+                         beta * Y[ld * (9 + a) + b];
+  }
+}
+// dst = alpha * Y(0:3, :) + beta * Y(6:9, :)
+QMPC_HD inline void blk_evenT(const double* Y, int ld, double alpha, double beta, double* dst, int ldd) {
+#pragma unroll 1
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) dst[ldd * a + b] = alpha * Y[ld * a + b] + beta * Y[ld * (6 + a) + b];
+  }
 }
 QMPC_HD inline void blk_store(double* dst, int ld, const double* v) {
 #pragma unroll
@@ -179,55 +185,124 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
                                         double* U, double* DX, const double* gK, const double* gd,
                                         const double* gmu, double rho, double alpha, int mode, double* Jout,
                                         double* violout) {
+  // Compact by construction (instruction-fetch bound otherwise): the input never
+  // exists as an array - each foot's force is formed, costed, cone-checked and folded into the net
+  // wrench inside one 4-trip loop; the wrench drives both midpoint evaluations.  Accumulation
+  // orders are exactly those of stage_cost() / knot_merit() / ct_dyn() / mid_dyn().
   using M = QuatModel<NF>;
   constexpr int NX = 13, NE = 12, NU = M::NU, NC = M::NC;
-  double x[NX], xn[NX], J = 0, vl = 0;
+  const double hd = (double)h, hh = (double)(h / 2);
+  double x[NX], J = 0, vl = 0;
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = X[i];
 #pragma unroll 1
-  for (int k = 0; k < N; ++k) {
-    double u[NU];
-    if (mode == 0) {
-#pragma unroll
-      for (int i = 0; i < NU; ++i) { u[i] = m.uref[i]; U[k * NU + i] = u[i]; }
-    } else {
-      double dx[NE];
-      state_diff<M>(x, X + k * NX, dx);
-      const double* Kk = gK + (size_t)k * NU * 12;
-#pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        double t = 0;
-#pragma unroll
-        for (int l = 0; l < NE; ++l) t += Kk[i * 12 + l] * dx[l];
-        u[i] = U[k * NU + i] + alpha * gd[k * NU + i] + t;
-      }
-      if (mode == 2) {
-#pragma unroll
-        for (int i = 0; i < NE; ++i) DX[k * NE + i] = dx[i];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) U[k * NU + i] = u[i];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) X[k * NX + i] = x[i];
-      }
-    }
-    if (mode != 2) knot_merit(m, cfg, k, N, x, u, gmu + k * NC, rho, J, vl);
-    mid_dyn(m, x, u, h, xn);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = xn[i];
-    if (mode == 0) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) X[(k + 1) * NX + i] = xn[i];
-    }
-  }
-  if (mode == 2) {
+  for (int k = 0; k <= N; ++k) {
     double dx[NE];
-    state_diff<M>(x, X + N * NX, dx);
+    if (mode != 0) state_diff<M>(x, X + k * NX, dx);
+    if (mode == 2) {
 #pragma unroll
-    for (int i = 0; i < NE; ++i) DX[N * NE + i] = dx[i];
+      for (int i = 0; i < NE; ++i) DX[k * NE + i] = dx[i];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) X[N * NX + i] = x[i];
-  } else {
-    knot_merit(m, cfg, N, N, x, x, gmu, rho, J, vl);
+      for (int i = 0; i < NX; ++i) X[k * NX + i] = x[i];
+    }
+    // ---- state part of the stage cost
+    double Jl = 0, sq = 0;
+    if (mode != 2) {
+      double xr[NX];
+      m.xref(k, xr);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - xr[i]; Jl += 0.5 * cfg.q_weights[i] * dxi * dxi; }
+      sq = xr[3] * x[3] + xr[4] * x[4] + xr[5] * x[5] + xr[6] * x[6];
+    }
+    if (k == N) {
+      if (mode != 2) {
+        if (cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
+        J += Jl;
+      }
+      break;
+    }
+    // ---- per foot: force, input cost, cone rows / AL merit, wrench
+    double mom0 = 0, mom1 = 0, mom2 = 0, fs0 = 0, fs1 = 0, fs2 = 0, acc = 0;
+    const double* Kk = gK + (size_t)k * NU * 12;
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+      double u0, u1, u2;
+      if (mode == 0) {
+        u0 = m.uref[3 * f]; u1 = m.uref[3 * f + 1]; u2 = m.uref[3 * f + 2];
+      } else {
+        double t0 = 0, t1 = 0, t2 = 0;
+        const double* K0 = Kk + (3 * f) * 12;
+#pragma unroll
+        for (int l = 0; l < NE; ++l) t0 += K0[l] * dx[l];
+#pragma unroll
+        for (int l = 0; l < NE; ++l) t1 += K0[12 + l] * dx[l];
+#pragma unroll
+        for (int l = 0; l < NE; ++l) t2 += K0[24 + l] * dx[l];
+        u0 = U[k * NU + 3 * f] + alpha * gd[k * NU + 3 * f] + t0;
+        u1 = U[k * NU + 3 * f + 1] + alpha * gd[k * NU + 3 * f + 1] + t1;
+        u2 = U[k * NU + 3 * f + 2] + alpha * gd[k * NU + 3 * f + 2] + t2;
+      }
+      if (mode != 1) { U[k * NU + 3 * f] = u0; U[k * NU + 3 * f + 1] = u1; U[k * NU + 3 * f + 2] = u2; }
+      if (mode != 2) {
+        const double d0 = u0 - m.uref[3 * f], d1 = u1 - m.uref[3 * f + 1], d2 = u2 - m.uref[3 * f + 2];
+        Jl += 0.5 * cfg.r_weights[3 * f] * d0 * d0;
+        Jl += 0.5 * cfg.r_weights[3 * f + 1] * d1 * d1;
+        Jl += 0.5 * cfg.r_weights[3 * f + 2] * d2 * d2;
+        const double* mu_f = gmu + k * NC + 6 * f;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double c = m.CR[3 * r] * u0 + m.CR[3 * r + 1] * u1 + m.CR[3 * r + 2] * u2;
+          if (r == 4) c += -m.fzc[f];
+          const double mui = mu_f[r];
+          const double est = mui + rho * c;
+          const double lh = est > 0 ? est : 0;
+          if (c > vl) vl = c;
+          acc += lh * lh - mui * mui;
+        }
+      }
+      const double* rf = m.foot + 3 * f;
+      const double c0 = rf[1] * u2 - rf[2] * u1, c1 = rf[2] * u0 - rf[0] * u2, c2 = rf[0] * u1 - rf[1] * u0;
+      mom0 += c0; fs0 += u0;
+      mom1 += c1; fs1 += u1;
+      mom2 += c2; fs2 += u2;
+    }
+    if (mode != 2) {
+      if (cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
+      J += Jl;
+      J += acc / (2 * rho);
+    }
+    // ---- explicit midpoint step driven by the net wrench (AltroUtils.cpp:9-22, 383-391)
+    mom0 += m.tau_g[0]; mom1 += m.tau_g[1]; mom2 += m.tau_g[2];
+    const double al0 = fs0 * m.inv_mass + m.g[0], al1 = fs1 * m.inv_mass + m.g[1], al2 = fs2 * m.inv_mass + m.g[2];
+    const double aw0 = m.Iinv[0] * mom0 + m.Iinv[1] * mom1 + m.Iinv[2] * mom2;
+    const double aw1 = m.Iinv[3] * mom0 + m.Iinv[4] * mom1 + m.Iinv[5] * mom2;
+    const double aw2 = m.Iinv[6] * mom0 + m.Iinv[7] * mom1 + m.Iinv[8] * mom2;
+    double xm[NX];
+    {
+      const double *q = x + 3, *w = x + 10;
+      xm[0] = x[7] * hh + x[0]; xm[1] = x[8] * hh + x[1]; xm[2] = x[9] * hh + x[2];
+      xm[3] = (0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2])) * hh + q[0];
+      xm[4] = (0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2])) * hh + q[1];
+      xm[5] = (0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2])) * hh + q[2];
+      xm[6] = (0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2])) * hh + q[3];
+      xm[7] = al0 * hh + x[7]; xm[8] = al1 * hh + x[8]; xm[9] = al2 * hh + x[9];
+      xm[10] = aw0 * hh + x[10]; xm[11] = aw1 * hh + x[11]; xm[12] = aw2 * hh + x[12];
+    }
+    {
+      const double *q = xm + 3, *w = xm + 10;
+      const double qd0 = 0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
+      const double qd1 = 0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
+      const double qd2 = 0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
+      const double qd3 = 0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
+      x[0] = x[0] + hd * xm[7]; x[1] = x[1] + hd * xm[8]; x[2] = x[2] + hd * xm[9];
+      x[3] = x[3] + hd * qd0; x[4] = x[4] + hd * qd1; x[5] = x[5] + hd * qd2; x[6] = x[6] + hd * qd3;
+      x[7] = x[7] + hd * al0; x[8] = x[8] + hd * al1; x[9] = x[9] + hd * al2;
+      x[10] = x[10] + hd * aw0; x[11] = x[11] + hd * aw1; x[12] = x[12] + hd * aw2;
+    }
+    if (mode == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) X[(k + 1) * NX + i] = x[i];
+    }
   }
   *Jout = J;
   *violout = vl;
@@ -415,7 +490,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           const int f = lane;
           const double* u = U + k * NU + 3 * f;
           double g0 = 0, g1 = 0, g2 = 0, hb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
+#pragma unroll 1
           for (int r = 0; r < 6; ++r) {
             double c = m.CR[3 * r] * u[0] + m.CR[3 * r + 1] * u[1] + m.CR[3 * r + 2] * u[2];
             if (r == 4) c += -m.fzc[f];
@@ -450,14 +525,11 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       COOP_PHASE {
         const int br = lane >> 2, bc = lane & 3;
         const double* Pr = Pc + 36 * br;
-        double o[9];
-        if (bc & 1) blk_right(Pr, 12, bc == 1 ? Aff : Afw, bc == 1 ? 0.0 : 1.0, o);
-        else blk_even(Pr, 12, bc == 0 ? 1.0 : hd, bc == 0 ? 0.0 : 1.0, o);
-        blk_store(Pw + 36 * br + 3 * bc, 12, o);
+        if (bc & 1) blk_right(Pr, 12, bc == 1 ? Aff : Afw, bc == 1 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
+        else blk_even(Pr, 12, bc == 0 ? 1.0 : hd, bc == 0 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
         if (bc < 2) {
-          if (bc == 1) blk_right(Pr, 12, Cf, hd, o);
-          else blk_even(Pr, 12, c1, hd, o);
-          blk_store(PM + 18 * br + 3 * bc, 6, o);
+          if (bc == 1) blk_right(Pr, 12, Cf, hd, PM + 18 * br + 3 * bc, 6);
+          else blk_even(Pr, 12, c1, hd, PM + 18 * br + 3 * bc, 6);
         }
         if (lane < 6) {
           const int e = lane;
@@ -479,24 +551,29 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       COOP_PHASE {
         const int br = lane >> 2, bc = lane & 3;
         const double* Yc = Pw + 3 * bc;
-        double o[9], lb[9];
-        if (br & 1) blk_left(Yc, 12, br == 1 ? Aff : Afw, br == 1 ? 0.0 : 1.0, o);
-        else blk_evenT(Yc, 12, br == 0 ? 1.0 : hd, br == 0 ? 0.0 : 1.0, o);
-        lxx_block(cfg, vec + cv::Hphi, br, bc, lb);
+        double* Pd = Pc + 36 * br + 3 * bc;
+        if (br & 1) blk_left(Yc, 12, br == 1 ? Aff : Afw, br == 1 ? 0.0 : 1.0, Pd, 12);
+        else blk_evenT(Yc, 12, br == 0 ? 1.0 : hd, br == 0 ? 0.0 : 1.0, Pd, 12);
+        if (br == bc) {   // + lxx on the diagonal blocks (the same lane just wrote the block)
+          if (br == 1) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) o[i] += lb[i];
-        blk_store(Pc + 36 * br + 3 * bc, 12, o);
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) Pd[12 * i + j] += vec[cv::Hphi + 3 * i + j];
+          } else {
+            const int q0 = br == 0 ? 0 : (br == 2 ? 7 : 10);
+            Pd[0] += cfg.q_weights[q0]; Pd[13] += cfg.q_weights[q0 + 1]; Pd[26] += cfg.q_weights[q0 + 2];
+          }
+        }
         if (br < 2) {
-          if (br == 1) blk_left(Yc, 12, Cf, hd, o);
-          else blk_evenT(Yc, 12, c1, hd, o);
-          blk_store(T + 36 * br + 3 * bc, 12, o);
+          if (br == 1) blk_left(Yc, 12, Cf, hd, T + 36 * br + 3 * bc, 12);
+          else blk_evenT(Yc, 12, c1, hd, T + 36 * br + 3 * bc, 12);
         }
         if (lane >= 8 && lane < 12) {
           const int r = (lane >> 1) & 1, c = lane & 1;
           const double* Ym = PM + 3 * c;
-          if (r == 1) blk_left(Ym, 6, Cf, hd, o);
-          else blk_evenT(Ym, 6, c1, hd, o);
-          blk_store(S + 18 * r + 3 * c, 6, o);
+          if (r == 1) blk_left(Ym, 6, Cf, hd, S + 18 * r + 3 * c, 6);
+          else blk_evenT(Ym, 6, c1, hd, S + 18 * r + 3 * c, 6);
         }
         if (lane < 12) vec[cv::Qx + lane] = vec[cv::Atp + lane] + vec[cv::lx + lane];
       }
@@ -504,26 +581,25 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       // ---- phase D: Qux = W^T T (NF x 4 blocks), SW = S W (2 x NF blocks), Qu = g + W^T s
       COOP_PHASE {
         const int br = lane >> 2, bc = lane & 3;
-        double o[9];
         if (br < NF) {
           const double* IS = m.IS + 9 * br;
           const double* Tc = T + 3 * bc;
-#pragma unroll
+          double* Qd = Qux + 36 * br + 3 * bc;
+#pragma unroll 1
           for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int b = 0; b < 3; ++b)
-              o[3 * a + b] = m.inv_mass * Tc[12 * a + b] + IS[a] * Tc[36 + b] + IS[3 + a] * Tc[48 + b] + IS[6 + a] * Tc[60 + b];
-          blk_store(Qux + 36 * br + 3 * bc, 12, o);
+              Qd[12 * a + b] = m.inv_mass * Tc[12 * a + b] + IS[a] * Tc[36 + b] + IS[3 + a] * Tc[48 + b] + IS[6 + a] * Tc[60 + b];
         }
         if (br < 2 && bc < NF) {
           const double* IS = m.IS + 9 * bc;
           const double* Sr = S + 18 * br;
-#pragma unroll
+          double* Wd = SW + 3 * NU * br + 3 * bc;
+#pragma unroll 1
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int b = 0; b < 3; ++b)
-              o[3 * i + b] = m.inv_mass * Sr[6 * i + b] + Sr[6 * i + 3] * IS[b] + Sr[6 * i + 4] * IS[3 + b] + Sr[6 * i + 5] * IS[6 + b];
-          blk_store(SW + 3 * NU * br + 3 * bc, NU, o);
+              Wd[NU * i + b] = m.inv_mass * Sr[6 * i + b] + Sr[6 * i + 3] * IS[b] + Sr[6 * i + 4] * IS[3 + b] + Sr[6 * i + 5] * IS[6 + b];
         }
         if (lane < NU) {
           const int f = lane / 3, a = lane % 3;
@@ -540,16 +616,15 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         if (br < NF && bc < NF) {
           const double* IS = m.IS + 9 * br;
           const double* Wc = SW + 3 * bc;
-          double o[9];
-#pragma unroll
+          double* Qd = Quu + 3 * NU * br + 3 * bc;
+#pragma unroll 1
           for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
               double v = m.inv_mass * Wc[NU * a + j] + IS[a] * Wc[NU * 3 + j] + IS[3 + a] * Wc[NU * 4 + j] + IS[6 + a] * Wc[NU * 5 + j];
               if (br == bc) v += vec[cv::Dblk + 9 * br + 3 * a + j];
-              o[3 * a + j] = v;
+              Qd[NU * a + j] = v;
             }
-          blk_store(Quu + 3 * NU * br + 3 * bc, NU, o);
         }
       }
       COOP_SYNC();
@@ -581,7 +656,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         COOP_SYNC();
       }
       if (!bp_ok) break;
-      // ---- solves: lane c <- right-hand side c (12 columns of Qux, then Qu)
+      // ---- solves: lane c <- right-hand side c (12 columns of Qux, then Qu); register-resident,
+      //      fully unrolled (the rolled shared-memory variant was measured slower: +40 % instructions)
       COOP_PHASE {
         for (int c = lane; c <= 12; c += G) {
           double rhs[NU];
@@ -627,22 +703,27 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       //      transposed reads of Pc), pv <- Qx - V^T vu ; then swap the two buffers
       COOP_PHASE {
         const int br = lane >> 2, bc = lane & 3;
-        double o[9];
+        double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+        for (int l = 0; l < NU; ++l) {
+          const double* Vr = Qux + 12 * l + 3 * br;
+          const double* Vc = Qux + 12 * l + 3 * bc;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) o[3 * a + b] += Vr[a] * Vc[b];
+        }
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            double t = 0;
-#pragma unroll
-            for (int l = 0; l < NU; ++l) t += Qux[12 * l + 3 * br + a] * Qux[12 * l + 3 * bc + b];
-            o[3 * a + b] = 0.5 * (Pc[12 * (3 * br + a) + 3 * bc + b] + Pc[12 * (3 * bc + b) + 3 * br + a]) - t;
-          }
+          for (int b = 0; b < 3; ++b)
+            o[3 * a + b] = 0.5 * (Pc[12 * (3 * br + a) + 3 * bc + b] + Pc[12 * (3 * bc + b) + 3 * br + a]) - o[3 * a + b];
         blk_store(Pw + 36 * br + 3 * bc, 12, o);
         blk_store(gP + (size_t)k * 144 + 36 * br + 3 * bc, 12, o);
         if (lane < 12) {
           const int a = lane;
           double t = 0;
-#pragma unroll
+#pragma unroll 4
           for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * vec[cv::vu + l];
           const double v = vec[cv::Qx + a] - t;
           vec[cv::pv + a] = v;
