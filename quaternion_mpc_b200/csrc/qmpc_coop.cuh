@@ -663,12 +663,13 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           double rhs[NU];
 #pragma unroll
           for (int i = 0; i < NU; ++i) rhs[i] = c < 12 ? Qux[12 * i + c] : vec[cv::Qu + i];
+          // column-oriented ("right-looking") substitutions: after x_i is final, every remaining
+          // entry is updated independently -> 12-deep critical path instead of 78 dependent FMAs
 #pragma unroll
           for (int i = 0; i < NU; ++i) {
-            double t = rhs[i];
+            rhs[i] = rhs[i] * vec[cv::rdiag + i];
 #pragma unroll
-            for (int l = 0; l < i; ++l) t -= Quu[NU * i + l] * rhs[l];
-            rhs[i] = t * vec[cv::rdiag + i];
+            for (int l = i + 1; l < NU; ++l) rhs[l] -= Quu[NU * l + i] * rhs[i];
           }
           if (c < 12) {
 #pragma unroll
@@ -679,10 +680,9 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           }
 #pragma unroll
           for (int i = NU - 1; i >= 0; --i) {
-            double t = rhs[i];
+            rhs[i] = rhs[i] * vec[cv::rdiag + i];
 #pragma unroll
-            for (int l = i + 1; l < NU; ++l) t -= Quu[NU * l + i] * rhs[l];
-            rhs[i] = t * vec[cv::rdiag + i];
+            for (int l = 0; l < i; ++l) rhs[l] -= Quu[NU * i + l] * rhs[i];
           }
           if (c < 12) {
 #pragma unroll
