@@ -38,6 +38,14 @@
 
 namespace qmpc {
 
+QMPC_HD inline double qmpc_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // ---- 3x3 block kernels used by the block-per-lane phases (lane = (block row, block col)) --------
 // The row loop is deliberately NOT unrolled: the kernel is instruction-fetch bound, compact code wins.
 // dst = X(:, 3:6) * Mt + beta * X(:, 9:12)   X: 3 rows of a row-major matrix with leading dim ld
@@ -89,7 +97,7 @@ struct CoopLayout {
   static constexpr int NU = 3 * NF, NC = 6 * NF;
   static constexpr int kModel = (int)((sizeof(QuatModel<NF>) + 7) / 8);
   // ---- shared memory (doubles) per problem
-  static constexpr int kVec = 172;
+  static constexpr int kVec = 180;
   QMPC_HD static int sX(int N) { return kModel; }
   QMPC_HD static int sU(int N) { return sX(N) + (N + 1) * 13; }
   QMPC_HD static int sDX(int N) { return sU(N) + N * NU; }
@@ -115,8 +123,8 @@ struct CoopLayout {
 
 // offsets inside the shared "vec" block
 namespace cv {
-constexpr int lx = 0, Qx = 12, Qu = 24, s = 36, Atp = 42, g = 54, Dblk = 66, Hphi = 102, vu = 111, tcol = 123,
-              pv = 135, scal = 147, rdiag = 148 + 8;  // scal[0]=dphi0 [1]=hphi [2]=phi [3]=viol
+constexpr int lx = 0, Qx = 12, Qu = 24, s = 36, Atp = 42, g = 54, Dblk = 66, Hphi = 102, vu = 111, pv = 123,
+              scal = 135, rdiag = 144, tcol = 156;  // scal[0]=dphi0 [1]=hphi [2]=phi [3]=viol
 }
 
 // stage cost + AL terms of one knot (same accumulation order as merit() in qmpc_dense.cuh)
@@ -628,29 +636,39 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         }
       }
       COOP_SYNC();
-      // ---- Cholesky of Quu (left-looking, one row per lane), same arithmetic as chol<NU>()
+      // ---- Cholesky of Quu (left-looking, one row per lane).  One sync per column: the column is
+      //      exchanged through a double-buffered tcol, and the only not-yet-visible factor entry a
+      //      lane needs, L(j, j-1), is recomputed from the previous tcol (bit-identical to what the
+      //      owning lane stored).  1/sqrt via one rsqrt instead of sqrt + reciprocal.
+      {
+        double rdg_prev = 0.0;
 #pragma unroll 1
-      for (int j = 0; j < NU && bp_ok; ++j) {
-        COOP_PHASE {
-          for (int i = j + lane; i < NU; i += G) {
-            double t = Quu[NU * i + j];
-#pragma unroll 4
-            for (int l = 0; l < j; ++l) t -= Quu[NU * i + l] * Quu[NU * j + l];
-            vec[cv::tcol + i] = t;
-          }
-        }
-        COOP_SYNC();
-        const double sjj = vec[cv::tcol + j];
-        if (!(sjj > 0.0)) {
-          bp_ok = false;
-        } else {
-          const double dg = sqrt(sjj);
-          const double rdg = 1.0 / dg;
+        for (int j = 0; j < NU && bp_ok; ++j) {
+          double* tc = vec + cv::tcol + (j & 1) * NU;
+          const double* tp = vec + cv::tcol + ((j & 1) ^ 1) * NU;
           COOP_PHASE {
             for (int i = j + lane; i < NU; i += G) {
-              if (i == j) { Quu[NU * i + j] = dg; vec[cv::rdiag + j] = rdg; }
-              else Quu[NU * i + j] = vec[cv::tcol + i] * rdg;
+              double t = Quu[NU * i + j];
+#pragma unroll 4
+              for (int l = 0; l + 1 < j; ++l) t -= Quu[NU * i + l] * Quu[NU * j + l];
+              if (j > 0) t -= Quu[NU * i + j - 1] * (i == j ? Quu[NU * j + j - 1] : tp[j] * rdg_prev);
+              tc[i] = t;
             }
+          }
+          COOP_SYNC();
+          const double sjj = tc[j];
+          if (!(sjj > 0.0)) {
+            bp_ok = false;
+          } else {
+            const double rdg = qmpc_rsqrt(sjj);
+            const double dg = sjj * rdg;
+            COOP_PHASE {
+              for (int i = j + lane; i < NU; i += G) {
+                if (i == j) { Quu[NU * i + j] = dg; vec[cv::rdiag + j] = rdg; }
+                else Quu[NU * i + j] = tc[i] * rdg;
+              }
+            }
+            rdg_prev = rdg;
           }
         }
         COOP_SYNC();
