@@ -31,7 +31,7 @@ struct QmpcHandle {
   int64_t launches;
   int kernel;          // 0 = dense (generic), 1 = srb (structured, thread per problem), 2 = coop (structured,
                        //     16 lanes per problem, shared-memory resident; default for the QUAT models)
-  int coop_grid, coop_smem_doubles;   // persistent launch geometry of the coop kernel
+  int coop_grid, coop_smem_doubles, coop_wide;   // persistent launch geometry of the coop kernel
   size_t coop_scratch_doubles;
   char err[256];
 };
@@ -117,7 +117,12 @@ template <int NF>
 static int coop_prepare_t(QmpcHandle* h) {
   using L = CoopLayout<NF, kCoopG>;
   const int N = h->cfg.horizon;
-  h->coop_smem_doubles = L::smem_doubles(N);
+  // 255 registers/thread cap residency at 4 blocks (16 problems) per SM; use the "wide" shared
+  // memory layout whenever it still fits 4 blocks
+  const int groups0 = kCoopBlock / kCoopG;
+  h->coop_wide = ((size_t)groups0 * L::smem_doubles(N, true) * sizeof(double) + 1024) * 4 <= 227 * 1024 ? 1 : 0;
+  if (const char* wenv = getenv("QMPC_COOP_WIDE")) h->coop_wide = atoi(wenv) != 0;
+  h->coop_smem_doubles = L::smem_doubles(N, h->coop_wide != 0);
   h->coop_scratch_doubles = L::scratch_doubles(N);
   const int groups = kCoopBlock / kCoopG;
   const size_t smem_bytes = (size_t)groups * h->coop_smem_doubles * sizeof(double);
@@ -227,7 +232,8 @@ static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, int batch, QmpcRe
   const int grid = need < h->coop_grid ? need : h->coop_grid;
   const size_t smem_bytes = (size_t)groups * h->coop_smem_doubles * sizeof(double);
   qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, d_out, h->ws, batch,
-                                                                   h->coop_smem_doubles, h->coop_scratch_doubles);
+                                                                   h->coop_smem_doubles, h->coop_scratch_doubles,
+                                                                   h->coop_wide);
   h->launches += 1;
   CU(cudaGetLastError());
   return QMPC_OK;

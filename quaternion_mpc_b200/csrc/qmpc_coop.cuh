@@ -100,8 +100,7 @@ struct CoopLayout {
   static constexpr int kVec = 180;
   QMPC_HD static int sX(int N) { return kModel; }
   QMPC_HD static int sU(int N) { return sX(N) + (N + 1) * 13; }
-  QMPC_HD static int sDX(int N) { return sU(N) + N * NU; }
-  QMPC_HD static int sP(int N) { return sDX(N) + (N + 1) * 12; }
+  QMPC_HD static int sP(int N) { return sU(N) + N * NU; }
   QMPC_HD static int sPA(int N) { return sP(N) + 144; }    // PA, later Quu / its Cholesky factor
   QMPC_HD static int sT(int N) { return sPA(N) + 144; }
   QMPC_HD static int sPM(int N) { return sT(N) + 72; }     // PM, later SW
@@ -110,7 +109,12 @@ struct CoopLayout {
   QMPC_HD static int sVec(int N) { return sQux(N) + NU * 12; }
   QMPC_HD static int sRed(int N) { return sVec(N) + kVec; }
   QMPC_HD static int sLin(int N) { return sRed(N) + 2 * G; }
-  QMPC_HD static int smem_doubles(int N) { return (sLin(N) + 27 + 1) / 2 * 2; }
+  // "wide" layout: the per-knot linearisation blocks (27 N) and the duals (NC N) also live in
+  // shared memory (used when it does not cost residency, i.e. short horizons); otherwise they stay
+  // in the L2-resident scratch.  Same code either way - only the pointers differ.
+  QMPC_HD static int sLinAll(int N) { return (sLin(N) + 27 + 1) / 2 * 2; }
+  QMPC_HD static int sMu(int N) { return sLinAll(N) + 27 * N; }
+  QMPC_HD static int smem_doubles(int N, bool wide) { return wide ? (sMu(N) + NC * N + 1) / 2 * 2 : sLinAll(N); }
   // ---- global scratch (doubles) per slot
   QMPC_HD static size_t gK(int N) { return 0; }
   QMPC_HD static size_t gd(int N) { return gK(N) + (size_t)N * NU * 12; }
@@ -118,7 +122,8 @@ struct CoopLayout {
   QMPC_HD static size_t gpv(int N) { return gP(N) + (size_t)(N + 1) * 144; }
   QMPC_HD static size_t gmu(int N) { return gpv(N) + (size_t)(N + 1) * 12; }
   QMPC_HD static size_t glin(int N) { return gmu(N) + (size_t)N * NC; }
-  QMPC_HD static size_t scratch_doubles(int N) { return (glin(N) + (size_t)N * 27 + 15) / 16 * 16; }
+  QMPC_HD static size_t gDX(int N) { return glin(N) + (size_t)N * 27; }
+  QMPC_HD static size_t scratch_doubles(int N) { return (gDX(N) + (size_t)(N + 1) * 12 + 15) / 16 * 16; }
 };
 
 // offsets inside the shared "vec" block
@@ -318,7 +323,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
 
 template <int NF, int G>
 QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in, QmpcResult* out,
-                            int pid, double* sm, double* gs, int lane_id, unsigned lane_mask) {
+                            int pid, double* sm, double* gs, int lane_id, unsigned lane_mask, bool wide) {
   using M = QuatModel<NF>;
   using L = CoopLayout<NF, G>;
   constexpr int NX = 13, NE = 12, NU = M::NU, NC = M::NC;
@@ -330,7 +335,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   M& m = *reinterpret_cast<M*>(sm);
   double* X = sm + L::sX(N);
   double* U = sm + L::sU(N);
-  double* DX = sm + L::sDX(N);
+  double* DX = gs + L::gDX(N);
   double* P = sm + L::sP(N);
   double* PA = sm + L::sPA(N);
     double* T = sm + L::sT(N);
@@ -345,8 +350,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   double* gd = gs + L::gd(N);
   double* gP = gs + L::gP(N);
   double* gpv = gs + L::gpv(N);
-  double* gmu = gs + L::gmu(N);
-  double* glin = gs + L::glin(N);
+  double* gmu = wide ? sm + L::sMu(N) : gs + L::gmu(N);
+  double* glin = wide ? sm + L::sLinAll(N) : gs + L::glin(N);
   double* scal = vec + cv::scal;
 
   // ------------------------------------------------------------------ set-up + nominal roll-out
@@ -840,7 +845,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 template <int NF, int G>
 __global__ void __launch_bounds__(64, QMPC_COOP_MIN_BLOCKS)
 qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in, QmpcResult* __restrict__ out,
-                 double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot) {
+                 double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot, int wide) {
   extern __shared__ double smem_pool[];
   const int groups_per_block = blockDim.x / G;
   const int group = threadIdx.x / G;
@@ -851,7 +856,7 @@ qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ i
   double* sm = smem_pool + (size_t)group * smem_per_problem;
   double* gs = scratch + (size_t)slot * scratch_per_slot;
   for (int pid = slot; pid < batch; pid += nslots) {
-    coop_solve_one<NF, G>(cfg, o, in, out, pid, sm, gs, lane_id, lane_mask);
+    coop_solve_one<NF, G>(cfg, o, in, out, pid, sm, gs, lane_id, lane_mask, wide != 0);
   }
 }
 #endif

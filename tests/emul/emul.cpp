@@ -63,8 +63,9 @@ template <int NF, int G>
 static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, int batch, QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
   using L = CoopLayout<NF, G>;
-  std::vector<double> sm(L::smem_doubles(cfg.horizon)), gs(L::scratch_doubles(cfg.horizon));
-  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, out, i, sm.data(), gs.data(), 0, 0u);
+  const bool wide = cfg.horizon <= 10;
+  std::vector<double> sm(L::smem_doubles(cfg.horizon, wide)), gs(L::scratch_doubles(cfg.horizon));
+  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, out, i, sm.data(), gs.data(), 0, 0u, wide);
   return 0;
 }
 extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, int batch, QmpcResult* out) {
@@ -73,6 +74,6 @@ extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, int
   return -1;
 }
 extern "C" int emul_coop_smem_bytes(int nf, int horizon) {
-  return 8 * (nf == 4 ? CoopLayout<4, 16>::smem_doubles(horizon) : CoopLayout<2, 16>::smem_doubles(horizon));
+  return 8 * (nf == 4 ? CoopLayout<4, 16>::smem_doubles(horizon, false) : CoopLayout<2, 16>::smem_doubles(horizon, false));
 }
 #endif
