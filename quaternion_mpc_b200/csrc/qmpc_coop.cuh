@@ -245,12 +245,24 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
       } else {
         double t0 = 0, t1 = 0, t2 = 0;
         const double* K0 = Kk + (3 * f) * 12;
+#if !defined(QMPC_COOP_NO_K128) && defined(__CUDA_ARCH__)
+        {   // three 96-byte gain rows as 18 x 16-byte loads (rows are 16-byte aligned in the scratch)
+          const double2* K2 = reinterpret_cast<const double2*>(K0);
+#pragma unroll
+          for (int l = 0; l < 6; ++l) { const double2 v = K2[l]; t0 += v.x * dx[2 * l]; t0 += v.y * dx[2 * l + 1]; }
+#pragma unroll
+          for (int l = 0; l < 6; ++l) { const double2 v = K2[6 + l]; t1 += v.x * dx[2 * l]; t1 += v.y * dx[2 * l + 1]; }
+#pragma unroll
+          for (int l = 0; l < 6; ++l) { const double2 v = K2[12 + l]; t2 += v.x * dx[2 * l]; t2 += v.y * dx[2 * l + 1]; }
+        }
+#else
 #pragma unroll
         for (int l = 0; l < NE; ++l) t0 += K0[l] * dx[l];
 #pragma unroll
         for (int l = 0; l < NE; ++l) t1 += K0[12 + l] * dx[l];
 #pragma unroll
         for (int l = 0; l < NE; ++l) t2 += K0[24 + l] * dx[l];
+#endif
         u0 = U[k * NU + 3 * f] + alpha * gd[k * NU + 3 * f] + t0;
         u1 = U[k * NU + 3 * f + 1] + alpha * gd[k * NU + 3 * f + 1] + t1;
         u2 = U[k * NU + 3 * f + 2] + alpha * gd[k * NU + 3 * f + 2] + t2;
@@ -647,14 +659,22 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       //      owning lane stored).  1/sqrt via one rsqrt instead of sqrt + reciprocal.
       {
         double rdg_prev = 0.0;
+#ifdef QMPC_COOP_CHOL_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int j = 0; j < NU && bp_ok; ++j) {
           double* tc = vec + cv::tcol + (j & 1) * NU;
           const double* tp = vec + cv::tcol + ((j & 1) ^ 1) * NU;
           COOP_PHASE {
             for (int i = j + lane; i < NU; i += G) {
               double t = Quu[NU * i + j];
+#ifdef QMPC_COOP_CHOL_UNROLL
+#pragma unroll
+#else
 #pragma unroll 4
+#endif
               for (int l = 0; l + 1 < j; ++l) t -= Quu[NU * i + l] * Quu[NU * j + l];
               if (j > 0) t -= Quu[NU * i + j - 1] * (i == j ? Quu[NU * j + j - 1] : tp[j] * rdg_prev);
               tc[i] = t;
