@@ -123,7 +123,10 @@ struct CoopLayout {
   QMPC_HD static size_t gmu(int N) { return gpv(N) + (size_t)(N + 1) * 12; }
   QMPC_HD static size_t glin(int N) { return gmu(N) + (size_t)N * NC; }
   QMPC_HD static size_t gDX(int N) { return glin(N) + (size_t)N * 27; }
-  QMPC_HD static size_t scratch_doubles(int N) { return (gDX(N) + (size_t)(N + 1) * 12 + 15) / 16 * 16; }
+  // trial trajectories of the speculative line search, [element][lane] so the 16 lanes store coalesced
+  QMPC_HD static size_t gTX(int N) { return (gDX(N) + (size_t)(N + 1) * 12 + 15) / 16 * 16; }
+  QMPC_HD static size_t gTU(int N) { return gTX(N) + (size_t)(N + 1) * 13 * G; }
+  QMPC_HD static size_t scratch_doubles(int N) { return (gTU(N) + (size_t)N * NU * G + 15) / 16 * 16; }
 };
 
 // offsets inside the shared "vec" block
@@ -191,13 +194,15 @@ QMPC_HD inline void lxx_block(const QmpcConfig& cfg, const double* Hphi, int br,
 // roll-out, by the 16 speculative line-search lanes and by the accepted step, and inlining it three
 // times is what pushed the SASS far past the instruction cache).
 //   mode 0: open loop, u = u_ref: writes the nominal X, U; returns merit / violation
-//   mode 1: trial step `alpha` around (X, U) with gains (gK, gd): writes nothing, returns merit / violation
-//   mode 2: accepted step `alpha`: X, U updated in place, DX <- dx_k (error-state step per knot)
+//   mode 1: trial step `alpha` around (X, U) with gains (gK, gd): X, U untouched; the trial
+//           trajectory is recorded in the scratch (gTX/gTU, element-major, lane `tl` of `tstride`) so
+//           that the accepted one is simply copied back - no second roll-out; returns merit / violation
+//   mode 2: (unused by the kernel, kept for the host emulation tests) accepted step in place
 template <int NF>
 QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig& cfg, int N, float h, double* X,
                                         double* U, double* DX, const double* gK, const double* gd,
                                         const double* gmu, double rho, double alpha, int mode, double* Jout,
-                                        double* violout) {
+                                        double* violout, double* gTX, double* gTU, int tl, int tstride) {
   // Compact by construction (instruction-fetch bound otherwise): the input never
   // exists as an array - each foot's force is formed, costed, cone-checked and folded into the net
   // wrench inside one 4-trip loop; the wrench drives both midpoint evaluations.  Accumulation
@@ -212,6 +217,10 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
   for (int k = 0; k <= N; ++k) {
     double dx[NE];
     if (mode != 0) state_diff<M>(x, X + k * NX, dx);
+    if (mode == 1) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) gTX[(size_t)(k * NX + i) * tstride + tl] = x[i];
+    }
     if (mode == 2) {
 #pragma unroll
       for (int i = 0; i < NE; ++i) DX[k * NE + i] = dx[i];
@@ -268,6 +277,10 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
         u2 = U[k * NU + 3 * f + 2] + alpha * gd[k * NU + 3 * f + 2] + t2;
       }
       if (mode != 1) { U[k * NU + 3 * f] = u0; U[k * NU + 3 * f + 1] = u1; U[k * NU + 3 * f + 2] = u2; }
+      else {
+        double* tu = gTU + (size_t)(k * NU + 3 * f) * tstride + tl;
+        tu[0] = u0; tu[tstride] = u1; tu[2 * tstride] = u2;
+      }
       if (mode != 2) {
         const double d0 = u0 - m.uref[3 * f], d1 = u1 - m.uref[3 * f + 1], d2 = u2 - m.uref[3 * f + 2];
         Jl += 0.5 * cfg.r_weights[3 * f] * d0 * d0;
@@ -348,6 +361,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   double* X = sm + L::sX(N);
   double* U = sm + L::sU(N);
   double* DX = gs + L::gDX(N);
+  double* gTX = gs + L::gTX(N);
+  double* gTU = gs + L::gTU(N);
   double* P = sm + L::sP(N);
   double* PA = sm + L::sPA(N);
     double* T = sm + L::sT(N);
@@ -377,7 +392,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   COOP_SYNC();
   double rho = o.penalty_initial;
   COOP_PHASE {
-    if (lane == 0) coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3]);
+    if (lane == 0) coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3], gTX, gTU, 0, G);
   }
   COOP_SYNC();
   double phi = scal[2], viol = scal[3];
@@ -790,7 +805,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         if (j < o.ls_iters_max) {
           double alpha = 1.0;
           for (int q = 0; q < j; ++q) alpha *= o.ls_decrease;
-          coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, alpha, 1, &J, &vl);
+          coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, alpha, 1, &J, &vl, gTX, gTU, lane, G);
         }
         red[lane] = J;
         red[G + lane] = vl;
@@ -814,19 +829,17 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     }
     iters = it + 1;
     if (acc_j < 0) { status = QMPC_STATUS_LINESEARCH_FAILED; break; }
-    // ---------------- accepted step: redo its roll-out in place (X,U <- new; DX <- dx_k)
-    COOP_PHASE {
-      if (lane == 0) {
-        double Jd, vd;
-        coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, alpha_acc, 2, &Jd, &vd);
-      }
-    }
-    COOP_SYNC();
-    // ---------------- Riccati duals of the accepted step: y_k = P_k dx_k + p_k  (lane k <- knot k)
+    // ---------------- accepted step: the winning lane's trial trajectory is already in the scratch.
+    // lane k <- knot k: dx_k = x_new (-) x_old, Riccati dual y_k = P_k dx_k + p_k (stored in DX) ...
+    const int acc_lane = acc_j % G;
     COOP_PHASE {
       for (int k = lane; k <= N; k += G) {
-        double dx[NE], y[NE];
-        for (int i = 0; i < NE; ++i) { dx[i] = DX[k * NE + i]; y[i] = gpv[k * 12 + i]; }
+        double xn[NX], dx[NE], y[NE];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xn[i] = gTX[(size_t)(k * NX + i) * G + acc_lane];
+        state_diff<M>(xn, X + k * NX, dx);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) y[i] = gpv[k * 12 + i];
         const double* Pk = gP + (size_t)k * 144;
 #pragma unroll
         for (int a = 0; a < NE; ++a) {
@@ -835,8 +848,15 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           for (int b = 0; b < NE; ++b) t += Pk[12 * a + b] * dx[b];
           y[a] = t;
         }
+#pragma unroll
         for (int i = 0; i < NE; ++i) DX[k * NE + i] = y[i];
       }
+    }
+    COOP_SYNC();
+    // ... then X, U <- accepted trajectory (cooperative strided copy)
+    COOP_PHASE {
+      for (int e = lane; e < (N + 1) * NX; e += G) X[e] = gTX[(size_t)e * G + acc_lane];
+      for (int e = lane; e < N * NU; e += G) U[e] = gTU[(size_t)e * G + acc_lane];
     }
     COOP_SYNC();
     cost_decrease = phi - phin;
