@@ -153,3 +153,45 @@ def test_properties_at_full_size():
     assert np.abs(np.linalg.norm(r["grf_world"].reshape(B, 4, 3), axis=2) - np.linalg.norm(f, axis=2)).max() < 1e-9
     r2 = _solve_dev(mpc, probs)
     assert r.tobytes() == r2.tobytes()
+
+
+def test_edge_cases_nonfinite_zero_contacts_and_odd_batches(oracle):
+    """Edge cases the reference itself does not guard (QuatMpc.cpp:122 divides by num_contacts; no NaN
+    check on the GRFs): NaN state, no planned contact, batch sizes that do not fill a block/warp."""
+    from quaternion_mpc_b200 import QuatMpc
+    mpc = QuatMpc(horizon=10, max_batch=67)
+    probs = random_batch(67, seed=31, gait="mixed")
+    probs["torso_lin_vel_world"][5, 1] = np.nan          # non-finite input
+    probs["plan_contacts"][9] = 0                          # num_contacts == 0 -> u_ref = 0/0
+    res = _solve_dev(mpc, probs)
+    ref = oracle.solve_batch(mpc.cfg, probs, nthreads=NT)
+    assert res["status"][5] == 4 and ref["status"][5] == 4 and res["iterations"][5] == 0
+    assert res["status"][9] == 4 and ref["status"][9] == 4
+    keep = np.ones(67, bool); keep[[5, 9]] = False
+    _check(res[keep], ref[keep])
+    for b in (1, 2, 3, 5, 17, 33):                         # ragged batches on the 16-lane kernel
+        r = _solve_dev(mpc, probs[20:20 + b])
+        assert r.tobytes() == res[20:20 + b].tobytes()
+
+
+@pytest.mark.parametrize("N", [1, 2, 25, 32])
+def test_horizon_extremes(oracle, N):
+    from quaternion_mpc_b200 import QuatMpc
+    mpc = QuatMpc(horizon=N, max_batch=64)
+    probs = random_batch(64, seed=40 + N, gait="trot", max_angle=0.3)
+    _check(_solve_dev(mpc, probs), oracle.solve_batch(mpc.cfg, probs, nthreads=NT))
+
+
+def test_custom_weights_with_quaternion_entries(oracle):
+    """Non-default config: non-zero quaternion entries in Q (general attitude Hessian block), a
+    different friction coefficient and penalty schedule, measured angular velocity used."""
+    from quaternion_mpc_b200 import QuatMpc
+    cfg = default_config(0, 12)
+    cfg.q_weights[3:7] = [0.3, 0.2, 0.4, 0.1]
+    cfg.mu, cfg.fz_max, cfg.w = 0.5, 80.0, 20.0
+    cfg.penalty_initial, cfg.penalty_scaling, cfg.drop_omega0 = 10.0, 5.0, 0
+    for i in range(12):
+        cfg.r_weights[i] = 1e-4 if i % 3 == 2 else 1e-5
+    mpc = QuatMpc(max_batch=256, cfg=cfg)
+    probs = random_batch(256, seed=77, gait="mixed")
+    _check(_solve_dev(mpc, probs), oracle.solve_batch(cfg, probs, nthreads=NT))
