@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define QMPC_ABI_VERSION 1
+#define QMPC_ABI_VERSION 2
 
 /* ---- models ------------------------------------------------------------- */
 #define QMPC_MODEL_QUAT_4FOOT   0 /* QuatMpc: 13-state quaternion SRB, 4 feet, 24 cone rows
@@ -145,6 +145,74 @@ int qmpc_solve_batch_convex(QmpcHandle* h, const QmpcConvexProblem* d_in, int32_
 int qmpc_solve_batch_host(QmpcHandle* h, const QmpcProblem* in, int32_t batch, QmpcResult* out);
 int qmpc_solve_batch_convex_host(QmpcHandle* h, const QmpcConvexProblem* in, int32_t batch,
                                  QmpcResult* out);
+
+/* ================================================================================================
+ * Rows "next" of the hot-path scope: the data either side of the solve.
+ * ================================================================================================ */
+
+/* ---- N1: per-step contact schedules -------------------------------------------------------------
+ * The reference plans with ONE contact mask held over the horizon (QuatMpc.cpp:119-125,202) and
+ * flags the per-step schedule as TODO (ConvexMpc.cpp:82); LeggedContactFSM::predict_contact_state
+ * (LeggedContactFSM.cpp:272-286) exists but is unused.  mask[k] bit i = foot i (FL,FR,RL,RR) in
+ * contact at knot k, k < horizon.  Knot k uses its own mask for u_ref (weight shared by the feet in
+ * contact; 0 if none) and for the fz bound (fz <= fz_max * contact); the initial input guess stays
+ * SetInput(u_traj_ref.at(0)) (QuatMpc.cpp:253).  A schedule that repeats plan_contacts at every
+ * knot gives bit-identical results to the plain entry points. */
+typedef struct QmpcContactSchedule {
+  uint8_t mask[QMPC_MAX_HORIZON];
+} QmpcContactSchedule;
+
+#define QMPC_GAIT_TROT            0 /* set_default_gait_pattern          LeggedContactFSM.cpp:87-108  */
+#define QMPC_GAIT_TROT_WITH_STAND 1 /* set_trot_with_stand_gait_pattern  LeggedContactFSM.cpp:110-150 */
+#define QMPC_GAIT_CRAWL           2 /* set_crawl_gait_pattern            LeggedContactFSM.cpp:152-193 */
+#define QMPC_GAIT_STAND           3 /* set_default_stand_pattern         LeggedContactFSM.cpp:195-206 */
+
+/* The per-robot state of the four LeggedContactFSM objects that predict_contact_state reads. */
+typedef struct QmpcGaitState {
+  double  gait_phase[4];   /* leg_FSM[i].gait_phase, 0..1                LeggedContactFSM.h:76       */
+  double  gait_freq;       /* cycles per second (param.gait_freq)        LeggedState.cpp:77          */
+  int32_t gait;            /* QMPC_GAIT_*                                                            */
+  int32_t pad_;
+} QmpcGaitState;
+
+/* mask[k] bit i = (leg_FSM[i].predict_contact_state(k * cfg.dt) == STANCE), k = 0..horizon-1;
+ * bytes k >= horizon are 0.  Device pointers; enqueued on `cuda_stream`. */
+int qmpc_predict_contact_schedule(QmpcHandle* h, const QmpcGaitState* d_gait, int32_t batch,
+                                  QmpcContactSchedule* d_sched, void* cuda_stream);
+
+/* qmpc_solve_batch / _convex with a per-problem schedule (d_sched may be NULL = plain solve). */
+int qmpc_solve_batch_sched(QmpcHandle* h, const QmpcProblem* d_in, const QmpcContactSchedule* d_sched,
+                           int32_t batch, QmpcResult* d_out, void* cuda_stream);
+int qmpc_solve_batch_convex_sched(QmpcHandle* h, const QmpcConvexProblem* d_in,
+                                  const QmpcContactSchedule* d_sched, int32_t batch, QmpcResult* d_out,
+                                  void* cuda_stream);
+int qmpc_solve_batch_sched_host(QmpcHandle* h, const QmpcProblem* in, const QmpcContactSchedule* sched,
+                                int32_t batch, QmpcResult* out);
+
+/* ---- N2: leg kinematics in, joint torques out ---------------------------------------------------
+ * Producer of the solve's foot_pos_body and consumer of its GRFs:
+ *   fbk.foot_pos_body(:, i) = a1_kin.fk(joint_pos_i, rho_opt_i, rho_fix_i)   BaseInterface.cpp:204-207
+ *   fbk.jac_foot(:, 3i:3i+3) = a1_kin.jac(joint_pos_i, ...)                  BaseInterface.cpp:208-212
+ *   ctrl.joint_tau_tgt_i = -jac_i^T * optimized_input_i   (0 for a swing leg when movement_mode > 0)
+ *                                                                            BaseInterface.cpp:343-405 */
+typedef struct QmpcLegParams {
+  double rho_fix[4][5];  /* per leg: leg_offset_x, leg_offset_y, motor_offset, upper_leg_length,
+                            lower_leg_length                                  BaseInterface.cpp:12-30 */
+  double rho_opt[4][3];  /* foot contact offset, zero in the reference       BaseInterface.cpp:31    */
+} QmpcLegParams;
+int qmpc_default_leg_params(QmpcLegParams* lp); /* Go1 values, BaseInterface.cpp:12-33, LeggedParams.h */
+
+/* d_joint_pos: batch x 12 (FL hip, thigh, calf, FR ..., RL ..., RR ...).
+ * d_foot_pos_body: batch x 12, 3x4 column-major (layout of QmpcProblem.foot_pos_body), may be NULL.
+ * d_jac_foot: batch x 36, the 3x12 Eigen (column-major) fbk.jac_foot, may be NULL. */
+int qmpc_leg_kinematics(QmpcHandle* h, const QmpcLegParams* lp, const double* d_joint_pos, int32_t batch,
+                        double* d_foot_pos_body, double* d_jac_foot, void* cuda_stream);
+
+/* d_tau: batch x 12 joint torque targets from the solve results.  d_plan_contacts: batch x 4 (the
+ * QmpcProblem.plan_contacts values) or NULL = all legs in stance; movement_mode as ctrl.movement_mode. */
+int qmpc_joint_torques(QmpcHandle* h, const QmpcResult* d_results, const double* d_jac_foot,
+                       const int32_t* d_plan_contacts, int32_t movement_mode, int32_t batch, double* d_tau,
+                       void* cuda_stream);
 
 void qmpc_destroy(QmpcHandle* h);
 

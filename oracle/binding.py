@@ -9,7 +9,8 @@ import subprocess
 
 import numpy as np
 
-from quaternion_mpc_b200.abi import (CONVEX_PROBLEM_DTYPE, PROBLEM_DTYPE, RESULT_DTYPE, QmpcConfig)
+from quaternion_mpc_b200.abi import (CONVEX_PROBLEM_DTYPE, GAIT_STATE_DTYPE, PROBLEM_DTYPE, QMPC_MAX_HORIZON,
+                                     RESULT_DTYPE, QmpcConfig, QmpcLegParams)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -35,6 +36,11 @@ def lib():
         dp, vp = C.POINTER(C.c_double), C.c_void_p
         _LIB.qmpc_ref_solve_batch.argtypes = [C.POINTER(QmpcConfig), vp, C.c_int, vp, C.c_int]
         _LIB.qmpc_ref_solve_batch_convex.argtypes = [C.POINTER(QmpcConfig), vp, C.c_int, vp, C.c_int]
+        _LIB.qmpc_ref_solve_batch_sched.argtypes = [C.POINTER(QmpcConfig), vp, vp, C.c_int, vp, C.c_int]
+        _LIB.qmpc_ref_solve_batch_convex_sched.argtypes = [C.POINTER(QmpcConfig), vp, vp, C.c_int, vp, C.c_int]
+        _LIB.qmpc_ref_predict_schedule.argtypes = [C.POINTER(QmpcConfig), vp, C.c_int, vp]
+        _LIB.qmpc_ref_leg_kinematics.argtypes = [C.POINTER(QmpcLegParams), vp, C.c_int, vp, vp]
+        _LIB.qmpc_ref_joint_torques.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
         _LIB.kat_double_integrator.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.POINTER(Stats)]
         _LIB.kat_pendulum.argtypes = [C.c_int, dp, dp, C.POINTER(Stats)]
         _LIB.kat_quat_golden.argtypes = [C.c_int, dp, dp, C.POINTER(Stats)]
@@ -65,6 +71,65 @@ def solve_batch_convex(cfg, problems, nthreads=1):
     if rc:
         raise RuntimeError(f"oracle failed rc={rc}")
     return out
+
+
+def _sched_bytes(schedule, batch):
+    from quaternion_mpc_b200.abi import QMPC_MAX_HORIZON
+    schedule = np.ascontiguousarray(schedule, dtype=np.uint8)
+    assert schedule.shape == (batch, QMPC_MAX_HORIZON), schedule.shape
+    return schedule
+
+
+def solve_batch_sched(cfg, problems, schedule, nthreads=1):
+    """Per-step contact-schedule extension: schedule[b, k] = contact bit mask of knot k."""
+    problems = np.ascontiguousarray(problems, dtype=PROBLEM_DTYPE)
+    schedule = _sched_bytes(schedule, problems.shape[0])
+    out = np.zeros(problems.shape[0], dtype=RESULT_DTYPE)
+    rc = lib().qmpc_ref_solve_batch_sched(C.byref(cfg), problems.ctypes.data, schedule.ctypes.data,
+                                          problems.shape[0], out.ctypes.data, nthreads)
+    if rc:
+        raise RuntimeError(f"oracle failed rc={rc}")
+    return out
+
+
+def solve_batch_convex_sched(cfg, problems, schedule, nthreads=1):
+    problems = np.ascontiguousarray(problems, dtype=CONVEX_PROBLEM_DTYPE)
+    schedule = _sched_bytes(schedule, problems.shape[0])
+    out = np.zeros(problems.shape[0], dtype=RESULT_DTYPE)
+    rc = lib().qmpc_ref_solve_batch_convex_sched(C.byref(cfg), problems.ctypes.data, schedule.ctypes.data,
+                                                 problems.shape[0], out.ctypes.data, nthreads)
+    if rc:
+        raise RuntimeError(f"oracle failed rc={rc}")
+    return out
+
+
+def predict_schedule(cfg, gait_states):
+    """LeggedContactFSM::predict_contact_state at t + k*dt, k < horizon -> (batch, QMPC_MAX_HORIZON) uint8."""
+    g = np.ascontiguousarray(gait_states, dtype=GAIT_STATE_DTYPE)
+    out = np.zeros((g.shape[0], QMPC_MAX_HORIZON), dtype=np.uint8)
+    rc = lib().qmpc_ref_predict_schedule(C.byref(cfg), g.ctypes.data, g.shape[0], out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def leg_kinematics(leg_params, joint_pos):
+    """a1_kin.fk / a1_kin.jac for all legs -> (foot_pos_body (batch,12), jac_foot (batch,36))."""
+    q = np.ascontiguousarray(joint_pos, dtype=np.float64)
+    foot, jac = np.zeros((q.shape[0], 12)), np.zeros((q.shape[0], 36))
+    rc = lib().qmpc_ref_leg_kinematics(C.byref(leg_params), q.ctypes.data, q.shape[0], foot.ctypes.data, jac.ctypes.data)
+    assert rc == 0
+    return foot, jac
+
+
+def joint_torques(results, jac_foot, plan_contacts, movement_mode):
+    results = np.ascontiguousarray(results, dtype=RESULT_DTYPE)
+    jac = np.ascontiguousarray(jac_foot, dtype=np.float64)
+    pc = None if plan_contacts is None else np.ascontiguousarray(plan_contacts, dtype=np.int32)
+    tau = np.zeros((results.shape[0], 12))
+    rc = lib().qmpc_ref_joint_torques(results.ctypes.data, jac.ctypes.data, pc.ctypes.data if pc is not None else None,
+                                      int(movement_mode), results.shape[0], tau.ctypes.data)
+    assert rc == 0
+    return tau
 
 
 def kat_double_integrator(variant, penalty_initial=0.0, penalty_scaling=0.0, iterations_max=0):

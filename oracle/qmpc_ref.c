@@ -202,12 +202,13 @@ void qref_mid_jac(void* ctx, double* J, const double* x, const double* u, float 
 
 /* ---- friction-cone rows (QuatMpc.cpp:194-215; ConvexMpc.cpp:14-35,130-140) */
 void qref_cone_con(void* ctx, int k, double* c, const double* x, const double* u) {
-  (void)k; (void)x;
+  (void)x;
   const Model* M = (const Model*)ctx;
+  const double* fzb = M->fzmax_ck ? M->fzmax_ck + 4 * k : M->fzmax_c;
   for (int i = 0; i < M->nf; ++i) {
     for (int r = 0; r < 6; ++r)
       c[6 * i + r] = M->CR[3 * r] * u[3 * i] + M->CR[3 * r + 1] * u[3 * i + 1] + M->CR[3 * r + 2] * u[3 * i + 2];
-    c[6 * i + 4] += -M->fzmax_c[i];
+    c[6 * i + 4] += -fzb[i];
   }
 }
 void qref_cone_jac(void* ctx, int k, double* J, const double* x, const double* u) {
@@ -242,7 +243,13 @@ static void opts_from_cfg(const QmpcConfig* cfg, AltroRefOptions* o) {
 }
 
 /* ============================================================ QuatMpc::grf_update, one problem */
-int qmpc_ref_solve_one(const QmpcConfig* cfg, const QmpcProblem* in, QmpcResult* out) {
+/* `sched` = NULL: the reference's behaviour (one contact mask over the horizon).  Otherwise
+ * QMPC_MAX_HORIZON bytes, bit i of byte k = foot i in contact at knot k: the per-step contact
+ * schedule the reference flags as TODO (ConvexMpc.cpp:82; LeggedContactFSM.cpp:272-286 is the
+ * unused predictor).  Extension semantics: u_traj_ref[k] and the fz bound of knot k use mask k;
+ * a knot with no contact has u_ref = 0; SetInput(u_traj_ref.at(0)) is kept verbatim. */
+int qmpc_ref_solve_one_sched(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched,
+                             QmpcResult* out) {
   const int N = cfg->horizon;
   const int nf = cfg->model == QMPC_MODEL_QUAT_2FOOT ? 2 : 4;
   const int n = 13, m = 3 * nf;
@@ -291,6 +298,22 @@ int qmpc_ref_solve_one(const QmpcConfig* cfg, const QmpcProblem* in, QmpcResult*
   double Q[(QMPC_MAX_HORIZON + 1) * 13], R[(QMPC_MAX_HORIZON + 1) * 12], xref[(QMPC_MAX_HORIZON + 1) * 13],
       ur[(QMPC_MAX_HORIZON + 1) * 12], wq[QMPC_MAX_HORIZON + 1];
   int p[QMPC_MAX_HORIZON + 1], ct[QMPC_MAX_HORIZON + 1];
+  double fzk[(QMPC_MAX_HORIZON + 1) * 4] = {0};
+  if (sched) {
+    M.fzmax_ck = fzk;
+    for (int k = 0; k < N; ++k) {
+      int nc = 0;
+      for (int i = 0; i < nf; ++i) nc += (sched[k] >> i) & 1;
+      for (int i = 0; i < nf; ++i) {
+        const double c = ((sched[k] >> i) & 1) ? 1.0 : 0.0;
+        ur[k * m + 3 * i] = 0; ur[k * m + 3 * i + 1] = 0;
+        ur[k * m + 3 * i + 2] = nc ? c * cfg->robot_mass * cfg->gravity / nc : 0.0;
+        fzk[4 * k + i] = cfg->fz_max * c;
+      }
+    }
+    memcpy(ur + N * m, ur + (N - 1) * m, sizeof(double) * m); /* terminal knot has no input cost */
+    memcpy(uref, ur, sizeof(double) * m);                     /* SetInput(u_traj_ref.at(0)) :253 */
+  }
   for (int k = 0; k <= N; ++k) {
     double* xr = xref + k * n;
     memset(xr, 0, sizeof(double) * n);
@@ -302,7 +325,7 @@ int qmpc_ref_solve_one(const QmpcConfig* cfg, const QmpcProblem* in, QmpcResult*
     memcpy(xr + 7, in->torso_lin_vel_d_body, sizeof(double) * 3);
     memcpy(Q + k * n, cfg->q_weights, sizeof(double) * n);
     memcpy(R + k * m, cfg->r_weights, sizeof(double) * m);
-    memcpy(ur + k * m, uref, sizeof(double) * m);
+    if (!sched) memcpy(ur + k * m, uref, sizeof(double) * m);
     wq[k] = cfg->w;
     /* SetConstraint(..., 0, horizon): knots 0..N-1 (QuatMpc.cpp:229) */
     p[k] = k < N ? 6 * nf : 0;
@@ -344,8 +367,13 @@ int qmpc_ref_solve_one(const QmpcConfig* cfg, const QmpcProblem* in, QmpcResult*
   return QMPC_OK;
 }
 
+int qmpc_ref_solve_one(const QmpcConfig* cfg, const QmpcProblem* in, QmpcResult* out) {
+  return qmpc_ref_solve_one_sched(cfg, in, NULL, out);
+}
+
 /* ============================================================ ConvexMpc::grf_update, one problem */
-int qmpc_ref_solve_one_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in, QmpcResult* out) {
+int qmpc_ref_solve_one_convex_sched(const QmpcConfig* cfg, const QmpcConvexProblem* in, const unsigned char* sched,
+                                    QmpcResult* out) {
   const int N = cfg->horizon, n = 12, m = 12;
   if (N < 1 || N > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
   Model M;
@@ -364,6 +392,22 @@ int qmpc_ref_solve_one_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in
   double Q[(QMPC_MAX_HORIZON + 1) * 12], R[(QMPC_MAX_HORIZON + 1) * 12], xref[(QMPC_MAX_HORIZON + 1) * 12],
       ur[(QMPC_MAX_HORIZON + 1) * 12], wq[QMPC_MAX_HORIZON + 1];
   int p[QMPC_MAX_HORIZON + 1], ct[QMPC_MAX_HORIZON + 1];
+  double fzk[(QMPC_MAX_HORIZON + 1) * 4] = {0};
+  if (sched) { /* per-step contacts: the TODO at ConvexMpc.cpp:82 (same extension rules as QuatMpc) */
+    M.fzmax_ck = fzk;
+    for (int k = 0; k < N; ++k) {
+      int nc = 0;
+      for (int i = 0; i < 4; ++i) nc += (sched[k] >> i) & 1;
+      for (int i = 0; i < 4; ++i) {
+        const double c = ((sched[k] >> i) & 1) ? 1.0 : 0.0;
+        ur[k * m + 3 * i] = 0; ur[k * m + 3 * i + 1] = 0;
+        ur[k * m + 3 * i + 2] = nc ? cfg->robot_mass * cfg->gravity / nc * c : 0.0;
+        fzk[4 * k + i] = cfg->fz_max * c;
+      }
+    }
+    memcpy(ur + N * m, ur + (N - 1) * m, sizeof(double) * m);
+    memcpy(uref, ur, sizeof(double) * m);
+  }
   for (int k = 0; k <= N; ++k) {
     double* xr = xref + k * n; /* ConvexMpc.cpp:95-108 */
     memset(xr, 0, sizeof(double) * n);
@@ -373,7 +417,7 @@ int qmpc_ref_solve_one_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in
     xr[9] = in->torso_lin_vel_d_world[0]; xr[10] = in->torso_lin_vel_d_world[1];
     memcpy(Q + k * n, cfg->q_weights, sizeof(double) * n);
     memcpy(R + k * m, cfg->r_weights, sizeof(double) * m);
-    memcpy(ur + k * m, uref, sizeof(double) * m);
+    if (!sched) memcpy(ur + k * m, uref, sizeof(double) * m);
     wq[k] = 0.0;
     /* reference range is [0, N+1) (ConvexMpc.cpp:153-154); at knot N the rows depend on no
        optimisation variable (u_N does not exist, Jx = 0) so they are a no-op and are dropped */
@@ -410,23 +454,30 @@ int qmpc_ref_solve_one_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in
   return QMPC_OK;
 }
 
+int qmpc_ref_solve_one_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in, QmpcResult* out) {
+  return qmpc_ref_solve_one_convex_sched(cfg, in, NULL, out);
+}
+
 /* ============================================================ batch drivers (one worker per core) */
 typedef struct Job {
   const QmpcConfig* cfg;
   const void* in;
+  const unsigned char* sched; /* NULL or batch x QMPC_MAX_HORIZON mask bytes */
   QmpcResult* out;
   int lo, hi, convex, rc;
 } Job;
 static void* worker(void* arg) {
   Job* j = (Job*)arg;
   for (int i = j->lo; i < j->hi; ++i) {
-    int rc = j->convex ? qmpc_ref_solve_one_convex(j->cfg, (const QmpcConvexProblem*)j->in + i, j->out + i)
-                       : qmpc_ref_solve_one(j->cfg, (const QmpcProblem*)j->in + i, j->out + i);
+    const unsigned char* sc = j->sched ? j->sched + (size_t)i * QMPC_MAX_HORIZON : NULL;
+    int rc = j->convex ? qmpc_ref_solve_one_convex_sched(j->cfg, (const QmpcConvexProblem*)j->in + i, sc, j->out + i)
+                       : qmpc_ref_solve_one_sched(j->cfg, (const QmpcProblem*)j->in + i, sc, j->out + i);
     if (rc) j->rc = rc;
   }
   return NULL;
 }
-static int run_batch(const QmpcConfig* cfg, const void* in, int batch, QmpcResult* out, int nthreads, int convex) {
+static int run_batch(const QmpcConfig* cfg, const void* in, const unsigned char* sched, int batch, QmpcResult* out,
+                     int nthreads, int convex) {
   if (!cfg || !in || !out || batch < 0) return QMPC_ERR_ARG;
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
@@ -434,7 +485,7 @@ static int run_batch(const QmpcConfig* cfg, const void* in, int batch, QmpcResul
   pthread_t th[256];
   Job jobs[256];
   for (int t = 0; t < nthreads; ++t) {
-    jobs[t].cfg = cfg; jobs[t].in = in; jobs[t].out = out; jobs[t].convex = convex; jobs[t].rc = 0;
+    jobs[t].cfg = cfg; jobs[t].in = in; jobs[t].sched = sched; jobs[t].out = out; jobs[t].convex = convex; jobs[t].rc = 0;
     jobs[t].lo = (int)((long long)batch * t / nthreads);
     jobs[t].hi = (int)((long long)batch * (t + 1) / nthreads);
     if (nthreads == 1) worker(&jobs[t]);
@@ -448,9 +499,17 @@ static int run_batch(const QmpcConfig* cfg, const void* in, int batch, QmpcResul
   return rc;
 }
 int qmpc_ref_solve_batch(const QmpcConfig* cfg, const QmpcProblem* in, int batch, QmpcResult* out, int nthreads) {
-  return run_batch(cfg, in, batch, out, nthreads, 0);
+  return run_batch(cfg, in, NULL, batch, out, nthreads, 0);
 }
 int qmpc_ref_solve_batch_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in, int batch, QmpcResult* out,
                                 int nthreads) {
-  return run_batch(cfg, in, batch, out, nthreads, 1);
+  return run_batch(cfg, in, NULL, batch, out, nthreads, 1);
+}
+int qmpc_ref_solve_batch_sched(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, int batch,
+                               QmpcResult* out, int nthreads) {
+  return run_batch(cfg, in, sched, batch, out, nthreads, 0);
+}
+int qmpc_ref_solve_batch_convex_sched(const QmpcConfig* cfg, const QmpcConvexProblem* in, const unsigned char* sched,
+                                      int batch, QmpcResult* out, int nthreads) {
+  return run_batch(cfg, in, sched, batch, out, nthreads, 1);
 }

@@ -12,6 +12,7 @@ typedef struct Model {
   double mass, g_vec[3], tau_g[3];
   double CR[18];     /* 6x3 row-major: C_mat * R0 (QuatMpc.cpp:203) or C_mat (ConvexMpc) */
   double fzmax_c[4]; /* fz_max * plan_contacts[i] */
+  const double* fzmax_ck; /* optional per-knot bounds [k][4] (contact-schedule extension); NULL = fzmax_c */
   ct_fn f;
   ctj_fn df;
 } Model;

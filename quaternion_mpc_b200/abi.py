@@ -55,7 +55,18 @@ RESULT_DTYPE = np.dtype([
     ("max_violation", "f8"), ("iterations", "i4"), ("status", "i4"),
 ], align=True)
 
+SCHEDULE_DTYPE = np.dtype([("mask", "u1", QMPC_MAX_HORIZON)])
+GAIT_STATE_DTYPE = np.dtype([("gait_phase", "f8", 4), ("gait_freq", "f8"), ("gait", "i4"), ("pad_", "i4")],
+                            align=True)
+QMPC_GAIT_TROT, QMPC_GAIT_TROT_WITH_STAND, QMPC_GAIT_CRAWL, QMPC_GAIT_STAND = 0, 1, 2, 3
+
+
+class QmpcLegParams(C.Structure):
+    _fields_ = [("rho_fix", (C.c_double * 5) * 4), ("rho_opt", (C.c_double * 3) * 4)]
+
+
 assert PROBLEM_DTYPE.itemsize == 35 * 8 + 16
+assert SCHEDULE_DTYPE.itemsize == 32 and GAIT_STATE_DTYPE.itemsize == 48
 assert CONVEX_PROBLEM_DTYPE.itemsize == 40 * 8 + 24
 assert RESULT_DTYPE.itemsize == 29 * 8 + 8
 
@@ -63,6 +74,8 @@ EXPORTED_SYMBOLS = [
     "qmpc_default_config", "qmpc_create", "qmpc_solve_batch", "qmpc_solve_batch_convex",
     "qmpc_solve_batch_host", "qmpc_solve_batch_convex_host", "qmpc_destroy", "qmpc_launch_count",
     "qmpc_last_error", "qmpc_status_string", "qmpc_abi_version", "qmpc_measure_fma_peak",
+    "qmpc_predict_contact_schedule", "qmpc_solve_batch_sched", "qmpc_solve_batch_convex_sched",
+    "qmpc_solve_batch_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques",
 ]
 
 _LIB = None
@@ -98,6 +111,20 @@ def load_library():
         f = getattr(lib, name)
         f.argtypes = [vp, vp, i32, vp]
         f.restype = C.c_int
+    for name in ("qmpc_solve_batch_sched", "qmpc_solve_batch_convex_sched"):
+        f = getattr(lib, name)
+        f.argtypes = [vp, vp, vp, i32, vp, vp]
+        f.restype = C.c_int
+    lib.qmpc_solve_batch_sched_host.argtypes = [vp, vp, vp, i32, vp]
+    lib.qmpc_solve_batch_sched_host.restype = C.c_int
+    lib.qmpc_predict_contact_schedule.argtypes = [vp, vp, i32, vp, vp]
+    lib.qmpc_predict_contact_schedule.restype = C.c_int
+    lib.qmpc_default_leg_params.argtypes = [C.POINTER(QmpcLegParams)]
+    lib.qmpc_default_leg_params.restype = C.c_int
+    lib.qmpc_leg_kinematics.argtypes = [vp, C.POINTER(QmpcLegParams), vp, i32, vp, vp, vp]
+    lib.qmpc_leg_kinematics.restype = C.c_int
+    lib.qmpc_joint_torques.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.qmpc_joint_torques.restype = C.c_int
     lib.qmpc_destroy.argtypes = [vp]
     lib.qmpc_destroy.restype = None
     lib.qmpc_launch_count.argtypes = [vp]

@@ -14,6 +14,7 @@
 #include "qmpc_dense.cuh"
 #include "qmpc_srb.cuh"
 #include "qmpc_coop.cuh"
+#include "qmpc_periph.cuh"
 
 using namespace qmpc;
 
@@ -26,6 +27,7 @@ struct QmpcHandle {
   double* ws;          // device workspace
   size_t ws_bytes;
   void* d_in;          // staging for the *_host entry points
+  QmpcContactSchedule* d_sched;
   QmpcResult* d_out;
   cudaStream_t stream; // stream used by the *_host entry points
   int64_t launches;
@@ -187,6 +189,7 @@ extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t dev
   size_t in_sz = cfg->model == QMPC_MODEL_EULER_CONVEX ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
   CU(cudaMalloc(&h->d_in, in_sz * (size_t)max_batch));
   CU(cudaMalloc(&h->d_out, sizeof(QmpcResult) * (size_t)max_batch));
+  CU(cudaMalloc(&h->d_sched, sizeof(QmpcContactSchedule) * (size_t)max_batch));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   return QMPC_OK;
 }
@@ -198,6 +201,7 @@ extern "C" void qmpc_destroy(QmpcHandle* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
+  if (h->d_sched) cudaFree(h->d_sched);
   delete h;
 }
 
@@ -205,33 +209,35 @@ extern "C" int64_t qmpc_launch_count(const QmpcHandle* h) { return h ? h->launch
 extern "C" const char* qmpc_last_error(const QmpcHandle* h) { return h ? h->err : "null handle"; }
 
 template <class M>
-static int launch_dense(QmpcHandle* h, const typename M::Problem* d_in, int batch, QmpcResult* d_out,
-                        cudaStream_t s) {
+static int launch_dense(QmpcHandle* h, const typename M::Problem* d_in, const unsigned char* sched, int batch,
+                        QmpcResult* d_out, cudaStream_t s) {
   const int block = 64;
   const int grid = (batch + block - 1) / block;
-  qmpc_dense_kernel<M><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, d_out, h->ws, batch, h->stride);
+  qmpc_dense_kernel<M><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, sched, d_out, h->ws, batch, h->stride);
   h->launches += 1;
   CU(cudaGetLastError());
   return QMPC_OK;
 }
 
 template <int NF>
-static int launch_srb(QmpcHandle* h, const QmpcProblem* d_in, int batch, QmpcResult* d_out, cudaStream_t s) {
+static int launch_srb(QmpcHandle* h, const QmpcProblem* d_in, const unsigned char* sched, int batch, QmpcResult* d_out,
+                      cudaStream_t s) {
   const int block = 64;
   const int grid = (batch + block - 1) / block;
-  qmpc_srb_kernel<NF><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, d_out, h->ws, batch, h->stride);
+  qmpc_srb_kernel<NF><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, sched, d_out, h->ws, batch, h->stride);
   h->launches += 1;
   CU(cudaGetLastError());
   return QMPC_OK;
 }
 
 template <int NF>
-static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, int batch, QmpcResult* d_out, cudaStream_t s) {
+static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned char* sched, int batch, QmpcResult* d_out,
+                       cudaStream_t s) {
   const int groups = kCoopBlock / kCoopG;
   const int need = (batch + groups - 1) / groups;
   const int grid = need < h->coop_grid ? need : h->coop_grid;
   const size_t smem_bytes = (size_t)groups * h->coop_smem_doubles * sizeof(double);
-  qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, d_out, h->ws, batch,
+  qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, sched, d_out, h->ws, batch,
                                                                    h->coop_smem_doubles, h->coop_scratch_doubles,
                                                                    h->coop_wide);
   h->launches += 1;
@@ -239,7 +245,8 @@ static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, int batch, QmpcRe
   return QMPC_OK;
 }
 
-static int solve_any(QmpcHandle* h, const void* d_in, int32_t batch, QmpcResult* d_out, void* stream, bool convex) {
+static int solve_any(QmpcHandle* h, const void* d_in, const QmpcContactSchedule* d_sched, int32_t batch,
+                     QmpcResult* d_out, void* stream, bool convex) {
   if (!h || !h->ws) return h ? QMPC_ERR_CUDA : QMPC_ERR_ARG;
   if (!d_in || !d_out || batch < 0) return QMPC_ERR_ARG;
   if (convex != (h->cfg.model == QMPC_MODEL_EULER_CONVEX)) return QMPC_ERR_ARG;
@@ -247,29 +254,40 @@ static int solve_any(QmpcHandle* h, const void* d_in, int32_t batch, QmpcResult*
   if (batch == 0) return QMPC_OK;
   CU(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
+  const unsigned char* sc = reinterpret_cast<const unsigned char*>(d_sched);
   switch (h->cfg.model) {
     case QMPC_MODEL_QUAT_4FOOT:
-      if (h->kernel == 2) return launch_coop<4>(h, (const QmpcProblem*)d_in, batch, d_out, s);
-      if (h->kernel == 1) return launch_srb<4>(h, (const QmpcProblem*)d_in, batch, d_out, s);
-      return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
+      if (h->kernel == 2) return launch_coop<4>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
+      if (h->kernel == 1) return launch_srb<4>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
+      return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
     case QMPC_MODEL_QUAT_2FOOT:
-      if (h->kernel == 2) return launch_coop<2>(h, (const QmpcProblem*)d_in, batch, d_out, s);
-      if (h->kernel == 1) return launch_srb<2>(h, (const QmpcProblem*)d_in, batch, d_out, s);
-      return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, batch, d_out, s);
-    default: return launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, batch, d_out, s);
+      if (h->kernel == 2) return launch_coop<2>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
+      if (h->kernel == 1) return launch_srb<2>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
+      return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
+    default: return launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, sc, batch, d_out, s);
   }
 }
 
 extern "C" int qmpc_solve_batch(QmpcHandle* h, const QmpcProblem* d_in, int32_t batch, QmpcResult* d_out,
                                 void* cuda_stream) {
-  return solve_any(h, d_in, batch, d_out, cuda_stream, false);
+  return solve_any(h, d_in, nullptr, batch, d_out, cuda_stream, false);
+}
+extern "C" int qmpc_solve_batch_sched(QmpcHandle* h, const QmpcProblem* d_in, const QmpcContactSchedule* d_sched,
+                                      int32_t batch, QmpcResult* d_out, void* cuda_stream) {
+  return solve_any(h, d_in, d_sched, batch, d_out, cuda_stream, false);
+}
+extern "C" int qmpc_solve_batch_convex_sched(QmpcHandle* h, const QmpcConvexProblem* d_in,
+                                             const QmpcContactSchedule* d_sched, int32_t batch, QmpcResult* d_out,
+                                             void* cuda_stream) {
+  return solve_any(h, d_in, d_sched, batch, d_out, cuda_stream, true);
 }
 extern "C" int qmpc_solve_batch_convex(QmpcHandle* h, const QmpcConvexProblem* d_in, int32_t batch,
                                        QmpcResult* d_out, void* cuda_stream) {
-  return solve_any(h, d_in, batch, d_out, cuda_stream, true);
+  return solve_any(h, d_in, nullptr, batch, d_out, cuda_stream, true);
 }
 
-static int solve_host_any(QmpcHandle* h, const void* in, int32_t batch, QmpcResult* out, bool convex) {
+static int solve_host_any(QmpcHandle* h, const void* in, const QmpcContactSchedule* sched, int32_t batch,
+                          QmpcResult* out, bool convex) {
   if (!h || !h->ws) return h ? QMPC_ERR_CUDA : QMPC_ERR_ARG;
   if (!in || !out || batch < 0) return QMPC_ERR_ARG;
   if (batch > h->max_batch) return QMPC_ERR_CAPACITY;
@@ -277,7 +295,9 @@ static int solve_host_any(QmpcHandle* h, const void* in, int32_t batch, QmpcResu
   CU(cudaSetDevice(h->device));
   size_t in_sz = convex ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
   CU(cudaMemcpyAsync(h->d_in, in, in_sz * batch, cudaMemcpyHostToDevice, h->stream));
-  int rc = solve_any(h, h->d_in, batch, h->d_out, h->stream, convex);
+  if (sched)
+    CU(cudaMemcpyAsync(h->d_sched, sched, sizeof(QmpcContactSchedule) * batch, cudaMemcpyHostToDevice, h->stream));
+  int rc = solve_any(h, h->d_in, sched ? h->d_sched : nullptr, batch, h->d_out, h->stream, convex);
   if (rc) return rc;
   CU(cudaMemcpyAsync(out, h->d_out, sizeof(QmpcResult) * batch, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -285,9 +305,80 @@ static int solve_host_any(QmpcHandle* h, const void* in, int32_t batch, QmpcResu
 }
 
 extern "C" int qmpc_solve_batch_host(QmpcHandle* h, const QmpcProblem* in, int32_t batch, QmpcResult* out) {
-  return solve_host_any(h, in, batch, out, false);
+  return solve_host_any(h, in, nullptr, batch, out, false);
+}
+extern "C" int qmpc_solve_batch_sched_host(QmpcHandle* h, const QmpcProblem* in, const QmpcContactSchedule* sched,
+                                           int32_t batch, QmpcResult* out) {
+  return solve_host_any(h, in, sched, batch, out, false);
 }
 extern "C" int qmpc_solve_batch_convex_host(QmpcHandle* h, const QmpcConvexProblem* in, int32_t batch,
                                             QmpcResult* out) {
-  return solve_host_any(h, in, batch, out, true);
+  return solve_host_any(h, in, nullptr, batch, out, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rows N1 / N2 of the scope table: streaming kernels either side of the solve (qmpc_periph.cuh)
+static int periph_check(QmpcHandle* h, int32_t batch) {
+  if (!h) return QMPC_ERR_ARG;
+  if (batch < 0) return QMPC_ERR_ARG;
+  if (batch > h->max_batch) return QMPC_ERR_CAPACITY;
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_predict_contact_schedule(QmpcHandle* h, const QmpcGaitState* d_gait, int32_t batch,
+                                             QmpcContactSchedule* d_sched, void* cuda_stream) {
+  int rc = periph_check(h, batch);
+  if (rc) return rc;
+  if (!d_gait || !d_sched) return QMPC_ERR_ARG;
+  if (batch == 0) return QMPC_OK;
+  CU(cudaSetDevice(h->device));
+  qmpc_predict_schedule_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(
+      d_gait, batch, h->cfg.horizon, h->cfg.dt, d_sched);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_default_leg_params(QmpcLegParams* lp) {
+  if (!lp) return QMPC_ERR_ARG;
+  memset(lp, 0, sizeof(*lp));
+  for (int i = 0; i < 4; ++i) {
+    lp->rho_fix[i][0] = i < 2 ? 0.1881 : -0.1881;        // leg_offset_x   BaseInterface.cpp:12-15
+    lp->rho_fix[i][1] = (i & 1) ? -0.04675 : 0.04675;    // leg_offset_y   :16-19
+    lp->rho_fix[i][2] = (i & 1) ? -0.0812 : 0.0812;      // motor_offset   :20-23
+    lp->rho_fix[i][3] = 0.213;                           // UPPER_LEG_LENGTH  LeggedParams.h:14
+    lp->rho_fix[i][4] = 0.213;                           // LOWER_LEG_LENGTH  LeggedParams.h:15
+  }
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_leg_kinematics(QmpcHandle* h, const QmpcLegParams* lp, const double* d_joint_pos, int32_t batch,
+                                   double* d_foot_pos_body, double* d_jac_foot, void* cuda_stream) {
+  int rc = periph_check(h, batch);
+  if (rc) return rc;
+  if (!lp || !d_joint_pos || (!d_foot_pos_body && !d_jac_foot)) return QMPC_ERR_ARG;
+  if (batch == 0) return QMPC_OK;
+  CU(cudaSetDevice(h->device));
+  const int n = batch * 4;
+  qmpc_leg_kinematics_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(*lp, d_joint_pos, batch,
+                                                                                    d_foot_pos_body, d_jac_foot);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_joint_torques(QmpcHandle* h, const QmpcResult* d_results, const double* d_jac_foot,
+                                  const int32_t* d_plan_contacts, int32_t movement_mode, int32_t batch, double* d_tau,
+                                  void* cuda_stream) {
+  int rc = periph_check(h, batch);
+  if (rc) return rc;
+  if (!d_results || !d_jac_foot || !d_tau) return QMPC_ERR_ARG;
+  if (batch == 0) return QMPC_OK;
+  CU(cudaSetDevice(h->device));
+  const int n = batch * 4;
+  qmpc_joint_torque_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(d_results, d_jac_foot, d_plan_contacts,
+                                                                                  movement_mode, batch, d_tau);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
 }

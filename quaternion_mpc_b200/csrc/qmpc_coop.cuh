@@ -142,7 +142,7 @@ QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, int k, int N, 
   J += stage_cost(m, cfg, k, N, x, u);
   if (k < N) {
     double c[M::NC];
-    cone_eval(m, u, c);
+    cone_eval(m, k, u, c);
     double acc = 0;
 #pragma unroll
     for (int i = 0; i < M::NC; ++i) {
@@ -250,7 +250,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
     for (int f = 0; f < NF; ++f) {
       double u0, u1, u2;
       if (mode == 0) {
-        u0 = m.uref[3 * f]; u1 = m.uref[3 * f + 1]; u2 = m.uref[3 * f + 2];
+        u0 = 0.0; u1 = 0.0; u2 = m.urefz(0, f);   // SetInput(u_traj_ref.at(0)), QuatMpc.cpp:253
       } else {
         double t0 = 0, t1 = 0, t2 = 0;
         const double* K0 = Kk + (3 * f) * 12;
@@ -282,15 +282,16 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
         tu[0] = u0; tu[tstride] = u1; tu[2 * tstride] = u2;
       }
       if (mode != 2) {
-        const double d0 = u0 - m.uref[3 * f], d1 = u1 - m.uref[3 * f + 1], d2 = u2 - m.uref[3 * f + 2];
+        const double d0 = u0, d1 = u1, d2 = u2 - m.urefz(k, f);   // u_ref = (0, 0, weight share)
         Jl += 0.5 * cfg.r_weights[3 * f] * d0 * d0;
         Jl += 0.5 * cfg.r_weights[3 * f + 1] * d1 * d1;
         Jl += 0.5 * cfg.r_weights[3 * f + 2] * d2 * d2;
         const double* mu_f = gmu + k * NC + 6 * f;
+        const double fzc_f = m.fzc(k, f);
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
           double c = m.CR[3 * r] * u0 + m.CR[3 * r + 1] * u1 + m.CR[3 * r + 2] * u2;
-          if (r == 4) c += -m.fzc[f];
+          if (r == 4) c += -fzc_f;
           const double mui = mu_f[r];
           const double est = mui + rho * c;
           const double lh = est > 0 ? est : 0;
@@ -347,7 +348,8 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
 }
 
 template <int NF, int G>
-QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in, QmpcResult* out,
+QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in,
+                            const unsigned char* sched, QmpcResult* out,
                             int pid, double* sm, double* gs, int lane_id, unsigned lane_mask, bool wide) {
   using M = QuatModel<NF>;
   using L = CoopLayout<NF, G>;
@@ -386,7 +388,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     for (int i = lane; i < N * NC; i += G) gmu[i] = 0.0;
     if (lane == 0) {
       QmpcProblem prob = in[pid];
-      m.setup(cfg, prob, X);
+      m.setup(cfg, prob, sched ? sched + (size_t)pid * QMPC_MAX_HORIZON : nullptr, X);
     }
   }
   COOP_SYNC();
@@ -438,7 +440,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
             const double* u = U + k * NU;
             const double* yn = DX + (k + 1) * NE;
             double gu[NU], Hb[9 * NF], Aty[NE], t6[6], Bty[NU];
-            al_terms(m, u, GVec{gmu + k * NC, 1}, rho, gu, Hb);
+            al_terms(m, k, u, GVec{gmu + k * NC, 1}, rho, gu, Hb);
             srb_At_vec(Lk, hd, yn, Aty);
             srb_Mt_vec(Lk, hd, hh, yn, t6);
             srb_Wt_vec(m, t6, Bty);
@@ -447,7 +449,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
               if (v > rx) rx = v;
             }
             for (int a = 0; a < NU; ++a) {
-              double v = fabs(cfg.r_weights[a] * (u[a] - m.uref[a]) + gu[a] + Bty[a]);
+              double v = fabs(cfg.r_weights[a] * (u[a] - m.uref_at(k, a)) + gu[a] + Bty[a]);
               if (v > ru) ru = v;
             }
           }
@@ -469,7 +471,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
             const int k = idx / NC, r = idx % NC, f = r / 6, rr = r % 6;
             const double* u = U + k * NU + 3 * f;
             double c = m.CR[3 * rr] * u[0] + m.CR[3 * rr + 1] * u[1] + m.CR[3 * rr + 2] * u[2];
-            if (rr == 4) c += -m.fzc[f];
+            if (rr == 4) c += -m.fzc(k, f);
             const double est = gmu[idx] + rho * c;
             gmu[idx] = est > 0 ? est : 0;
           }
@@ -533,7 +535,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 #pragma unroll 1
           for (int r = 0; r < 6; ++r) {
             double c = m.CR[3 * r] * u[0] + m.CR[3 * r + 1] * u[1] + m.CR[3 * r + 2] * u[2];
-            if (r == 4) c += -m.fzc[f];
+            if (r == 4) c += -m.fzc(k, f);
             const double est = gmu[k * NC + 6 * f + r] + rho * c;
             if (est > 0) {
               const double j0 = m.CR[3 * r], j1 = m.CR[3 * r + 1], j2 = m.CR[3 * r + 2];
@@ -546,9 +548,9 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           hb[0] += cfg.r_weights[3 * f]; hb[4] += cfg.r_weights[3 * f + 1]; hb[8] += cfg.r_weights[3 * f + 2];
 #pragma unroll
           for (int a = 0; a < 9; ++a) vec[cv::Dblk + 9 * f + a] = hb[a];
-          vec[cv::g + 3 * f] = cfg.r_weights[3 * f] * (u[0] - m.uref[3 * f]) + g0;
-          vec[cv::g + 3 * f + 1] = cfg.r_weights[3 * f + 1] * (u[1] - m.uref[3 * f + 1]) + g1;
-          vec[cv::g + 3 * f + 2] = cfg.r_weights[3 * f + 2] * (u[2] - m.uref[3 * f + 2]) + g2;
+          vec[cv::g + 3 * f] = cfg.r_weights[3 * f] * u[0] + g0;
+          vec[cv::g + 3 * f + 1] = cfg.r_weights[3 * f + 1] * u[1] + g1;
+          vec[cv::g + 3 * f + 2] = cfg.r_weights[3 * f + 2] * (u[2] - m.urefz(k, f)) + g2;
         }
         if (lane == NF) {
           double hphi;
@@ -884,7 +886,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 #endif
 template <int NF, int G>
 __global__ void __launch_bounds__(64, QMPC_COOP_MIN_BLOCKS)
-qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in, QmpcResult* __restrict__ out,
+qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in,
+                 const unsigned char* __restrict__ sched, QmpcResult* __restrict__ out,
                  double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot, int wide) {
   extern __shared__ double smem_pool[];
   const int groups_per_block = blockDim.x / G;
@@ -896,7 +899,7 @@ qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ i
   double* sm = smem_pool + (size_t)group * smem_per_problem;
   double* gs = scratch + (size_t)slot * scratch_per_slot;
   for (int pid = slot; pid < batch; pid += nslots) {
-    coop_solve_one<NF, G>(cfg, o, in, out, pid, sm, gs, lane_id, lane_mask, wide != 0);
+    coop_solve_one<NF, G>(cfg, o, in, sched, out, pid, sm, gs, lane_id, lane_mask, wide != 0);
   }
 }
 #endif

@@ -68,6 +68,39 @@ QMPC_HD inline void fill_cone(double mu, const double* Rc /* nullptr = identity 
     }
 }
 
+
+// Per-knot contact schedule shared by the models.  byte k: bits 0..3 = foot i in contact at knot
+// k, bits 4..6 = number of feet in contact.  The reference holds ONE mask over the whole horizon
+// (QuatMpc.cpp:119-125, 202; ConvexMpc.cpp:82 "TODO"); a null `sched` reproduces exactly that.
+// With a schedule (LeggedContactFSM::predict_contact_state) knot k uses its own mask
+// for u_ref and the fz bounds; a knot without any contact gets u_ref = 0 instead of the reference's
+// 0/0 (which a constant all-swing mask still reproduces: QuatMpc.cpp:122).
+struct ContactPlan {
+  unsigned char cm[QMPC_MAX_HORIZON];
+  double wz[5];   // u_ref z of a stance foot when n feet are in contact; wz[0] = NaN (plain) or 0 (schedule)
+  double fzmax;
+  QMPC_HD void fill(int nf, int N, const int32_t* plan_contacts, const unsigned char* sched, double weight,
+                    double fz_max, bool weight_first) {
+    int m0 = 0;
+    for (int i = 0; i < nf; ++i) m0 |= plan_contacts[i] ? (1 << i) : 0;
+    for (int k = 0; k < QMPC_MAX_HORIZON; ++k) {
+      int mk = (sched && k < N) ? (sched[k] & ((1 << nf) - 1)) : m0;
+      int nc = (mk & 1) + ((mk >> 1) & 1) + ((mk >> 2) & 1) + ((mk >> 3) & 1);
+      cm[k] = (unsigned char)(mk | (nc << 4));
+    }
+    // QuatMpc.cpp:122 evaluates c * m * 9.81 / nc, ConvexMpc.cpp:93 m * 9.81 / nc * c (c = 1 here)
+    for (int n = 1; n <= 4; ++n) wz[n] = weight_first ? weight / n * 1.0 : 1.0 * weight / n;
+    wz[0] = sched ? 0.0 : NAN;   // the reference's 0 * m g / 0 (QuatMpc.cpp:122) and m g / 0 * 0 (ConvexMpc.cpp:93)
+    fzmax = fz_max;
+  }
+  QMPC_HD bool in_contact(int k, int f) const { return (cm[k] >> f) & 1; }
+  QMPC_HD double urefz(int k, int f) const {
+    const int c = cm[k], nc = c >> 4;
+    return (((c >> f) & 1) || nc == 0) ? wz[nc] : 0.0;
+  }
+  QMPC_HD double fzc(int k, int f) const { return ((cm[k] >> f) & 1) ? fzmax : 0.0; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Quaternion SRB with NF feet (QuatMpc: NF = 4; 2-contact model: NF = 2)
 template <int NF>
@@ -80,13 +113,17 @@ struct QuatModel {
   double IS[9 * NF];  // Iinv * skew(r_i), 3x3 row-major per foot  (AltroUtils.cpp:433)
   double Iinv[9];
   double inv_mass, g[3], tau_g[3];
-  double CR[18], fzc[NF];
-  double uref[NU];
+  double CR[18];
+  ContactPlan cp;
   double qd[4], pd[3], vd[3];
   double R0[9];
   double dtk;  // reference time step for x_ref (double, QuatMpc.cpp:156)
 
-  QMPC_HD void setup(const QmpcConfig& cfg, const QmpcProblem& in, double* x0) {
+  QMPC_HD double urefz(int k, int f) const { return cp.urefz(k, f); }
+  QMPC_HD double uref_at(int k, int i) const { return (i % 3 == 2) ? cp.urefz(k, i / 3) : 0.0; }
+  QMPC_HD double fzc(int k, int f) const { return cp.fzc(k, f); }
+
+  QMPC_HD void setup(const QmpcConfig& cfg, const QmpcProblem& in, const unsigned char* sched, double* x0) {
     for (int i = 0; i < 3 * NF; ++i) foot[i] = in.foot_pos_body[i];
     inv3(cfg.inertia, Iinv);
     inv_mass = 1.0 / cfg.robot_mass;
@@ -110,14 +147,7 @@ struct QuatModel {
           IS[9 * i + 3 * a + b] = s;
         }
     }
-    int nc = 0;
-    for (int i = 0; i < NF; ++i) nc += in.plan_contacts[i] ? 1 : 0;
-    for (int i = 0; i < NU; ++i) uref[i] = 0;
-    for (int i = 0; i < NF; ++i) {
-      double c = in.plan_contacts[i] ? 1.0 : 0.0;
-      uref[3 * i + 2] = c * cfg.robot_mass * cfg.gravity / nc;
-      fzc[i] = cfg.fz_max * c;
-    }
+    cp.fill(NF, cfg.horizon, in.plan_contacts, sched, cfg.robot_mass * cfg.gravity, cfg.fz_max, false);
     {
       const double *q = in.torso_quat_d, *w = in.torso_ang_vel_d_body;
       double s = 0.5 * cfg.quat_d_dt;
@@ -211,23 +241,20 @@ struct ConvexModel {
   using Problem = QmpcConvexProblem;
 
   double foot[12];
-  double CR[18], fzc[4];
-  double uref[12];
+  double CR[18];
+  ContactPlan cp;
   double xr0[12], yaw_rate, dtk;
   double R0[9];
 
-  QMPC_HD void setup(const QmpcConfig& cfg, const QmpcConvexProblem& in, double* x0) {
+  QMPC_HD double urefz(int k, int f) const { return cp.urefz(k, f); }
+  QMPC_HD double uref_at(int k, int i) const { return (i % 3 == 2) ? cp.urefz(k, i / 3) : 0.0; }
+  QMPC_HD double fzc(int k, int f) const { return cp.fzc(k, f); }
+
+  QMPC_HD void setup(const QmpcConfig& cfg, const QmpcConvexProblem& in, const unsigned char* sched, double* x0) {
     for (int i = 0; i < 12; ++i) foot[i] = in.foot_pos_abs_com[i];
     for (int i = 0; i < 9; ++i) R0[i] = in.torso_rot_mat[i];
     fill_cone(cfg.mu, nullptr, CR);
-    int nc = 0;
-    for (int i = 0; i < 4; ++i) nc += in.plan_contacts[i] ? 1 : 0;
-    for (int i = 0; i < 12; ++i) uref[i] = 0;
-    for (int i = 0; i < 4; ++i) {
-      double c = in.plan_contacts[i] ? 1.0 : 0.0;
-      uref[3 * i + 2] = cfg.robot_mass * cfg.gravity / nc * c;
-      fzc[i] = cfg.fz_max * c;
-    }
+    cp.fill(4, cfg.horizon, in.plan_contacts, sched, cfg.robot_mass * cfg.gravity, cfg.fz_max, true);
     for (int i = 0; i < 12; ++i) xr0[i] = 0;
     xr0[2] = in.torso_euler[2];
     for (int i = 0; i < 3; ++i) xr0[3 + i] = in.torso_pos_d_world[i];

@@ -1,0 +1,180 @@
+// qmpc_periph.cuh — the data either side of the solve, batched.
+//
+//   N1  LeggedContactFSM::predict_contact_state over the shipped gait tables
+//         legged_ctrl/src/utils/LeggedContactFSM.cpp:87-206 (tables), :272-286 (predictor)
+//   N2  A1Kinematics::fk / jac for the four legs      legged_ctrl/src/utils/A1Kinematics.cpp:10-21
+//         as called from BaseInterface.cpp:204-212 (foot_pos_body, jac_foot)
+//       joint torque targets tau_i = -J_i^T f_i       BaseInterface.cpp:343-405
+//
+// All three are streaming, HBM-bound element-wise kernels (tens of bytes per robot): one thread per
+// robot (N1) or per (robot, leg) (N2), consecutive threads touch consecutive addresses, grid sized
+// to the batch.  The bodies are QMPC_HD so tests/emul can run them on the host.
+#pragma once
+#include "qmpc_models.cuh"
+
+namespace qmpc {
+
+// no-FMA arithmetic where the result feeds a comparison that must match the reference bit for bit
+QMPC_HD inline double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+QMPC_HD inline double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+
+// One leg's gait pattern: up to 3 segments (switch time, STANCE?) over the unit gait cycle.
+struct GaitLegPattern {
+  int n;
+  double sw[3];
+  int stance[3];
+};
+
+// LeggedContactFSM.cpp:87-206.  leg: 0 FL, 1 FR, 2 RL, 3 RR.
+QMPC_HD inline GaitLegPattern gait_pattern(int gait, int leg) {
+  GaitLegPattern p{};
+  const bool diagA = (leg == 0 || leg == 3);
+  switch (gait) {
+    case QMPC_GAIT_TROT:   // FL/RR stance first, FR/RL swing first, switch at half cycle
+      p.n = 2; p.sw[0] = 0.5; p.sw[1] = 1.0;
+      p.stance[0] = diagA ? 1 : 0; p.stance[1] = diagA ? 0 : 1;
+      break;
+    case QMPC_GAIT_TROT_WITH_STAND:
+      if (diagA) { p.n = 2; p.sw[0] = 0.6; p.sw[1] = 1.0; p.stance[0] = 1; p.stance[1] = 0; }
+      else { p.n = 3; p.sw[0] = 0.1; p.sw[1] = 0.5; p.sw[2] = 1.0; p.stance[0] = 1; p.stance[1] = 0; p.stance[2] = 1; }
+      break;
+    case QMPC_GAIT_CRAWL:
+      if (leg == 0) { p.n = 2; p.sw[0] = 0.25; p.sw[1] = 1.0; p.stance[0] = 0; p.stance[1] = 1; }
+      else if (leg == 1) { p.n = 3; p.sw[0] = 0.25; p.sw[1] = 0.5; p.sw[2] = 1.0; p.stance[0] = 1; p.stance[1] = 0; p.stance[2] = 1; }
+      else if (leg == 2) { p.n = 3; p.sw[0] = 0.5; p.sw[1] = 0.75; p.sw[2] = 1.0; p.stance[0] = 1; p.stance[1] = 0; p.stance[2] = 1; }
+      else { p.n = 2; p.sw[0] = 0.75; p.sw[1] = 1.0; p.stance[0] = 1; p.stance[1] = 0; }
+      break;
+    default:  // QMPC_GAIT_STAND
+      p.n = 1; p.sw[0] = 1.0; p.stance[0] = 1;
+      break;
+  }
+  return p;
+}
+
+// predict_contact_state(dt) of one leg (LeggedContactFSM.cpp:272-286); falls through to STANCE
+QMPC_HD inline int predict_contact(const GaitLegPattern& p, double gait_phase, double gait_freq, double dt) {
+  double ph = add_rn(gait_phase, mul_rn(gait_freq, dt));
+  while (ph > 1.0) ph = add_rn(ph, -1.0);
+  for (int i = 0; i < p.n; ++i)
+    if (ph <= p.sw[i]) return p.stance[i];
+  return 1;
+}
+
+QMPC_HD inline void predict_schedule_one(const QmpcGaitState& g, int N, double dt, QmpcContactSchedule& out) {
+  GaitLegPattern pat[4];
+  for (int leg = 0; leg < 4; ++leg) pat[leg] = gait_pattern(g.gait, leg);
+  for (int k = 0; k < QMPC_MAX_HORIZON; ++k) {
+    int m = 0;
+    if (k < N) {
+      const double t = mul_rn((double)k, dt);
+      for (int leg = 0; leg < 4; ++leg) m |= predict_contact(pat[leg], g.gait_phase[leg], g.gait_freq, t) << leg;
+    }
+    out.mask[k] = (uint8_t)m;
+  }
+}
+
+// Forward kinematics + Jacobian of one leg in closed form.  q = (hip, thigh, calf);
+// rho_fix = (ox, oy, d, lt, lc), rho_opt = (cx, cy, cz) foot-contact offset.  With
+// a = lc - cz, s12 = sin(q1 + q2), c12 = cos(q1 + q2), L = lt cos q1 + cx s12 + a c12 :
+//   p = [ ox - lt sin q1 - a s12 + cx c12 ;  oy + (cy + d) cos q0 + L sin q0 ;  (cy + d) sin q0 - L cos q0 ]
+// which is the polynomial A1Kinematics::autoFunc_fk_derive expands term by term
+// (A1Kinematics.cpp:40-75); J = dp/dq follows by differentiation (autoFunc_d_fk_dq, :77-140).
+// jac is written column-major (Eigen): jac[3 * col + row].
+QMPC_HD inline void leg_fk_jac(const double* q, const double* rf, const double* ro, double* p, double* jac) {
+  const double ox = rf[0], oy = rf[1], d = rf[2], lt = rf[3], lc = rf[4];
+  const double cx = ro[0], cy = ro[1], cz = ro[2];
+  double s0, c0, s1, c1, s12, c12;
+  s0 = sin(q[0]); c0 = cos(q[0]);
+  s1 = sin(q[1]); c1 = cos(q[1]);
+  s12 = sin(q[1] + q[2]); c12 = cos(q[1] + q[2]);
+  const double a = lc - cz, e = cy + d;
+  const double L = lt * c1 + cx * s12 + a * c12;
+  const double dL2 = cx * c12 - a * s12;   // dL/dq2
+  const double dL1 = dL2 - lt * s1;        // dL/dq1
+  if (p) {
+    p[0] = ox - lt * s1 - a * s12 + cx * c12;
+    p[1] = oy + e * c0 + L * s0;
+    p[2] = e * s0 - L * c0;
+  }
+  if (jac) {
+    jac[0] = 0.0;                    jac[3] = -L;        jac[6] = -(a * c12 + cx * s12);
+    jac[1] = -e * s0 + L * c0;       jac[4] = s0 * dL1;  jac[7] = s0 * dL2;
+    jac[2] = e * c0 + L * s0;        jac[5] = -c0 * dL1; jac[8] = -c0 * dL2;
+  }
+}
+
+// tau = -J^T f (BaseInterface.cpp:379, :398); zero for a planned swing leg when movement_mode > 0 (:381)
+QMPC_HD inline void leg_torque(const double* jac /* 3x3 column-major */, const double* f, bool active, double* tau) {
+  for (int j = 0; j < 3; ++j) {
+    double t = 0;
+    for (int a = 0; a < 3; ++a) t += -jac[3 * j + a] * f[a];
+    tau[j] = active ? t : 0.0;
+  }
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(256)
+qmpc_predict_schedule_kernel(const QmpcGaitState* __restrict__ g, int batch, int N, double dt,
+                             QmpcContactSchedule* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  QmpcContactSchedule s;
+  predict_schedule_one(g[i], N, dt, s);
+  // 32 bytes per robot: two 16-byte stores
+  const uint4* src = reinterpret_cast<const uint4*>(&s);
+  uint4* dst = reinterpret_cast<uint4*>(out + i);
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+
+__global__ void __launch_bounds__(256)
+qmpc_leg_kinematics_kernel(QmpcLegParams lp, const double* __restrict__ joint_pos, int batch,
+                           double* __restrict__ foot_pos_body, double* __restrict__ jac_foot) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // (robot, leg)
+  if (t >= batch * 4) return;
+  const int leg = t & 3;
+  const double q[3] = {joint_pos[3 * (size_t)t], joint_pos[3 * (size_t)t + 1], joint_pos[3 * (size_t)t + 2]};
+  double p[3], J[9];
+  leg_fk_jac(q, lp.rho_fix[leg], lp.rho_opt[leg], p, J);
+  if (foot_pos_body) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) foot_pos_body[3 * (size_t)t + a] = p[a];
+  }
+  if (jac_foot) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) jac_foot[9 * (size_t)t + a] = J[a];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+qmpc_joint_torque_kernel(const QmpcResult* __restrict__ res, const double* __restrict__ jac_foot,
+                         const int32_t* __restrict__ plan_contacts, int movement_mode, int batch,
+                         double* __restrict__ tau) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // (robot, leg)
+  if (t >= batch * 4) return;
+  const int b = t >> 2, leg = t & 3;
+  double J[9], f[3], out[3];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) J[a] = jac_foot[9 * (size_t)t + a];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) f[a] = res[b].grf_body[3 * leg + a];   // ctrl.optimized_input[3 leg ..]
+  const bool active = movement_mode <= 0 || !plan_contacts || plan_contacts[t] != 0;
+  leg_torque(J, f, active, out);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) tau[3 * (size_t)t + a] = out[a];
+}
+#endif
+
+}  // namespace qmpc

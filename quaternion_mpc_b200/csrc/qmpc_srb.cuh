@@ -298,10 +298,10 @@ QMPC_HD bool srb_backward_step(const QuatModel<NF>& m, const KnotLin& L, double 
 
 // AL gradient (NU) and D blocks = diag(R) + rho J_a^T J_a per foot (NF*9)
 template <int NF>
-QMPC_HD void srb_al_terms(const QuatModel<NF>& m, const QmpcConfig& cfg, const double* u, const GVec& mu_k, double rho,
+QMPC_HD void srb_al_terms(const QuatModel<NF>& m, const QmpcConfig& cfg, int k, const double* u, const GVec& mu_k, double rho,
                           double* gu, double* Dblk) {
   double Hb[9 * NF];
-  al_terms(m, u, mu_k, rho, gu, Hb);
+  al_terms(m, k, u, mu_k, rho, gu, Hb);
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
 #pragma unroll
@@ -313,7 +313,8 @@ QMPC_HD void srb_al_terms(const QuatModel<NF>& m, const QmpcConfig& cfg, const d
 }
 
 template <int NF>
-QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in, QmpcResult* out,
+QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in,
+                           const unsigned char* sched, QmpcResult* out,
                            double* ws, int pid, size_t stride) {
   using M = QuatModel<NF>;
   using L = SrbLayout<NF>;
@@ -333,18 +334,19 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
   double x0[NX];
   {
     QmpcProblem prob = in[pid];
-    m.setup(cfg, prob, x0);
+    m.setup(cfg, prob, sched ? sched + (size_t)pid * QMPC_MAX_HORIZON : nullptr, x0);
   }
   double rho = o.penalty_initial;
   for (int i = 0; i < N * NC; ++i) gmu[i] = 0.0;
 
   {
-    double x[NX], xn[NX];
+    double x[NX], xn[NX], u0[NU];
     for (int i = 0; i < NX; ++i) { x[i] = x0[i]; X[i] = x0[i]; }
+    for (int i = 0; i < NU; ++i) u0[i] = m.uref_at(0, i);   // SetInput(u_traj_ref.at(0)), QuatMpc.cpp:253
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
-      st<NU>(U.off(k * NU), m.uref);
-      mid_dyn(m, x, m.uref, h, xn);
+      st<NU>(U.off(k * NU), u0);
+      mid_dyn(m, x, u0, h, xn);
       for (int i = 0; i < NX; ++i) { x[i] = xn[i]; X[(k + 1) * NX + i] = xn[i]; }
     }
   }
@@ -393,7 +395,7 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
         ld<9>(Lk.Afw, glin.off(k * 27 + 9));
         ld<9>(Lk.Cf, glin.off(k * 27 + 18));
         cost_expand(m, cfg, k, x, lx, &hphi);
-        al_terms(m, u, gmu.off(k * NC), rho, gu, Hb);
+        al_terms(m, k, u, gmu.off(k * NC), rho, gu, Hb);
         srb_At_vec(Lk, hd, yn, Aty);
         srb_Mt_vec(Lk, hd, hh, yn, t6);
         srb_Wt_vec(m, t6, Bty);
@@ -402,7 +404,7 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
           if (v > rx) rx = v;
         }
         for (int a = 0; a < NU; ++a) {
-          double v = fabs(cfg.r_weights[a] * (u[a] - m.uref[a]) + gu[a] + Bty[a]);
+          double v = fabs(cfg.r_weights[a] * (u[a] - m.uref_at(k, a)) + gu[a] + Bty[a]);
           if (v > ru) ru = v;
         }
       }
@@ -416,7 +418,7 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
         for (int k = 0; k < N; ++k) {
           double u[NU], c[NC];
           ld<NU>(u, U.off(k * NU));
-          cone_eval(m, u, c);
+          cone_eval(m, k, u, c);
           for (int i = 0; i < NC; ++i) {
             double est = gmu[k * NC + i] + rho * c[i];
             gmu[k * NC + i] = est > 0 ? est : 0;
@@ -455,8 +457,8 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
         ld<9>(Lk.Cf, glin.off(k * 27 + 18));
         cost_expand(m, cfg, k, x, lx, &hphi);
         cost_hessian<M>(cfg, x, hphi, lxx);
-        srb_al_terms(m, cfg, u, gmu.off(k * NC), rho, gu, Dblk);
-        for (int i = 0; i < NU; ++i) g[i] = cfg.r_weights[i] * (u[i] - m.uref[i]) + gu[i];
+        srb_al_terms(m, cfg, k, u, gmu.off(k * NC), rho, gu, Dblk);
+        for (int i = 0; i < NU; ++i) g[i] = cfg.r_weights[i] * (u[i] - m.uref_at(k, i)) + gu[i];
         if (!srb_backward_step(m, Lk, hd, hh, lx, lxx, g, Dblk, P, pv, Kk, dk, &dphi0)) {
           bp_ok = false;
           break;
@@ -539,11 +541,12 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
 #ifdef __CUDACC__
 template <int NF>
 __global__ void __launch_bounds__(64)
-qmpc_srb_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in, QmpcResult* __restrict__ out,
+qmpc_srb_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in,
+                const unsigned char* __restrict__ sched, QmpcResult* __restrict__ out,
                 double* __restrict__ ws, int batch, size_t stride) {
   const int pid = blockIdx.x * blockDim.x + threadIdx.x;
   if (pid >= batch) return;
-  srb_solve_one<NF>(cfg, o, in, out, ws, pid, stride);
+  srb_solve_one<NF>(cfg, o, in, sched, out, ws, pid, stride);
 }
 #endif
 

@@ -24,10 +24,12 @@ class _BatchedMpc:
     PROBLEM_DTYPE = None
     _solve_dev = None
     _solve_host = None
+    _solve_sched_dev = None
+    _solve_sched_host = None
 
     def __init__(self, horizon=10, max_batch=4096, device=0, cfg=None):
         self.lib = abi.load_library()
-        if self.lib.qmpc_abi_version() != 1:
+        if self.lib.qmpc_abi_version() != 2:
             raise QmpcError("libqmpc_b200.so ABI mismatch")
         self.cfg = cfg if cfg is not None else default_config(self.MODEL, horizon)
         if self.cfg.model != self.MODEL and not (
@@ -66,6 +68,78 @@ class _BatchedMpc:
         self._check(rc)
         return d_results
 
+    # -- per-step contact schedules ------------------------------------------------
+    def schedule_to_device(self, schedule):
+        """(batch, QMPC_MAX_HORIZON) uint8 contact masks -> device tensor of QmpcContactSchedule."""
+        import torch
+        schedule = np.ascontiguousarray(schedule, dtype=np.uint8)
+        assert schedule.ndim == 2 and schedule.shape[1] == abi.QMPC_MAX_HORIZON
+        return torch.from_numpy(schedule).to(f"cuda:{self.device}")
+
+    def predict_contact_schedule(self, d_gait, d_sched=None, stream=None):
+        """Batched LeggedContactFSM::predict_contact_state at t + k*dt (LeggedContactFSM.cpp:272-286).
+        d_gait: uint8 device tensor of GAIT_STATE_DTYPE records."""
+        import torch
+        batch = d_gait.shape[0]
+        assert d_gait.is_cuda and d_gait.dtype == torch.uint8 and d_gait.shape[1] == abi.GAIT_STATE_DTYPE.itemsize
+        if d_sched is None:
+            d_sched = torch.empty((batch, abi.QMPC_MAX_HORIZON), dtype=torch.uint8, device=d_gait.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.qmpc_predict_contact_schedule(self._h, d_gait.data_ptr(), batch, d_sched.data_ptr(), s))
+        return d_sched
+
+    def grf_update_sched_device(self, d_problems, d_sched, d_results=None, stream=None):
+        """grf_update_device with one contact mask per knot (d_sched from schedule_to_device /
+        predict_contact_schedule; None = the reference's constant mask)."""
+        import torch
+        batch = d_problems.shape[0]
+        assert d_problems.is_cuda and d_problems.dtype == torch.uint8 and d_problems.is_contiguous()
+        assert d_problems.shape[1] == self.PROBLEM_DTYPE.itemsize
+        if d_sched is not None:
+            assert d_sched.is_cuda and d_sched.dtype == torch.uint8 and d_sched.is_contiguous()
+            assert tuple(d_sched.shape) == (batch, abi.QMPC_MAX_HORIZON)
+        if d_results is None:
+            d_results = self.alloc_results(batch)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        rc = getattr(self.lib, self._solve_sched_dev)(self._h, d_problems.data_ptr(),
+                                                      d_sched.data_ptr() if d_sched is not None else None,
+                                                      batch, d_results.data_ptr(), s)
+        self._check(rc)
+        return d_results
+
+    # -- leg kinematics in / joint torques out (SURVEY 8f N2) -------------------------------------
+    def leg_kinematics(self, d_joint_pos, leg_params=None, want_foot=True, want_jac=True, stream=None):
+        """a1_kin.fk / a1_kin.jac for the four legs (BaseInterface.cpp:204-212).
+        d_joint_pos: (batch, 12) float64 device tensor -> (foot_pos_body (batch,12), jac_foot (batch,36))."""
+        import torch
+        assert d_joint_pos.is_cuda and d_joint_pos.dtype == torch.float64 and d_joint_pos.is_contiguous()
+        batch = d_joint_pos.shape[0]
+        if leg_params is None:
+            leg_params = abi.QmpcLegParams()
+            self.lib.qmpc_default_leg_params(C.byref(leg_params))
+        foot = torch.empty((batch, 12), dtype=torch.float64, device=d_joint_pos.device) if want_foot else None
+        jac = torch.empty((batch, 36), dtype=torch.float64, device=d_joint_pos.device) if want_jac else None
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.qmpc_leg_kinematics(self._h, C.byref(leg_params), d_joint_pos.data_ptr(), batch,
+                                                 foot.data_ptr() if want_foot else None,
+                                                 jac.data_ptr() if want_jac else None, s))
+        return foot, jac
+
+    def joint_torques(self, d_results, d_jac_foot, d_plan_contacts=None, movement_mode=1, stream=None):
+        """ctrl.joint_tau_tgt = -jac^T * optimized_input per leg (BaseInterface.cpp:343-405)."""
+        import torch
+        batch = d_results.shape[0]
+        assert d_jac_foot.dtype == torch.float64 and tuple(d_jac_foot.shape) == (batch, 36)
+        if d_plan_contacts is not None:
+            assert d_plan_contacts.dtype == torch.int32 and tuple(d_plan_contacts.shape) == (batch, 4)
+            assert d_plan_contacts.is_contiguous()
+        tau = torch.empty((batch, 12), dtype=torch.float64, device=d_results.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.qmpc_joint_torques(self._h, d_results.data_ptr(), d_jac_foot.data_ptr(),
+                                                d_plan_contacts.data_ptr() if d_plan_contacts is not None else None,
+                                                int(movement_mode), batch, tau.data_ptr(), s))
+        return tau
+
     @staticmethod
     def results_to_numpy(d_results):
         return d_results.cpu().numpy().reshape(-1).view(abi.RESULT_DTYPE)
@@ -77,6 +151,20 @@ class _BatchedMpc:
         if out is None:
             out = np.empty(problems.shape[0], dtype=abi.RESULT_DTYPE)
         rc = getattr(self.lib, self._solve_host)(self._h, problems.ctypes.data, problems.shape[0], out.ctypes.data)
+        self._check(rc)
+        return out
+
+    def grf_update_sched(self, problems, schedule, out=None):
+        """Host-buffer solve with per-knot contact masks ((batch, QMPC_MAX_HORIZON) uint8)."""
+        problems = np.ascontiguousarray(problems, dtype=self.PROBLEM_DTYPE)
+        schedule = np.ascontiguousarray(schedule, dtype=np.uint8)
+        assert schedule.shape == (problems.shape[0], abi.QMPC_MAX_HORIZON)
+        if self._solve_sched_host is None:
+            raise QmpcError("no host schedule entry point for this model; use grf_update_sched_device")
+        if out is None:
+            out = np.empty(problems.shape[0], dtype=abi.RESULT_DTYPE)
+        rc = getattr(self.lib, self._solve_sched_host)(self._h, problems.ctypes.data, schedule.ctypes.data,
+                                                       problems.shape[0], out.ctypes.data)
         self._check(rc)
         return out
 
@@ -110,6 +198,8 @@ class QuatMpc(_BatchedMpc):
     PROBLEM_DTYPE = abi.PROBLEM_DTYPE
     _solve_dev = "qmpc_solve_batch"
     _solve_host = "qmpc_solve_batch_host"
+    _solve_sched_dev = "qmpc_solve_batch_sched"
+    _solve_sched_host = "qmpc_solve_batch_sched_host"
 
 
 class ConvexMpc(_BatchedMpc):
@@ -118,3 +208,5 @@ class ConvexMpc(_BatchedMpc):
     PROBLEM_DTYPE = abi.CONVEX_PROBLEM_DTYPE
     _solve_dev = "qmpc_solve_batch_convex"
     _solve_host = "qmpc_solve_batch_convex_host"
+    _solve_sched_dev = "qmpc_solve_batch_convex_sched"
+    _solve_sched_host = None

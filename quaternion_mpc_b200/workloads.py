@@ -101,3 +101,53 @@ def random_convex_batch(batch, seed=0, gait="trot"):
     else:
         p["plan_contacts"] = 1
     return p
+
+
+# Gait phase tables of LeggedContactFSM (legged_ctrl/src/utils/LeggedContactFSM.cpp:87-206):
+# per leg (FL, FR, RL, RR) a list of (switch_time, in_stance) segments over one gait cycle.
+GAIT_TROT, GAIT_TROT_WITH_STAND, GAIT_CRAWL, GAIT_STAND = 0, 1, 2, 3
+GAIT_TABLES = {
+    GAIT_TROT: [[(0.5, 1), (1.0, 0)], [(0.5, 0), (1.0, 1)], [(0.5, 0), (1.0, 1)], [(0.5, 1), (1.0, 0)]],
+    GAIT_TROT_WITH_STAND: [[(0.6, 1), (1.0, 0)], [(0.1, 1), (0.5, 0), (1.0, 1)],
+                           [(0.1, 1), (0.5, 0), (1.0, 1)], [(0.6, 1), (1.0, 0)]],
+    GAIT_CRAWL: [[(0.25, 0), (1.0, 1)], [(0.25, 1), (0.5, 0), (1.0, 1)],
+                 [(0.5, 1), (0.75, 0), (1.0, 1)], [(0.75, 1), (1.0, 0)]],
+    GAIT_STAND: [[(1.0, 1)]] * 4,
+}
+
+from .abi import GAIT_STATE_DTYPE  # noqa: E402
+
+
+def random_gait_states(batch, seed=0, gaits=(GAIT_TROT, GAIT_TROT_WITH_STAND, GAIT_CRAWL), gait_freq=2.2):
+    """Per-robot gait clocks: one phase per leg FSM (all four legs of a robot share the clock in the
+    reference's main loop, QuatMpc.cpp:288-300, so the four phases are equal), uniform in [0,1)."""
+    rng = np.random.default_rng(seed)
+    g = np.zeros(batch, dtype=GAIT_STATE_DTYPE)
+    g["gait_phase"] = rng.uniform(0, 1, batch)[:, None]
+    g["gait_freq"] = gait_freq
+    g["gait"] = np.asarray(gaits)[rng.integers(0, len(gaits), batch)]
+    return g
+
+
+def predict_schedule_numpy(gait_states, horizon, dt):
+    """Host restatement of LeggedContactFSM::predict_contact_state (LeggedContactFSM.cpp:272-286) at
+    t + k*dt for k = 0..horizon-1 -> (batch, QMPC_MAX_HORIZON) uint8 contact masks (input generator
+    for tests; the product's batched predictor is qmpc_predict_contact_schedule)."""
+    from .abi import QMPC_MAX_HORIZON
+    out = np.zeros((len(gait_states), QMPC_MAX_HORIZON), dtype=np.uint8)
+    for b, g in enumerate(gait_states):
+        table = GAIT_TABLES[int(g["gait"])]
+        for k in range(horizon):
+            m = 0
+            for leg in range(4):
+                ph = g["gait_phase"][leg] + g["gait_freq"] * (k * dt)
+                while ph > 1.0:
+                    ph -= 1.0
+                stance = 1
+                for sw, st in table[leg]:
+                    if ph <= sw:
+                        stance = st
+                        break
+                m |= stance << leg
+            out[b, k] = m
+    return out

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../quaternion_mpc_b200/csrc/qmpc_dense.cuh"
+#include "../../quaternion_mpc_b200/csrc/qmpc_periph.cuh"
 #ifdef QMPC_EMUL_SRB
 #include "../../quaternion_mpc_b200/csrc/qmpc_srb.cuh"
 #include "../../quaternion_mpc_b200/csrc/qmpc_coop.cuh"
@@ -27,53 +28,67 @@ static SolverOpts make_opts(const QmpcConfig& cfg) {
 }
 
 template <class M>
-static int run_dense(const QmpcConfig& cfg, const void* in, int batch, QmpcResult* out) {
+static int run_dense(const QmpcConfig& cfg, const void* in, const unsigned char* sched, int batch, QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
   size_t stride = batch;
   std::vector<double> ws(DenseLayout<M>::total(cfg.horizon) * stride);
   for (int i = 0; i < batch; ++i)
-    dense_solve_one<M>(cfg, o, (const typename M::Problem*)in, out, ws.data(), i, stride);
+    dense_solve_one<M>(cfg, o, (const typename M::Problem*)in, sched, out, ws.data(), i, stride);
   return 0;
 }
 
-extern "C" int emul_solve_dense(const QmpcConfig* cfg, const void* in, int batch, QmpcResult* out) {
+// `sched`: null, or batch x QMPC_MAX_HORIZON contact-mask bytes (include/qmpc.h QmpcContactSchedule)
+extern "C" int emul_solve_dense(const QmpcConfig* cfg, const void* in, const unsigned char* sched, int batch,
+                                QmpcResult* out) {
   switch (cfg->model) {
-    case QMPC_MODEL_QUAT_4FOOT: return run_dense<QuatModel<4>>(*cfg, in, batch, out);
-    case QMPC_MODEL_QUAT_2FOOT: return run_dense<QuatModel<2>>(*cfg, in, batch, out);
-    default: return run_dense<ConvexModel>(*cfg, in, batch, out);
+    case QMPC_MODEL_QUAT_4FOOT: return run_dense<QuatModel<4>>(*cfg, in, sched, batch, out);
+    case QMPC_MODEL_QUAT_2FOOT: return run_dense<QuatModel<2>>(*cfg, in, sched, batch, out);
+    default: return run_dense<ConvexModel>(*cfg, in, sched, batch, out);
   }
 }
 
 #ifdef QMPC_EMUL_SRB
 template <int NF>
-static int run_srb(const QmpcConfig& cfg, const QmpcProblem* in, int batch, QmpcResult* out) {
+static int run_srb(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned char* sched, int batch, QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
   size_t stride = batch;
   std::vector<double> ws(SrbLayout<NF>::total(cfg.horizon) * stride);
-  for (int i = 0; i < batch; ++i) srb_solve_one<NF>(cfg, o, in, out, ws.data(), i, stride);
+  for (int i = 0; i < batch; ++i) srb_solve_one<NF>(cfg, o, in, sched, out, ws.data(), i, stride);
   return 0;
 }
-extern "C" int emul_solve_srb(const QmpcConfig* cfg, const QmpcProblem* in, int batch, QmpcResult* out) {
-  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_srb<4>(*cfg, in, batch, out);
-  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_srb<2>(*cfg, in, batch, out);
+extern "C" int emul_solve_srb(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, int batch,
+                              QmpcResult* out) {
+  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_srb<4>(*cfg, in, sched, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_srb<2>(*cfg, in, sched, batch, out);
   return -1;
 }
 
 template <int NF, int G>
-static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, int batch, QmpcResult* out) {
+static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned char* sched, int batch, QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
   using L = CoopLayout<NF, G>;
   const bool wide = cfg.horizon <= 10;
   std::vector<double> sm(L::smem_doubles(cfg.horizon, wide)), gs(L::scratch_doubles(cfg.horizon));
-  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, out, i, sm.data(), gs.data(), 0, 0u, wide);
+  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, sched, out, i, sm.data(), gs.data(), 0, 0u, wide);
   return 0;
 }
-extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, int batch, QmpcResult* out) {
-  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_coop<4, 16>(*cfg, in, batch, out);
-  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_coop<2, 16>(*cfg, in, batch, out);
+extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, int batch,
+                               QmpcResult* out) {
+  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_coop<4, 16>(*cfg, in, sched, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_coop<2, 16>(*cfg, in, sched, batch, out);
   return -1;
 }
 extern "C" int emul_coop_smem_bytes(int nf, int horizon) {
   return 8 * (nf == 4 ? CoopLayout<4, 16>::smem_doubles(horizon, false) : CoopLayout<2, 16>::smem_doubles(horizon, false));
 }
 #endif
+
+// ---- rows N1 / N2: the streaming kernels' bodies on the host
+extern "C" int emul_predict_schedule(const QmpcConfig* cfg, const QmpcGaitState* g, int batch, QmpcContactSchedule* out) {
+  for (int i = 0; i < batch; ++i) predict_schedule_one(g[i], cfg->horizon, cfg->dt, out[i]);
+  return 0;
+}
+extern "C" int emul_leg_kinematics(const QmpcLegParams* lp, const double* q, int batch, double* foot, double* jac) {
+  for (int t = 0; t < 4 * batch; ++t) leg_fk_jac(q + 3 * t, lp->rho_fix[t & 3], lp->rho_opt[t & 3], foot + 3 * t, jac + 9 * t);
+  return 0;
+}

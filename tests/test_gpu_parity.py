@@ -195,3 +195,68 @@ def test_custom_weights_with_quaternion_entries(oracle):
     mpc = QuatMpc(max_batch=256, cfg=cfg)
     probs = random_batch(256, seed=77, gait="mixed")
     _check(_solve_dev(mpc, probs), oracle.solve_batch(cfg, probs, nthreads=NT))
+
+
+# ---------------------------------------------------------------------------- row N1: contact schedules
+def _solve_sched_dev(mpc, probs, sched):
+    import torch
+    d = mpc.grf_update_sched_device(mpc.to_device(probs), mpc.schedule_to_device(sched))
+    torch.cuda.synchronize()
+    return mpc.results_to_numpy(d)
+
+
+@pytest.mark.parametrize("N,B,seed", [(10, 4096, 0), (16, 2048, 1), (32, 256, 2)])
+def test_contact_schedule_solves_match_oracle(oracle, N, B, seed):
+    """Per-knot contact masks from the reference's gait tables (trot, trot-with-stand, crawl) at
+    random gait phases: QuatMpc on the coop kernel against the oracle's schedule extension."""
+    from quaternion_mpc_b200 import QuatMpc
+    from quaternion_mpc_b200.workloads import predict_schedule_numpy, random_gait_states
+    mpc = QuatMpc(horizon=N, max_batch=B)
+    probs = random_batch(B, seed=seed, gait="trot")
+    sched = predict_schedule_numpy(random_gait_states(B, seed=seed), N, mpc.cfg.dt)
+    res = _solve_sched_dev(mpc, probs, sched)
+    ref = oracle.solve_batch_sched(mpc.cfg, probs, sched, nthreads=NT)
+    worst = _check(res, ref, max_undetermined=2e-2)
+    # a swing foot at knot 0 must carry no force in converged solves
+    sw0 = np.stack([((sched[:, 0] >> i) & 1) == 0 for i in range(4)], 1)
+    conv = res["status"] == 0
+    if conv.any() and sw0[conv].any():
+        assert np.abs(res["grf_body"].reshape(B, 4, 3)[conv][sw0[conv]]).max() < 1e-3
+    print(f"sched N={N} B={B}: max|dGRF| = {worst:.3e} N")
+    # host entry point, ragged batch
+    r2 = mpc.grf_update_sched(probs[:77], sched[:77])
+    assert r2.tobytes() == res[:77].tobytes()
+
+
+def test_constant_schedule_bit_identical_and_flight_phase(oracle):
+    from quaternion_mpc_b200 import QuatMpc
+    B = 512
+    mpc = QuatMpc(horizon=10, max_batch=B)
+    probs = random_batch(B, seed=9, gait="mixed")
+    m = (probs["plan_contacts"] * np.array([1, 2, 4, 8])).sum(1).astype(np.uint8)
+    sched = np.repeat(m[:, None], abi.QMPC_MAX_HORIZON, 1)
+    assert _solve_sched_dev(mpc, probs, sched).tobytes() == _solve_dev(mpc, probs).tobytes()
+    # a flight phase (no contact on some knots) is well defined with a schedule: u_ref = 0 there
+    sched[:, 3:6] = 0
+    res = _solve_sched_dev(mpc, probs, sched)
+    ref = oracle.solve_batch_sched(mpc.cfg, probs, sched, nthreads=NT)
+    assert np.isfinite(res["grf_body"]).all()
+    _check(res, ref, max_undetermined=5e-2)
+
+
+def test_convex_and_cross_check_kernels_with_schedule(oracle, monkeypatch):
+    from quaternion_mpc_b200 import ConvexMpc, QuatMpc
+    from quaternion_mpc_b200.workloads import predict_schedule_numpy, random_gait_states
+    B = 256
+    cmpc = ConvexMpc(horizon=10, max_batch=B)
+    cp = random_convex_batch(B, seed=12)
+    sched = predict_schedule_numpy(random_gait_states(B, seed=12), 10, cmpc.cfg.dt)
+    res = _solve_sched_dev(cmpc, cp, sched)
+    _check(res, oracle.solve_batch_convex_sched(cmpc.cfg, cp, sched, nthreads=NT), max_undetermined=5e-2)
+    probs = random_batch(B, seed=13, gait="trot")
+    ref = oracle.solve_batch_sched(default_config(0, 10), probs, sched, nthreads=NT)
+    for k in ("dense", "srb"):
+        monkeypatch.setenv("QMPC_KERNEL", k)
+        mpc = QuatMpc(horizon=10, max_batch=B)
+        monkeypatch.delenv("QMPC_KERNEL")
+        _check(_solve_sched_dev(mpc, probs, sched), ref, max_undetermined=5e-2)
