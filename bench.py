@@ -268,7 +268,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "horizon": a.horizon, "gait": a.gait, "batch_per_gpu": B,
                    "global_batch": B * world, "iterations_max": cfg.iterations_max,
-                   "l2": "256 MiB flush between timed steps", "parallelism": f"batch-sharded x{world}"},
+                   "l2": "256 MiB flush between timed steps", "parallelism": f"batch-sharded x{world}",
+                   "kernel": mpc.describe()},
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": B * IN_BYTES,
                 "d2h_bytes_per_step": B * OUT_BYTES},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -220,6 +220,8 @@ void qmpc_destroy(QmpcHandle* h);
 int64_t     qmpc_launch_count(const QmpcHandle* h);
 const char* qmpc_last_error(const QmpcHandle* h);
 const char* qmpc_status_string(int32_t status);
+/* One-line description of the kernel and launch geometry the handle uses (for logs / bench.py). */
+int         qmpc_describe(const QmpcHandle* h, char* buf, int32_t n);
 int32_t     qmpc_abi_version(void);
 
 /* Measurement utility (not on the solve path): sustained FP64 / FP32 vector-FMA throughput of

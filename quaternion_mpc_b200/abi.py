@@ -75,7 +75,7 @@ EXPORTED_SYMBOLS = [
     "qmpc_solve_batch_host", "qmpc_solve_batch_convex_host", "qmpc_destroy", "qmpc_launch_count",
     "qmpc_last_error", "qmpc_status_string", "qmpc_abi_version", "qmpc_measure_fma_peak",
     "qmpc_predict_contact_schedule", "qmpc_solve_batch_sched", "qmpc_solve_batch_convex_sched",
-    "qmpc_solve_batch_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques",
+    "qmpc_solve_batch_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques", "qmpc_describe",
 ]
 
 _LIB = None
@@ -125,6 +125,8 @@ def load_library():
     lib.qmpc_leg_kinematics.restype = C.c_int
     lib.qmpc_joint_torques.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.qmpc_joint_torques.restype = C.c_int
+    lib.qmpc_describe.argtypes = [vp, C.c_char_p, i32]
+    lib.qmpc_describe.restype = C.c_int
     lib.qmpc_destroy.argtypes = [vp]
     lib.qmpc_destroy.restype = None
     lib.qmpc_launch_count.argtypes = [vp]

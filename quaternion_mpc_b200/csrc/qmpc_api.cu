@@ -33,7 +33,7 @@ struct QmpcHandle {
   int64_t launches;
   int kernel;          // 0 = dense (generic), 1 = srb (structured, thread per problem), 2 = coop (structured,
                        //     16 lanes per problem, shared-memory resident; default for the QUAT models)
-  int coop_grid, coop_smem_doubles, coop_wide;   // persistent launch geometry of the coop kernel
+  int coop_grid, coop_smem_doubles, coop_wide, coop_blocks_per_sm;   // persistent launch geometry of the coop kernel
   size_t coop_scratch_doubles;
   char err[256];
 };
@@ -112,32 +112,52 @@ static size_t ws_elems(const QmpcConfig& c, int kernel) {
   }
 }
 
-constexpr int kCoopG = 16, kCoopBlock = 64;
+constexpr int kCoopG = 16, kCoopBlock = QMPC_COOP_BLOCK;
 
 // persistent-kernel geometry: as many resident blocks as the device holds (or the batch needs)
 template <int NF>
 static int coop_prepare_t(QmpcHandle* h) {
   using L = CoopLayout<NF, kCoopG>;
   const int N = h->cfg.horizon;
-  // 255 registers/thread cap residency at 4 blocks (16 problems) per SM; use the "wide" shared
-  // memory layout whenever it still fits 4 blocks
-  const int groups0 = kCoopBlock / kCoopG;
-  h->coop_wide = ((size_t)groups0 * L::smem_doubles(N, true) * sizeof(double) + 1024) * 4 <= 227 * 1024 ? 1 : 0;
-  if (const char* wenv = getenv("QMPC_COOP_WIDE")) h->coop_wide = atoi(wenv) != 0;
-  h->coop_smem_doubles = L::smem_doubles(N, h->coop_wide != 0);
-  h->coop_scratch_doubles = L::scratch_doubles(N);
   const int groups = kCoopBlock / kCoopG;
-  const size_t smem_bytes = (size_t)groups * h->coop_smem_doubles * sizeof(double);
-  CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  auto smem_bytes_of = [&](int flags) {
+    return (size_t)(groups * L::smem_doubles(N, flags) + kCoopBlockShared) * sizeof(double);
+  };
+  auto blocks_per_sm = [&](int flags, int* per_sm) -> int {
+    const size_t b = smem_bytes_of(flags);
+    *per_sm = 0;
+    if (b > 227 * 1024) return QMPC_OK;
+    CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, qmpc_coop_kernel<NF, kCoopG>, kCoopBlock, b));
+    return QMPC_OK;
+  };
   CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           (int)cudaSharedmemCarveoutMaxShared));
+  // Residency is what this latency-bound kernel lives on: first find the block count the bare layout
+  // reaches (registers cap it at QMPC_COOP_MIN_BLOCKS), then keep the duals / linearisation blocks in
+  // shared memory too if that does not cost a block.
+  int best = 0, rc;
+  if ((rc = blocks_per_sm(0, &best))) return rc;
+  if (best < 1) { snprintf(h->err, sizeof(h->err), "coop kernel does not fit on an SM"); return QMPC_ERR_CUDA; }
+  int flags = 0;
+  const int order[3] = {3, 2, 1};
+  for (int c = 0; c < 3; ++c) {
+    int per = 0;
+    if ((rc = blocks_per_sm(order[c], &per))) return rc;
+    if (per >= best) { flags = order[c]; break; }
+  }
+  if (const char* wenv = getenv("QMPC_COOP_WIDE")) flags = atoi(wenv) & 3;
   int per_sm = 0, sms = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_coop_kernel<NF, kCoopG>, kCoopBlock, smem_bytes));
-  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  if ((rc = blocks_per_sm(flags, &per_sm))) return rc;
   if (per_sm < 1) { snprintf(h->err, sizeof(h->err), "coop kernel does not fit on an SM"); return QMPC_ERR_CUDA; }
+  h->coop_wide = flags;
+  h->coop_smem_doubles = L::smem_doubles(N, flags);
+  h->coop_scratch_doubles = L::scratch_doubles(N);
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
   const int need = (h->max_batch + groups - 1) / groups;
   const int resident = per_sm * sms;
   h->coop_grid = need < resident ? need : resident;
+  h->coop_blocks_per_sm = per_sm;
   h->ws_bytes = (size_t)h->coop_grid * groups * h->coop_scratch_doubles * sizeof(double);
   return QMPC_OK;
 }
@@ -208,6 +228,19 @@ extern "C" void qmpc_destroy(QmpcHandle* h) {
 extern "C" int64_t qmpc_launch_count(const QmpcHandle* h) { return h ? h->launches : 0; }
 extern "C" const char* qmpc_last_error(const QmpcHandle* h) { return h ? h->err : "null handle"; }
 
+extern "C" int qmpc_describe(const QmpcHandle* h, char* buf, int32_t n) {
+  if (!h || !buf || n < 1) return QMPC_ERR_ARG;
+  const char* names[3] = {"dense", "srb", "coop"};
+  if (h->kernel == 2)
+    snprintf(buf, n, "kernel=coop lanes_per_problem=%d block=%d blocks_per_sm=%d grid=%d smem_per_problem=%dB "
+                     "smem_residents=%s%s scratch_per_slot=%zuB",
+             kCoopG, kCoopBlock, h->coop_blocks_per_sm, h->coop_grid, h->coop_smem_doubles * 8,
+             (h->coop_wide & 1) ? "lin" : "", (h->coop_wide & 2) ? "+duals" : "", h->coop_scratch_doubles * 8);
+  else
+    snprintf(buf, n, "kernel=%s threads_per_problem=1 workspace=%zuB", names[h->kernel], h->ws_bytes);
+  return QMPC_OK;
+}
+
 template <class M>
 static int launch_dense(QmpcHandle* h, const typename M::Problem* d_in, const unsigned char* sched, int batch,
                         QmpcResult* d_out, cudaStream_t s) {
@@ -234,9 +267,15 @@ template <int NF>
 static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned char* sched, int batch, QmpcResult* d_out,
                        cudaStream_t s) {
   const int groups = kCoopBlock / kCoopG;
-  const int need = (batch + groups - 1) / groups;
-  const int grid = need < h->coop_grid ? need : h->coop_grid;
-  const size_t smem_bytes = (size_t)groups * h->coop_smem_doubles * sizeof(double);
+  // Persistent slots stride over the batch.  Balance the waves: with S resident slots a batch needs
+  // w = ceil(batch / S) passes, so launch only ceil(batch / w) slots - every slot then solves w (or
+  // w - 1) problems and no SM idles through a mostly empty last pass at full-residency latency.
+  const long long slots_max = (long long)h->coop_grid * groups;
+  const long long waves = (batch + slots_max - 1) / slots_max;
+  const long long slots = (batch + waves - 1) / waves;
+  int grid = (int)((slots + groups - 1) / groups);
+  if (grid > h->coop_grid) grid = h->coop_grid;
+  const size_t smem_bytes = (size_t)(groups * h->coop_smem_doubles + kCoopBlockShared) * sizeof(double);
   qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, sched, d_out, h->ws, batch,
                                                                    h->coop_smem_doubles, h->coop_scratch_doubles,
                                                                    h->coop_wide);

@@ -48,14 +48,22 @@ QMPC_HD inline double qmpc_rsqrt(double x) {
 
 // ---- 3x3 block kernels used by the block-per-lane phases (lane = (block row, block col)) --------
 // The row loop is deliberately NOT unrolled: the kernel is instruction-fetch bound, compact code wins.
+// Operands that are reused across the rows are read into registers ONCE, before the first store:
+// source and destination are plain pointers into the same shared-memory pool, so the compiler must
+// otherwise assume every store clobbers them and reload (measured: 7 LDS per 4 flops; now ~3).
 // dst = X(:, 3:6) * Mt + beta * X(:, 9:12)   X: 3 rows of a row-major matrix with leading dim ld
 QMPC_HD inline void blk_right(const double* X, int ld, const double* Mt, double beta, double* dst, int ldd) {
+  double m[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] = Mt[i];
 #pragma unroll 1
   for (int a = 0; a < 3; ++a) {
     const double* Xa = X + ld * a;
-#pragma unroll
-    for (int b = 0; b < 3; ++b)
-      dst[ldd * a + b] = Xa[3] * Mt[b] + Xa[4] * Mt[3 + b] + Xa[5] * Mt[6 + b] + beta * Xa[9 + b];
+    const double x3 = Xa[3], x4 = Xa[4], x5 = Xa[5], y0 = Xa[9], y1 = Xa[10], y2 = Xa[11];
+    const double r0 = x3 * m[0] + x4 * m[3] + x5 * m[6] + beta * y0;
+    const double r1 = x3 * m[1] + x4 * m[4] + x5 * m[7] + beta * y1;
+    const double r2 = x3 * m[2] + x4 * m[5] + x5 * m[8] + beta * y2;
+    dst[ldd * a] = r0; dst[ldd * a + 1] = r1; dst[ldd * a + 2] = r2;
   }
 }
 // dst = alpha * X(:, 0:3) + beta * X(:, 6:9)
@@ -63,26 +71,76 @@ QMPC_HD inline void blk_even(const double* X, int ld, double alpha, double beta,
 #pragma unroll 1
   for (int a = 0; a < 3; ++a) {
     const double* Xa = X + ld * a;
-#pragma unroll
-    for (int b = 0; b < 3; ++b) dst[ldd * a + b] = alpha * Xa[b] + beta * Xa[6 + b];
+    const double x0 = Xa[0], x1 = Xa[1], x2 = Xa[2], y0 = Xa[6], y1 = Xa[7], y2 = Xa[8];
+    dst[ldd * a] = alpha * x0 + beta * y0;
+    dst[ldd * a + 1] = alpha * x1 + beta * y1;
+    dst[ldd * a + 2] = alpha * x2 + beta * y2;
   }
 }
 // dst = Mt^T * Y(3:6, :) + beta * Y(9:12, :)   Y: 3 columns (starting at Y) of a row-major matrix
 QMPC_HD inline void blk_left(const double* Y, int ld, const double* Mt, double beta, double* dst, int ldd) {
-#pragma unroll 1
-  for (int a = 0; a < 3; ++a) {
+  double m[9], y[9];
 #pragma unroll
-    for (int b = 0; b < 3; ++b)
-      dst[ldd * a + b] = Mt[a] * Y[ld * 3 + b] + Mt[3 + a] * Y[ld * 4 + b] + Mt[6 + a] * Y[ld * 5 + b] +
-                         beta * Y[ld * (9 + a) + b];
+  for (int i = 0; i < 9; ++i) m[i] = Mt[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) y[3 * i + b] = Y[ld * (3 + i) + b];
+#pragma unroll   // unrolled: m[a] must stay a compile-time register index
+  for (int a = 0; a < 3; ++a) {
+    const double* Ya = Y + ld * (9 + a);
+    const double z0 = Ya[0], z1 = Ya[1], z2 = Ya[2];
+    const double m0 = m[a], m1 = m[3 + a], m2 = m[6 + a];
+    const double r0 = m0 * y[0] + m1 * y[3] + m2 * y[6] + beta * z0;
+    const double r1 = m0 * y[1] + m1 * y[4] + m2 * y[7] + beta * z1;
+    const double r2 = m0 * y[2] + m1 * y[5] + m2 * y[8] + beta * z2;
+    dst[ldd * a] = r0; dst[ldd * a + 1] = r1; dst[ldd * a + 2] = r2;
   }
 }
 // dst = alpha * Y(0:3, :) + beta * Y(6:9, :)
 QMPC_HD inline void blk_evenT(const double* Y, int ld, double alpha, double beta, double* dst, int ldd) {
 #pragma unroll 1
   for (int a = 0; a < 3; ++a) {
+    const double x0 = Y[ld * a], x1 = Y[ld * a + 1], x2 = Y[ld * a + 2];
+    const double y0 = Y[ld * (6 + a)], y1 = Y[ld * (6 + a) + 1], y2 = Y[ld * (6 + a) + 2];
+    dst[ldd * a] = alpha * x0 + beta * y0;
+    dst[ldd * a + 1] = alpha * x1 + beta * y1;
+    dst[ldd * a + 2] = alpha * x2 + beta * y2;
+  }
+}
+// dst = s * T(0:3, :) + Mt^T * T(3:6, :)   (rows of T have leading dim ld); W^T-type products of phases D / E
+QMPC_HD inline void blk_wt(const double* T, int ld, double s, const double* Mt, double* dst, int ldd,
+                           const double* add /* nullable 3x3 row-major, added to the result */) {
+  double m[9], y[9];
 #pragma unroll
-    for (int b = 0; b < 3; ++b) dst[ldd * a + b] = alpha * Y[ld * a + b] + beta * Y[ld * (6 + a) + b];
+  for (int i = 0; i < 9; ++i) m[i] = Mt[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) y[3 * i + b] = T[ld * (3 + i) + b];
+#pragma unroll   // unrolled: m[a] must stay a compile-time register index
+  for (int a = 0; a < 3; ++a) {
+    const double t0 = T[ld * a], t1 = T[ld * a + 1], t2 = T[ld * a + 2];
+    const double m0 = m[a], m1 = m[3 + a], m2 = m[6 + a];
+    double r0 = s * t0 + m0 * y[0] + m1 * y[3] + m2 * y[6];
+    double r1 = s * t1 + m0 * y[1] + m1 * y[4] + m2 * y[7];
+    double r2 = s * t2 + m0 * y[2] + m1 * y[5] + m2 * y[8];
+    if (add) { r0 += add[3 * a]; r1 += add[3 * a + 1]; r2 += add[3 * a + 2]; }
+    dst[ldd * a] = r0; dst[ldd * a + 1] = r1; dst[ldd * a + 2] = r2;
+  }
+}
+// dst = s * S(:, 0:3) + S(:, 3:6) * Mt   (3 rows of S with leading dim ld): the S W product of phase D
+QMPC_HD inline void blk_w(const double* S, int ld, double s, const double* Mt, double* dst, int ldd) {
+  double m[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] = Mt[i];
+#pragma unroll 1
+  for (int a = 0; a < 3; ++a) {
+    const double* Sa = S + ld * a;
+    const double t0 = Sa[0], t1 = Sa[1], t2 = Sa[2], x3 = Sa[3], x4 = Sa[4], x5 = Sa[5];
+    dst[ldd * a] = s * t0 + x3 * m[0] + x4 * m[3] + x5 * m[6];
+    dst[ldd * a + 1] = s * t1 + x3 * m[1] + x4 * m[4] + x5 * m[7];
+    dst[ldd * a + 2] = s * t2 + x3 * m[2] + x4 * m[5] + x5 * m[8];
   }
 }
 QMPC_HD inline void blk_store(double* dst, int ld, const double* v) {
@@ -92,29 +150,37 @@ QMPC_HD inline void blk_store(double* dst, int ld, const double* v) {
     for (int b = 0; b < 3; ++b) dst[ld * a + b] = v[3 * a + b];
 }
 
+constexpr int kCoopBlockShared = 26;   // doubles at the head of the block's shared memory: q[13], r[12], pad
+
+template <int V>
+struct IntTag { static constexpr int value = V; };
+
 template <int NF, int G>
 struct CoopLayout {
   static constexpr int NU = 3 * NF, NC = 6 * NF;
   static constexpr int kModel = (int)((sizeof(QuatModel<NF>) + 7) / 8);
   // ---- shared memory (doubles) per problem
+#if !defined(QMPC_COOP_NO_CHOL_REG) || (defined(__CUDACC__) && !defined(QMPC_COOP_NO_CHOL_SHFL))
+  static constexpr int kVec = 156;   // the register/shuffle Cholesky needs no column-exchange buffer (cv::tcol)
+#else
   static constexpr int kVec = 180;
+#endif
   QMPC_HD static int sX(int N) { return kModel; }
   QMPC_HD static int sU(int N) { return sX(N) + (N + 1) * 13; }
-  QMPC_HD static int sP(int N) { return sU(N) + N * NU; }
+  QMPC_HD static int sP(int N) { return (sU(N) + N * NU + 1) / 2 * 2; }   // 16-byte aligned: cp.async target
   QMPC_HD static int sPA(int N) { return sP(N) + 144; }    // PA, later Quu / its Cholesky factor
   QMPC_HD static int sT(int N) { return sPA(N) + 144; }
   QMPC_HD static int sPM(int N) { return sT(N) + 72; }     // PM, later SW
   QMPC_HD static int sS(int N) { return sPM(N) + 72; }
   QMPC_HD static int sQux(int N) { return sS(N) + 36; }    // Qux, later V = L^-1 Qux
   QMPC_HD static int sVec(int N) { return sQux(N) + NU * 12; }
-  QMPC_HD static int sRed(int N) { return sVec(N) + kVec; }
-  QMPC_HD static int sLin(int N) { return sRed(N) + 2 * G; }
-  // "wide" layout: the per-knot linearisation blocks (27 N) and the duals (NC N) also live in
-  // shared memory (used when it does not cost residency, i.e. short horizons); otherwise they stay
-  // in the L2-resident scratch.  Same code either way - only the pointers differ.
+  QMPC_HD static int sLin(int N) { return sVec(N) + kVec; }
+  // Optional residents (`flags`): bit 0 = the per-knot linearisation blocks (27 N), bit 1 = the duals
+  // (NC N) also live in shared memory - used when they do not cost residency (short horizons);
+  // otherwise they stay in the L2-resident scratch.  Same code either way, only the pointers differ.
   QMPC_HD static int sLinAll(int N) { return (sLin(N) + 27 + 1) / 2 * 2; }
-  QMPC_HD static int sMu(int N) { return sLinAll(N) + 27 * N; }
-  QMPC_HD static int smem_doubles(int N, bool wide) { return wide ? (sMu(N) + NC * N + 1) / 2 * 2 : sLinAll(N); }
+  QMPC_HD static int sMu(int N, int flags) { return sLinAll(N) + ((flags & 1) ? 27 * N : 0); }
+  QMPC_HD static int smem_doubles(int N, int flags) { return (sMu(N, flags) + ((flags & 2) ? NC * N : 0) + 1) / 2 * 2; }
   // ---- global scratch (doubles) per slot
   QMPC_HD static size_t gK(int N) { return 0; }
   QMPC_HD static size_t gd(int N) { return gK(N) + (size_t)N * NU * 12; }
@@ -156,14 +222,6 @@ QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, int k, int N, 
   }
 }
 
-// cost Hessian entry (a,b) in error coordinates given the attitude block Hphi (3x3)
-QMPC_HD inline double lxx_entry(const QmpcConfig& cfg, const double* Hphi, int a, int b) {
-  const int ab = a / 3, bb = b / 3;
-  if (ab == 1 && bb == 1) return Hphi[3 * (a - 3) + (b - 3)];
-  if (a != b) return 0.0;
-  return a < 3 ? cfg.q_weights[a] : cfg.q_weights[a + 1];
-}
-
 // attitude block of the cost Hessian: G^T diag(Qq) G + hphi I
 QMPC_HD inline void hphi_block(const QmpcConfig& cfg, const double* x, double hphi, double* H) {
   double Gq[12];
@@ -177,7 +235,7 @@ QMPC_HD inline void hphi_block(const QmpcConfig& cfg, const double* x, double hp
 }
 
 // 3x3 block (br, bc) of the cost Hessian in error coordinates
-QMPC_HD inline void lxx_block(const QmpcConfig& cfg, const double* Hphi, int br, int bc, double* out) {
+QMPC_HD inline void lxx_block(const double* wq, const double* Hphi, int br, int bc, double* out) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) out[i] = 0.0;
   if (br != bc) return;
@@ -186,7 +244,7 @@ QMPC_HD inline void lxx_block(const QmpcConfig& cfg, const double* Hphi, int br,
     for (int i = 0; i < 9; ++i) out[i] = Hphi[i];
   } else {
     const int q0 = br == 0 ? 0 : (br == 2 ? 7 : 10);
-    out[0] = cfg.q_weights[q0]; out[4] = cfg.q_weights[q0 + 1]; out[8] = cfg.q_weights[q0 + 2];
+    out[0] = wq[q0]; out[4] = wq[q0 + 1]; out[8] = wq[q0 + 2];
   }
 }
 
@@ -199,10 +257,11 @@ QMPC_HD inline void lxx_block(const QmpcConfig& cfg, const double* Hphi, int br,
 //           that the accepted one is simply copied back - no second roll-out; returns merit / violation
 //   mode 2: (unused by the kernel, kept for the host emulation tests) accepted step in place
 template <int NF>
-QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig& cfg, int N, float h, double* X,
+QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig& cfg, const double* wr, int N, float h, double* X,
                                         double* U, double* DX, const double* gK, const double* gd,
                                         const double* gmu, double rho, double alpha, int mode, double* Jout,
-                                        double* violout, double* gTX, double* gTU, int tl, int tstride) {
+                                        double* violout, double* gTX, double* gTU, int tl, int tstride,
+                                        double* kstage, unsigned lane_mask) {
   // Compact by construction (instruction-fetch bound otherwise): the input never
   // exists as an array - each foot's force is formed, costed, cone-checked and folded into the net
   // wrench inside one 4-trip loop; the wrench drives both midpoint evaluations.  Accumulation
@@ -213,6 +272,25 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
   double x[NX], J = 0, vl = 0;
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = X[i];
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_KSTAGE)
+  // Mode 1 runs on all `tstride` lanes of the problem in lock-step: the gain matrix of knot k+1 is
+  // copied (cp.async, 16 bytes per request, the lanes split the rows) from the L2-resident scratch
+  // into a double buffer in shared memory while knot k is being computed, so the 72 broadcast reads
+  // of K_k per lane are shared-memory reads instead of L2 round trips.
+  constexpr int kChunks = NU * 12 / 2;
+  auto stage_gain = [&](int k) {
+    const double* src = gK + (size_t)k * NU * 12;
+    double* dst = kstage + (k & 1) * NU * 12;
+    for (int c = tl; c < kChunks; c += tstride) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 2 * c) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (mode == 1) stage_gain(0);
+#else
+  (void)kstage; (void)lane_mask;
+#endif
 #pragma unroll 1
   for (int k = 0; k <= N; ++k) {
     double dx[NE];
@@ -245,7 +323,16 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
     }
     // ---- per foot: force, input cost, cone rows / AL merit, wrench
     double mom0 = 0, mom1 = 0, mom2 = 0, fs0 = 0, fs1 = 0, fs2 = 0, acc = 0;
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_KSTAGE)
+    const double* Kk = mode == 1 ? kstage + (k & 1) * NU * 12 : gK;
+    if (mode == 1) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp(lane_mask);              // K_k visible to all lanes; everyone is done with K_{k-1}
+      if (k + 1 < N) stage_gain(k + 1);
+    }
+#else
     const double* Kk = gK + (size_t)k * NU * 12;
+#endif
 #pragma unroll 1
     for (int f = 0; f < NF; ++f) {
       double u0, u1, u2;
@@ -256,13 +343,19 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
         const double* K0 = Kk + (3 * f) * 12;
 #if !defined(QMPC_COOP_NO_K128) && defined(__CUDA_ARCH__)
         {   // three 96-byte gain rows as 18 x 16-byte loads (rows are 16-byte aligned in the scratch)
+#ifndef QMPC_COOP_NO_KSTAGE
+          const unsigned ks = (unsigned)__cvta_generic_to_shared(K0);
+          auto ldk = [&](int l) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ks + 16u * l)); return v; };
+#else
           const double2* K2 = reinterpret_cast<const double2*>(K0);
+          auto ldk = [&](int l) { return K2[l]; };
+#endif
 #pragma unroll
-          for (int l = 0; l < 6; ++l) { const double2 v = K2[l]; t0 += v.x * dx[2 * l]; t0 += v.y * dx[2 * l + 1]; }
+          for (int l = 0; l < 6; ++l) { const double2 v = ldk(l); t0 += v.x * dx[2 * l]; t0 += v.y * dx[2 * l + 1]; }
 #pragma unroll
-          for (int l = 0; l < 6; ++l) { const double2 v = K2[6 + l]; t1 += v.x * dx[2 * l]; t1 += v.y * dx[2 * l + 1]; }
+          for (int l = 0; l < 6; ++l) { const double2 v = ldk(6 + l); t1 += v.x * dx[2 * l]; t1 += v.y * dx[2 * l + 1]; }
 #pragma unroll
-          for (int l = 0; l < 6; ++l) { const double2 v = K2[12 + l]; t2 += v.x * dx[2 * l]; t2 += v.y * dx[2 * l + 1]; }
+          for (int l = 0; l < 6; ++l) { const double2 v = ldk(12 + l); t2 += v.x * dx[2 * l]; t2 += v.y * dx[2 * l + 1]; }
         }
 #else
 #pragma unroll
@@ -283,9 +376,9 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
       }
       if (mode != 2) {
         const double d0 = u0, d1 = u1, d2 = u2 - m.urefz(k, f);   // u_ref = (0, 0, weight share)
-        Jl += 0.5 * cfg.r_weights[3 * f] * d0 * d0;
-        Jl += 0.5 * cfg.r_weights[3 * f + 1] * d1 * d1;
-        Jl += 0.5 * cfg.r_weights[3 * f + 2] * d2 * d2;
+        Jl += 0.5 * wr[3 * f] * d0 * d0;
+        Jl += 0.5 * wr[3 * f + 1] * d1 * d1;
+        Jl += 0.5 * wr[3 * f + 2] * d2 * d2;
         const double* mu_f = gmu + k * NC + 6 * f;
         const double fzc_f = m.fzc(k, f);
 #pragma unroll
@@ -350,11 +443,16 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
 template <int NF, int G>
 QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in,
                             const unsigned char* sched, QmpcResult* out,
-                            int pid, double* sm, double* gs, int lane_id, unsigned lane_mask, bool wide) {
+                            int pid, double* sm, double* gs, int lane_id, unsigned lane_mask, int flags,
+                            const double* wts) {
   using M = QuatModel<NF>;
   using L = CoopLayout<NF, G>;
   constexpr int NX = 13, NE = 12, NU = M::NU, NC = M::NC;
   (void)lane_id; (void)lane_mask;
+  // weights with run-time indices come from `wts` (q[13], r[12]): a block-shared copy in shared memory on
+  // the device - an indexed read of the kernel parameter bank is an LDC that stalls like a global load
+  const double* wq = wts;
+  const double* wr = wts + 13;
   const int N = o.N;
   const float h = o.h;
   const double hd = (double)h, hh = (double)(h / 2), c1 = hd * hh;
@@ -373,14 +471,15 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   double* S = sm + L::sS(N);
   double* Qux = sm + L::sQux(N);
   double* vec = sm + L::sVec(N);
-  double* red = sm + L::sRed(N);
+  double* red = T;   // 2 G reduction slots; only used outside the backward pass, where T is dead
+  static_assert(2 * G <= 72, "reduction slots alias T");
   double* lin = sm + L::sLin(N);
   double* gK = gs + L::gK(N);
   double* gd = gs + L::gd(N);
   double* gP = gs + L::gP(N);
   double* gpv = gs + L::gpv(N);
-  double* gmu = wide ? sm + L::sMu(N) : gs + L::gmu(N);
-  double* glin = wide ? sm + L::sLinAll(N) : gs + L::glin(N);
+  double* gmu = (flags & 2) ? sm + L::sMu(N, flags) : gs + L::gmu(N);
+  double* glin = (flags & 1) ? sm + L::sLinAll(N) : gs + L::glin(N);
   double* scal = vec + cv::scal;
 
   // ------------------------------------------------------------------ set-up + nominal roll-out
@@ -394,7 +493,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   COOP_SYNC();
   double rho = o.penalty_initial;
   COOP_PHASE {
-    if (lane == 0) coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3], gTX, gTU, 0, G);
+    if (lane == 0) coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3], gTX, gTU, 0, G, P, lane_mask);
   }
   COOP_SYNC();
   double phi = scal[2], viol = scal[3];
@@ -449,7 +548,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
               if (v > rx) rx = v;
             }
             for (int a = 0; a < NU; ++a) {
-              double v = fabs(cfg.r_weights[a] * (u[a] - m.uref_at(k, a)) + gu[a] + Bty[a]);
+              double v = fabs(wr[a] * (u[a] - m.uref_at(k, a)) + gu[a] + Bty[a]);
               if (v > ru) ru = v;
             }
           }
@@ -516,7 +615,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     COOP_PHASE {
       const int br = lane >> 2, bc = lane & 3;
       double o[9];
-      lxx_block(cfg, vec + cv::Hphi, br, bc, o);
+      lxx_block(wq, vec + cv::Hphi, br, bc, o);
       blk_store(Pc + 36 * br + 3 * bc, 12, o);
       blk_store(gP + (size_t)N * 144 + 36 * br + 3 * bc, 12, o);
       if (lane < 12) gpv[N * 12 + lane] = vec[cv::pv + lane];
@@ -545,12 +644,12 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
               hb[6] += rho * j2 * j0; hb[7] += rho * j2 * j1; hb[8] += rho * j2 * j2;
             }
           }
-          hb[0] += cfg.r_weights[3 * f]; hb[4] += cfg.r_weights[3 * f + 1]; hb[8] += cfg.r_weights[3 * f + 2];
+          hb[0] += wr[3 * f]; hb[4] += wr[3 * f + 1]; hb[8] += wr[3 * f + 2];
 #pragma unroll
           for (int a = 0; a < 9; ++a) vec[cv::Dblk + 9 * f + a] = hb[a];
-          vec[cv::g + 3 * f] = cfg.r_weights[3 * f] * u[0] + g0;
-          vec[cv::g + 3 * f + 1] = cfg.r_weights[3 * f + 1] * u[1] + g1;
-          vec[cv::g + 3 * f + 2] = cfg.r_weights[3 * f + 2] * (u[2] - m.urefz(k, f)) + g2;
+          vec[cv::g + 3 * f] = wr[3 * f] * u[0] + g0;
+          vec[cv::g + 3 * f + 1] = wr[3 * f + 1] * u[1] + g1;
+          vec[cv::g + 3 * f + 2] = wr[3 * f + 2] * (u[2] - m.urefz(k, f)) + g2;
         }
         if (lane == NF) {
           double hphi;
@@ -604,7 +703,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
               for (int j = 0; j < 3; ++j) Pd[12 * i + j] += vec[cv::Hphi + 3 * i + j];
           } else {
             const int q0 = br == 0 ? 0 : (br == 2 ? 7 : 10);
-            Pd[0] += cfg.q_weights[q0]; Pd[13] += cfg.q_weights[q0 + 1]; Pd[26] += cfg.q_weights[q0 + 2];
+            Pd[0] += wq[q0]; Pd[13] += wq[q0 + 1]; Pd[26] += wq[q0 + 2];
           }
         }
         if (br < 2) {
@@ -623,26 +722,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       // ---- phase D: Qux = W^T T (NF x 4 blocks), SW = S W (2 x NF blocks), Qu = g + W^T s
       COOP_PHASE {
         const int br = lane >> 2, bc = lane & 3;
-        if (br < NF) {
-          const double* IS = m.IS + 9 * br;
-          const double* Tc = T + 3 * bc;
-          double* Qd = Qux + 36 * br + 3 * bc;
-#pragma unroll 1
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b)
-              Qd[12 * a + b] = m.inv_mass * Tc[12 * a + b] + IS[a] * Tc[36 + b] + IS[3 + a] * Tc[48 + b] + IS[6 + a] * Tc[60 + b];
-        }
-        if (br < 2 && bc < NF) {
-          const double* IS = m.IS + 9 * bc;
-          const double* Sr = S + 18 * br;
-          double* Wd = SW + 3 * NU * br + 3 * bc;
-#pragma unroll 1
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int b = 0; b < 3; ++b)
-              Wd[NU * i + b] = m.inv_mass * Sr[6 * i + b] + Sr[6 * i + 3] * IS[b] + Sr[6 * i + 4] * IS[3 + b] + Sr[6 * i + 5] * IS[6 + b];
-        }
+        if (br < NF) blk_wt(T + 3 * bc, 12, m.inv_mass, m.IS + 9 * br, Qux + 36 * br + 3 * bc, 12, nullptr);
+        if (br < 2 && bc < NF) blk_w(S + 18 * br, 6, m.inv_mass, m.IS + 9 * bc, SW + 3 * NU * br + 3 * bc, NU);
         if (lane < NU) {
           const int f = lane / 3, a = lane % 3;
           const double* IS = m.IS + 9 * f;
@@ -655,22 +736,125 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       double* Quu = Pw;
       COOP_PHASE {
         const int br = lane >> 2, bc = lane & 3;
-        if (br < NF && bc < NF) {
-          const double* IS = m.IS + 9 * br;
-          const double* Wc = SW + 3 * bc;
-          double* Qd = Quu + 3 * NU * br + 3 * bc;
-#pragma unroll 1
-          for (int a = 0; a < 3; ++a)
+        if (br < NF && bc < NF)
+          blk_wt(SW + 3 * bc, NU, m.inv_mass, m.IS + 9 * br, Quu + 3 * NU * br + 3 * bc, NU,
+                 br == bc ? vec + cv::Dblk + 9 * br : nullptr);
+      }
+      COOP_SYNC();
+#ifndef QMPC_COOP_NO_CHOL_REG
+      // ---- Cholesky + both triangular solves, fused, per lane, entirely in registers.  Every lane
+      //      factors the 12x12 Quu redundantly (the kernel is latency- and shared-memory-bound, not
+      //      FLOP-bound: 16 lanes doing the same 364 flops cost the same issue slots as one) and then
+      //      solves for its own right-hand side (column `lane` of Qux; lane 12: Qu) with L still in
+      //      registers: no column exchange, no barrier, no shared-memory traffic for L (this replaced
+      //      ~300 LDS/STS and 24 barriers per knot).  Straight-line code; a non-positive pivot poisons
+      //      the lane's result and is reported through `ok`.  Same operation order per entry as the
+      //      variants below, so the results are bit-identical.
+      COOP_PHASE {
+        const int c = lane < 12 ? lane : 12;   // lanes 13..15 shadow the Qu column and store nothing
+        constexpr int NT = NU * (NU + 1) / 2;
+#define QMPC_TRI(i_, l_) ((i_) * ((i_) + 1) / 2 + (l_))
+        double Lr[NT], rd[NU], rhs[NU];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              double v = m.inv_mass * Wc[NU * a + j] + IS[a] * Wc[NU * 3 + j] + IS[3 + a] * Wc[NU * 4 + j] + IS[6 + a] * Wc[NU * 5 + j];
-              if (br == bc) v += vec[cv::Dblk + 9 * br + 3 * a + j];
-              Qd[NU * a + j] = v;
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+          for (int l = 0; l <= i; ++l) Lr[QMPC_TRI(i, l)] = Quu[NU * i + l];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) rhs[i] = c < 12 ? Qux[12 * i + c] : vec[cv::Qu + i];
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          const double sjj = Lr[QMPC_TRI(j, j)];
+          ok = ok && (sjj > 0.0);
+          const double rdg = qmpc_rsqrt(sjj);
+          rd[j] = rdg;
+#pragma unroll
+          for (int i = j + 1; i < NU; ++i) Lr[QMPC_TRI(i, j)] *= rdg;
+#pragma unroll
+          for (int i = j + 1; i < NU; ++i)
+#pragma unroll
+            for (int l = j + 1; l <= i; ++l) Lr[QMPC_TRI(i, l)] -= Lr[QMPC_TRI(i, j)] * Lr[QMPC_TRI(l, j)];
+        }
+        if (!ok) bp_ok = false;
+        // forward substitution, column oriented: after y_i is final every remaining entry updates independently
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          rhs[i] = rhs[i] * rd[i];
+#pragma unroll
+          for (int l = i + 1; l < NU; ++l) rhs[l] -= Lr[QMPC_TRI(l, i)] * rhs[i];
+        }
+        if (ok && lane <= 12) {
+          if (c < 12) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) Qux[12 * i + c] = rhs[i];   // V = L^-1 Qux
+          } else {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) vec[cv::vu + i] = rhs[i];
+          }
+        }
+#pragma unroll
+        for (int i = NU - 1; i >= 0; --i) {
+          rhs[i] = rhs[i] * rd[i];
+#pragma unroll
+          for (int l = 0; l < i; ++l) rhs[l] -= Lr[QMPC_TRI(i, l)] * rhs[i];
+        }
+#undef QMPC_TRI
+        if (ok && lane <= 12) {
+          if (c < 12) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) gK[((size_t)k * NU + i) * 12 + c] = -rhs[i];
+          } else {
+            double t = 0;
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+              gd[k * NU + i] = -rhs[i];
+              t += vec[cv::Qu + i] * (-rhs[i]);
             }
+            scal[0] += t;
+          }
         }
       }
       COOP_SYNC();
-      // ---- Cholesky of Quu (left-looking, one row per lane).  One sync per column: the column is
+      if (!bp_ok) break;
+#else
+      // ---- Cholesky of Quu.  Device: lane i keeps row i in registers, right-looking, the pivot and the
+      //      finished column travel by warp shuffles: 12 dependent steps of (shuffle, rsqrt, mul,
+      //      shuffle, fma), no shared-memory round trips and no barriers inside the factorisation.
+      //      Every entry sees exactly the same sequence of fused multiply-adds as in the left-looking
+      //      shared-memory variant below (kept for the host emulation), so the two are bit-identical.
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_CHOL_SHFL)
+      {
+        // a[l] is the current value of entry (row, j + l): the register window slides with the
+        // column, so the loop body has fixed register indices and stays ROLLED (the kernel is
+        // instruction-cache bound: the fully unrolled form cost 40 KB of SASS and ran slower).
+        const int row = lane_id < NU ? lane_id : NU - 1;   // spare lanes shadow the last row
+        double a[NU];
+#pragma unroll
+        for (int l = 0; l < NU; ++l) a[l] = Quu[NU * row + l];
+        auto column = [&](int j, auto lmax_tag) {
+          constexpr int LMAX = decltype(lmax_tag)::value;
+          const double sjj = __shfl_sync(lane_mask, a[0], j, G);
+          if (!(sjj > 0.0)) return false;                   // uniform over the problem's lanes
+          const double rdg = qmpc_rsqrt(sjj);
+          const double lj = (row == j) ? sjj * rdg : a[0] * rdg;   // L(row, j)
+          if (lane_id < NU && j <= lane_id) Quu[NU * lane_id + j] = lj;
+          if (lane_id == j) vec[cv::rdiag + j] = rdg;
+#pragma unroll
+          for (int l = 1; l <= LMAX; ++l) {
+            const double cl = __shfl_sync(lane_mask, lj, j + l, G);   // L(j + l, j); wraps harmlessly past NU
+            a[l - 1] = a[l] - lj * cl;
+          }
+          return true;
+        };
+        constexpr int H = NU / 2;
+#pragma unroll 1
+        for (int j = 0; j < H && bp_ok; ++j) bp_ok = column(j, IntTag<NU - 1>{});
+#pragma unroll 1
+        for (int j = H; j < NU && bp_ok; ++j) bp_ok = column(j, IntTag<NU - 1 - H>{});
+        COOP_SYNC();
+      }
+#else
+      // (left-looking, one row per lane).  One sync per column: the column is
       //      exchanged through a double-buffered tcol, and the only not-yet-visible factor entry a
       //      lane needs, L(j, j-1), is recomputed from the previous tcol (bit-identical to what the
       //      owning lane stored).  1/sqrt via one rsqrt instead of sqrt + reciprocal.
@@ -715,6 +899,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         }
         COOP_SYNC();
       }
+#endif
       if (!bp_ok) break;
       // ---- solves: lane c <- right-hand side c (12 columns of Qux, then Qu); register-resident,
       //      fully unrolled (the rolled shared-memory variant was measured slower: +40 % instructions)
@@ -759,6 +944,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         }
       }
       COOP_SYNC();
+#endif
       // ---- phase F: new P = sym(P) - V^T V (16 blocks, written to the work buffer: no race with the
       //      transposed reads of Pc), pv <- Qx - V^T vu ; then swap the two buffers
       COOP_PHASE {
@@ -803,13 +989,12 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     for (int round = 0; round * G < o.ls_iters_max && acc_j < 0; ++round) {
       COOP_PHASE {
         const int j = round * G + lane;
-        double J = NAN, vl = 0;
-        if (j < o.ls_iters_max) {
-          double alpha = 1.0;
-          for (int q = 0; q < j; ++q) alpha *= o.ls_decrease;
-          coop_rollout<NF>(m, cfg, N, h, X, U, DX, gK, gd, gmu, rho, alpha, 1, &J, &vl, gTX, gTU, lane, G);
-        }
-        red[lane] = J;
+        // every lane rolls out (lanes past ls_iters_max too: the roll-out stages the gains
+        // cooperatively); their result is discarded below
+        double J = NAN, vl = 0, alpha = 1.0;
+        for (int q = 0; q < j; ++q) alpha *= o.ls_decrease;
+        coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, alpha, 1, &J, &vl, gTX, gTU, lane, G, P, lane_mask);
+        red[lane] = j < o.ls_iters_max ? J : NAN;
         red[G + lane] = vl;
       }
       COOP_SYNC();
@@ -884,22 +1069,28 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 #ifndef QMPC_COOP_MIN_BLOCKS
 #define QMPC_COOP_MIN_BLOCKS 4
 #endif
+#ifndef QMPC_COOP_BLOCK
+#define QMPC_COOP_BLOCK 64
+#endif
 template <int NF, int G>
-__global__ void __launch_bounds__(64, QMPC_COOP_MIN_BLOCKS)
+__global__ void __launch_bounds__(QMPC_COOP_BLOCK, QMPC_COOP_MIN_BLOCKS)
 qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in,
                  const unsigned char* __restrict__ sched, QmpcResult* __restrict__ out,
                  double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot, int wide) {
-  extern __shared__ double smem_pool[];
+  extern __shared__ __align__(16) double smem_pool[];
+  if (threadIdx.x < 13) smem_pool[threadIdx.x] = cfg.q_weights[threadIdx.x];
+  else if (threadIdx.x < 25) smem_pool[threadIdx.x] = cfg.r_weights[threadIdx.x - 13];
+  __syncthreads();
   const int groups_per_block = blockDim.x / G;
   const int group = threadIdx.x / G;
   const int lane_id = threadIdx.x % G;
   const int slot = blockIdx.x * groups_per_block + group;
   const int nslots = gridDim.x * groups_per_block;
   const unsigned lane_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
-  double* sm = smem_pool + (size_t)group * smem_per_problem;
+  double* sm = smem_pool + kCoopBlockShared + (size_t)group * smem_per_problem;
   double* gs = scratch + (size_t)slot * scratch_per_slot;
   for (int pid = slot; pid < batch; pid += nslots) {
-    coop_solve_one<NF, G>(cfg, o, in, sched, out, pid, sm, gs, lane_id, lane_mask, wide != 0);
+    coop_solve_one<NF, G>(cfg, o, in, sched, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
   }
 }
 #endif

@@ -172,6 +172,11 @@ class _BatchedMpc:
         """Same with raw (e.g. pinned) host pointers — used by bench.py's e2e leg."""
         self._check(getattr(self.lib, self._solve_host)(self._h, in_ptr, batch, out_ptr))
 
+    def describe(self):
+        buf = C.create_string_buffer(512)
+        self._check(self.lib.qmpc_describe(self._h, buf, 512))
+        return buf.value.decode()
+
     @property
     def launch_count(self):
         return int(self.lib.qmpc_launch_count(self._h))

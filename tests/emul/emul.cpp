@@ -67,9 +67,12 @@ template <int NF, int G>
 static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned char* sched, int batch, QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
   using L = CoopLayout<NF, G>;
-  const bool wide = cfg.horizon <= 10;
+  const int wide = cfg.horizon <= 10 ? 3 : (cfg.horizon <= 16 ? 2 : 0);
   std::vector<double> sm(L::smem_doubles(cfg.horizon, wide)), gs(L::scratch_doubles(cfg.horizon));
-  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, sched, out, i, sm.data(), gs.data(), 0, 0u, wide);
+  double wts[26];
+  for (int i = 0; i < 13; ++i) wts[i] = cfg.q_weights[i];
+  for (int i = 0; i < 12; ++i) wts[13 + i] = cfg.r_weights[i];
+  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, sched, out, i, sm.data(), gs.data(), 0, 0u, wide, wts);
   return 0;
 }
 extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, int batch,
@@ -79,7 +82,7 @@ extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, con
   return -1;
 }
 extern "C" int emul_coop_smem_bytes(int nf, int horizon) {
-  return 8 * (nf == 4 ? CoopLayout<4, 16>::smem_doubles(horizon, false) : CoopLayout<2, 16>::smem_doubles(horizon, false));
+  return 8 * (nf == 4 ? CoopLayout<4, 16>::smem_doubles(horizon, 0) : CoopLayout<2, 16>::smem_doubles(horizon, 0));
 }
 #endif
 
