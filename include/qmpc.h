@@ -214,6 +214,25 @@ int qmpc_joint_torques(QmpcHandle* h, const QmpcResult* d_results, const double*
                        const int32_t* d_plan_contacts, int32_t movement_mode, int32_t batch, double* d_tau,
                        void* cuda_stream);
 
+/* ---- N4: warm start (trajectory shift) ------------------------------------------------------------
+ * legged_ctrl builds a fresh ALTROSolver every tick and starts from u_ref (QuatMpc.cpp:218,253); the
+ * ALTRO API offers ShiftTrajectory() for receding-horizon use (pattern shown in
+ * test_altro/TestBicycle.cpp:181-199) which the controller never calls.  This extension keeps the
+ * previous input trajectory per problem: when `valid`, knot k starts from u_prev[min(k + 1, N - 1)]
+ * (one-knot shift, last input repeated) instead of u_ref; duals and penalty start fresh as in the
+ * reference.  After the solve the buffer holds the new trajectory (valid = 0 after a non-finite
+ * solve).  With valid = 0 the result is bit-identical to the plain entry points. */
+typedef struct QmpcWarmStart {
+  double  u[QMPC_MAX_HORIZON][12];  /* input trajectory of the last solve (body-frame GRFs per knot) */
+  int32_t valid;
+  int32_t pad_;
+} QmpcWarmStart;
+
+/* qmpc_solve_batch_sched with a per-problem warm-start buffer (device pointers; d_sched may be NULL,
+ * d_warm is read and updated in place). */
+int qmpc_solve_batch_warm(QmpcHandle* h, const QmpcProblem* d_in, const QmpcContactSchedule* d_sched,
+                          QmpcWarmStart* d_warm, int32_t batch, QmpcResult* d_out, void* cuda_stream);
+
 void qmpc_destroy(QmpcHandle* h);
 
 /* Introspection: number of kernel launches issued by this handle so far; last CUDA error text. */

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 from quaternion_mpc_b200.abi import (CONVEX_PROBLEM_DTYPE, GAIT_STATE_DTYPE, PROBLEM_DTYPE, QMPC_MAX_HORIZON,
-                                     RESULT_DTYPE, QmpcConfig, QmpcLegParams)
+                                     RESULT_DTYPE, WARM_DTYPE, QmpcConfig, QmpcLegParams)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -38,6 +38,7 @@ def lib():
         _LIB.qmpc_ref_solve_batch_convex.argtypes = [C.POINTER(QmpcConfig), vp, C.c_int, vp, C.c_int]
         _LIB.qmpc_ref_solve_batch_sched.argtypes = [C.POINTER(QmpcConfig), vp, vp, C.c_int, vp, C.c_int]
         _LIB.qmpc_ref_solve_batch_convex_sched.argtypes = [C.POINTER(QmpcConfig), vp, vp, C.c_int, vp, C.c_int]
+        _LIB.qmpc_ref_solve_batch_warm.argtypes = [C.POINTER(QmpcConfig), vp, vp, vp, C.c_int, vp, C.c_int]
         _LIB.qmpc_ref_predict_schedule.argtypes = [C.POINTER(QmpcConfig), vp, C.c_int, vp]
         _LIB.qmpc_ref_leg_kinematics.argtypes = [C.POINTER(QmpcLegParams), vp, C.c_int, vp, vp]
         _LIB.qmpc_ref_joint_torques.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
@@ -87,6 +88,19 @@ def solve_batch_sched(cfg, problems, schedule, nthreads=1):
     out = np.zeros(problems.shape[0], dtype=RESULT_DTYPE)
     rc = lib().qmpc_ref_solve_batch_sched(C.byref(cfg), problems.ctypes.data, schedule.ctypes.data,
                                           problems.shape[0], out.ctypes.data, nthreads)
+    if rc:
+        raise RuntimeError(f"oracle failed rc={rc}")
+    return out
+
+
+def solve_batch_warm(cfg, problems, warm, schedule=None, nthreads=1):
+    """Warm-started solve (row N4): `warm` (WARM_DTYPE array) is read and updated IN PLACE."""
+    problems = np.ascontiguousarray(problems, dtype=PROBLEM_DTYPE)
+    assert warm.dtype == WARM_DTYPE and warm.flags.c_contiguous and warm.shape[0] == problems.shape[0]
+    sched = None if schedule is None else _sched_bytes(schedule, problems.shape[0])
+    out = np.zeros(problems.shape[0], dtype=RESULT_DTYPE)
+    rc = lib().qmpc_ref_solve_batch_warm(C.byref(cfg), problems.ctypes.data, sched.ctypes.data if sched is not None else None,
+                                         warm.ctypes.data, problems.shape[0], out.ctypes.data, nthreads)
     if rc:
         raise RuntimeError(f"oracle failed rc={rc}")
     return out

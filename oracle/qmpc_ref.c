@@ -248,8 +248,10 @@ static void opts_from_cfg(const QmpcConfig* cfg, AltroRefOptions* o) {
  * schedule the reference flags as TODO (ConvexMpc.cpp:82; LeggedContactFSM.cpp:272-286 is the
  * unused predictor).  Extension semantics: u_traj_ref[k] and the fz bound of knot k use mask k;
  * a knot with no contact has u_ref = 0; SetInput(u_traj_ref.at(0)) is kept verbatim. */
-int qmpc_ref_solve_one_sched(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched,
-                             QmpcResult* out) {
+/* `warm` (nullable): the trajectory-shift warm start of include/qmpc.h (extension; ALTRO's
+ * ShiftTrajectory pattern of TestBicycle.cpp:181-199, which legged_ctrl never calls). */
+int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched,
+                            QmpcWarmStart* warm, QmpcResult* out) {
   const int N = cfg->horizon;
   const int nf = cfg->model == QMPC_MODEL_QUAT_2FOOT ? 2 : 4;
   const int n = 13, m = 3 * nf;
@@ -352,6 +354,8 @@ int qmpc_ref_solve_one_sched(const QmpcConfig* cfg, const QmpcProblem* in, const
 
   double X[(QMPC_MAX_HORIZON + 1) * 13], U[QMPC_MAX_HORIZON * 12];
   for (int k = 0; k < N; ++k) memcpy(U + k * m, uref, sizeof(double) * m); /* SetInput(u_ref[0]) :253 */
+  if (warm && warm->valid)
+    for (int k = 0; k < N; ++k) memcpy(U + k * m, warm->u[k + 1 < N ? k + 1 : N - 1], sizeof(double) * m);
   AltroRefStats st;
   if (altro_ref_solve(&P, &o, X, U, &st)) return QMPC_ERR_ARG;
 
@@ -364,7 +368,17 @@ int qmpc_ref_solve_one_sched(const QmpcConfig* cfg, const QmpcProblem* in, const
   out->max_violation = st.max_violation;
   out->iterations = st.iterations;
   out->status = st.status;
+  if (warm) {
+    for (int k = 0; k < N; ++k)
+      for (int i = 0; i < 12; ++i) warm->u[k][i] = i < m ? U[k * m + i] : 0.0;
+    warm->valid = st.status != QMPC_STATUS_NONFINITE;
+  }
   return QMPC_OK;
+}
+
+int qmpc_ref_solve_one_sched(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched,
+                             QmpcResult* out) {
+  return qmpc_ref_solve_one_warm(cfg, in, sched, NULL, out);
 }
 
 int qmpc_ref_solve_one(const QmpcConfig* cfg, const QmpcProblem* in, QmpcResult* out) {
@@ -463,6 +477,7 @@ typedef struct Job {
   const QmpcConfig* cfg;
   const void* in;
   const unsigned char* sched; /* NULL or batch x QMPC_MAX_HORIZON mask bytes */
+  QmpcWarmStart* warm;        /* NULL or batch warm-start buffers (quat models) */
   QmpcResult* out;
   int lo, hi, convex, rc;
 } Job;
@@ -471,12 +486,14 @@ static void* worker(void* arg) {
   for (int i = j->lo; i < j->hi; ++i) {
     const unsigned char* sc = j->sched ? j->sched + (size_t)i * QMPC_MAX_HORIZON : NULL;
     int rc = j->convex ? qmpc_ref_solve_one_convex_sched(j->cfg, (const QmpcConvexProblem*)j->in + i, sc, j->out + i)
-                       : qmpc_ref_solve_one_sched(j->cfg, (const QmpcProblem*)j->in + i, sc, j->out + i);
+                       : qmpc_ref_solve_one_warm(j->cfg, (const QmpcProblem*)j->in + i, sc, j->warm ? j->warm + i : NULL,
+                                                 j->out + i);
     if (rc) j->rc = rc;
   }
   return NULL;
 }
-static int run_batch(const QmpcConfig* cfg, const void* in, const unsigned char* sched, int batch, QmpcResult* out,
+static int run_batch(const QmpcConfig* cfg, const void* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                     QmpcResult* out,
                      int nthreads, int convex) {
   if (!cfg || !in || !out || batch < 0) return QMPC_ERR_ARG;
   if (nthreads < 1) nthreads = 1;
@@ -485,7 +502,7 @@ static int run_batch(const QmpcConfig* cfg, const void* in, const unsigned char*
   pthread_t th[256];
   Job jobs[256];
   for (int t = 0; t < nthreads; ++t) {
-    jobs[t].cfg = cfg; jobs[t].in = in; jobs[t].sched = sched; jobs[t].out = out; jobs[t].convex = convex; jobs[t].rc = 0;
+    jobs[t].cfg = cfg; jobs[t].in = in; jobs[t].sched = sched; jobs[t].warm = warm; jobs[t].out = out; jobs[t].convex = convex; jobs[t].rc = 0;
     jobs[t].lo = (int)((long long)batch * t / nthreads);
     jobs[t].hi = (int)((long long)batch * (t + 1) / nthreads);
     if (nthreads == 1) worker(&jobs[t]);
@@ -499,17 +516,21 @@ static int run_batch(const QmpcConfig* cfg, const void* in, const unsigned char*
   return rc;
 }
 int qmpc_ref_solve_batch(const QmpcConfig* cfg, const QmpcProblem* in, int batch, QmpcResult* out, int nthreads) {
-  return run_batch(cfg, in, NULL, batch, out, nthreads, 0);
+  return run_batch(cfg, in, NULL, NULL, batch, out, nthreads, 0);
 }
 int qmpc_ref_solve_batch_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in, int batch, QmpcResult* out,
                                 int nthreads) {
-  return run_batch(cfg, in, NULL, batch, out, nthreads, 1);
+  return run_batch(cfg, in, NULL, NULL, batch, out, nthreads, 1);
 }
 int qmpc_ref_solve_batch_sched(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, int batch,
                                QmpcResult* out, int nthreads) {
-  return run_batch(cfg, in, sched, batch, out, nthreads, 0);
+  return run_batch(cfg, in, sched, NULL, batch, out, nthreads, 0);
+}
+int qmpc_ref_solve_batch_warm(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched,
+                              QmpcWarmStart* warm, int batch, QmpcResult* out, int nthreads) {
+  return run_batch(cfg, in, sched, warm, batch, out, nthreads, 0);
 }
 int qmpc_ref_solve_batch_convex_sched(const QmpcConfig* cfg, const QmpcConvexProblem* in, const unsigned char* sched,
                                       int batch, QmpcResult* out, int nthreads) {
-  return run_batch(cfg, in, sched, batch, out, nthreads, 1);
+  return run_batch(cfg, in, sched, NULL, batch, out, nthreads, 1);
 }

@@ -56,6 +56,7 @@ RESULT_DTYPE = np.dtype([
 ], align=True)
 
 SCHEDULE_DTYPE = np.dtype([("mask", "u1", QMPC_MAX_HORIZON)])
+WARM_DTYPE = np.dtype([("u", "f8", (QMPC_MAX_HORIZON, 12)), ("valid", "i4"), ("pad_", "i4")], align=True)
 GAIT_STATE_DTYPE = np.dtype([("gait_phase", "f8", 4), ("gait_freq", "f8"), ("gait", "i4"), ("pad_", "i4")],
                             align=True)
 QMPC_GAIT_TROT, QMPC_GAIT_TROT_WITH_STAND, QMPC_GAIT_CRAWL, QMPC_GAIT_STAND = 0, 1, 2, 3
@@ -67,6 +68,7 @@ class QmpcLegParams(C.Structure):
 
 assert PROBLEM_DTYPE.itemsize == 35 * 8 + 16
 assert SCHEDULE_DTYPE.itemsize == 32 and GAIT_STATE_DTYPE.itemsize == 48
+assert WARM_DTYPE.itemsize == QMPC_MAX_HORIZON * 12 * 8 + 8
 assert CONVEX_PROBLEM_DTYPE.itemsize == 40 * 8 + 24
 assert RESULT_DTYPE.itemsize == 29 * 8 + 8
 
@@ -75,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "qmpc_solve_batch_host", "qmpc_solve_batch_convex_host", "qmpc_destroy", "qmpc_launch_count",
     "qmpc_last_error", "qmpc_status_string", "qmpc_abi_version", "qmpc_measure_fma_peak",
     "qmpc_predict_contact_schedule", "qmpc_solve_batch_sched", "qmpc_solve_batch_convex_sched",
-    "qmpc_solve_batch_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques", "qmpc_describe",
+    "qmpc_solve_batch_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques", "qmpc_describe", "qmpc_solve_batch_warm",
 ]
 
 _LIB = None
@@ -115,6 +117,8 @@ def load_library():
         f = getattr(lib, name)
         f.argtypes = [vp, vp, vp, i32, vp, vp]
         f.restype = C.c_int
+    lib.qmpc_solve_batch_warm.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    lib.qmpc_solve_batch_warm.restype = C.c_int
     lib.qmpc_solve_batch_sched_host.argtypes = [vp, vp, vp, i32, vp]
     lib.qmpc_solve_batch_sched_host.restype = C.c_int
     lib.qmpc_predict_contact_schedule.argtypes = [vp, vp, i32, vp, vp]

@@ -242,29 +242,32 @@ extern "C" int qmpc_describe(const QmpcHandle* h, char* buf, int32_t n) {
 }
 
 template <class M>
-static int launch_dense(QmpcHandle* h, const typename M::Problem* d_in, const unsigned char* sched, int batch,
+static int launch_dense(QmpcHandle* h, const typename M::Problem* d_in, const unsigned char* sched,
+                        QmpcWarmStart* warm, int batch,
                         QmpcResult* d_out, cudaStream_t s) {
   const int block = 64;
   const int grid = (batch + block - 1) / block;
-  qmpc_dense_kernel<M><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, sched, d_out, h->ws, batch, h->stride);
+  qmpc_dense_kernel<M><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, sched, warm, d_out, h->ws, batch, h->stride);
   h->launches += 1;
   CU(cudaGetLastError());
   return QMPC_OK;
 }
 
 template <int NF>
-static int launch_srb(QmpcHandle* h, const QmpcProblem* d_in, const unsigned char* sched, int batch, QmpcResult* d_out,
+static int launch_srb(QmpcHandle* h, const QmpcProblem* d_in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                      QmpcResult* d_out,
                       cudaStream_t s) {
   const int block = 64;
   const int grid = (batch + block - 1) / block;
-  qmpc_srb_kernel<NF><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, sched, d_out, h->ws, batch, h->stride);
+  qmpc_srb_kernel<NF><<<grid, block, 0, s>>>(h->cfg, h->opts, d_in, sched, warm, d_out, h->ws, batch, h->stride);
   h->launches += 1;
   CU(cudaGetLastError());
   return QMPC_OK;
 }
 
 template <int NF>
-static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned char* sched, int batch, QmpcResult* d_out,
+static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                       QmpcResult* d_out,
                        cudaStream_t s) {
   const int groups = kCoopBlock / kCoopG;
   // Persistent slots stride over the batch.  Balance the waves: with S resident slots a batch needs
@@ -276,7 +279,7 @@ static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned ch
   int grid = (int)((slots + groups - 1) / groups);
   if (grid > h->coop_grid) grid = h->coop_grid;
   const size_t smem_bytes = (size_t)(groups * h->coop_smem_doubles + kCoopBlockShared) * sizeof(double);
-  qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, sched, d_out, h->ws, batch,
+  qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, sched, warm, d_out, h->ws, batch,
                                                                    h->coop_smem_doubles, h->coop_scratch_doubles,
                                                                    h->coop_wide);
   h->launches += 1;
@@ -284,7 +287,7 @@ static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned ch
   return QMPC_OK;
 }
 
-static int solve_any(QmpcHandle* h, const void* d_in, const QmpcContactSchedule* d_sched, int32_t batch,
+static int solve_any(QmpcHandle* h, const void* d_in, const QmpcContactSchedule* d_sched, QmpcWarmStart* warm, int32_t batch,
                      QmpcResult* d_out, void* stream, bool convex) {
   if (!h || !h->ws) return h ? QMPC_ERR_CUDA : QMPC_ERR_ARG;
   if (!d_in || !d_out || batch < 0) return QMPC_ERR_ARG;
@@ -296,33 +299,38 @@ static int solve_any(QmpcHandle* h, const void* d_in, const QmpcContactSchedule*
   const unsigned char* sc = reinterpret_cast<const unsigned char*>(d_sched);
   switch (h->cfg.model) {
     case QMPC_MODEL_QUAT_4FOOT:
-      if (h->kernel == 2) return launch_coop<4>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
-      if (h->kernel == 1) return launch_srb<4>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
-      return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
+      if (h->kernel == 2) return launch_coop<4>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      if (h->kernel == 1) return launch_srb<4>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
     case QMPC_MODEL_QUAT_2FOOT:
-      if (h->kernel == 2) return launch_coop<2>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
-      if (h->kernel == 1) return launch_srb<2>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
-      return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, sc, batch, d_out, s);
-    default: return launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, sc, batch, d_out, s);
+      if (h->kernel == 2) return launch_coop<2>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      if (h->kernel == 1) return launch_srb<2>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+    default: return launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, sc, warm, batch, d_out, s);
   }
 }
 
 extern "C" int qmpc_solve_batch(QmpcHandle* h, const QmpcProblem* d_in, int32_t batch, QmpcResult* d_out,
                                 void* cuda_stream) {
-  return solve_any(h, d_in, nullptr, batch, d_out, cuda_stream, false);
+  return solve_any(h, d_in, nullptr, nullptr, batch, d_out, cuda_stream, false);
 }
 extern "C" int qmpc_solve_batch_sched(QmpcHandle* h, const QmpcProblem* d_in, const QmpcContactSchedule* d_sched,
                                       int32_t batch, QmpcResult* d_out, void* cuda_stream) {
-  return solve_any(h, d_in, d_sched, batch, d_out, cuda_stream, false);
+  return solve_any(h, d_in, d_sched, nullptr, batch, d_out, cuda_stream, false);
+}
+extern "C" int qmpc_solve_batch_warm(QmpcHandle* h, const QmpcProblem* d_in, const QmpcContactSchedule* d_sched,
+                                     QmpcWarmStart* d_warm, int32_t batch, QmpcResult* d_out, void* cuda_stream) {
+  if (!d_warm) return QMPC_ERR_ARG;
+  return solve_any(h, d_in, d_sched, d_warm, batch, d_out, cuda_stream, false);
 }
 extern "C" int qmpc_solve_batch_convex_sched(QmpcHandle* h, const QmpcConvexProblem* d_in,
                                              const QmpcContactSchedule* d_sched, int32_t batch, QmpcResult* d_out,
                                              void* cuda_stream) {
-  return solve_any(h, d_in, d_sched, batch, d_out, cuda_stream, true);
+  return solve_any(h, d_in, d_sched, nullptr, batch, d_out, cuda_stream, true);
 }
 extern "C" int qmpc_solve_batch_convex(QmpcHandle* h, const QmpcConvexProblem* d_in, int32_t batch,
                                        QmpcResult* d_out, void* cuda_stream) {
-  return solve_any(h, d_in, nullptr, batch, d_out, cuda_stream, true);
+  return solve_any(h, d_in, nullptr, nullptr, batch, d_out, cuda_stream, true);
 }
 
 static int solve_host_any(QmpcHandle* h, const void* in, const QmpcContactSchedule* sched, int32_t batch,
@@ -336,7 +344,7 @@ static int solve_host_any(QmpcHandle* h, const void* in, const QmpcContactSchedu
   CU(cudaMemcpyAsync(h->d_in, in, in_sz * batch, cudaMemcpyHostToDevice, h->stream));
   if (sched)
     CU(cudaMemcpyAsync(h->d_sched, sched, sizeof(QmpcContactSchedule) * batch, cudaMemcpyHostToDevice, h->stream));
-  int rc = solve_any(h, h->d_in, sched ? h->d_sched : nullptr, batch, h->d_out, h->stream, convex);
+  int rc = solve_any(h, h->d_in, sched ? h->d_sched : nullptr, nullptr, batch, h->d_out, h->stream, convex);
   if (rc) return rc;
   CU(cudaMemcpyAsync(out, h->d_out, sizeof(QmpcResult) * batch, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

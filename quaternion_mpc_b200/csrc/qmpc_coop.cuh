@@ -38,6 +38,23 @@
 
 namespace qmpc {
 
+// trial trajectories are written 16x per iteration and read once: keep them from displacing the
+// gains / value functions in L2 (evict-first stores and loads)
+QMPC_HD inline void st_stream(double* p, double v) {
+#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_TRIAL_CS)
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+QMPC_HD inline double ld_stream(const double* p) {
+#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_TRIAL_CS)
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+
 QMPC_HD inline double qmpc_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
   return rsqrt(x);
@@ -261,7 +278,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
                                         double* U, double* DX, const double* gK, const double* gd,
                                         const double* gmu, double rho, double alpha, int mode, double* Jout,
                                         double* violout, double* gTX, double* gTU, int tl, int tstride,
-                                        double* kstage, unsigned lane_mask) {
+                                        double* kstage, unsigned lane_mask, const QmpcWarmStart* winit) {
   // Compact by construction (instruction-fetch bound otherwise): the input never
   // exists as an array - each foot's force is formed, costed, cone-checked and folded into the net
   // wrench inside one 4-trip loop; the wrench drives both midpoint evaluations.  Accumulation
@@ -297,7 +314,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
     if (mode != 0) state_diff<M>(x, X + k * NX, dx);
     if (mode == 1) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) gTX[(size_t)(k * NX + i) * tstride + tl] = x[i];
+      for (int i = 0; i < NX; ++i) st_stream(gTX + (size_t)(k * NX + i) * tstride + tl, x[i]);
     }
     if (mode == 2) {
 #pragma unroll
@@ -337,7 +354,12 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
     for (int f = 0; f < NF; ++f) {
       double u0, u1, u2;
       if (mode == 0) {
-        u0 = 0.0; u1 = 0.0; u2 = m.urefz(0, f);   // SetInput(u_traj_ref.at(0)), QuatMpc.cpp:253
+        if (winit) {   // warm start: previous solution shifted by one knot
+          const double* wrow = warm_row(winit, k, N) + 3 * f;
+          u0 = wrow[0]; u1 = wrow[1]; u2 = wrow[2];
+        } else {
+          u0 = 0.0; u1 = 0.0; u2 = m.urefz(0, f);   // SetInput(u_traj_ref.at(0)), QuatMpc.cpp:253
+        }
       } else {
         double t0 = 0, t1 = 0, t2 = 0;
         const double* K0 = Kk + (3 * f) * 12;
@@ -372,7 +394,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
       if (mode != 1) { U[k * NU + 3 * f] = u0; U[k * NU + 3 * f + 1] = u1; U[k * NU + 3 * f + 2] = u2; }
       else {
         double* tu = gTU + (size_t)(k * NU + 3 * f) * tstride + tl;
-        tu[0] = u0; tu[tstride] = u1; tu[2 * tstride] = u2;
+        st_stream(tu, u0); st_stream(tu + tstride, u1); st_stream(tu + 2 * tstride, u2);
       }
       if (mode != 2) {
         const double d0 = u0, d1 = u1, d2 = u2 - m.urefz(k, f);   // u_ref = (0, 0, weight share)
@@ -442,7 +464,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
 
 template <int NF, int G>
 QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in,
-                            const unsigned char* sched, QmpcResult* out,
+                            const unsigned char* sched, QmpcWarmStart* warm, QmpcResult* out,
                             int pid, double* sm, double* gs, int lane_id, unsigned lane_mask, int flags,
                             const double* wts) {
   using M = QuatModel<NF>;
@@ -493,7 +515,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   COOP_SYNC();
   double rho = o.penalty_initial;
   COOP_PHASE {
-    if (lane == 0) coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3], gTX, gTU, 0, G, P, lane_mask);
+    if (lane == 0) coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3], gTX, gTU, 0, G, P, lane_mask,
+                                     (warm && warm[pid].valid) ? warm + pid : nullptr);
   }
   COOP_SYNC();
   double phi = scal[2], viol = scal[3];
@@ -993,7 +1016,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         // cooperatively); their result is discarded below
         double J = NAN, vl = 0, alpha = 1.0;
         for (int q = 0; q < j; ++q) alpha *= o.ls_decrease;
-        coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, alpha, 1, &J, &vl, gTX, gTU, lane, G, P, lane_mask);
+        coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, alpha, 1, &J, &vl, gTX, gTU, lane, G, P, lane_mask, nullptr);
         red[lane] = j < o.ls_iters_max ? J : NAN;
         red[G + lane] = vl;
       }
@@ -1021,29 +1044,25 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     const int acc_lane = acc_j % G;
     COOP_PHASE {
       for (int k = lane; k <= N; k += G) {
-        double xn[NX], dx[NE], y[NE];
+        double xn[NX], dx[NE];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) xn[i] = gTX[(size_t)(k * NX + i) * G + acc_lane];
+        for (int i = 0; i < NX; ++i) xn[i] = ld_stream(gTX + (size_t)(k * NX + i) * G + acc_lane);
         state_diff<M>(xn, X + k * NX, dx);
-#pragma unroll
-        for (int i = 0; i < NE; ++i) y[i] = gpv[k * 12 + i];
         const double* Pk = gP + (size_t)k * 144;
-#pragma unroll
+#pragma unroll 1   // rolled over the rows: once per iteration, 12x less code (instruction-cache bound kernel)
         for (int a = 0; a < NE; ++a) {
-          double t = y[a];
+          double t = gpv[k * 12 + a];
 #pragma unroll
           for (int b = 0; b < NE; ++b) t += Pk[12 * a + b] * dx[b];
-          y[a] = t;
+          DX[k * NE + a] = t;
         }
-#pragma unroll
-        for (int i = 0; i < NE; ++i) DX[k * NE + i] = y[i];
       }
     }
     COOP_SYNC();
     // ... then X, U <- accepted trajectory (cooperative strided copy)
     COOP_PHASE {
-      for (int e = lane; e < (N + 1) * NX; e += G) X[e] = gTX[(size_t)e * G + acc_lane];
-      for (int e = lane; e < N * NU; e += G) U[e] = gTU[(size_t)e * G + acc_lane];
+      for (int e = lane; e < (N + 1) * NX; e += G) X[e] = ld_stream(gTX + (size_t)e * G + acc_lane);
+      for (int e = lane; e < N * NU; e += G) U[e] = ld_stream(gTU + (size_t)e * G + acc_lane);
     }
     COOP_SYNC();
     cost_decrease = phi - phin;
@@ -1059,6 +1078,13 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       r.iterations = iters;
       r.status = status;
       out[pid] = r;
+      if (warm) warm[pid].valid = status != QMPC_STATUS_NONFINITE;
+    }
+    if (warm) {
+      for (int e = lane; e < N * 12; e += G) {
+        const int k = e / 12, i = e % 12;
+        warm[pid].u[k][i] = i < NU ? U[k * NU + i] : 0.0;
+      }
     }
   }
   COOP_SYNC();
@@ -1075,7 +1101,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 template <int NF, int G>
 __global__ void __launch_bounds__(QMPC_COOP_BLOCK, QMPC_COOP_MIN_BLOCKS)
 qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in,
-                 const unsigned char* __restrict__ sched, QmpcResult* __restrict__ out,
+                 const unsigned char* __restrict__ sched, QmpcWarmStart* __restrict__ warm,
+                 QmpcResult* __restrict__ out,
                  double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot, int wide) {
   extern __shared__ __align__(16) double smem_pool[];
   if (threadIdx.x < 13) smem_pool[threadIdx.x] = cfg.q_weights[threadIdx.x];
@@ -1090,7 +1117,7 @@ qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ i
   double* sm = smem_pool + kCoopBlockShared + (size_t)group * smem_per_problem;
   double* gs = scratch + (size_t)slot * scratch_per_slot;
   for (int pid = slot; pid < batch; pid += nslots) {
-    coop_solve_one<NF, G>(cfg, o, in, sched, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
+    coop_solve_one<NF, G>(cfg, o, in, sched, warm, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
   }
 }
 #endif

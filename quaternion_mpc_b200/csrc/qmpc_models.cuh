@@ -101,6 +101,11 @@ struct ContactPlan {
   QMPC_HD double fzc(int k, int f) const { return ((cm[k] >> f) & 1) ? fzmax : 0.0; }
 };
 
+// Warm start (include/qmpc.h QmpcWarmStart): initial input of knot k = previous solution shifted by one knot
+QMPC_HD inline const double* warm_row(const QmpcWarmStart* w, int k, int N) {
+  return w->u[k + 1 < N ? k + 1 : N - 1];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Quaternion SRB with NF feet (QuatMpc: NF = 4; 2-contact model: NF = 2)
 template <int NF>

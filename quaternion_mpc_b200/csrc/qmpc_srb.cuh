@@ -314,7 +314,7 @@ QMPC_HD void srb_al_terms(const QuatModel<NF>& m, const QmpcConfig& cfg, int k, 
 
 template <int NF>
 QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in,
-                           const unsigned char* sched, QmpcResult* out,
+                           const unsigned char* sched, QmpcWarmStart* warm, QmpcResult* out,
                            double* ws, int pid, size_t stride) {
   using M = QuatModel<NF>;
   using L = SrbLayout<NF>;
@@ -344,7 +344,12 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
     for (int i = 0; i < NX; ++i) { x[i] = x0[i]; X[i] = x0[i]; }
     for (int i = 0; i < NU; ++i) u0[i] = m.uref_at(0, i);   // SetInput(u_traj_ref.at(0)), QuatMpc.cpp:253
 #pragma unroll 1
+    const QmpcWarmStart* wsrc = (warm && warm[pid].valid) ? warm + pid : nullptr;
     for (int k = 0; k < N; ++k) {
+      if (wsrc) {
+        const double* wr = warm_row(wsrc, k, N);
+        for (int i = 0; i < NU; ++i) u0[i] = wr[i];
+      }
       st<NU>(U.off(k * NU), u0);
       mid_dyn(m, x, u0, h, xn);
       for (int i = 0; i < NX; ++i) { x[i] = xn[i]; X[(k + 1) * NX + i] = xn[i]; }
@@ -536,17 +541,23 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
   r.iterations = iters;
   r.status = status;
   out[pid] = r;
+  if (warm) {
+    for (int k = 0; k < N; ++k)
+      for (int i = 0; i < 12; ++i) warm[pid].u[k][i] = i < NU ? U[k * NU + i] : 0.0;
+    warm[pid].valid = status != QMPC_STATUS_NONFINITE;
+  }
 }
 
 #ifdef __CUDACC__
 template <int NF>
 __global__ void __launch_bounds__(64)
 qmpc_srb_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in,
-                const unsigned char* __restrict__ sched, QmpcResult* __restrict__ out,
+                const unsigned char* __restrict__ sched, QmpcWarmStart* __restrict__ warm,
+                QmpcResult* __restrict__ out,
                 double* __restrict__ ws, int batch, size_t stride) {
   const int pid = blockIdx.x * blockDim.x + threadIdx.x;
   if (pid >= batch) return;
-  srb_solve_one<NF>(cfg, o, in, sched, out, ws, pid, stride);
+  srb_solve_one<NF>(cfg, o, in, sched, warm, out, ws, pid, stride);
 }
 #endif
 

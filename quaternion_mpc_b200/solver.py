@@ -107,6 +107,30 @@ class _BatchedMpc:
         self._check(rc)
         return d_results
 
+    # -- warm start / trajectory shift ---------------------------------------------
+    def alloc_warm(self, batch):
+        """Device buffer of `batch` QmpcWarmStart records, all invalid (first solve starts cold)."""
+        import torch
+        return torch.zeros((batch, abi.WARM_DTYPE.itemsize), dtype=torch.uint8, device=f"cuda:{self.device}")
+
+    def grf_update_warm_device(self, d_problems, d_warm, d_sched=None, d_results=None, stream=None):
+        """Solve starting from the previous solution shifted by one knot; d_warm is updated in place."""
+        import torch
+        batch = d_problems.shape[0]
+        assert d_problems.is_cuda and d_problems.dtype == torch.uint8 and d_problems.is_contiguous()
+        assert d_warm.is_cuda and d_warm.dtype == torch.uint8 and d_warm.is_contiguous()
+        assert tuple(d_warm.shape) == (batch, abi.WARM_DTYPE.itemsize)
+        if self.MODEL == abi.QMPC_MODEL_EULER_CONVEX:
+            raise QmpcError("warm start is implemented for the quaternion models")
+        if d_results is None:
+            d_results = self.alloc_results(batch)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.qmpc_solve_batch_warm(self._h, d_problems.data_ptr(),
+                                            d_sched.data_ptr() if d_sched is not None else None,
+                                            d_warm.data_ptr(), batch, d_results.data_ptr(), s)
+        self._check(rc)
+        return d_results
+
     # -- leg kinematics in / joint torques out (SURVEY 8f N2) -------------------------------------
     def leg_kinematics(self, d_joint_pos, leg_params=None, want_foot=True, want_jac=True, stream=None):
         """a1_kin.fk / a1_kin.jac for the four legs (BaseInterface.cpp:204-212).

@@ -28,43 +28,43 @@ static SolverOpts make_opts(const QmpcConfig& cfg) {
 }
 
 template <class M>
-static int run_dense(const QmpcConfig& cfg, const void* in, const unsigned char* sched, int batch, QmpcResult* out) {
+static int run_dense(const QmpcConfig& cfg, const void* in, const unsigned char* sched, QmpcWarmStart* warm, int batch, QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
   size_t stride = batch;
   std::vector<double> ws(DenseLayout<M>::total(cfg.horizon) * stride);
   for (int i = 0; i < batch; ++i)
-    dense_solve_one<M>(cfg, o, (const typename M::Problem*)in, sched, out, ws.data(), i, stride);
+    dense_solve_one<M>(cfg, o, (const typename M::Problem*)in, sched, warm, out, ws.data(), i, stride);
   return 0;
 }
 
 // `sched`: null, or batch x QMPC_MAX_HORIZON contact-mask bytes (include/qmpc.h QmpcContactSchedule)
-extern "C" int emul_solve_dense(const QmpcConfig* cfg, const void* in, const unsigned char* sched, int batch,
+extern "C" int emul_solve_dense(const QmpcConfig* cfg, const void* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
                                 QmpcResult* out) {
   switch (cfg->model) {
-    case QMPC_MODEL_QUAT_4FOOT: return run_dense<QuatModel<4>>(*cfg, in, sched, batch, out);
-    case QMPC_MODEL_QUAT_2FOOT: return run_dense<QuatModel<2>>(*cfg, in, sched, batch, out);
-    default: return run_dense<ConvexModel>(*cfg, in, sched, batch, out);
+    case QMPC_MODEL_QUAT_4FOOT: return run_dense<QuatModel<4>>(*cfg, in, sched, warm, batch, out);
+    case QMPC_MODEL_QUAT_2FOOT: return run_dense<QuatModel<2>>(*cfg, in, sched, warm, batch, out);
+    default: return run_dense<ConvexModel>(*cfg, in, sched, warm, batch, out);
   }
 }
 
 #ifdef QMPC_EMUL_SRB
 template <int NF>
-static int run_srb(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned char* sched, int batch, QmpcResult* out) {
+static int run_srb(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned char* sched, QmpcWarmStart* warm, int batch, QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
   size_t stride = batch;
   std::vector<double> ws(SrbLayout<NF>::total(cfg.horizon) * stride);
-  for (int i = 0; i < batch; ++i) srb_solve_one<NF>(cfg, o, in, sched, out, ws.data(), i, stride);
+  for (int i = 0; i < batch; ++i) srb_solve_one<NF>(cfg, o, in, sched, warm, out, ws.data(), i, stride);
   return 0;
 }
-extern "C" int emul_solve_srb(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, int batch,
+extern "C" int emul_solve_srb(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
                               QmpcResult* out) {
-  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_srb<4>(*cfg, in, sched, batch, out);
-  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_srb<2>(*cfg, in, sched, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_srb<4>(*cfg, in, sched, warm, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_srb<2>(*cfg, in, sched, warm, batch, out);
   return -1;
 }
 
 template <int NF, int G>
-static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned char* sched, int batch, QmpcResult* out) {
+static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned char* sched, QmpcWarmStart* warm, int batch, QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
   using L = CoopLayout<NF, G>;
   const int wide = cfg.horizon <= 10 ? 3 : (cfg.horizon <= 16 ? 2 : 0);
@@ -72,13 +72,13 @@ static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned
   double wts[26];
   for (int i = 0; i < 13; ++i) wts[i] = cfg.q_weights[i];
   for (int i = 0; i < 12; ++i) wts[13 + i] = cfg.r_weights[i];
-  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, sched, out, i, sm.data(), gs.data(), 0, 0u, wide, wts);
+  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, sched, warm, out, i, sm.data(), gs.data(), 0, 0u, wide, wts);
   return 0;
 }
-extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, int batch,
+extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
                                QmpcResult* out) {
-  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_coop<4, 16>(*cfg, in, sched, batch, out);
-  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_coop<2, 16>(*cfg, in, sched, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_coop<4, 16>(*cfg, in, sched, warm, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_coop<2, 16>(*cfg, in, sched, warm, batch, out);
   return -1;
 }
 extern "C" int emul_coop_smem_bytes(int nf, int horizon) {

@@ -26,24 +26,25 @@ def emul(tmp_path_factory):
                            "-o", so, os.path.join(HERE, "emul", "emul.cpp")])
     lib = C.CDLL(so)
     for name in ("emul_solve_dense", "emul_solve_srb", "emul_solve_coop"):
-        getattr(lib, name).argtypes = [C.POINTER(abi.QmpcConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        getattr(lib, name).argtypes = [C.POINTER(abi.QmpcConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p]
     lib.emul_predict_schedule.argtypes = [C.POINTER(abi.QmpcConfig), C.c_void_p, C.c_int, C.c_void_p]
     lib.emul_leg_kinematics.argtypes = [C.POINTER(abi.QmpcLegParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
 
-def _run(lib, fn, cfg, probs, sched=None):
+def _run(lib, fn, cfg, probs, sched=None, warm=None):
     out = np.zeros(len(probs), dtype=abi.RESULT_DTYPE)
     rc = getattr(lib, fn)(C.byref(cfg), probs.ctypes.data, sched.ctypes.data if sched is not None else None,
-                          len(probs), out.ctypes.data)
+                          warm.ctypes.data if warm is not None else None, len(probs), out.ctypes.data)
     assert rc == 0
     return out
 
 
-def _agree(res, ref):
+def _agree(res, ref, max_flagged=0.1):
     flagged = (res["status"] >= 2) | (ref["status"] >= 2)
     ok = ~flagged
-    assert flagged.sum() <= max(1, len(res) // 10)
+    assert flagged.sum() <= max(1, int(len(res) * max_flagged))
     assert (res["status"][ok] == ref["status"][ok]).all()
     assert (res["iterations"][ok] == ref["iterations"][ok]).all()
     err = np.abs(res["grf_body"][ok] - ref["grf_body"][ok]).max()
@@ -84,6 +85,23 @@ def test_convex_body_with_schedule(emul, oracle):
     sched = predict_schedule_numpy(random_gait_states(12, seed=4), 10, cfg.dt)
     _agree(_run(emul, "emul_solve_dense", cfg, p, sched), oracle.solve_batch_convex_sched(cfg, p, sched, nthreads=4))
     _agree(_run(emul, "emul_solve_dense", cfg, p), oracle.solve_batch_convex(cfg, p, nthreads=4))
+
+
+@pytest.mark.parametrize("kernel", ["emul_solve_coop", "emul_solve_srb", "emul_solve_dense"])
+def test_warm_start_bodies(emul, oracle, kernel):
+    """Row N4: two consecutive ticks with the trajectory-shift warm start; the buffer written by the
+    kernel body must match the oracle's, and an invalid buffer must give the cold result bit for bit."""
+    cfg = default_config(abi.QMPC_MODEL_QUAT_4FOOT, 10)
+    p = random_batch(16, seed=8, gait="trot")
+    w, wr = np.zeros(16, dtype=abi.WARM_DTYPE), np.zeros(16, dtype=abi.WARM_DTYPE)
+    a0, r0 = _run(emul, kernel, cfg, p, None, w), oracle.solve_batch_warm(cfg, p, wr, nthreads=4)
+    assert np.array_equal(a0["grf_body"], _run(emul, kernel, cfg, p)["grf_body"])
+    _agree(a0, r0)
+    assert (w["valid"] == 1).all() and np.abs(w["u"] - wr["u"]).max() < TOL
+    assert np.abs(w["u"][:, 0, :] - a0["grf_body"]).max() == 0.0      # knot 0 of the buffer is the returned GRF
+    a1, r1 = _run(emul, kernel, cfg, p, None, w), oracle.solve_batch_warm(cfg, p, wr, nthreads=4)
+    _agree(a1, r1, max_flagged=0.3)   # warm-started iterates sit closer to the line-search floor
+    assert np.abs(a1["grf_body"] - a0["grf_body"]).max() > 1e-6        # the warm start changed the iterate
 
 
 def test_two_foot_model_body(emul, oracle):
