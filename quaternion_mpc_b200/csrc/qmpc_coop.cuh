@@ -218,22 +218,46 @@ constexpr int lx = 0, Qx = 12, Qu = 24, s = 36, Atp = 42, g = 54, Dblk = 66, Hph
               scal = 135, rdiag = 144, tcol = 156;  // scal[0]=dphi0 [1]=hphi [2]=phi [3]=viol
 }
 
-// stage cost + AL terms of one knot (same accumulation order as merit() in qmpc_dense.cuh)
+// stage cost + AL terms of one knot: same accumulation order as stage_cost() / merit() in
+// qmpc_dense.cuh, but rolled per foot - it runs once per dual update, compact code matters more
 template <class M>
-QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, int k, int N, const double* x, const double* u,
-                               const double* mu_k, double rho, double& J, double& viol) {
-  J += stage_cost(m, cfg, k, N, x, u);
-  if (k < N) {
-    double c[M::NC];
-    cone_eval(m, k, u, c);
-    double acc = 0;
+QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, const double* wr, int k, int N, const double* x,
+                               const double* u, const double* mu_k, double rho, double& J, double& viol) {
+  constexpr int NF = M::NU / 3;
+  double xr[M::NX], Jl = 0;
+  m.xref(k, xr);
 #pragma unroll
-    for (int i = 0; i < M::NC; ++i) {
-      const double mui = mu_k[i];
-      const double est = mui + rho * c[i];
-      const double lh = est > 0 ? est : 0;
-      if (c[i] > viol) viol = c[i];
-      acc += lh * lh - mui * mui;
+  for (int i = 0; i < M::NX; ++i) { const double dxi = x[i] - xr[i]; Jl += 0.5 * cfg.q_weights[i] * dxi * dxi; }
+  if (k < N) {
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+      const double d0 = u[3 * f], d1 = u[3 * f + 1], d2 = u[3 * f + 2] - m.urefz(k, f);
+      Jl += 0.5 * wr[3 * f] * d0 * d0;
+      Jl += 0.5 * wr[3 * f + 1] * d1 * d1;
+      Jl += 0.5 * wr[3 * f + 2] * d2 * d2;
+    }
+  }
+  if (cfg.w != 0.0) {
+    const double s = xr[3] * x[3] + xr[4] * x[4] + xr[5] * x[5] + xr[6] * x[6];
+    Jl += cfg.w * (1.0 - fabs(s));
+  }
+  J += Jl;
+  if (k < N) {
+    double acc = 0;
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+      const double u0 = u[3 * f], u1 = u[3 * f + 1], u2 = u[3 * f + 2];
+      const double fzc_f = m.fzc(k, f);
+#pragma unroll 1
+      for (int r = 0; r < 6; ++r) {
+        double c = m.CR[3 * r] * u0 + m.CR[3 * r + 1] * u1 + m.CR[3 * r + 2] * u2;
+        if (r == 4) c += -fzc_f;
+        const double mui = mu_k[6 * f + r];
+        const double est = mui + rho * c;
+        const double lh = est > 0 ? est : 0;
+        if (c > viol) viol = c;
+        acc += lh * lh - mui * mui;
+      }
     }
     J += acc / (2 * rho);
   }
@@ -506,6 +530,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 
   // ------------------------------------------------------------------ set-up + nominal roll-out
   COOP_PHASE {
+#pragma unroll 1
     for (int i = lane; i < N * NC; i += G) gmu[i] = 0.0;
     if (lane == 0) {
       QmpcProblem prob = in[pid];
@@ -528,6 +553,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   for (int it = 0; it < o.iterations_max && status == QMPC_STATUS_MAX_ITERATIONS; ++it) {
     // ---------------- linearise: lane k <- knot k (27 doubles to the scratch)
     COOP_PHASE {
+#pragma unroll 1
       for (int k = lane; k < N; k += G) {
         KnotLin Lk;
         srb_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
@@ -544,6 +570,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       // ---------------- stationarity with the Riccati duals of the accepted step (DX holds y_k)
       COOP_PHASE {
         double rx = 0, ru = 0;
+#pragma unroll 1
         for (int k = lane; k <= N; k += G) {
           double lx[NE], hphi;
           cost_expand(m, cfg, k, X + k * NX, lx, &hphi);
@@ -561,18 +588,38 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
             }
             const double* u = U + k * NU;
             const double* yn = DX + (k + 1) * NE;
-            double gu[NU], Hb[9 * NF], Aty[NE], t6[6], Bty[NU];
-            al_terms(m, k, u, GVec{gmu + k * NC, 1}, rho, gu, Hb);
+            double Aty[NE], t6[6];
             srb_At_vec(Lk, hd, yn, Aty);
             srb_Mt_vec(Lk, hd, hh, yn, t6);
-            srb_Wt_vec(m, t6, Bty);
             for (int a = 0; a < NE; ++a) {
               double v = fabs(lx[a] + Aty[a] - DX[k * NE + a]);
               if (v > rx) rx = v;
             }
-            for (int a = 0; a < NU; ++a) {
-              double v = fabs(wr[a] * (u[a] - m.uref_at(k, a)) + gu[a] + Bty[a]);
-              if (v > ru) ru = v;
+            // input residual per foot, rolled (once per iteration: compact code beats unrolled speed):
+            // R (u - u_ref) + J^T max(0, mu + rho c) + W^T M^T y   (same accumulation order as al_terms)
+#pragma unroll 1
+            for (int f = 0; f < NF; ++f) {
+              const double* uf = u + 3 * f;
+              const double* IS = m.IS + 9 * f;
+              const double fzc_f = m.fzc(k, f);
+              double g0 = 0, g1 = 0, g2 = 0;
+#pragma unroll 1
+              for (int r = 0; r < 6; ++r) {
+                const double j0 = m.CR[3 * r], j1 = m.CR[3 * r + 1], j2 = m.CR[3 * r + 2];
+                double c = j0 * uf[0] + j1 * uf[1] + j2 * uf[2];
+                if (r == 4) c += -fzc_f;
+                const double est = gmu[k * NC + 6 * f + r] + rho * c;
+                if (est > 0) { g0 += j0 * est; g1 += j1 * est; g2 += j2 * est; }
+              }
+              const double b0 = m.inv_mass * t6[0] + IS[0] * t6[3] + IS[3] * t6[4] + IS[6] * t6[5];
+              const double b1 = m.inv_mass * t6[1] + IS[1] * t6[3] + IS[4] * t6[4] + IS[7] * t6[5];
+              const double b2 = m.inv_mass * t6[2] + IS[2] * t6[3] + IS[5] * t6[4] + IS[8] * t6[5];
+              const double v0 = fabs(wr[3 * f] * uf[0] + g0 + b0);
+              const double v1 = fabs(wr[3 * f + 1] * uf[1] + g1 + b1);
+              const double v2 = fabs(wr[3 * f + 2] * (uf[2] - m.urefz(k, f)) + g2 + b2);
+              if (v0 > ru) ru = v0;
+              if (v1 > ru) ru = v1;
+              if (v2 > ru) ru = v2;
             }
           }
         }
@@ -589,6 +636,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       if (fabs(cost_decrease) < o.tol_cost_intermediate || stat < o.tol_stationarity) {
         // dual update (row-parallel), penalty update, merit refresh (knot-parallel)
         COOP_PHASE {
+#pragma unroll 1
           for (int idx = lane; idx < N * NC; idx += G) {
             const int k = idx / NC, r = idx % NC, f = r / 6, rr = r % 6;
             const double* u = U + k * NU + 3 * f;
@@ -605,7 +653,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         }
         COOP_PHASE {
           double J = 0, vl = 0;
-          for (int k = lane; k <= N; k += G) knot_merit(m, cfg, k, N, X + k * NX, U + k * NU, gmu + k * NC, rho, J, vl);
+#pragma unroll 1
+          for (int k = lane; k <= N; k += G) knot_merit(m, cfg, wr, k, N, X + k * NX, U + k * NU, gmu + k * NC, rho, J, vl);
           red[lane] = J;
           red[G + lane] = vl;
         }
@@ -649,6 +698,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     for (int k = N - 1; k >= 0 && bp_ok; --k) {
       // ---- phase A: stage the knot's 3x3 blocks; per-foot AL terms; cost expansion
       COOP_PHASE {
+#pragma unroll 1
         for (int e = lane; e < 27; e += G) lin[e] = glin[k * 27 + e];
         if (lane < NF) {
           const int f = lane;
@@ -1043,6 +1093,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     // lane k <- knot k: dx_k = x_new (-) x_old, Riccati dual y_k = P_k dx_k + p_k (stored in DX) ...
     const int acc_lane = acc_j % G;
     COOP_PHASE {
+#pragma unroll 1
       for (int k = lane; k <= N; k += G) {
         double xn[NX], dx[NE];
 #pragma unroll
@@ -1061,7 +1112,9 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     COOP_SYNC();
     // ... then X, U <- accepted trajectory (cooperative strided copy)
     COOP_PHASE {
+#pragma unroll 1
       for (int e = lane; e < (N + 1) * NX; e += G) X[e] = ld_stream(gTX + (size_t)e * G + acc_lane);
+#pragma unroll 1
       for (int e = lane; e < N * NU; e += G) U[e] = ld_stream(gTU + (size_t)e * G + acc_lane);
     }
     COOP_SYNC();
@@ -1081,6 +1134,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       if (warm) warm[pid].valid = status != QMPC_STATUS_NONFINITE;
     }
     if (warm) {
+#pragma unroll 1
       for (int e = lane; e < N * 12; e += G) {
         const int k = e / 12, i = e % 12;
         warm[pid].u[k][i] = i < NU ? U[k * NU + i] : 0.0;

@@ -343,8 +343,8 @@ QMPC_HD void srb_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qmp
     double x[NX], xn[NX], u0[NU];
     for (int i = 0; i < NX; ++i) { x[i] = x0[i]; X[i] = x0[i]; }
     for (int i = 0; i < NU; ++i) u0[i] = m.uref_at(0, i);   // SetInput(u_traj_ref.at(0)), QuatMpc.cpp:253
-#pragma unroll 1
     const QmpcWarmStart* wsrc = (warm && warm[pid].valid) ? warm + pid : nullptr;
+#pragma unroll 1
     for (int k = 0; k < N; ++k) {
       if (wsrc) {
         const double* wr = warm_row(wsrc, k, N);

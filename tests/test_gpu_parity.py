@@ -272,10 +272,12 @@ def test_warm_start_closed_loop_matches_oracle(oracle):
     mpc = QuatMpc(horizon=10, max_batch=B)
     probs = random_batch(B, seed=21, gait="trot")
     d_warm = mpc.alloc_warm(B)
-    w_ref = np.zeros(B, dtype=abi.WARM_DTYPE)
     cold = _solve_dev(mpc, probs)
     viol = []
     for tick in range(3):
+        # every tick is a parity check on IDENTICAL inputs: the oracle starts from the buffer the GPU
+        # chain holds (a receding-horizon chain amplifies round-off level differences tick over tick)
+        w_ref = d_warm.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE).copy()
         d_res = mpc.grf_update_warm_device(mpc.to_device(probs), d_warm)
         torch.cuda.synchronize()
         res = mpc.results_to_numpy(d_res)
@@ -284,10 +286,9 @@ def test_warm_start_closed_loop_matches_oracle(oracle):
             assert res.tobytes() == cold.tobytes()          # invalid buffer -> cold start, bit-identical
         _check(res, ref, max_undetermined=5e-2)
         w = d_warm.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE)
-        ok = (res["status"] < 2) & (ref["status"] < 2)
+        ok = (res["status"] < 2) & (ref["status"] < 2) & (res["iterations"] == ref["iterations"])
         assert np.abs(w["u"][ok] - w_ref["u"][ok]).max() < TOL and (w["valid"] == w_ref["valid"]).all()
-        # failed solves are numerically undetermined: keep both chains on the same buffer from here on
-        w_ref[~ok] = w[~ok]
+        assert np.abs(w["u"][:, 0, :] - res["grf_body"]).max() == 0.0   # knot 0 of the buffer = returned GRFs
         viol.append(float(res["max_violation"].mean()))
         probs["torso_lin_vel_world"] += 0.01                 # the robot moved a little
     assert viol[-1] < viol[0]                                 # warm starts get closer to feasibility at the cap
