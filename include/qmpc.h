@@ -214,6 +214,43 @@ int qmpc_joint_torques(QmpcHandle* h, const QmpcResult* d_results, const double*
                        const int32_t* d_plan_contacts, int32_t movement_mode, int32_t batch, double* d_tau,
                        void* cuda_stream);
 
+/* ---- N3: reference generation ------------------------------------------------------------------
+ * The step immediately before the solve: QuatMpc::goal_update (QuatMpc.cpp:68-107) turns joystick
+ * commands and the torso feedback into the filtered references QuatMpc::grf_update reads
+ * (torso_pos_d_body / torso_lin_vel_d_body through six MovingWindowFilter(100) channels,
+ * MovingWindowFilter.hpp:16-71; torso_ang_vel_d_body), and the Raibert heuristic
+ * (BaseInterface.cpp:265-288) places the foot-hold targets.  Both are batched here with the
+ * per-robot controller state (desired torso position, filter windows) resident on the device. */
+typedef struct QmpcGoalInput {
+  double joy_vel[2];             /* state.joy.velx, vely                         QuatMpc.cpp:80-81     */
+  double joy_ang_rate[3];        /* state.joy.roll_rate, pitch_rate, yaw_rate    QuatMpc.cpp:93-95     */
+  double joy_body_height;        /* state.joy.body_height                        QuatMpc.cpp:100       */
+  double torso_pos_world[3];     /* fbk.torso_pos_world                          QuatMpc.cpp:74,102    */
+  double torso_quat[4];          /* fbk.torso_quat (w,x,y,z); torso_rot_mat and the yaw-only
+                                    torso_rot_mat_z are derived as in           BaseInterface.cpp:196-200 */
+  double torso_lin_vel_world[3]; /* fbk.torso_lin_vel_world                      BaseInterface.cpp:266 */
+} QmpcGoalInput;
+
+typedef struct QmpcRaibertParams {
+  double gait_freq;                  /* param.gait_freq                          LeggedState.cpp:77    */
+  double default_foot_pos_rel[12];   /* param.default_foot_pos_rel, 3x4 column-major  yaml:16-30       */
+  double delta_x_limit, delta_y_limit; /* FOOT_DELTA_X_LIMIT / _Y_LIMIT          LeggedParams.h        */
+} QmpcRaibertParams;
+int qmpc_default_raibert_params(QmpcRaibertParams* rp);
+
+/* Bytes of device memory holding the goal_update state of max_batch robots (zero-filled = freshly
+ * constructed controllers: no desired position yet, empty filter windows). */
+int64_t qmpc_goal_state_bytes(const QmpcHandle* h);
+/* One goal_update tick for `batch` robots (robot i keeps using slot i of d_goal_state).  Writes
+ * torso_pos_d_body, torso_lin_vel_d_body (filtered), torso_ang_vel_d_body, torso_quat and
+ * torso_lin_vel_world of d_problems[i]; the other QmpcProblem fields are left untouched. */
+int qmpc_goal_update(QmpcHandle* h, void* d_goal_state, const QmpcGoalInput* d_in, int32_t batch,
+                     QmpcProblem* d_problems, void* cuda_stream);
+/* ctrl.foot_pos_target_world / foot_pos_target_rel (batch x 12 each, 3x4 column-major; either may
+ * be NULL) from the Raibert heuristic. */
+int qmpc_raibert_targets(QmpcHandle* h, const QmpcRaibertParams* rp, const QmpcGoalInput* d_in, int32_t batch,
+                         double* d_foot_pos_target_world, double* d_foot_pos_target_rel, void* cuda_stream);
+
 /* ---- N4: warm start (trajectory shift) ------------------------------------------------------------
  * legged_ctrl builds a fresh ALTROSolver every tick and starts from u_ref (QuatMpc.cpp:218,253); the
  * ALTRO API offers ShiftTrajectory() for receding-horizon use (pattern shown in

@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from quaternion_mpc_b200.abi import (CONVEX_PROBLEM_DTYPE, GAIT_STATE_DTYPE, PROBLEM_DTYPE, QMPC_MAX_HORIZON,
+from quaternion_mpc_b200.abi import (CONVEX_PROBLEM_DTYPE, GAIT_STATE_DTYPE, GOAL_INPUT_DTYPE, QmpcRaibertParams, PROBLEM_DTYPE, QMPC_MAX_HORIZON,
                                      RESULT_DTYPE, WARM_DTYPE, QmpcConfig, QmpcLegParams)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -39,6 +39,8 @@ def lib():
         _LIB.qmpc_ref_solve_batch_sched.argtypes = [C.POINTER(QmpcConfig), vp, vp, C.c_int, vp, C.c_int]
         _LIB.qmpc_ref_solve_batch_convex_sched.argtypes = [C.POINTER(QmpcConfig), vp, vp, C.c_int, vp, C.c_int]
         _LIB.qmpc_ref_solve_batch_warm.argtypes = [C.POINTER(QmpcConfig), vp, vp, vp, C.c_int, vp, C.c_int]
+        _LIB.qmpc_ref_goal_update.argtypes = [vp, vp, C.c_int, vp]
+        _LIB.qmpc_ref_raibert_targets.argtypes = [C.POINTER(QmpcRaibertParams), vp, C.c_int, vp, vp]
         _LIB.qmpc_ref_predict_schedule.argtypes = [C.POINTER(QmpcConfig), vp, C.c_int, vp]
         _LIB.qmpc_ref_leg_kinematics.argtypes = [C.POINTER(QmpcLegParams), vp, C.c_int, vp, vp]
         _LIB.qmpc_ref_joint_torques.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
@@ -115,6 +117,28 @@ def solve_batch_convex_sched(cfg, problems, schedule, nthreads=1):
     if rc:
         raise RuntimeError(f"oracle failed rc={rc}")
     return out
+
+
+def new_goal_state(batch):
+    """Zero-filled per-robot state of QuatMpc::goal_update (filters + desired position), opaque bytes."""
+    return np.zeros((batch, lib().qmpc_ref_goal_state_bytes()), dtype=np.uint8)
+
+
+def goal_update(state, goal_inputs, problems):
+    """One QuatMpc::goal_update tick; `state` (from new_goal_state) and `problems` are updated IN PLACE."""
+    g = np.ascontiguousarray(goal_inputs, dtype=GOAL_INPUT_DTYPE)
+    assert problems.dtype == PROBLEM_DTYPE and problems.flags.c_contiguous and state.flags.c_contiguous
+    rc = lib().qmpc_ref_goal_update(state.ctypes.data, g.ctypes.data, g.shape[0], problems.ctypes.data)
+    assert rc == 0
+    return problems
+
+
+def raibert_targets(rp, goal_inputs):
+    g = np.ascontiguousarray(goal_inputs, dtype=GOAL_INPUT_DTYPE)
+    tw, tr = np.zeros((g.shape[0], 12)), np.zeros((g.shape[0], 12))
+    rc = lib().qmpc_ref_raibert_targets(C.byref(rp), g.ctypes.data, g.shape[0], tw.ctypes.data, tr.ctypes.data)
+    assert rc == 0
+    return tw, tr
 
 
 def predict_schedule(cfg, gait_states):

@@ -147,3 +147,130 @@ int qmpc_ref_joint_torques(const QmpcResult* res, const double* jac_foot, const 
     }
   return QMPC_OK;
 }
+
+/* ---------------------------------------------------------------- N3: reference generation */
+/* MovingWindowFilter (include/utils/MovingWindowFilter.hpp:16-71): Neumaier moving-window average.
+ * The std::deque is restated as a FIFO ring: front() is the oldest of the window_size_ samples. */
+#define MWF_WINDOW 100
+typedef struct MovingWindowFilter {
+  double sum_, correction_;
+  double value_deque_[MWF_WINDOW];
+  int size_, front_;
+} MovingWindowFilter;
+
+static void UpdateNeumaierSum(MovingWindowFilter* f, double value) {
+  double new_sum = f->sum_ + value;
+  if (fabs(f->sum_) >= fabs(value)) f->correction_ += (f->sum_ - new_sum) + value;
+  else f->correction_ += (value - new_sum) + f->sum_;
+  f->sum_ = new_sum;
+}
+static double CalculateAverage(MovingWindowFilter* f, double new_value) {
+  if (f->size_ < MWF_WINDOW) {
+    /* pass */
+  } else {
+    UpdateNeumaierSum(f, -f->value_deque_[f->front_]); /* -value_deque_.front(); pop_front() */
+    f->front_ = (f->front_ + 1) % MWF_WINDOW;
+    f->size_--;
+  }
+  UpdateNeumaierSum(f, new_value);
+  f->value_deque_[(f->front_ + f->size_) % MWF_WINDOW] = new_value; /* push_back */
+  f->size_++;
+  return (f->sum_ + f->correction_) / (double)MWF_WINDOW;
+}
+
+/* The members of QuatMpc + LeggedState.ctrl that goal_update keeps between ticks */
+typedef struct QmpcRefGoalState {
+  MovingWindowFilter torso_lin_vel_d_body_filter[3], torso_pos_d_body_filter[3]; /* QuatMpc.cpp:9-12 */
+  double torso_pos_d_world[3];
+  int torso_pos_d_world_init;
+} QmpcRefGoalState;
+
+int qmpc_ref_goal_state_bytes(void) { return (int)sizeof(QmpcRefGoalState); }
+
+/* Eigen::Quaterniond::toRotationMatrix (BaseInterface.cpp:196), row-major */
+static void quat_to_rot_ref(const double* q, double* R) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+/* Utils::quat_to_euler, yaw component (Utils.cpp:29-31) */
+static double quat_yaw_ref(const double* q) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  double y_sqr = y * y;
+  double t3 = +2.0 * (w * z + x * y);
+  double t4 = +1.0 - 2.0 * (y_sqr + z * z);
+  return atan2(t3, t4);
+}
+
+/* QuatMpc::goal_update (QuatMpc.cpp:68-107) for every robot of the batch; state[i] persists across calls
+ * (zero-filled = freshly constructed QuatMpc with torso_pos_d_world_init == false) */
+int qmpc_ref_goal_update(QmpcRefGoalState* state, const QmpcGoalInput* in, int batch, QmpcProblem* out) {
+  if (!state || !in || !out || batch < 0) return QMPC_ERR_ARG;
+  for (int b = 0; b < batch; ++b) {
+    QmpcRefGoalState* s = &state[b];
+    const QmpcGoalInput* g = &in[b];
+    double R[9];
+    quat_to_rot_ref(g->torso_quat, R);
+    const double yaw = quat_yaw_ref(g->torso_quat);
+    const double Rz[9] = {cos(yaw), -sin(yaw), 0, sin(yaw), cos(yaw), 0, 0, 0, 1}; /* AngleAxisd(yaw, UnitZ) */
+    if (!s->torso_pos_d_world_init) { /* :74-77 */
+      memcpy(s->torso_pos_d_world, g->torso_pos_world, sizeof(double) * 3);
+      s->torso_pos_d_world_init = 1;
+    }
+    const double v_rel[3] = {g->joy_vel[0], g->joy_vel[1], 0.0}; /* :80-82 */
+    double v_world[3], v_body[3], p_body[3];
+    for (int i = 0; i < 3; ++i) v_world[i] = Rz[3 * i] * v_rel[0] + Rz[3 * i + 1] * v_rel[1] + Rz[3 * i + 2] * v_rel[2];
+    for (int i = 0; i < 3; ++i) v_body[i] = R[i] * v_world[0] + R[3 + i] * v_world[1] + R[6 + i] * v_world[2];
+    for (int i = 0; i < 3; ++i) out[b].torso_lin_vel_d_body[i] = CalculateAverage(&s->torso_lin_vel_d_body_filter[i], v_body[i]);
+    for (int i = 0; i < 3; ++i) out[b].torso_ang_vel_d_body[i] = g->joy_ang_rate[i]; /* :93-95 */
+    s->torso_pos_d_world[0] += v_world[0] * 5.0 / 1000.0; /* :98-100 */
+    s->torso_pos_d_world[1] += v_world[1] * 5.0 / 1000.0;
+    s->torso_pos_d_world[2] = g->joy_body_height;
+    double dp[3];
+    for (int i = 0; i < 3; ++i) dp[i] = s->torso_pos_d_world[i] - g->torso_pos_world[i];
+    for (int i = 0; i < 3; ++i) p_body[i] = R[i] * dp[0] + R[3 + i] * dp[1] + R[6 + i] * dp[2]; /* :102 */
+    for (int i = 0; i < 3; ++i) out[b].torso_pos_d_body[i] = CalculateAverage(&s->torso_pos_d_body_filter[i], p_body[i]);
+    memcpy(out[b].torso_quat, g->torso_quat, sizeof(double) * 4);
+    memcpy(out[b].torso_lin_vel_world, g->torso_lin_vel_world, sizeof(double) * 3);
+  }
+  return QMPC_OK;
+}
+
+/* Raibert heuristic (BaseInterface.cpp:265-288) */
+int qmpc_ref_raibert_targets(const QmpcRaibertParams* rp, const QmpcGoalInput* in, int batch, double* tgt_world,
+                             double* tgt_rel) {
+  if (!rp || !in || batch < 0) return QMPC_ERR_ARG;
+  for (int b = 0; b < batch; ++b) {
+    const QmpcGoalInput* g = &in[b];
+    double R[9];
+    quat_to_rot_ref(g->torso_quat, R);
+    const double yaw = quat_yaw_ref(g->torso_quat);
+    const double c = cos(yaw), s = sin(yaw);
+    const double vrel0 = c * g->torso_lin_vel_world[0] + s * g->torso_lin_vel_world[1]; /* Rz^T v */
+    const double vrel1 = -s * g->torso_lin_vel_world[0] + c * g->torso_lin_vel_world[1];
+    const double k = sqrt(fabs(g->torso_pos_world[2]) / 9.81);
+    double d[2];
+    d[0] = k * (vrel0 - g->joy_vel[0]) + (1.0 / rp->gait_freq) / 2.0 * g->joy_vel[0];
+    if (d[0] < -rp->delta_x_limit) d[0] = -rp->delta_x_limit;
+    if (d[0] > rp->delta_x_limit) d[0] = rp->delta_x_limit;
+    d[1] = k * (vrel1 - g->joy_vel[1]) + (1.0 / rp->gait_freq) / 2.0 * g->joy_vel[1];
+    if (d[1] < -rp->delta_y_limit) d[1] = -rp->delta_y_limit;
+    if (d[1] > rp->delta_y_limit) d[1] = rp->delta_y_limit;
+    const double abs_d[2] = {c * d[0] - s * d[1], s * d[0] + c * d[1]};
+    for (int i = 0; i < 4; ++i) {
+      const double* p = rp->default_foot_pos_rel + 3 * i;
+      double a[3] = {c * p[0] - s * p[1], s * p[0] + c * p[1], p[2]}; /* Rz * default_foot_pos_rel */
+      a[0] += abs_d[0];
+      a[1] += abs_d[1];
+      if (tgt_rel)
+        for (int r = 0; r < 3; ++r) tgt_rel[12 * (size_t)b + 3 * i + r] = R[r] * a[0] + R[3 + r] * a[1] + R[6 + r] * a[2];
+      if (tgt_world)
+        for (int r = 0; r < 3; ++r) tgt_world[12 * (size_t)b + 3 * i + r] = a[r] + g->torso_pos_world[r];
+    }
+  }
+  return QMPC_OK;
+}

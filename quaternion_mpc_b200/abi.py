@@ -59,7 +59,15 @@ SCHEDULE_DTYPE = np.dtype([("mask", "u1", QMPC_MAX_HORIZON)])
 WARM_DTYPE = np.dtype([("u", "f8", (QMPC_MAX_HORIZON, 12)), ("valid", "i4"), ("pad_", "i4")], align=True)
 GAIT_STATE_DTYPE = np.dtype([("gait_phase", "f8", 4), ("gait_freq", "f8"), ("gait", "i4"), ("pad_", "i4")],
                             align=True)
+GOAL_INPUT_DTYPE = np.dtype([("joy_vel", "f8", 2), ("joy_ang_rate", "f8", 3), ("joy_body_height", "f8"),
+                             ("torso_pos_world", "f8", 3), ("torso_quat", "f8", 4), ("torso_lin_vel_world", "f8", 3)],
+                            align=True)
 QMPC_GAIT_TROT, QMPC_GAIT_TROT_WITH_STAND, QMPC_GAIT_CRAWL, QMPC_GAIT_STAND = 0, 1, 2, 3
+
+
+class QmpcRaibertParams(C.Structure):
+    _fields_ = [("gait_freq", C.c_double), ("default_foot_pos_rel", C.c_double * 12),
+                ("delta_x_limit", C.c_double), ("delta_y_limit", C.c_double)]
 
 
 class QmpcLegParams(C.Structure):
@@ -68,6 +76,7 @@ class QmpcLegParams(C.Structure):
 
 assert PROBLEM_DTYPE.itemsize == 35 * 8 + 16
 assert SCHEDULE_DTYPE.itemsize == 32 and GAIT_STATE_DTYPE.itemsize == 48
+assert GOAL_INPUT_DTYPE.itemsize == 16 * 8
 assert WARM_DTYPE.itemsize == QMPC_MAX_HORIZON * 12 * 8 + 8
 assert CONVEX_PROBLEM_DTYPE.itemsize == 40 * 8 + 24
 assert RESULT_DTYPE.itemsize == 29 * 8 + 8
@@ -77,7 +86,8 @@ EXPORTED_SYMBOLS = [
     "qmpc_solve_batch_host", "qmpc_solve_batch_convex_host", "qmpc_destroy", "qmpc_launch_count",
     "qmpc_last_error", "qmpc_status_string", "qmpc_abi_version", "qmpc_measure_fma_peak",
     "qmpc_predict_contact_schedule", "qmpc_solve_batch_sched", "qmpc_solve_batch_convex_sched",
-    "qmpc_solve_batch_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques", "qmpc_describe", "qmpc_solve_batch_warm",
+    "qmpc_solve_batch_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques", "qmpc_describe", "qmpc_solve_batch_warm", "qmpc_goal_state_bytes", "qmpc_goal_update",
+    "qmpc_default_raibert_params", "qmpc_raibert_targets",
 ]
 
 _LIB = None
@@ -129,6 +139,14 @@ def load_library():
     lib.qmpc_leg_kinematics.restype = C.c_int
     lib.qmpc_joint_torques.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.qmpc_joint_torques.restype = C.c_int
+    lib.qmpc_goal_state_bytes.argtypes = [vp]
+    lib.qmpc_goal_state_bytes.restype = i64
+    lib.qmpc_goal_update.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.qmpc_goal_update.restype = C.c_int
+    lib.qmpc_default_raibert_params.argtypes = [C.POINTER(QmpcRaibertParams)]
+    lib.qmpc_default_raibert_params.restype = C.c_int
+    lib.qmpc_raibert_targets.argtypes = [vp, C.POINTER(QmpcRaibertParams), vp, i32, vp, vp, vp]
+    lib.qmpc_raibert_targets.restype = C.c_int
     lib.qmpc_describe.argtypes = [vp, C.c_char_p, i32]
     lib.qmpc_describe.restype = C.c_int
     lib.qmpc_destroy.argtypes = [vp]

@@ -429,3 +429,47 @@ extern "C" int qmpc_joint_torques(QmpcHandle* h, const QmpcResult* d_results, co
   CU(cudaGetLastError());
   return QMPC_OK;
 }
+
+// ---- row N3: reference generation
+extern "C" int64_t qmpc_goal_state_bytes(const QmpcHandle* h) {
+  return h ? (int64_t)kGoalFields * (int64_t)sizeof(double) * h->max_batch : 0;
+}
+
+extern "C" int qmpc_goal_update(QmpcHandle* h, void* d_goal_state, const QmpcGoalInput* d_in, int32_t batch,
+                                QmpcProblem* d_problems, void* cuda_stream) {
+  int rc = periph_check(h, batch);
+  if (rc) return rc;
+  if (!d_goal_state || !d_in || !d_problems) return QMPC_ERR_ARG;
+  if (batch == 0) return QMPC_OK;
+  CU(cudaSetDevice(h->device));
+  qmpc_goal_update_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(
+      (double*)d_goal_state, (size_t)h->max_batch, d_in, batch, d_problems);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_default_raibert_params(QmpcRaibertParams* rp) {
+  if (!rp) return QMPC_ERR_ARG;
+  memset(rp, 0, sizeof(*rp));
+  rp->gait_freq = 2.2;                                  // gazebo_go1_quat_mpc.yaml:33
+  const double feet[12] = {0.20, 0.14, -0.30, 0.20, -0.14, -0.30, -0.20, 0.14, -0.30, -0.20, -0.14, -0.30};  // yaml:16-30
+  memcpy(rp->default_foot_pos_rel, feet, sizeof(feet));
+  rp->delta_x_limit = 0.5;                              // FOOT_DELTA_X_LIMIT  LeggedParams.h:21
+  rp->delta_y_limit = 0.3;                              // FOOT_DELTA_Y_LIMIT  LeggedParams.h:22
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_raibert_targets(QmpcHandle* h, const QmpcRaibertParams* rp, const QmpcGoalInput* d_in, int32_t batch,
+                                    double* d_foot_pos_target_world, double* d_foot_pos_target_rel, void* cuda_stream) {
+  int rc = periph_check(h, batch);
+  if (rc) return rc;
+  if (!rp || !d_in || (!d_foot_pos_target_world && !d_foot_pos_target_rel)) return QMPC_ERR_ARG;
+  if (batch == 0) return QMPC_OK;
+  CU(cudaSetDevice(h->device));
+  qmpc_raibert_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(*rp, d_in, batch, d_foot_pos_target_world,
+                                                                                 d_foot_pos_target_rel);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}

@@ -124,7 +124,121 @@ QMPC_HD inline void leg_torque(const double* jac /* 3x3 column-major */, const d
   }
 }
 
+// ---- N3: QuatMpc::goal_update (QuatMpc.cpp:68-107) with its per-robot state on the device ----------
+// State layout: element-major [field][robot] doubles (stride = robots the handle was created for), so
+// consecutive threads touch consecutive addresses.  Fields: desired world position (3), its
+// initialised flag, samples seen n, then for each of the six MovingWindowFilter(100) channels
+// (lin-vel x,y,z then pos x,y,z; QuatMpc.cpp:9-12): Neumaier sum, correction, ring of 100 samples.
+constexpr int kGoalWindow = 100;
+constexpr int kGoalFields = 5 + 6 * (2 + kGoalWindow);
+struct GoalStateRef {   // view of one robot's state
+  double* base;
+  size_t stride;
+  QMPC_HD double& at(int field) const { return base[(size_t)field * stride]; }
+};
+
+// Utils::quat_to_euler yaw (Utils.cpp:29-31), q = (w, x, y, z)
+QMPC_HD inline double quat_yaw(const double* q) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double t3 = +2.0 * (w * z + x * y);
+  const double t4 = +1.0 - 2.0 * (y * y + z * z);
+  return atan2(t3, t4);
+}
+
+// MovingWindowFilter::CalculateAverage (MovingWindowFilter.hpp:26-39): Neumaier sum over the last 100 samples
+QMPC_HD inline void neumaier_add(double& sum, double& corr, double v) {
+  const double ns = add_rn(sum, v);
+  if (fabs(sum) >= fabs(v)) corr = add_rn(corr, add_rn(add_rn(sum, -ns), v));
+  else corr = add_rn(corr, add_rn(add_rn(v, -ns), sum));
+  sum = ns;
+}
+QMPC_HD inline double window_average(const GoalStateRef& s, int ch, long long n, double v) {
+  const int f0 = 5 + ch * (2 + kGoalWindow);
+  double sum = s.at(f0), corr = s.at(f0 + 1);
+  double& slot = s.at(f0 + 2 + (int)(n % kGoalWindow));
+  if (n >= kGoalWindow) neumaier_add(sum, corr, -slot);   // the left-most value leaves the window first
+  neumaier_add(sum, corr, v);
+  slot = v;
+  s.at(f0) = sum;
+  s.at(f0 + 1) = corr;
+  return add_rn(sum, corr) / (double)kGoalWindow;
+}
+
+QMPC_HD inline void goal_update_one(const GoalStateRef& s, const QmpcGoalInput& in, QmpcProblem& out) {
+  double R[9];
+  quat_to_rot(in.torso_quat, R);                       // fbk.torso_rot_mat   BaseInterface.cpp:196
+  const double yaw = quat_yaw(in.torso_quat);          // fbk.torso_euler[2]  :197-198
+  const double cy = cos(yaw), sy = sin(yaw);           // torso_rot_mat_z = AngleAxis(yaw, UnitZ)  :200
+  if (s.at(3) == 0.0) {                                // torso_pos_d_world_init  QuatMpc.cpp:74-77
+    for (int i = 0; i < 3; ++i) s.at(i) = in.torso_pos_world[i];
+    s.at(3) = 1.0;
+  }
+  const double vrel[3] = {in.joy_vel[0], in.joy_vel[1], 0.0};                    // :80-82
+  const double vw[3] = {cy * vrel[0] - sy * vrel[1], sy * vrel[0] + cy * vrel[1], vrel[2]};   // :84
+  double vb[3], pb[3], pdw[3];
+  for (int i = 0; i < 3; ++i) vb[i] = R[i] * vw[0] + R[3 + i] * vw[1] + R[6 + i] * vw[2];    // R^T v  :85
+  pdw[0] = s.at(0) + vw[0] * 5.0 / 1000.0;             // :98-100
+  pdw[1] = s.at(1) + vw[1] * 5.0 / 1000.0;
+  pdw[2] = in.joy_body_height;
+  for (int i = 0; i < 3; ++i) s.at(i) = pdw[i];
+  const double dp[3] = {pdw[0] - in.torso_pos_world[0], pdw[1] - in.torso_pos_world[1], pdw[2] - in.torso_pos_world[2]};
+  for (int i = 0; i < 3; ++i) pb[i] = R[i] * dp[0] + R[3 + i] * dp[1] + R[6 + i] * dp[2];    // :102
+  const long long n = (long long)s.at(4);
+  for (int i = 0; i < 3; ++i) out.torso_lin_vel_d_body[i] = window_average(s, i, n, vb[i]);      // :86-89
+  for (int i = 0; i < 3; ++i) out.torso_pos_d_body[i] = window_average(s, 3 + i, n, pb[i]);      // :103-106
+  s.at(4) = (double)(n + 1);
+  for (int i = 0; i < 3; ++i) out.torso_ang_vel_d_body[i] = in.joy_ang_rate[i];                  // :93-95
+  for (int i = 0; i < 4; ++i) out.torso_quat[i] = in.torso_quat[i];
+  for (int i = 0; i < 3; ++i) out.torso_lin_vel_world[i] = in.torso_lin_vel_world[i];
+}
+
+// Raibert heuristic foot-hold targets (BaseInterface.cpp:265-288)
+QMPC_HD inline void raibert_one(const QmpcRaibertParams& rp, const QmpcGoalInput& in, double* tgt_world, double* tgt_rel) {
+  double R[9];
+  quat_to_rot(in.torso_quat, R);
+  const double yaw = quat_yaw(in.torso_quat);
+  const double cy = cos(yaw), sy = sin(yaw);
+  // torso_lin_vel_rel = Rz^T v_world
+  const double v0 = cy * in.torso_lin_vel_world[0] + sy * in.torso_lin_vel_world[1];
+  const double v1 = -sy * in.torso_lin_vel_world[0] + cy * in.torso_lin_vel_world[1];
+  const double k = sqrt(fabs(in.torso_pos_world[2]) / 9.81);
+  double d0 = k * (v0 - in.joy_vel[0]) + (1.0 / rp.gait_freq) / 2.0 * in.joy_vel[0];
+  if (d0 < -rp.delta_x_limit) d0 = -rp.delta_x_limit;
+  if (d0 > rp.delta_x_limit) d0 = rp.delta_x_limit;
+  double d1 = k * (v1 - in.joy_vel[1]) + (1.0 / rp.gait_freq) / 2.0 * in.joy_vel[1];
+  if (d1 < -rp.delta_y_limit) d1 = -rp.delta_y_limit;
+  if (d1 > rp.delta_y_limit) d1 = rp.delta_y_limit;
+  const double a0 = cy * d0 - sy * d1, a1 = sy * d0 + cy * d1;       // raibert_delta_abs = Rz delta_rel
+  for (int i = 0; i < 4; ++i) {
+    const double* p = rp.default_foot_pos_rel + 3 * i;
+    const double abs0 = cy * p[0] - sy * p[1] + a0, abs1 = sy * p[0] + cy * p[1] + a1, abs2 = p[2];
+    if (tgt_rel)
+      for (int a = 0; a < 3; ++a) tgt_rel[3 * i + a] = R[a] * abs0 + R[3 + a] * abs1 + R[6 + a] * abs2;
+    if (tgt_world) {
+      tgt_world[3 * i] = abs0 + in.torso_pos_world[0];
+      tgt_world[3 * i + 1] = abs1 + in.torso_pos_world[1];
+      tgt_world[3 * i + 2] = abs2 + in.torso_pos_world[2];
+    }
+  }
+}
+
 #ifdef __CUDACC__
+__global__ void __launch_bounds__(256)
+qmpc_goal_update_kernel(double* __restrict__ state, size_t stride, const QmpcGoalInput* __restrict__ in, int batch,
+                        QmpcProblem* __restrict__ problems) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  goal_update_one(GoalStateRef{state + i, stride}, in[i], problems[i]);
+}
+
+__global__ void __launch_bounds__(256)
+qmpc_raibert_kernel(QmpcRaibertParams rp, const QmpcGoalInput* __restrict__ in, int batch,
+                    double* __restrict__ tgt_world, double* __restrict__ tgt_rel) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  raibert_one(rp, in[i], tgt_world ? tgt_world + 12 * (size_t)i : nullptr, tgt_rel ? tgt_rel + 12 * (size_t)i : nullptr);
+}
+
 __global__ void __launch_bounds__(256)
 qmpc_predict_schedule_kernel(const QmpcGaitState* __restrict__ g, int batch, int N, double dt,
                              QmpcContactSchedule* __restrict__ out) {

@@ -107,6 +107,40 @@ class _BatchedMpc:
         self._check(rc)
         return d_results
 
+    # -- reference generation ------------------------------------------------------
+    def alloc_goal_state(self):
+        """Device state of QuatMpc::goal_update for max_batch robots (zero = freshly constructed)."""
+        import torch
+        n = int(self.lib.qmpc_goal_state_bytes(self._h))
+        return torch.zeros(n, dtype=torch.uint8, device=f"cuda:{self.device}")
+
+    def goal_update(self, d_goal_state, d_goal_inputs, d_problems, stream=None):
+        """One batched QuatMpc::goal_update tick (QuatMpc.cpp:68-107): fills the reference fields of
+        d_problems in place from joystick + torso feedback (GOAL_INPUT_DTYPE records, uint8 tensor)."""
+        import torch
+        batch = d_goal_inputs.shape[0]
+        assert d_goal_inputs.is_cuda and d_goal_inputs.dtype == torch.uint8
+        assert d_goal_inputs.shape[1] == abi.GOAL_INPUT_DTYPE.itemsize and d_problems.shape[0] == batch
+        assert d_problems.shape[1] == self.PROBLEM_DTYPE.itemsize and d_problems.is_contiguous()
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.qmpc_goal_update(self._h, d_goal_state.data_ptr(), d_goal_inputs.data_ptr(), batch,
+                                              d_problems.data_ptr(), s))
+        return d_problems
+
+    def raibert_targets(self, d_goal_inputs, params=None, stream=None):
+        """Raibert foot-hold targets (BaseInterface.cpp:265-288) -> (world (batch,12), rel (batch,12))."""
+        import torch
+        batch = d_goal_inputs.shape[0]
+        if params is None:
+            params = abi.QmpcRaibertParams()
+            self.lib.qmpc_default_raibert_params(C.byref(params))
+        tw = torch.empty((batch, 12), dtype=torch.float64, device=d_goal_inputs.device)
+        tr = torch.empty((batch, 12), dtype=torch.float64, device=d_goal_inputs.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.qmpc_raibert_targets(self._h, C.byref(params), d_goal_inputs.data_ptr(), batch,
+                                                  tw.data_ptr(), tr.data_ptr(), s))
+        return tw, tr
+
     # -- warm start / trajectory shift (SURVEY 8f N4) ---------------------------------------------
     def alloc_warm(self, batch):
         """Device buffer of `batch` QmpcWarmStart records, all invalid (first solve starts cold)."""

@@ -95,3 +95,14 @@ extern "C" int emul_leg_kinematics(const QmpcLegParams* lp, const double* q, int
   for (int t = 0; t < 4 * batch; ++t) leg_fk_jac(q + 3 * t, lp->rho_fix[t & 3], lp->rho_opt[t & 3], foot + 3 * t, jac + 9 * t);
   return 0;
 }
+
+// ---- row N3: goal_update / Raibert bodies on the host (state: element-major doubles, stride = capacity)
+extern "C" int emul_goal_state_doubles(void) { return kGoalFields; }
+extern "C" int emul_goal_update(double* state, int capacity, const QmpcGoalInput* in, int batch, QmpcProblem* out) {
+  for (int i = 0; i < batch; ++i) goal_update_one(GoalStateRef{state + i, (size_t)capacity}, in[i], out[i]);
+  return 0;
+}
+extern "C" int emul_raibert(const QmpcRaibertParams* rp, const QmpcGoalInput* in, int batch, double* tw, double* tr) {
+  for (int i = 0; i < batch; ++i) raibert_one(*rp, in[i], tw + 12 * i, tr + 12 * i);
+  return 0;
+}

@@ -162,3 +162,114 @@ def test_gpu_pipeline_joints_to_torques(oracle):
     assert np.abs(res["grf_body"][ok] - ref["grf_body"][ok]).max() < 1e-4
     rtau = oracle.joint_torques(ref, rj, pc.cpu().numpy(), 1)
     assert np.abs(tau[ok] - rtau[ok]).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ row N3
+def _goal_inputs(n, seed, tick=0):
+    rng = np.random.default_rng(seed * 1000 + tick)
+    g = np.zeros(n, dtype=abi.GOAL_INPUT_DTYPE)
+    g["joy_vel"] = np.stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.1, 0.1, n)], 1)   # joystick scales, yaml:100-101
+    g["joy_ang_rate"] = rng.uniform(-0.3, 0.3, (n, 3))
+    g["joy_body_height"] = rng.uniform(0.25, 0.32, n)
+    g["torso_pos_world"] = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(0.24, 0.33, n)], 1)
+    q = rng.normal(size=(n, 4)) * np.array([1, 0.1, 0.1, 0.5]) + np.array([2.0, 0, 0, 0])
+    g["torso_quat"] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    g["torso_lin_vel_world"] = rng.normal(0, 0.3, (n, 3))
+    return g
+
+
+def test_oracle_goal_update_filter_and_frames(oracle):
+    """The restated MovingWindowFilter(100) against a plain numpy moving average over >2 windows, and
+    the reference frames of goal_update against a direct evaluation (QuatMpc.cpp:80-106)."""
+    n, ticks = 8, 230
+    st = oracle.new_goal_state(n)
+    probs = np.zeros(n, dtype=abi.PROBLEM_DTYPE)
+    hist_v, hist_p = [], []
+    pos_d = None
+    for t in range(ticks):
+        g = _goal_inputs(n, 3, t)
+        if t:
+            g["torso_pos_world"] = prev_pos + 0.002          # slowly moving robot
+        prev_pos = g["torso_pos_world"].copy()
+        oracle.goal_update(st, g, probs)
+        w, x, y, z = g["torso_quat"].T
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]]).transpose(2, 0, 1)
+        yaw = np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+        vw = np.stack([np.cos(yaw) * g["joy_vel"][:, 0] - np.sin(yaw) * g["joy_vel"][:, 1],
+                       np.sin(yaw) * g["joy_vel"][:, 0] + np.cos(yaw) * g["joy_vel"][:, 1], np.zeros(n)], 1)
+        if pos_d is None:
+            pos_d = g["torso_pos_world"].copy()
+        pos_d[:, :2] += vw[:, :2] * 5.0 / 1000.0
+        pos_d[:, 2] = g["joy_body_height"]
+        hist_v.append(np.einsum("bji,bj->bi", R, vw))
+        hist_p.append(np.einsum("bji,bj->bi", R, pos_d - g["torso_pos_world"]))
+        want_v = np.sum(hist_v[-100:], axis=0) / 100.0       # divides by the window size even while filling
+        want_p = np.sum(hist_p[-100:], axis=0) / 100.0
+        assert np.abs(probs["torso_lin_vel_d_body"] - want_v).max() < 1e-12
+        assert np.abs(probs["torso_pos_d_body"] - want_p).max() < 1e-12
+        assert np.array_equal(probs["torso_ang_vel_d_body"], g["joy_ang_rate"])
+
+
+def test_emulated_goal_update_and_raibert_bodies(oracle, tmp_path):
+    """The kernel bodies (tests/emul) against the oracle over 250 ticks: the Neumaier filter state is
+    carried in the element-major device layout."""
+    import os
+    import subprocess
+    so = str(tmp_path / "libqmpc_emul.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so,
+                           os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul", "emul.cpp")])
+    em = C.CDLL(so)
+    n, cap = 33, 40
+    state = np.zeros(em.emul_goal_state_doubles() * cap)
+    st = oracle.new_goal_state(n)
+    a, b = np.zeros(n, dtype=abi.PROBLEM_DTYPE), np.zeros(n, dtype=abi.PROBLEM_DTYPE)
+    em.emul_goal_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    for t in range(250):
+        g = _goal_inputs(n, 5, t)
+        assert em.emul_goal_update(state.ctypes.data, cap, g.ctypes.data, n, a.ctypes.data) == 0
+        oracle.goal_update(st, g, b)
+        for f in ("torso_lin_vel_d_body", "torso_pos_d_body", "torso_ang_vel_d_body", "torso_quat", "torso_lin_vel_world"):
+            assert np.abs(a[f] - b[f]).max() < 1e-12, (t, f)
+    rp = abi.QmpcRaibertParams()
+    abi.load_library().qmpc_default_raibert_params(C.byref(rp))
+    g = _goal_inputs(n, 6)
+    tw, tr = np.zeros((n, 12)), np.zeros((n, 12))
+    em.emul_raibert.argtypes = [C.POINTER(abi.QmpcRaibertParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    assert em.emul_raibert(C.byref(rp), g.ctypes.data, n, tw.ctypes.data, tr.ctypes.data) == 0
+    rw, rr = oracle.raibert_targets(rp, g)
+    assert np.abs(tw - rw).max() < 1e-12 and np.abs(tr - rr).max() < 1e-12
+    # standing still, no command: targets are the default stance rotated by the yaw, under the torso
+    g["torso_lin_vel_world"] = 0
+    g["joy_vel"] = 0
+    rw, rr = oracle.raibert_targets(rp, g)
+    assert np.abs(rw.reshape(n, 4, 3)[:, :, 2] - (g["torso_pos_world"][:, 2:3] - 0.30)).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_goal_update_and_raibert(oracle):
+    import torch
+    from quaternion_mpc_b200 import QuatMpc
+    B = 5000
+    mpc = QuatMpc(horizon=10, max_batch=B + 7)       # stride of the state layout != batch
+    d_state = mpc.alloc_goal_state()
+    st = oracle.new_goal_state(B)
+    ref = np.zeros(B, dtype=abi.PROBLEM_DTYPE)
+    d_probs = mpc.to_device(np.zeros(B, dtype=abi.PROBLEM_DTYPE))
+    for t in range(130):                               # past one full filter window
+        g = _goal_inputs(B, 9, t)
+        d_g = torch.from_numpy(g.view(np.uint8).reshape(B, -1)).cuda()
+        mpc.goal_update(d_state, d_g, d_probs)
+        oracle.goal_update(st, g, ref)
+        if t in (0, 1, 99, 100, 129):
+            got = d_probs.cpu().numpy().reshape(-1).view(abi.PROBLEM_DTYPE)
+            for f in ("torso_lin_vel_d_body", "torso_pos_d_body", "torso_ang_vel_d_body", "torso_quat",
+                      "torso_lin_vel_world"):
+                assert np.abs(got[f] - ref[f]).max() < 1e-11, (t, f)   # fp64; device atan2/sin/cos differ in the last ulp
+            assert (got["foot_pos_body"] == 0).all()    # fields goal_update does not own are untouched
+    tw, tr = mpc.raibert_targets(d_g)
+    rp = abi.QmpcRaibertParams()
+    mpc.lib.qmpc_default_raibert_params(C.byref(rp))
+    rw, rr = oracle.raibert_targets(rp, g)
+    assert np.abs(tw.cpu().numpy() - rw).max() < 1e-11 and np.abs(tr.cpu().numpy() - rr).max() < 1e-11
