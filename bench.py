@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--gait", default="trot")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the streaming kernels either side of the solve")
     return ap.parse_args()
 
 
@@ -95,6 +96,52 @@ def cpu_arm(cfg, probs, threads):
     out = oracle.solve_batch(cfg, probs, nthreads=threads)
     dt = time.perf_counter() - t0
     return len(probs) / dt, dt, out
+
+
+def aux_kernels(device, cfg, hbm_peak, robots=1 << 20, reps=20):
+    """The HBM-bound streaming kernels either side of the solve, timed with CUDA events
+    on 2^20 robots (inputs resident, > L2): achieved GB/s of the ALGORITHMIC bytes against the HBM peak."""
+    import torch
+    from quaternion_mpc_b200 import QuatMpc, abi
+    from quaternion_mpc_b200.workloads import random_gait_states
+    mpc = QuatMpc(max_batch=robots, device=device, cfg=cfg)
+    dev = f"cuda:{device}"
+    g = torch.from_numpy(random_gait_states(robots, seed=0).view(np.uint8).reshape(robots, -1)).to(dev)
+    q = (torch.rand((robots, 12), dtype=torch.float64, device=dev) - 0.5)
+    gin = np.zeros(robots, dtype=abi.GOAL_INPUT_DTYPE)
+    gin["torso_quat"][:, 0] = 1.0
+    gin["joy_vel"][:, 0] = 0.3
+    gin["torso_pos_world"][:, 2] = 0.3
+    d_gin = torch.from_numpy(gin.view(np.uint8).reshape(robots, -1)).to(dev)
+    d_probs = torch.zeros((robots, abi.PROBLEM_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_res = torch.zeros((robots, abi.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_state = mpc.alloc_goal_state()
+    foot, jac = mpc.leg_kinematics(q)
+    pc = torch.ones((robots, 4), dtype=torch.int32, device=dev)
+    cases = {
+        # bytes per robot: what the kernel must read + write (struct sizes from include/qmpc.h)
+        "predict_contact_schedule": (48 + 32, lambda: mpc.predict_contact_schedule(g)),
+        "leg_kinematics": (96 + 96 + 288, lambda: mpc.leg_kinematics(q)),
+        "joint_torques": (96 + 288 + 16 + 96, lambda: mpc.joint_torques(d_res, jac, pc)),
+        "goal_update": (128 + 5 * 16 + 6 * (2 * 16 + 16) + 128, lambda: mpc.goal_update(d_state, d_gin, d_probs)),
+        "raibert_targets": (128 + 192, lambda: mpc.raibert_targets(d_gin)),
+    }
+    out = {"robots": robots}
+    for name, (bpr, fn) in cases.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        gbs = robots * bpr / (us * 1e-6) / 1e9
+        out[name] = {"us_per_launch": us, "bytes_per_robot": bpr, "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak}
+    mpc.close()
+    return out
 
 
 def main():
@@ -246,6 +293,10 @@ def main():
                 "algorithmic_bytes_per_solve": IN_BYTES + OUT_BYTES},
     }
 
+    aux = None
+    if not a.no_aux:
+        aux = aux_kernels(local, cfg, hbm_peak)
+
     cpu = None
     if not a.no_cpu_baseline:
         # bounded sample: probe the host rate on 16 problems per core, then time ~8 s worth of the
@@ -273,6 +324,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": B * IN_BYTES,
                 "d2h_bytes_per_step": B * OUT_BYTES},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "aux_kernels": aux,
     }
     print(json.dumps(line))
     if world > 1:

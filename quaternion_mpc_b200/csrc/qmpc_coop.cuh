@@ -317,14 +317,16 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
   // Mode 1 runs on all `tstride` lanes of the problem in lock-step: the gain matrix of knot k+1 is
   // copied (cp.async, 16 bytes per request, the lanes split the rows) from the L2-resident scratch
   // into a double buffer in shared memory while knot k is being computed, so the 72 broadcast reads
-  // of K_k per lane are shared-memory reads instead of L2 round trips.
-  constexpr int kChunks = NU * 12 / 2;
+  // of K_k per lane are shared-memory reads instead of L2 round trips.  The feed-forward d_k rides along.
+  constexpr int kChunksK = NU * 12 / 2, kChunks = kChunksK + NU / 2, kStage = NU * 12 + NU;
   auto stage_gain = [&](int k) {
-    const double* src = gK + (size_t)k * NU * 12;
-    double* dst = kstage + (k & 1) * NU * 12;
+    const double* srcK = gK + (size_t)k * NU * 12;
+    const double* srcd = gd + (size_t)k * NU - 2 * kChunksK;
+    double* dst = kstage + (k & 1) * kStage;
     for (int c = tl; c < kChunks; c += tstride) {
       const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 2 * c) : "memory");
+      const double* src = (c < kChunksK ? srcK : srcd) + 2 * c;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -365,7 +367,8 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
     // ---- per foot: force, input cost, cone rows / AL merit, wrench
     double mom0 = 0, mom1 = 0, mom2 = 0, fs0 = 0, fs1 = 0, fs2 = 0, acc = 0;
 #if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_KSTAGE)
-    const double* Kk = mode == 1 ? kstage + (k & 1) * NU * 12 : gK;
+    const double* Kk = mode == 1 ? kstage + (k & 1) * kStage : gK;
+    const double* dk = mode == 1 ? Kk + NU * 12 : gd;
     if (mode == 1) {
       asm volatile("cp.async.wait_all;" ::: "memory");
       __syncwarp(lane_mask);              // K_k visible to all lanes; everyone is done with K_{k-1}
@@ -373,6 +376,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
     }
 #else
     const double* Kk = gK + (size_t)k * NU * 12;
+    const double* dk = gd + k * NU;
 #endif
 #pragma unroll 1
     for (int f = 0; f < NF; ++f) {
@@ -411,9 +415,9 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
 #pragma unroll
         for (int l = 0; l < NE; ++l) t2 += K0[24 + l] * dx[l];
 #endif
-        u0 = U[k * NU + 3 * f] + alpha * gd[k * NU + 3 * f] + t0;
-        u1 = U[k * NU + 3 * f + 1] + alpha * gd[k * NU + 3 * f + 1] + t1;
-        u2 = U[k * NU + 3 * f + 2] + alpha * gd[k * NU + 3 * f + 2] + t2;
+        u0 = U[k * NU + 3 * f] + alpha * dk[3 * f] + t0;
+        u1 = U[k * NU + 3 * f + 1] + alpha * dk[3 * f + 1] + t1;
+        u2 = U[k * NU + 3 * f + 2] + alpha * dk[3 * f + 2] + t2;
       }
       if (mode != 1) { U[k * NU + 3 * f] = u0; U[k * NU + 3 * f + 1] = u1; U[k * NU + 3 * f + 2] = u2; }
       else {
@@ -517,8 +521,10 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   double* S = sm + L::sS(N);
   double* Qux = sm + L::sQux(N);
   double* vec = sm + L::sVec(N);
-  double* red = T;   // 2 G reduction slots; only used outside the backward pass, where T is dead
-  static_assert(2 * G <= 72, "reduction slots alias T");
+  // 2 G reduction slots at the tail of T (only used outside the backward pass, where T is dead); the
+  // roll-out's gain stage (2 x (NU * 12 + NU) doubles) occupies P, PA and the head of T meanwhile
+  double* red = T + 72 - 2 * G;
+  static_assert(2 * (NU * 12 + NU) <= 288 + 72 - 2 * G, "gain stage overlaps the reduction slots");
   double* lin = sm + L::sLin(N);
   double* gK = gs + L::gK(N);
   double* gd = gs + L::gd(N);
@@ -1100,7 +1106,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         for (int i = 0; i < NX; ++i) xn[i] = ld_stream(gTX + (size_t)(k * NX + i) * G + acc_lane);
         state_diff<M>(xn, X + k * NX, dx);
         const double* Pk = gP + (size_t)k * 144;
-#pragma unroll 1   // rolled over the rows: once per iteration, 12x less code (instruction-cache bound kernel)
+#pragma unroll 3   // nearly rolled (once per iteration, 4x less code than unrolled: the kernel is instruction-cache
+                    // bound) yet three rows of P_k - 36 L2 loads - are in flight per trip
         for (int a = 0; a < NE; ++a) {
           double t = gpv[k * 12 + a];
 #pragma unroll

@@ -139,7 +139,16 @@ bool CudaQuatMpc::grf_update(LeggedState& state) {
   }
   // ---- solve on the GPU (batch = 1; H2D, kernel, D2H, sync inside the call)
   QmpcResult r;
-  const int rc = qmpc_solve_batch_host(handle_, &p, 1, &r);
+  int rc;
+  if (use_schedule_ && state.ctrl.movement_mode != 0) {
+    std::memset(&sched_, 0, sizeof(sched_));
+    for (int k = 0; k < horizon && k < QMPC_MAX_HORIZON; ++k)
+      for (int leg = 0; leg < NUM_LEG; ++leg)
+        if (leg_FSM[leg].predict_contact_state(k * h / 1000.0) == STANCE) sched_.mask[k] |= (uint8_t)(1u << leg);
+    rc = qmpc_solve_batch_sched_host(handle_, &p, &sched_, 1, &r);
+  } else {
+    rc = qmpc_solve_batch_host(handle_, &p, 1, &r);
+  }
   if (rc != QMPC_OK) return true;  // drop-in: the reference never reports failure; outputs left untouched
   last_ = r;
   // ---- unpack what QuatMpc::grf_update writes (QuatMpc.cpp:133-137, 231, 261-272)

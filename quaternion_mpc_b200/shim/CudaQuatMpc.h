@@ -33,6 +33,13 @@ class CudaQuatMpc : public LeggedMpc {
   bool foot_update(LeggedState& state) override;  // QuatMpc.cpp:278-305
   bool terrain_update(LeggedState&) override { return true; }
 
+  // Optional (off by default = reference behaviour): plan with the per-knot contact schedule that
+  // the reference's own, unused, LeggedContactFSM::predict_contact_state yields at t + k h
+  // (LeggedContactFSM.cpp:272-286; TODO at ConvexMpc.cpp:82) instead of one mask for the horizon.
+  void enable_contact_schedule(bool on) { use_schedule_ = on; }
+  const QmpcContactSchedule& last_schedule() const { return sched_; }
+  LeggedContactFSM& leg_fsm(int leg) { return leg_FSM[leg]; }   // the inherited per-leg gait FSM
+
   // last solve's status / iteration count (the reference discards ALTRO's SolveStatus)
   int last_status() const { return last_.status; }
   int last_iterations() const { return last_.iterations; }
@@ -53,6 +60,8 @@ class CudaQuatMpc : public LeggedMpc {
   QmpcConfig cfg_;
   QmpcProblem prob_;
   QmpcResult last_;
+  bool use_schedule_ = false;
+  QmpcContactSchedule sched_{};
 };
 
 }  // namespace legged

@@ -80,10 +80,21 @@ struct LeggedState {
   LeggedParam param;
   bool estimator_init = true;
 };
+enum LeggedContactState { SWING, STANCE };   // utils/LeggedContactFSM.h:12-15
 struct LeggedContactFSM {
   Eigen::Vector3d FSM_foot_pos_target_world, FSM_foot_vel_target_world, FSM_foot_acc_target_world;
   bool contact = true;
-  void reset_params(LeggedState&, int) {}
+  int leg_id = 0;
+  double gait_phase = 0.0, gait_freq = 2.2;
+  // stub of LeggedContactFSM::predict_contact_state for the default trot pattern (LeggedContactFSM.cpp:87-108, 272-286)
+  LeggedContactState predict_contact_state(double dt) {
+    double ph = gait_phase + gait_freq * dt;
+    while (ph > 1.0) ph -= 1.0;
+    const bool first_half = ph <= 0.5;
+    const bool diag = leg_id == 0 || leg_id == 3;
+    return (first_half == diag) ? STANCE : SWING;
+  }
+  void reset_params(LeggedState&, int id) { leg_id = id; }
   void reset() { contact = true; }
   double update(double, double, Eigen::Vector3d, Eigen::Vector3d, bool) { return 0.0; }
   bool get_contact_state() const { return contact; }

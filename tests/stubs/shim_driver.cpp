@@ -20,8 +20,9 @@ extern "C" int shim_construct_only(int device, char* err, int errlen) {
 
 // in: QmpcProblem (desired quantities are fed through joystick-free state: see below); ticks >= 1
 // out_problem: the QmpcProblem the shim packed on the last tick; out_grf_body/out_grf_world: 12 each
-extern "C" int shim_run(const QmpcProblem* in, int horizon, int ticks, QmpcProblem* out_problem,
-                        double* out_grf_body, double* out_grf_world, int* status_iters) {
+static int shim_run_impl(const QmpcProblem* in, int horizon, int ticks, QmpcProblem* out_problem,
+                         double* out_grf_body, double* out_grf_world, int* status_iters, double gait_phase,
+                         unsigned char* out_sched) {
   using namespace legged;
   LeggedState st;
   st.param.mpc_horizon = horizon;
@@ -51,15 +52,20 @@ extern "C" int shim_run(const QmpcProblem* in, int horizon, int ticks, QmpcProbl
   st.ctrl.torso_quat_d.w() = in->torso_quat_d[0]; st.ctrl.torso_quat_d.x() = in->torso_quat_d[1];
   st.ctrl.torso_quat_d.y() = in->torso_quat_d[2]; st.ctrl.torso_quat_d.z() = in->torso_quat_d[3];
   st.joy.velx = 0.3; st.joy.vely = -0.05; st.joy.yaw_rate = 0.2; st.joy.body_height = 0.31;
-  st.ctrl.movement_mode = 0;  // stand: foot_update sets all plan_contacts
+  st.ctrl.movement_mode = out_sched ? 1 : 0;  // 0 = stand: foot_update sets all plan_contacts
   std::unique_ptr<LeggedMpc> mpc_ptr;
   try {
     mpc_ptr = std::make_unique<CudaQuatMpc>(st, 0);
   } catch (const std::exception&) {
     return 1;
   }
-  for (int t = 0; t < ticks; ++t) mpc_ptr->update(st);
   auto* q = static_cast<CudaQuatMpc*>(mpc_ptr.get());
+  if (out_sched) {   // walking: plan with the FSM's predicted per-knot contacts
+    q->enable_contact_schedule(true);
+    for (int leg = 0; leg < 4; ++leg) q->leg_fsm(leg).gait_phase = gait_phase;
+  }
+  for (int t = 0; t < ticks; ++t) mpc_ptr->update(st);
+  if (out_sched) std::memcpy(out_sched, q->last_schedule().mask, QMPC_MAX_HORIZON);
   *out_problem = q->last_problem();
   for (int i = 0; i < 12; ++i) {
     out_grf_body[i] = st.ctrl.optimized_input[i];
@@ -68,4 +74,14 @@ extern "C" int shim_run(const QmpcProblem* in, int horizon, int ticks, QmpcProbl
   status_iters[0] = q->last_status();
   status_iters[1] = q->last_iterations();
   return 0;
+}
+
+extern "C" int shim_run(const QmpcProblem* in, int horizon, int ticks, QmpcProblem* out_problem, double* out_grf_body,
+                        double* out_grf_world, int* status_iters) {
+  return shim_run_impl(in, horizon, ticks, out_problem, out_grf_body, out_grf_world, status_iters, 0.0, nullptr);
+}
+// same with enable_contact_schedule(true): also returns the schedule the shim built from leg_FSM[i].predict_contact_state
+extern "C" int shim_run_sched(const QmpcProblem* in, int horizon, int ticks, double gait_phase, QmpcProblem* out_problem,
+                              unsigned char* out_sched, double* out_grf_body, double* out_grf_world, int* status_iters) {
+  return shim_run_impl(in, horizon, ticks, out_problem, out_grf_body, out_grf_world, status_iters, gait_phase, out_sched);
 }

@@ -53,3 +53,22 @@ def test_shim_tick_matches_oracle(shim, oracle):
     assert np.abs(ref["grf_body"][0] - gb).max() < 1e-4
     assert np.abs(ref["grf_world"][0] - gw).max() < 1e-4
     assert si[1] == ref["iterations"][0]
+
+
+@pytest.mark.gpu
+def test_shim_contact_schedule_mode(shim, oracle):
+    """enable_contact_schedule(true): the shim asks the (stub of the) reference's own
+    LeggedContactFSM::predict_contact_state for every knot and solves through the schedule entry point."""
+    p = random_batch(1, seed=22, gait="stand")
+    out_p = np.zeros(1, dtype=abi.PROBLEM_DTYPE)
+    sched = np.zeros((1, abi.QMPC_MAX_HORIZON), dtype=np.uint8)
+    gb, gw, si = np.zeros(12), np.zeros(12), np.zeros(2, dtype=np.int32)
+    shim.shim_run_sched.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    rc = shim.shim_run_sched(p.ctypes.data, 10, 2, 0.43, out_p.ctypes.data, sched.ctypes.data, gb.ctypes.data,
+                             gw.ctypes.data, si.ctypes.data)
+    assert rc == 0
+    # trot from phase 0.43 at 2.2 Hz, 10 ms knots: FL+RR (1001b) until the phase passes 0.5, then FR+RL (0110b)
+    assert sched[0, :4].tolist() == [9, 9, 9, 9] and sched[0, 4:10].tolist() == [6] * 6 and (sched[0, 10:] == 0).all()
+    ref = oracle.solve_batch_sched(default_config(0, 10), out_p, sched)
+    assert np.abs(ref["grf_body"][0] - gb).max() < 1e-4 and si[1] == ref["iterations"][0]
