@@ -379,7 +379,7 @@ extern "C" int qmpc_predict_contact_schedule(QmpcHandle* h, const QmpcGaitState*
   if (!d_gait || !d_sched) return QMPC_ERR_ARG;
   if (batch == 0) return QMPC_OK;
   CU(cudaSetDevice(h->device));
-  qmpc_predict_schedule_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(
+  qmpc_predict_schedule_kernel<<<(4 * batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(
       d_gait, batch, h->cfg.horizon, h->cfg.dt, d_sched);
   h->launches += 1;
   CU(cudaGetLastError());

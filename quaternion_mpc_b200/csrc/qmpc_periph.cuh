@@ -30,6 +30,26 @@ QMPC_HD inline double add_rn(double a, double b) {
 #endif
 }
 
+QMPC_HD inline void sincos_rn(double a, double* s, double* c) {
+#ifdef __CUDA_ARCH__
+  sincos(a, s, c);   // one argument reduction for both (these kernels are fp64-trig bound, not HBM bound, otherwise)
+#else
+  *s = sin(a); *c = cos(a);
+#endif
+}
+
+// cos / sin of the yaw angle of q = (w, x, y, z) without going through the angle: Utils::quat_to_euler
+// returns yaw = atan2(t3, t4) (Utils.cpp:29-31) and BaseInterface.cpp:200 builds AngleAxis(yaw, UnitZ) from
+// it; (t4, t3) / |(t4, t3)| is the same pair to 1 ulp and saves an fp64 atan2 + sincos per robot.
+QMPC_HD inline void quat_yaw_cs(const double* q, double* cy, double* sy) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double t3 = +2.0 * (w * z + x * y);
+  const double t4 = +1.0 - 2.0 * (y * y + z * z);
+  const double r = sqrt(t3 * t3 + t4 * t4);
+  if (r > 0.0) { *cy = t4 / r; *sy = t3 / r; }
+  else { *cy = 1.0; *sy = 0.0; }   // atan2(0, 0) = 0
+}
+
 // One leg's gait pattern: up to 3 segments (switch time, STANCE?) over the unit gait cycle.
 struct GaitLegPattern {
   int n;
@@ -96,9 +116,9 @@ QMPC_HD inline void leg_fk_jac(const double* q, const double* rf, const double* 
   const double ox = rf[0], oy = rf[1], d = rf[2], lt = rf[3], lc = rf[4];
   const double cx = ro[0], cy = ro[1], cz = ro[2];
   double s0, c0, s1, c1, s12, c12;
-  s0 = sin(q[0]); c0 = cos(q[0]);
-  s1 = sin(q[1]); c1 = cos(q[1]);
-  s12 = sin(q[1] + q[2]); c12 = cos(q[1] + q[2]);
+  sincos_rn(q[0], &s0, &c0);
+  sincos_rn(q[1], &s1, &c1);
+  sincos_rn(q[1] + q[2], &s12, &c12);
   const double a = lc - cz, e = cy + d;
   const double L = lt * c1 + cx * s12 + a * c12;
   const double dL2 = cx * c12 - a * s12;   // dL/dq2
@@ -167,8 +187,8 @@ QMPC_HD inline double window_average(const GoalStateRef& s, int ch, long long n,
 QMPC_HD inline void goal_update_one(const GoalStateRef& s, const QmpcGoalInput& in, QmpcProblem& out) {
   double R[9];
   quat_to_rot(in.torso_quat, R);                       // fbk.torso_rot_mat   BaseInterface.cpp:196
-  const double yaw = quat_yaw(in.torso_quat);          // fbk.torso_euler[2]  :197-198
-  const double cy = cos(yaw), sy = sin(yaw);           // torso_rot_mat_z = AngleAxis(yaw, UnitZ)  :200
+  double cy, sy;                                       // torso_rot_mat_z = AngleAxis(fbk.torso_euler[2], UnitZ)  :197-200
+  quat_yaw_cs(in.torso_quat, &cy, &sy);
   if (s.at(3) == 0.0) {                                // torso_pos_d_world_init  QuatMpc.cpp:74-77
     for (int i = 0; i < 3; ++i) s.at(i) = in.torso_pos_world[i];
     s.at(3) = 1.0;
@@ -196,8 +216,8 @@ QMPC_HD inline void goal_update_one(const GoalStateRef& s, const QmpcGoalInput& 
 QMPC_HD inline void raibert_one(const QmpcRaibertParams& rp, const QmpcGoalInput& in, double* tgt_world, double* tgt_rel) {
   double R[9];
   quat_to_rot(in.torso_quat, R);
-  const double yaw = quat_yaw(in.torso_quat);
-  const double cy = cos(yaw), sy = sin(yaw);
+  double cy, sy;
+  quat_yaw_cs(in.torso_quat, &cy, &sy);
   // torso_lin_vel_rel = Rz^T v_world
   const double v0 = cy * in.torso_lin_vel_world[0] + sy * in.torso_lin_vel_world[1];
   const double v1 = -sy * in.torso_lin_vel_world[0] + cy * in.torso_lin_vel_world[1];
@@ -239,18 +259,31 @@ qmpc_raibert_kernel(QmpcRaibertParams rp, const QmpcGoalInput* __restrict__ in, 
   raibert_one(rp, in[i], tgt_world ? tgt_world + 12 * (size_t)i : nullptr, tgt_rel ? tgt_rel + 12 * (size_t)i : nullptr);
 }
 
+// One thread per (robot, leg): 32 stance bits of its leg, exchanged inside the quad by shuffles; lane `leg`
+// of the quad then stores knots 8 leg .. 8 leg + 7 (one 8-byte store, 32 contiguous bytes per robot).
 __global__ void __launch_bounds__(256)
 qmpc_predict_schedule_kernel(const QmpcGaitState* __restrict__ g, int batch, int N, double dt,
                              QmpcContactSchedule* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= batch) return;
-  QmpcContactSchedule s;
-  predict_schedule_one(g[i], N, dt, s);
-  // 32 bytes per robot: two 16-byte stores
-  const uint4* src = reinterpret_cast<const uint4*>(&s);
-  uint4* dst = reinterpret_cast<uint4*>(out + i);
-  dst[0] = src[0];
-  dst[1] = src[1];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int leg = t & 3;
+  const int robot = (t >> 2) < batch ? (t >> 2) : batch - 1;   // tail threads shadow the last robot (full-warp shuffles)
+  const QmpcGaitState* gs = g + robot;
+  const GaitLegPattern pat = gait_pattern(gs->gait, leg);
+  const double phase = gs->gait_phase[leg], freq = gs->gait_freq;
+  unsigned bits = 0;
+  for (int k = 0; k < N; ++k) bits |= (unsigned)predict_contact(pat, phase, freq, mul_rn((double)k, dt)) << k;
+  const unsigned b0 = __shfl_sync(0xffffffffu, bits, (threadIdx.x & ~3) + 0);
+  const unsigned b1 = __shfl_sync(0xffffffffu, bits, (threadIdx.x & ~3) + 1);
+  const unsigned b2 = __shfl_sync(0xffffffffu, bits, (threadIdx.x & ~3) + 2);
+  const unsigned b3 = __shfl_sync(0xffffffffu, bits, (threadIdx.x & ~3) + 3);
+  unsigned long long w = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = 8 * leg + j;
+    const unsigned m = ((b0 >> k) & 1u) | (((b1 >> k) & 1u) << 1) | (((b2 >> k) & 1u) << 2) | (((b3 >> k) & 1u) << 3);
+    w |= (unsigned long long)m << (8 * j);
+  }
+  if ((t >> 2) < batch) reinterpret_cast<unsigned long long*>(out + robot)[leg] = w;
 }
 
 __global__ void __launch_bounds__(256)
