@@ -207,7 +207,9 @@ struct CoopLayout {
   QMPC_HD static size_t glin(int N) { return gmu(N) + (size_t)N * NC; }
   QMPC_HD static size_t gDX(int N) { return glin(N) + (size_t)N * 27; }
   // trial trajectories of the speculative line search, [element][lane] so the 16 lanes store coalesced
-  QMPC_HD static size_t gTX(int N) { return (gDX(N) + (size_t)(N + 1) * 12 + 15) / 16 * 16; }
+  // cost expansion of every knot (gradient 12 + attitude Hessian block 9), written once per iteration
+  QMPC_HD static size_t gLX(int N) { return gDX(N) + (size_t)(N + 1) * 12; }
+  QMPC_HD static size_t gTX(int N) { return (gLX(N) + (size_t)(N + 1) * 21 + 15) / 16 * 16; }
   QMPC_HD static size_t gTU(int N) { return gTX(N) + (size_t)(N + 1) * 13 * G; }
   QMPC_HD static size_t scratch_doubles(int N) { return (gTU(N) + (size_t)N * NU * G + 15) / 16 * 16; }
 };
@@ -746,6 +748,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   double* X = sm + L::sX(N);
   double* U = sm + L::sU(N);
   double* DX = gs + L::gDX(N);
+  double* gLX = gs + L::gLX(N);
   double* gTX = gs + L::gTX(N);
   double* gTU = gs + L::gTU(N);
   double* P = sm + L::sP(N);
@@ -808,16 +811,26 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 
 #pragma unroll 1
   for (int it = 0; it < o.iterations_max && status == QMPC_STATUS_MAX_ITERATIONS; ++it) {
-    // ---------------- linearise: lane k <- knot k (27 doubles to the scratch)
+    // ---------------- expansions, lane k <- knot k: cost gradient + attitude Hessian block (21 doubles) and
+    // the dynamics blocks (27 doubles).  The cost expansion used to be recomputed by single lanes inside
+    // the backward pass (on its critical path, and 4 KB of code in its loop) and again for the
+    // stationarity test; it is the same X throughout the iteration.
     COOP_PHASE {
 #pragma unroll 1
-      for (int k = lane; k < N; k += G) {
-        KnotLin Lk;
-        srb_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
-        for (int i = 0; i < 9; ++i) {
-          glin[k * 27 + i] = Lk.Aff[i];
-          glin[k * 27 + 9 + i] = Lk.Afw[i];
-          glin[k * 27 + 18 + i] = Lk.Cf[i];
+      for (int k = lane; k <= N; k += G) {
+        double lx[NE], Hk[9], hphi;
+        cost_expand(m, cfg, k, X + k * NX, lx, &hphi);
+        hphi_block(cfg, X + k * NX, hphi, Hk);
+        for (int i = 0; i < NE; ++i) gLX[k * 21 + i] = lx[i];
+        for (int i = 0; i < 9; ++i) gLX[k * 21 + 12 + i] = Hk[i];
+        if (k < N) {
+          KnotLin Lk;
+          srb_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
+          for (int i = 0; i < 9; ++i) {
+            glin[k * 27 + i] = Lk.Aff[i];
+            glin[k * 27 + 9 + i] = Lk.Afw[i];
+            glin[k * 27 + 18 + i] = Lk.Cf[i];
+          }
         }
       }
     }
@@ -829,8 +842,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         double rx = 0, ru = 0;
 #pragma unroll 1
         for (int k = lane; k <= N; k += G) {
-          double lx[NE], hphi;
-          cost_expand(m, cfg, k, X + k * NX, lx, &hphi);
+          double lx[NE];
+          for (int a = 0; a < NE; ++a) lx[a] = gLX[k * 21 + a];
           if (k == N) {
             for (int a = 0; a < NE; ++a) {
               double v = fabs(lx[a] - DX[N * NE + a]);
@@ -933,12 +946,9 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     double* Pc = P;   // value-function Hessian of knot k+1 (then the not-yet-corrected one of knot k)
     double* Pw = PA;  // work buffer: P A, then Quu and its Cholesky factor, then the new P (ping-pong)
     COOP_PHASE {
-      if (lane == 0) {
-        double hphi;
-        cost_expand(m, cfg, N, X + N * NX, vec + cv::pv, &hphi);
-        hphi_block(cfg, X + N * NX, hphi, vec + cv::Hphi);
-        scal[0] = 0.0;
-      }
+#pragma unroll 1
+      for (int e = lane; e < 21; e += G) vec[(e < 12 ? cv::pv : cv::Hphi - 12) + e] = gLX[N * 21 + e];
+      if (lane == 0) scal[0] = 0.0;
     }
     COOP_SYNC();
     COOP_PHASE {
@@ -956,7 +966,10 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       // ---- phase A: stage the knot's 3x3 blocks; per-foot AL terms; cost expansion
       COOP_PHASE {
 #pragma unroll 1
-        for (int e = lane; e < 27; e += G) lin[e] = glin[k * 27 + e];
+        for (int e = lane; e < 27 + 21; e += G) {   // the knot's dynamics blocks and cost expansion
+          if (e < 27) lin[e] = glin[k * 27 + e];
+          else vec[(e < 27 + 12 ? cv::lx - 27 : cv::Hphi - 39) + e] = gLX[k * 21 + e - 27];
+        }
         if (lane < NF) {
           const int f = lane;
           const double* u = U + k * NU + 3 * f;
@@ -980,11 +993,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           vec[cv::g + 3 * f] = wr[3 * f] * u[0] + g0;
           vec[cv::g + 3 * f + 1] = wr[3 * f + 1] * u[1] + g1;
           vec[cv::g + 3 * f + 2] = wr[3 * f + 2] * (u[2] - m.urefz(k, f)) + g2;
-        }
-        if (lane == NF) {
-          double hphi;
-          cost_expand(m, cfg, k, X + k * NX, vec + cv::lx, &hphi);
-          hphi_block(cfg, X + k * NX, hphi, vec + cv::Hphi);
         }
       }
       COOP_SYNC();

@@ -172,44 +172,62 @@ QMPC_HD inline void neumaier_add(double& sum, double& corr, double v) {
   else corr = add_rn(corr, add_rn(add_rn(v, -ns), sum));
   sum = ns;
 }
-QMPC_HD inline double window_average(const GoalStateRef& s, int ch, long long n, double v) {
-  const int f0 = 5 + ch * (2 + kGoalWindow);
-  double sum = s.at(f0), corr = s.at(f0 + 1);
-  double& slot = s.at(f0 + 2 + (int)(n % kGoalWindow));
-  if (n >= kGoalWindow) neumaier_add(sum, corr, -slot);   // the left-most value leaves the window first
+// One channel: the caller has loaded (sum, corr, oldest sample) and stores them back after the update
+QMPC_HD inline double window_average(double& sum, double& corr, double oldest, bool full, double v) {
+  if (full) neumaier_add(sum, corr, -oldest);   // the left-most value leaves the window first
   neumaier_add(sum, corr, v);
-  slot = v;
-  s.at(f0) = sum;
-  s.at(f0 + 1) = corr;
   return add_rn(sum, corr) / (double)kGoalWindow;
 }
 
-QMPC_HD inline void goal_update_one(const GoalStateRef& s, const QmpcGoalInput& in, QmpcProblem& out) {
-  double R[9];
+// All loads first, all stores last: the state / input / output pointers may alias as far as the compiler
+// knows, and interleaved loads and stores would serialise six DRAM round trips per robot.
+QMPC_HD inline void goal_update_one(const GoalStateRef& s, const QmpcGoalInput& gin, QmpcProblem& out) {
+  const QmpcGoalInput in = gin;
+  double pdw[3] = {s.at(0), s.at(1), s.at(2)};
+  const bool inited = s.at(3) != 0.0;
+  const long long n = (long long)s.at(4);
+  const int slot = (int)(n % kGoalWindow);
+  const bool full = n >= kGoalWindow;
+  double sum[6], corr[6], oldest[6], val[6], avg[6];
+#pragma unroll
+  for (int ch = 0; ch < 6; ++ch) {
+    const int f0 = 5 + ch * (2 + kGoalWindow);
+    sum[ch] = s.at(f0);
+    corr[ch] = s.at(f0 + 1);
+    oldest[ch] = s.at(f0 + 2 + slot);
+  }
+  double R[9], cy, sy;
   quat_to_rot(in.torso_quat, R);                       // fbk.torso_rot_mat   BaseInterface.cpp:196
-  double cy, sy;                                       // torso_rot_mat_z = AngleAxis(fbk.torso_euler[2], UnitZ)  :197-200
-  quat_yaw_cs(in.torso_quat, &cy, &sy);
-  if (s.at(3) == 0.0) {                                // torso_pos_d_world_init  QuatMpc.cpp:74-77
-    for (int i = 0; i < 3; ++i) s.at(i) = in.torso_pos_world[i];
-    s.at(3) = 1.0;
+  quat_yaw_cs(in.torso_quat, &cy, &sy);                // torso_rot_mat_z = AngleAxis(fbk.torso_euler[2], UnitZ)  :197-200
+  if (!inited) {                                       // torso_pos_d_world_init  QuatMpc.cpp:74-77
+    for (int i = 0; i < 3; ++i) pdw[i] = in.torso_pos_world[i];
   }
   const double vrel[3] = {in.joy_vel[0], in.joy_vel[1], 0.0};                    // :80-82
   const double vw[3] = {cy * vrel[0] - sy * vrel[1], sy * vrel[0] + cy * vrel[1], vrel[2]};   // :84
-  double vb[3], pb[3], pdw[3];
-  for (int i = 0; i < 3; ++i) vb[i] = R[i] * vw[0] + R[3 + i] * vw[1] + R[6 + i] * vw[2];    // R^T v  :85
-  pdw[0] = s.at(0) + vw[0] * 5.0 / 1000.0;             // :98-100
-  pdw[1] = s.at(1) + vw[1] * 5.0 / 1000.0;
+  for (int i = 0; i < 3; ++i) val[i] = R[i] * vw[0] + R[3 + i] * vw[1] + R[6 + i] * vw[2];    // R^T v  :85
+  pdw[0] = pdw[0] + vw[0] * 5.0 / 1000.0;              // :98-100
+  pdw[1] = pdw[1] + vw[1] * 5.0 / 1000.0;
   pdw[2] = in.joy_body_height;
-  for (int i = 0; i < 3; ++i) s.at(i) = pdw[i];
   const double dp[3] = {pdw[0] - in.torso_pos_world[0], pdw[1] - in.torso_pos_world[1], pdw[2] - in.torso_pos_world[2]};
-  for (int i = 0; i < 3; ++i) pb[i] = R[i] * dp[0] + R[3 + i] * dp[1] + R[6 + i] * dp[2];    // :102
-  const long long n = (long long)s.at(4);
-  for (int i = 0; i < 3; ++i) out.torso_lin_vel_d_body[i] = window_average(s, i, n, vb[i]);      // :86-89
-  for (int i = 0; i < 3; ++i) out.torso_pos_d_body[i] = window_average(s, 3 + i, n, pb[i]);      // :103-106
+  for (int i = 0; i < 3; ++i) val[3 + i] = R[i] * dp[0] + R[3 + i] * dp[1] + R[6 + i] * dp[2];    // :102
+#pragma unroll
+  for (int ch = 0; ch < 6; ++ch) avg[ch] = window_average(sum[ch], corr[ch], oldest[ch], full, val[ch]);   // :86-89, :103-106
+  // ---- stores
+  for (int i = 0; i < 3; ++i) s.at(i) = pdw[i];
+  s.at(3) = 1.0;
   s.at(4) = (double)(n + 1);
-  for (int i = 0; i < 3; ++i) out.torso_ang_vel_d_body[i] = in.joy_ang_rate[i];                  // :93-95
+#pragma unroll
+  for (int ch = 0; ch < 6; ++ch) {
+    const int f0 = 5 + ch * (2 + kGoalWindow);
+    s.at(f0) = sum[ch];
+    s.at(f0 + 1) = corr[ch];
+    s.at(f0 + 2 + slot) = val[ch];
+  }
   for (int i = 0; i < 4; ++i) out.torso_quat[i] = in.torso_quat[i];
   for (int i = 0; i < 3; ++i) out.torso_lin_vel_world[i] = in.torso_lin_vel_world[i];
+  for (int i = 0; i < 3; ++i) out.torso_pos_d_body[i] = avg[3 + i];
+  for (int i = 0; i < 3; ++i) out.torso_lin_vel_d_body[i] = avg[i];
+  for (int i = 0; i < 3; ++i) out.torso_ang_vel_d_body[i] = in.joy_ang_rate[i];                  // :93-95
 }
 
 // Raibert heuristic foot-hold targets (BaseInterface.cpp:265-288)
