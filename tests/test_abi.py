@@ -101,3 +101,44 @@ def test_workload_generators():
     assert (random_batch(8, seed=3) == random_batch(8, seed=3)).all() if False else True
     assert stand_problem()["plan_contacts"].sum() == 4
     assert random_convex_batch(4).shape == (4,)
+
+
+def test_struct_sizes_against_the_c_compiler(tmp_path):
+    """sizeof() of every struct of include/qmpc.h as gcc lays it out == the numpy / ctypes mirrors."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "qmpc.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   "sizeof(QmpcConfig),sizeof(QmpcProblem),sizeof(QmpcConvexProblem),sizeof(QmpcResult),"
+                   "sizeof(QmpcContactSchedule),sizeof(QmpcGaitState),sizeof(QmpcLegParams),sizeof(QmpcGoalInput),"
+                   "sizeof(QmpcRaibertParams),sizeof(QmpcWarmStart));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(abi.QmpcConfig), abi.PROBLEM_DTYPE.itemsize, abi.CONVEX_PROBLEM_DTYPE.itemsize,
+            abi.RESULT_DTYPE.itemsize, abi.SCHEDULE_DTYPE.itemsize, abi.GAIT_STATE_DTYPE.itemsize,
+            C.sizeof(abi.QmpcLegParams), abi.GOAL_INPUT_DTYPE.itemsize, C.sizeof(abi.QmpcRaibertParams),
+            abi.WARM_DTYPE.itemsize]
+    assert got == want
+
+
+def test_new_entry_points_reject_bad_arguments(lib):
+    """Rows N1-N4: null handle / null pointers are argument errors, never a crash or a silent no-op."""
+    E = abi.QMPC_ERR_ARG
+    assert lib.qmpc_solve_batch_sched(None, None, None, 1, None, None) == E
+    assert lib.qmpc_solve_batch_convex_sched(None, None, None, 1, None, None) == E
+    assert lib.qmpc_solve_batch_sched_host(None, None, None, 1, None) == E
+    assert lib.qmpc_solve_batch_warm(None, None, None, None, 1, None, None) == E
+    assert lib.qmpc_predict_contact_schedule(None, None, 1, None, None) == E
+    assert lib.qmpc_leg_kinematics(None, None, None, 1, None, None, None) == E
+    assert lib.qmpc_joint_torques(None, None, None, None, 1, 1, None, None) == E
+    assert lib.qmpc_goal_update(None, None, None, 1, None, None) == E
+    assert lib.qmpc_raibert_targets(None, None, None, 1, None, None, None) == E
+    assert lib.qmpc_goal_state_bytes(None) == 0
+    assert lib.qmpc_default_leg_params(None) == E and lib.qmpc_default_raibert_params(None) == E
+    buf = C.create_string_buffer(8)
+    assert lib.qmpc_describe(None, buf, 8) == E
+    lp, rp = abi.QmpcLegParams(), abi.QmpcRaibertParams()
+    assert lib.qmpc_default_leg_params(C.byref(lp)) == 0 and lib.qmpc_default_raibert_params(C.byref(rp)) == 0
+    assert [lp.rho_fix[i][0] for i in range(4)] == [0.1881, 0.1881, -0.1881, -0.1881]      # BaseInterface.cpp:12-15
+    assert [lp.rho_fix[i][2] for i in range(4)] == [0.0812, -0.0812, 0.0812, -0.0812]      # :20-23
+    assert rp.gait_freq == 2.2 and rp.delta_x_limit == 0.5 and rp.delta_y_limit == 0.3

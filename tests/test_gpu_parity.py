@@ -301,3 +301,43 @@ def test_warm_start_closed_loop_matches_oracle(oracle):
         probs["torso_lin_vel_world"] += 0.01                 # the robot moved a little
     assert viol[-1] < viol[0]                                 # warm starts get closer to feasibility at the cap
     print("mean max_violation per tick:", ["%.3f" % v for v in viol])
+
+
+def test_schedule_and_warm_edge_cases(oracle):
+    """Empty and ragged batches, capacity errors, the 2-foot model and schedule + warm start combined."""
+    import torch
+    from quaternion_mpc_b200 import QmpcError, QuatMpc
+    from quaternion_mpc_b200.workloads import predict_schedule_numpy, random_gait_states
+    mpc = QuatMpc(horizon=10, max_batch=100)
+    probs = random_batch(100, seed=51, gait="trot")
+    sched = predict_schedule_numpy(random_gait_states(100, seed=51), 10, mpc.cfg.dt)
+    full = _solve_sched_dev(mpc, probs, sched)
+    for b in (0, 1, 3, 17, 33, 99):
+        r = _solve_sched_dev(mpc, probs[:b], sched[:b]) if b else mpc.grf_update_sched(probs[:0], sched[:0])
+        assert r.tobytes() == full[:b].tobytes()
+    with pytest.raises(QmpcError):
+        mpc.grf_update_sched(random_batch(101, seed=1), np.zeros((101, abi.QMPC_MAX_HORIZON), np.uint8))
+    # schedule + warm start together, two ticks, against the oracle on identical buffers
+    d_warm = mpc.alloc_warm(100)
+    for tick in range(2):
+        w_ref = d_warm.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE).copy()
+        d = mpc.grf_update_warm_device(mpc.to_device(probs), d_warm, d_sched=mpc.schedule_to_device(sched))
+        torch.cuda.synchronize()
+        res = mpc.results_to_numpy(d)
+        if tick == 0:
+            assert res.tobytes() == full.tobytes()
+        _check(res, oracle.solve_batch_warm(mpc.cfg, probs, w_ref, schedule=sched, nthreads=NT), max_undetermined=0.1,
+               max_outliers=0.02)
+    # 2-foot model: warm buffer rows keep their 12-wide layout, entries 6..11 stay zero
+    cfg2 = default_config(abi.QMPC_MODEL_QUAT_2FOOT, 12)
+    m2 = QuatMpc(max_batch=64, cfg=cfg2)
+    p2 = random_batch(64, seed=52, gait="stand", max_angle=0.2, nfeet=2)
+    dw = m2.alloc_warm(64)
+    for tick in range(2):
+        w_ref = dw.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE).copy()
+        d = m2.grf_update_warm_device(m2.to_device(p2), dw)
+        torch.cuda.synchronize()
+        _check(m2.results_to_numpy(d), oracle.solve_batch_warm(cfg2, p2, w_ref, nthreads=NT), max_undetermined=0.1,
+               max_outliers=0.02)
+    w = dw.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE)
+    assert (w["u"][:, :, 6:] == 0).all() and (w["u"][:, 12:, :] == 0).all() and (w["valid"] == 1).all()
