@@ -1449,8 +1449,13 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         for (int i = 0; i < NX; ++i) xn[i] = ld_stream(gTX + (size_t)(k * NX + i) * NCAND + acc_lane);
         state_diff<M>(xn, X + k * NX, dx);
         const double* Pk = gP + (size_t)k * 144;
-#pragma unroll 3   // nearly rolled (once per iteration, 4x less code than unrolled: the kernel is instruction-cache
-                    // bound) yet three rows of P_k - 36 L2 loads - are in flight per trip
+#ifndef QMPC_COOP_ACCEPT_UNROLL
+#define QMPC_COOP_ACCEPT_UNROLL 3
+#endif
+        // nearly rolled (once per iteration; the kernel is instruction-cache sensitive) yet several rows of
+        // P_k - 12 L2 loads each - are in flight per trip
+        constexpr int kAcceptUnroll = QMPC_COOP_ACCEPT_UNROLL;
+#pragma unroll(kAcceptUnroll)
         for (int a = 0; a < NE; ++a) {
           double t = gpv[k * 12 + a];
 #pragma unroll
