@@ -66,7 +66,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
+
+    def mark(self):
+        """Start of the window whose samples are reported (the sampler itself is started earlier: nvidia-smi
+        needs ~100 ms before its first line, longer than a whole default run's timed region)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -76,11 +81,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        t0 = getattr(self, "t_mark", 0.0)
+        rows = [r[1:] for r in self.rows if r[0] >= t0] or [r[1:] for r in self.rows[-3:]]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for n, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
@@ -210,14 +217,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()      # before the warm-up: nvidia-smi takes ~100 ms to produce its first sample
     for _ in range(a.warmup):
         flush.fill_(1)
         mpc.grf_update_device(d_in, d_out)
     barrier()
     launches0 = mpc.launch_count
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()           # samples from here (timed region + the e2e loop, GPU busy throughout) are reported
     evs = []
     for _ in range(a.steps):
         flush.fill_(1)                        # L2 flush between timed iterations (outside the event pair)
@@ -230,7 +238,6 @@ def main():
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     total_ms = float(sum(kernel_ms))
     launches = mpc.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D + solve + D2H per step)
     h_in = torch.from_numpy(probs.view(np.uint8).reshape(B, -1).copy()).pin_memory()
@@ -243,6 +250,12 @@ def main():
         mpc.grf_update_host_ptr(h_in.data_ptr(), B, h_out.data_ptr())
     barrier()
     e2e_s = time.perf_counter() - t0
+    if rank == 0 and len([r for r in sampler.rows if r[0] >= sampler.t_mark]) < 3:
+        t_end = time.perf_counter() + 0.25          # very short runs: keep the GPU busy with the same solve
+        while time.perf_counter() < t_end:          # until a few samples under load exist (not timed)
+            mpc.grf_update_device(d_in, d_out)
+            torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     res = h_out.numpy().reshape(-1).view(abi.RESULT_DTYPE)
     mean_iters = float(res["iterations"].mean())
 

@@ -86,6 +86,30 @@ QMPC_HD inline double ld_stream(const double* p) {
 #endif
 }
 
+// gains / value functions are written once per backward pass and read once per forward pass while 16 trial
+// trajectories (33 KB per slot) stream through the same L2 in between: ask the L2 to keep them
+// (-DQMPC_COOP_L2_KEEP: evict_last priority on their stores and loads)
+QMPC_HD inline void st_keep(double* p, double v) {
+#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_L2_KEEP)
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+QMPC_HD inline double ld_keep(const double* p) {
+#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_L2_KEEP)
+  double v;
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  return *p;
+#endif
+}
+
 QMPC_HD inline double qmpc_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
   return rsqrt(x);
@@ -190,6 +214,12 @@ QMPC_HD inline void blk_w(const double* S, int ld, double s, const double* Mt, d
     dst[ldd * a + 1] = s * t1 + x3 * m[1] + x4 * m[4] + x5 * m[7];
     dst[ldd * a + 2] = s * t2 + x3 * m[2] + x4 * m[5] + x5 * m[8];
   }
+}
+QMPC_HD inline void blk_store_keep(double* dst, int ld, const double* v) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) st_keep(dst + ld * a + b, v[3 * a + b]);
 }
 QMPC_HD inline void blk_store(double* dst, int ld, const double* v) {
 #pragma unroll
@@ -1000,8 +1030,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       double o[9];
       lxx_block(wq, vec + cv::Hphi, br, bc, o);
       blk_store(Pc + 36 * br + 3 * bc, 12, o);
-      blk_store(gP + (size_t)N * 144 + 36 * br + 3 * bc, 12, o);
-      if (lane < 12) gpv[N * 12 + lane] = vec[cv::pv + lane];
+      blk_store_keep(gP + (size_t)N * 144 + 36 * br + 3 * bc, 12, o);
+      if (lane < 12) st_keep(gpv + N * 12 + lane, vec[cv::pv + lane]);
     }
     COOP_SYNC();
 
@@ -1192,12 +1222,12 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         if (ok && lane <= 12) {
           if (c < 12) {
 #pragma unroll
-            for (int i = 0; i < NU; ++i) gK[((size_t)k * NU + i) * 12 + c] = -rhs[i];
+            for (int i = 0; i < NU; ++i) st_keep(gK + ((size_t)k * NU + i) * 12 + c, -rhs[i]);
           } else {
             double t = 0;
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
-              gd[k * NU + i] = -rhs[i];
+              st_keep(gd + k * NU + i, -rhs[i]);
               t += vec[cv::Qu + i] * (-rhs[i]);
             }
             scal[0] += t;
@@ -1321,12 +1351,12 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           }
           if (c < 12) {
 #pragma unroll
-            for (int i = 0; i < NU; ++i) gK[((size_t)k * NU + i) * 12 + c] = -rhs[i];
+            for (int i = 0; i < NU; ++i) st_keep(gK + ((size_t)k * NU + i) * 12 + c, -rhs[i]);
           } else {
             double t = 0;
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
-              gd[k * NU + i] = -rhs[i];
+              st_keep(gd + k * NU + i, -rhs[i]);
               t += vec[cv::Qu + i] * (-rhs[i]);
             }
             scal[0] += t;
@@ -1359,7 +1389,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           for (int b = 0; b < 3; ++b)
             o[3 * a + b] = 0.5 * (Pc[12 * (3 * br + a) + 3 * bc + b] + Pc[12 * (3 * bc + b) + 3 * br + a]) - o[3 * a + b];
         blk_store(Pw + 36 * br + 3 * bc, 12, o);
-        blk_store(gP + (size_t)k * 144 + 36 * br + 3 * bc, 12, o);
+        blk_store_keep(gP + (size_t)k * 144 + 36 * br + 3 * bc, 12, o);
         if (lane < 12) {
           const int a = lane;
           double t = 0;
@@ -1367,7 +1397,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * vec[cv::vu + l];
           const double v = vec[cv::Qx + a] - t;
           vec[cv::pv + a] = v;
-          gpv[k * 12 + a] = v;
+          st_keep(gpv + k * 12 + a, v);
         }
       }
       COOP_SYNC();
@@ -1457,9 +1487,9 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         constexpr int kAcceptUnroll = QMPC_COOP_ACCEPT_UNROLL;
 #pragma unroll(kAcceptUnroll)
         for (int a = 0; a < NE; ++a) {
-          double t = gpv[k * 12 + a];
+          double t = ld_keep(gpv + k * 12 + a);
 #pragma unroll
-          for (int b = 0; b < NE; ++b) t += Pk[12 * a + b] * dx[b];
+          for (int b = 0; b < NE; ++b) t += ld_keep(Pk + 12 * a + b) * dx[b];
           DX[k * NE + a] = t;
         }
       }
