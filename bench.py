@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU per step")
     ap.add_argument("--horizon", type=int, default=10)
     ap.add_argument("--gait", default="trot")
+    ap.add_argument("--model", default="quat", choices=["quat", "quat2", "convex"],
+                    help="quat = QuatMpc (BASELINE metric); quat2 = 2-contact model (config 4); convex = ConvexMpc")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the streaming kernels either side of the solve")
@@ -99,9 +101,11 @@ class ClockSampler:
 def cpu_arm(cfg, probs, threads):
     """Times the fp64 oracle port (oracle/, test infrastructure) on the host cores."""
     from oracle import binding as oracle
-    oracle.solve_batch(cfg, probs[:min(64, len(probs))], nthreads=threads)  # warm the caches / pages
+    from quaternion_mpc_b200 import abi
+    solve = oracle.solve_batch_convex if cfg.model == abi.QMPC_MODEL_EULER_CONVEX else oracle.solve_batch
+    solve(cfg, probs[:min(64, len(probs))], nthreads=threads)  # warm the caches / pages
     t0 = time.perf_counter()
-    out = oracle.solve_batch(cfg, probs, nthreads=threads)
+    out = solve(cfg, probs, nthreads=threads)
     dt = time.perf_counter() - t0
     return len(probs) / dt, dt, out
 
@@ -159,10 +163,23 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     from quaternion_mpc_b200 import abi
     from quaternion_mpc_b200.config import default_config
-    from quaternion_mpc_b200.workloads import random_batch
+    from quaternion_mpc_b200 import workloads
 
-    cfg = default_config(abi.QMPC_MODEL_QUAT_4FOOT, a.horizon)
-    workload = f"go1_quat_mpc_N{a.horizon}_{a.gait}_batch{a.batch}_per_gpu_seed0"
+    global IN_BYTES, FLOPS_PER_KNOT_ITER
+    if a.model == "quat":
+        cfg = default_config(abi.QMPC_MODEL_QUAT_4FOOT, a.horizon)
+        random_batch = workloads.random_batch
+        workload = f"go1_quat_mpc_N{a.horizon}_{a.gait}_batch{a.batch}_per_gpu_seed0"
+    elif a.model == "quat2":   # BASELINE config 4: 2-contact model (ct_srb_trot_quat_*), m = 6, 12 cone rows
+        cfg = default_config(abi.QMPC_MODEL_QUAT_2FOOT, a.horizon)
+        random_batch = lambda n, seed=0, gait=None: workloads.random_batch(n, seed=seed, gait="stand", max_angle=0.2, nfeet=2)
+        workload = f"two_contact_quat_mpc_N{a.horizon}_batch{a.batch}_per_gpu_seed0"
+        FLOPS_PER_KNOT_ITER = 38e3   # SURVEY.md 8d, m = 6, p = 12
+    else:                       # ConvexMpc (row A8): Euler SRB on the generic dense kernel
+        cfg = default_config(abi.QMPC_MODEL_EULER_CONVEX, a.horizon)
+        random_batch = lambda n, seed=0, gait="trot": workloads.random_convex_batch(n, seed=seed, gait=gait)
+        workload = f"go1_convex_mpc_N{a.horizon}_{a.gait}_batch{a.batch}_per_gpu_seed0"
+        IN_BYTES = 344
     threads = os.cpu_count() or 1
 
     # ------------------------------------------------------------------ reference (CPU) arm
@@ -202,7 +219,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    from quaternion_mpc_b200 import QuatMpc
+    from quaternion_mpc_b200 import ConvexMpc, QuatMpc
+    if a.model == "convex":
+        QuatMpc = ConvexMpc   # same host mirror, other entry points
 
     B = a.batch
     probs = random_batch(B, seed=0 + rank, gait=a.gait)   # each rank owns its shard of the global batch
@@ -303,7 +322,7 @@ def main():
         # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
         # this kernel (profiles/r01_s3_ncu_coop_B16384.txt: 2.83 + 9.76 GB for 16384 solves = 769 kB per solve,
         # the L2-overflowing scratch of the trial trajectories / gains), scaled to this launch's batch
-        "traffic": NCU_DRAM_BYTES_PER_SOLVE * B if a.horizon == 10 else None,
+        "traffic": NCU_DRAM_BYTES_PER_SOLVE * B if (a.horizon == 10 and a.model == "quat") else None,
         "traffic_source": "ncu capture at batch 16384, scaled by batch; algorithmic bytes are 536 B/solve - the "
                           "difference is per-slot scratch spilling the 126 MB L2 (DRAM 14 % busy, not the bound)",
         "peak_source": "measured live by qmpc_measure_fma_peak (FP64 vector FMA; FP32 = %.1f TFLOP/s)" % f32.value,
@@ -314,7 +333,7 @@ def main():
     }
 
     aux = None
-    if not a.no_aux:
+    if not a.no_aux and a.model == "quat":
         aux = aux_kernels(local, cfg, hbm_peak)
 
     cpu = None
