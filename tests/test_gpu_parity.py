@@ -341,3 +341,17 @@ def test_schedule_and_warm_edge_cases(oracle):
                max_outliers=0.02)
     w = dw.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE)
     assert (w["u"][:, :, 6:] == 0).all() and (w["u"][:, 12:, :] == 0).all() and (w["valid"] == 1).all()
+
+
+def test_full_size_parity_against_oracle(oracle):
+    """BASELINE sizes against the oracle itself (not only size-independent properties): 65 536 trot solves at
+    N=10 and 16 384 mixed-mask solves at N=16, every one compared with the CPU oracle (about 15 s of host time)."""
+    from quaternion_mpc_b200 import QuatMpc
+    for N, B, gait, seed in ((10, 65536, "trot", 3), (16, 16384, "mixed", 1)):
+        mpc = QuatMpc(horizon=N, max_batch=B)
+        probs = random_batch(B, seed=seed, gait=gait)
+        res = _solve_dev(mpc, probs)
+        ref = oracle.solve_batch(mpc.cfg, probs, nthreads=NT)
+        worst = _check(res, ref)
+        print(f"N={N} B={B} {gait}: max|dGRF| = {worst:.3e} N over {B} solves")
+        mpc.close()
