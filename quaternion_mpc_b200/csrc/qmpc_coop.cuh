@@ -1175,6 +1175,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         constexpr int NT = NU * (NU + 1) / 2;
 #define QMPC_TRI(i_, l_) ((i_) * ((i_) + 1) / 2 + (l_))
         double Lr[NT], rd[NU], rhs[NU];
+#define QMPC_DIVD(x_, i_) { (x_) = (x_) * rd[i_]; }
 #pragma unroll
         for (int i = 0; i < NU; ++i)
 #pragma unroll
@@ -1186,10 +1187,28 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         for (int j = 0; j < NU; ++j) {
           const double sjj = Lr[QMPC_TRI(j, j)];
           ok = ok && (sjj > 0.0);
-          const double rdg = qmpc_rsqrt(sjj);
+#ifdef QMPC_COOP_FAST_RECIP
+          const double rdg = qmpc_rsqrt(sjj);   // L(i,j) = a * rsqrt: 1-2 ulp from a / sqrt(sjj)
           rd[j] = rdg;
 #pragma unroll
           for (int i = j + 1; i < NU; ++i) Lr[QMPC_TRI(i, j)] *= rdg;
+#else
+          // sqrt and the divisions of the reference Cholesky, built from rsqrt + FMA corrections (Markstein): the
+          // quotients come out correctly rounded, i.e. equal to a / sqrt(sjj), at 2 extra FMAs each instead of a
+          // ~25-instruction IEEE division.  The plain reciprocal form was 1-2 ulp off and, with cond(Quu) up to
+          // 1e14, moved 1 solve in 65 536 by 3e-4 N against the oracle (division-based kernels: 4e-5 N there).
+          // Only the factor's quotients matter; the substitutions below keep the plain reciprocal (measured).
+          const double r0 = qmpc_rsqrt(sjj);
+          double dg = sjj * r0;
+          dg = fma(0.5 * fma(-dg, dg, sjj), r0, dg);          // sqrt(sjj), correctly rounded
+          const double rdg = fma(fma(-dg, r0, 1.0), r0, r0);  // 1 / dg
+          rd[j] = rdg;
+#pragma unroll
+          for (int i = j + 1; i < NU; ++i) {
+            const double a = Lr[QMPC_TRI(i, j)], q = a * rdg;
+            Lr[QMPC_TRI(i, j)] = fma(fma(-q, dg, a), rdg, q);   // a / dg
+          }
+#endif
 #pragma unroll
           for (int i = j + 1; i < NU; ++i)
 #pragma unroll
@@ -1199,10 +1218,11 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         // forward substitution, column oriented: after y_i is final every remaining entry updates independently
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-          rhs[i] = rhs[i] * rd[i];
+          QMPC_DIVD(rhs[i], i);
 #pragma unroll
           for (int l = i + 1; l < NU; ++l) rhs[l] -= Lr[QMPC_TRI(l, i)] * rhs[i];
         }
+#ifndef QMPC_COOP_P_KFORM
         if (ok && lane <= 12) {
           if (c < 12) {
 #pragma unroll
@@ -1212,23 +1232,32 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
             for (int i = 0; i < NU; ++i) vec[cv::vu + i] = rhs[i];
           }
         }
+#endif
 #pragma unroll
         for (int i = NU - 1; i >= 0; --i) {
-          rhs[i] = rhs[i] * rd[i];
+          QMPC_DIVD(rhs[i], i);
 #pragma unroll
           for (int l = 0; l < i; ++l) rhs[l] -= Lr[QMPC_TRI(i, l)] * rhs[i];
         }
 #undef QMPC_TRI
+#undef QMPC_DIVD
         if (ok && lane <= 12) {
           if (c < 12) {
 #pragma unroll
             for (int i = 0; i < NU; ++i) st_keep(gK + ((size_t)k * NU + i) * 12 + c, -rhs[i]);
+#ifdef QMPC_COOP_P_KFORM
+#pragma unroll
+            for (int i = 0; i < NU; ++i) T[12 * i + c] = -rhs[i];   // K, in the T | PM region (free after phase E)
+#endif
           } else {
             double t = 0;
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
               st_keep(gd + k * NU + i, -rhs[i]);
               t += vec[cv::Qu + i] * (-rhs[i]);
+#ifdef QMPC_COOP_P_KFORM
+              vec[cv::vu + i] = -rhs[i];                            // d
+#endif
             }
             scal[0] += t;
           }
@@ -1367,6 +1396,41 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 #endif
       // ---- phase F: new P = sym(P) - V^T V (16 blocks, written to the work buffer: no race with the
       //      transposed reads of Pc), pv <- Qx - V^T vu ; then swap the two buffers
+#ifdef QMPC_COOP_P_KFORM
+      // reference-order variant: P <- sym(Qxx + Qux^T K), p <- Qx + Qux^T d (the oracle's / srb kernel's update; with
+      // cond(Quu) ~ 1e14 its rounding differs from the V^T V form at the 1e-4 N level in ~1 of 50 000 solves)
+      COOP_PHASE {
+        const int br = lane >> 2, bc = lane & 3;
+        const double* Ks = T;
+        double t1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, o[9];
+#pragma unroll 1
+        for (int l = 0; l < NU; ++l) {
+          const double *Qr = Qux + 12 * l + 3 * br, *Qc = Qux + 12 * l + 3 * bc;
+          const double *Kr = Ks + 12 * l + 3 * br, *Kc = Ks + 12 * l + 3 * bc;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) { t1[3 * a + b] += Qr[a] * Kc[b]; t2[3 * a + b] += Qc[b] * Kr[a]; }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+            o[3 * a + b] = 0.5 * ((Pc[12 * (3 * br + a) + 3 * bc + b] + t1[3 * a + b]) +
+                                  (Pc[12 * (3 * bc + b) + 3 * br + a] + t2[3 * a + b]));
+        blk_store(Pw + 36 * br + 3 * bc, 12, o);
+        blk_store_keep(gP + (size_t)k * 144 + 36 * br + 3 * bc, 12, o);
+        if (lane < 12) {
+          const int a = lane;
+          double t = 0;
+#pragma unroll 4
+          for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * vec[cv::vu + l];
+          const double v = vec[cv::Qx + a] + t;
+          vec[cv::pv + a] = v;
+          st_keep(gpv + k * 12 + a, v);
+        }
+      }
+#else
       COOP_PHASE {
         const int br = lane >> 2, bc = lane & 3;
         double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1400,6 +1464,7 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           st_keep(gpv + k * 12 + a, v);
         }
       }
+#endif
       COOP_SYNC();
       { double* t = Pc; Pc = Pw; Pw = t; }
     }
