@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_KNOT_ITER = 65.8e3   # dense reference-equivalent AL-iLQR, ne=12, m=12, p=24
 IN_BYTES, OUT_BYTES = 296, 240  # sizeof(QmpcProblem), sizeof(QmpcResult)
-NCU_DRAM_BYTES_PER_SOLVE = (2.834961e9 + 9.764638e9) / 16384   # profiles/r01_s3_ncu_coop_B16384.txt
+NCU_DRAM_BYTES_PER_SOLVE = (2.825775e9 + 9.770318e9) / 16384   # profiles/r01_s3_ncu_coop_B16384.txt
 
 
 def parse():
