@@ -42,18 +42,9 @@
 // non-aligned barrier: the two problems of a warp may arrive from different code paths (one finished,
 // one still iterating), which __syncthreads() / barrier.sync.aligned does not allow
 #define COOP_BLOCK_SYNC() asm volatile("barrier.sync 1, %0;" ::"r"(blockDim.x) : "memory")
-#ifdef QMPC_COOP_BLOCK_SYNC2   // a second alignment point per iteration, between the backward and the forward pass
-#define COOP_BLOCK_SYNC_MID() asm volatile("barrier.sync 2, %0;" ::"r"(blockDim.x) : "memory")
-#else
 #define COOP_BLOCK_SYNC_MID() ((void)0)
-#endif
-#ifdef QMPC_COOP_KNOT_SYNC     // ... and one per knot of the backward pass (exactly N per iteration for every thread)
-#define COOP_KNOT_SYNC() asm volatile("barrier.sync 3, %0;" ::"r"(blockDim.x) : "memory")
-#define COOP_KNOT_SYNC_ALL(N_) for (int kk_ = 0; kk_ < (N_); ++kk_) COOP_KNOT_SYNC()
-#else
 #define COOP_KNOT_SYNC() ((void)0)
 #define COOP_KNOT_SYNC_ALL(N_) ((void)0)
-#endif
 #else
 #define COOP_BLOCK_SYNC() ((void)0)
 #define COOP_BLOCK_SYNC_MID() ((void)0)
@@ -69,46 +60,14 @@
 
 namespace qmpc {
 
-// trial trajectories are written 16x per iteration and read once: keep them from displacing the
-// gains / value functions in L2 (evict-first stores and loads)
-QMPC_HD inline void st_stream(double* p, double v) {
-#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_TRIAL_CS)
-  __stcs(p, v);
-#else
-  *p = v;
-#endif
-}
-QMPC_HD inline double ld_stream(const double* p) {
-#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_TRIAL_CS)
-  return __ldcs(p);
-#else
-  return *p;
-#endif
-}
-
-// gains / value functions are written once per backward pass and read once per forward pass while 16 trial
-// trajectories (33 KB per slot) stream through the same L2 in between: ask the L2 to keep them
-// (-DQMPC_COOP_L2_KEEP: evict_last priority on their stores and loads)
-QMPC_HD inline void st_keep(double* p, double v) {
-#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_L2_KEEP)
-  unsigned long long pol;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
-#else
-  *p = v;
-#endif
-}
-QMPC_HD inline double ld_keep(const double* p) {
-#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_L2_KEEP)
-  double v;
-  unsigned long long pol;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-  return v;
-#else
-  return *p;
-#endif
-}
+// access points of the two classes of scratch traffic: trial trajectories (written 16x per iteration, read
+// once) and gains / value functions (written once per backward pass, read once per forward pass). Cache
+// hints were measured on both (evict-first: -6 %, evict_last: +0.7 %, profiles/r01_session3_experiments.md)
+// and dropped; the accessors stay so that the two streams remain distinguishable in the source.
+QMPC_HD inline void st_stream(double* p, double v) { *p = v; }
+QMPC_HD inline double ld_stream(const double* p) { return *p; }
+QMPC_HD inline void st_keep(double* p, double v) { *p = v; }
+QMPC_HD inline double ld_keep(const double* p) { return *p; }
 
 QMPC_HD inline double qmpc_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
@@ -238,11 +197,7 @@ struct CoopLayout {
   static constexpr int NU = 3 * NF, NC = 6 * NF;
   static constexpr int kModel = (int)((sizeof(QuatModel<NF>) + 7) / 8);
   // ---- shared memory (doubles) per problem
-#if !defined(QMPC_COOP_NO_CHOL_REG) || (defined(__CUDACC__) && !defined(QMPC_COOP_NO_CHOL_SHFL))
   static constexpr int kVec = 156;   // the register/shuffle Cholesky needs no column-exchange buffer (cv::tcol)
-#else
-  static constexpr int kVec = 180;
-#endif
   QMPC_HD static int sX(int N) { return kModel; }
   QMPC_HD static int sU(int N) { return sX(N) + (N + 1) * 13; }
   QMPC_HD static int sP(int N) { return (sU(N) + N * NU + 1) / 2 * 2; }   // 16-byte aligned: cp.async target
@@ -557,237 +512,6 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
   *violout = vl;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Cooperative roll-out: NF lanes share one trial step length (one foot each), G / NF step lengths
-// are evaluated per call.  Same arithmetic, in the same order, as coop_rollout() above - the per-foot
-// terms travel through a shared-memory exchange block and are folded by the candidate's first lane in
-// the sequential order - but ~3x fewer instructions on the critical path per knot (the 12x12 gain
-// product, the cone rows and the input cost are split over the feet) and 4x less trial-trajectory
-// traffic.  Work areas (all dead during the forward pass): `ex` 15 doubles per lane, `xs` 16 doubles
-// per candidate (state 13, merit, violation), `vls` one double per lane.
-//   mode 0: open loop (u = u_ref of knot 0, or the warm start): candidate 0 writes X, U
-//   mode 1: candidate c tries alpha = alpha0 * decrease^c around (X, U); trial trajectories go to
-//           gTX / gTU, element-major with stride G / NF
-// On return res[c] = merit, res[G / NF + c] = max violation of candidate c.
-template <int NF, int G>
-QMPC_HD QMPC_NOINLINE void coop_rollout_feet(const QuatModel<NF>& m, const QmpcConfig& cfg, const double* wr, int N,
-                                             float h, double* X, double* U, const double* gK, const double* gd,
-                                             const double* gmu, double rho, double alpha0, double decrease, int mode,
-                                             double* gTX, double* gTU, double* exA, double* exB, double* xs, double* vls, double* res,
-                                             double* kstage, int lane_id, unsigned lane_mask,
-                                             const QmpcWarmStart* winit) {
-  using M = QuatModel<NF>;
-  constexpr int NX = 13, NE = 12, NU = M::NU, NC = M::NC, NCAND = G / NF, XS = 16, EX = 15;
-  (void)lane_id; (void)lane_mask; (void)kstage;
-  // the exchange block lives in PM|S|Qux (room for EXA lanes) and, for the lanes beyond, in `exB`
-  constexpr int EXA = (72 + 36 + NU * 12) / EX < G ? (72 + 36 + NU * 12) / EX : G;
-  auto exl = [&](int l) { return l < EXA ? exA + EX * l : exB + EX * (l - EXA); };
-  const double hd = (double)h, hh = (double)(h / 2);
-  COOP_PHASE {
-    if (lane % NF == 0) {
-      double* s = xs + XS * (lane / NF);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) s[i] = X[i];
-      s[13] = 0.0;   // merit
-      s[14] = 0.0;   // max violation
-    }
-  }
-#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_KSTAGE)
-  constexpr int kChunksK = NU * 12 / 2, kChunks = kChunksK + NU / 2, kStage = NU * 12 + NU;
-  auto stage_gain = [&](int k) {
-    const double* srcK = gK + (size_t)k * NU * 12;
-    const double* srcd = gd + (size_t)k * NU - 2 * kChunksK;
-    double* dst = kstage + (k & 1) * kStage;
-    for (int c = lane_id; c < kChunks; c += G) {
-      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
-      const double* src = (c < kChunksK ? srcK : srcd) + 2 * c;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  if (mode == 1) stage_gain(0);
-#endif
-  COOP_SYNC();
-#pragma unroll 1
-  for (int k = 0; k < N; ++k) {
-#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_KSTAGE)
-    const double* Kk = kstage + (k & 1) * kStage;
-    const double* dk = Kk + NU * 12;
-    if (mode == 1) {
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      __syncwarp(lane_mask);              // K_k visible to all lanes; everyone is done with K_{k-1}
-      if (k + 1 < N) stage_gain(k + 1);
-    }
-#else
-    const double* Kk = gK + (size_t)k * NU * 12;
-    const double* dk = gd + k * NU;
-#endif
-    // ---- phase 1, lane (c, f): the force of foot f, its cost / cone / wrench terms -> exchange block
-    COOP_PHASE {
-      const int c = lane / NF, f = lane % NF;
-      const double* xc = xs + XS * c;
-      double u0, u1, u2;
-      if (mode == 0) {
-        if (winit) {   // warm start: previous solution shifted by one knot
-          const double* wrow = warm_row(winit, k, N) + 3 * f;
-          u0 = wrow[0]; u1 = wrow[1]; u2 = wrow[2];
-        } else {
-          u0 = 0.0; u1 = 0.0; u2 = m.urefz(0, f);   // SetInput(u_traj_ref.at(0)), QuatMpc.cpp:253
-        }
-        if (c == 0) { U[k * NU + 3 * f] = u0; U[k * NU + 3 * f + 1] = u1; U[k * NU + 3 * f + 2] = u2; }
-      } else {
-        double x[NX], dx[NE];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = xc[i];
-        state_diff<M>(x, X + k * NX, dx);
-        double alpha = alpha0;   // decrease^(j0 + c), continuing the caller's repeated product
-        for (int q = 0; q < c; ++q) alpha *= decrease;
-        double t0 = 0, t1 = 0, t2 = 0;
-        const double* K0 = Kk + (3 * f) * 12;
-#if !defined(QMPC_COOP_NO_KSTAGE) && defined(__CUDA_ARCH__)
-        const unsigned ks = (unsigned)__cvta_generic_to_shared(K0);
-        auto ldk = [&](int l) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ks + 16u * l)); return v; };
-#pragma unroll
-        for (int l = 0; l < 6; ++l) { const double2 v = ldk(l); t0 += v.x * dx[2 * l]; t0 += v.y * dx[2 * l + 1]; }
-#pragma unroll
-        for (int l = 0; l < 6; ++l) { const double2 v = ldk(6 + l); t1 += v.x * dx[2 * l]; t1 += v.y * dx[2 * l + 1]; }
-#pragma unroll
-        for (int l = 0; l < 6; ++l) { const double2 v = ldk(12 + l); t2 += v.x * dx[2 * l]; t2 += v.y * dx[2 * l + 1]; }
-#else
-#pragma unroll
-        for (int l = 0; l < NE; ++l) t0 += K0[l] * dx[l];
-#pragma unroll
-        for (int l = 0; l < NE; ++l) t1 += K0[12 + l] * dx[l];
-#pragma unroll
-        for (int l = 0; l < NE; ++l) t2 += K0[24 + l] * dx[l];
-#endif
-        u0 = U[k * NU + 3 * f] + alpha * dk[3 * f] + t0;
-        u1 = U[k * NU + 3 * f + 1] + alpha * dk[3 * f + 1] + t1;
-        u2 = U[k * NU + 3 * f + 2] + alpha * dk[3 * f + 2] + t2;
-        double* tu = gTU + (size_t)(k * NU + 3 * f) * NCAND + c;
-        tu[0] = u0; tu[NCAND] = u1; tu[2 * NCAND] = u2;
-      }
-      double* e = exl(lane);
-      const double d0 = u0, d1 = u1, d2 = u2 - m.urefz(k, f);   // u_ref = (0, 0, weight share)
-      e[0] = 0.5 * wr[3 * f] * d0 * d0;
-      e[1] = 0.5 * wr[3 * f + 1] * d1 * d1;
-      e[2] = 0.5 * wr[3 * f + 2] * d2 * d2;
-      const double* mu_f = gmu + k * NC + 6 * f;
-      const double fzc_f = m.fzc(k, f);
-      double vl = 0;
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        double cr = m.CR[3 * r] * u0 + m.CR[3 * r + 1] * u1 + m.CR[3 * r + 2] * u2;
-        if (r == 4) cr += -fzc_f;
-        const double mui = mu_f[r];
-        const double est = mui + rho * cr;
-        const double lh = est > 0 ? est : 0;
-        if (cr > vl) vl = cr;
-        e[3 + r] = lh * lh - mui * mui;
-      }
-      vls[lane] = vl;
-      const double* rf = m.foot + 3 * f;
-      e[9] = u0; e[10] = u1; e[11] = u2;
-      e[12] = rf[1] * u2 - rf[2] * u1; e[13] = rf[2] * u0 - rf[0] * u2; e[14] = rf[0] * u1 - rf[1] * u0;
-    }
-    COOP_SYNC();
-    // ---- phase 2, first lane of each candidate: fold the feet in order, stage merit, midpoint step
-    COOP_PHASE {
-      if (lane % NF == 0) {
-        const int c = lane / NF;
-        double* s = xs + XS * c;
-        double x[NX], xr[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = s[i];
-        if (mode == 1) {
-#pragma unroll
-          for (int i = 0; i < NX; ++i) gTX[(size_t)(k * NX + i) * NCAND + c] = x[i];
-        }
-        m.xref(k, xr);
-        double Jl = 0;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { const double dxi = x[i] - xr[i]; Jl += 0.5 * cfg.q_weights[i] * dxi * dxi; }
-        const double sq = xr[3] * x[3] + xr[4] * x[4] + xr[5] * x[5] + xr[6] * x[6];
-        double mom0 = 0, mom1 = 0, mom2 = 0, fs0 = 0, fs1 = 0, fs2 = 0, acc = 0, vl = s[14];
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-          const double* e = exl(lane + f);
-          Jl += e[0]; Jl += e[1]; Jl += e[2];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) acc += e[3 + r];
-          mom0 += e[12]; fs0 += e[9];
-          mom1 += e[13]; fs1 += e[10];
-          mom2 += e[14]; fs2 += e[11];
-          const double v = vls[lane + f];
-          if (v > vl) vl = v;
-        }
-        if (cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
-        double J = s[13];
-        J += Jl;
-        J += acc / (2 * rho);
-        s[13] = J;
-        s[14] = vl;
-        // explicit midpoint step driven by the net wrench (AltroUtils.cpp:9-22, 383-391)
-        mom0 += m.tau_g[0]; mom1 += m.tau_g[1]; mom2 += m.tau_g[2];
-        const double al0 = fs0 * m.inv_mass + m.g[0], al1 = fs1 * m.inv_mass + m.g[1], al2 = fs2 * m.inv_mass + m.g[2];
-        const double aw0 = m.Iinv[0] * mom0 + m.Iinv[1] * mom1 + m.Iinv[2] * mom2;
-        const double aw1 = m.Iinv[3] * mom0 + m.Iinv[4] * mom1 + m.Iinv[5] * mom2;
-        const double aw2 = m.Iinv[6] * mom0 + m.Iinv[7] * mom1 + m.Iinv[8] * mom2;
-        double xm[NX];
-        {
-          const double *q = x + 3, *w = x + 10;
-          xm[0] = x[7] * hh + x[0]; xm[1] = x[8] * hh + x[1]; xm[2] = x[9] * hh + x[2];
-          xm[3] = (0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2])) * hh + q[0];
-          xm[4] = (0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2])) * hh + q[1];
-          xm[5] = (0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2])) * hh + q[2];
-          xm[6] = (0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2])) * hh + q[3];
-          xm[7] = al0 * hh + x[7]; xm[8] = al1 * hh + x[8]; xm[9] = al2 * hh + x[9];
-          xm[10] = aw0 * hh + x[10]; xm[11] = aw1 * hh + x[11]; xm[12] = aw2 * hh + x[12];
-        }
-        {
-          const double *q = xm + 3, *w = xm + 10;
-          const double qd0 = 0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
-          const double qd1 = 0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
-          const double qd2 = 0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
-          const double qd3 = 0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
-          s[0] = x[0] + hd * xm[7]; s[1] = x[1] + hd * xm[8]; s[2] = x[2] + hd * xm[9];
-          s[3] = x[3] + hd * qd0; s[4] = x[4] + hd * qd1; s[5] = x[5] + hd * qd2; s[6] = x[6] + hd * qd3;
-          s[7] = x[7] + hd * al0; s[8] = x[8] + hd * al1; s[9] = x[9] + hd * al2;
-          s[10] = x[10] + hd * aw0; s[11] = x[11] + hd * aw1; s[12] = x[12] + hd * aw2;
-        }
-        if (mode == 0 && c == 0) {
-#pragma unroll
-          for (int i = 0; i < NX; ++i) X[(k + 1) * NX + i] = s[i];
-        }
-      }
-    }
-    COOP_SYNC();
-  }
-  // ---- terminal knot: state cost only
-  COOP_PHASE {
-    if (lane % NF == 0) {
-      const int c = lane / NF;
-      const double* s = xs + XS * c;
-      double x[NX], xr[NX];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] = s[i];
-      if (mode == 1) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) gTX[(size_t)(N * NX + i) * NCAND + c] = x[i];
-      }
-      m.xref(N, xr);
-      double Jl = 0;
-#pragma unroll
-      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - xr[i]; Jl += 0.5 * cfg.q_weights[i] * dxi * dxi; }
-      const double sq = xr[3] * x[3] + xr[4] * x[4] + xr[5] * x[5] + xr[6] * x[6];
-      if (cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
-      res[c] = s[13] + Jl;
-      res[NCAND + c] = s[14];
-    }
-  }
-  COOP_SYNC();
-}
-
 template <int NF, int G>
 QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in,
                             const unsigned char* sched, QmpcWarmStart* warm, QmpcResult* out,
@@ -844,20 +568,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   }
   COOP_SYNC();
   double rho = o.penalty_initial;
-#ifdef QMPC_COOP_FEET_ROLLOUT
-  constexpr int NCAND = G / NF;          // step lengths evaluated per line-search round
-  double* exA = PM;                      // exchange block: PM, S, Qux are dead outside the backward pass; what does
-  double* exB = P + 2 * (NU * 12 + NU);  // not fit there (2-foot model) goes behind the gain stage in P | PA | T
-  double* xs = vec;                      // candidate states: the vector block up to cv::scal is dead too
-  double* vls = red + G;
-  static_assert(16 * NCAND <= cv::scal && 2 * NCAND <= G, "roll-out work areas");
-  static_assert((72 + 36 + NU * 12) / 15 >= G || 2 * (NU * 12 + NU) + 15 * (G - (72 + 36 + NU * 12) / 15) <= 288 + 72 - 2 * G,
-                "exchange block overflow");
-  coop_rollout_feet<NF, G>(m, cfg, wr, N, h, X, U, gK, gd, gmu, rho, 1.0, o.ls_decrease, 0, gTX, gTU, exA, exB, xs, vls, red, P,
-                           lane_id, lane_mask, (warm && warm[pid].valid) ? warm + pid : nullptr);
-  double phi = red[0], viol = red[NCAND];
-  COOP_SYNC();
-#else
   constexpr int NCAND = G;
   COOP_PHASE {
     if (lane == 0) coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3], gTX, gTU, 0, G, P, lane_mask,
@@ -865,7 +575,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
   }
   COOP_SYNC();
   double phi = scal[2], viol = scal[3];
-#endif
   int status = QMPC_STATUS_MAX_ITERATIONS, iters = 0;
   double cost_decrease = INFINITY;
   if (!isfinite(phi)) status = QMPC_STATUS_NONFINITE;
@@ -1036,15 +745,8 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     COOP_SYNC();
 
 #pragma unroll 1
-#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_BLOCK_SYNC) && defined(QMPC_COOP_KNOT_SYNC)
-#define COOP_KNOT_LEAVE continue
-    for (int k = N - 1; k >= 0; --k) {
-      COOP_KNOT_SYNC();
-      if (!bp_ok) continue;
-#else
 #define COOP_KNOT_LEAVE break
     for (int k = N - 1; k >= 0 && bp_ok; --k) {
-#endif
       // ---- phase A: stage the knot's 3x3 blocks; per-foot AL terms; cost expansion
       COOP_PHASE {
 #pragma unroll 1
@@ -1161,7 +863,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
                  br == bc ? vec + cv::Dblk + 9 * br : nullptr);
       }
       COOP_SYNC();
-#ifndef QMPC_COOP_NO_CHOL_REG
       // ---- Cholesky + both triangular solves, fused, per lane, entirely in registers.  Every lane
       //      factors the 12x12 Quu redundantly (the kernel is latency- and shared-memory-bound, not
       //      FLOP-bound: 16 lanes doing the same 364 flops cost the same issue slots as one) and then
@@ -1222,7 +923,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 #pragma unroll
           for (int l = i + 1; l < NU; ++l) rhs[l] -= Lr[QMPC_TRI(l, i)] * rhs[i];
         }
-#ifndef QMPC_COOP_P_KFORM
         if (ok && lane <= 12) {
           if (c < 12) {
 #pragma unroll
@@ -1232,7 +932,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
             for (int i = 0; i < NU; ++i) vec[cv::vu + i] = rhs[i];
           }
         }
-#endif
 #pragma unroll
         for (int i = NU - 1; i >= 0; --i) {
           QMPC_DIVD(rhs[i], i);
@@ -1245,142 +944,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           if (c < 12) {
 #pragma unroll
             for (int i = 0; i < NU; ++i) st_keep(gK + ((size_t)k * NU + i) * 12 + c, -rhs[i]);
-#ifdef QMPC_COOP_P_KFORM
-#pragma unroll
-            for (int i = 0; i < NU; ++i) T[12 * i + c] = -rhs[i];   // K, in the T | PM region (free after phase E)
-#endif
-          } else {
-            double t = 0;
-#pragma unroll
-            for (int i = 0; i < NU; ++i) {
-              st_keep(gd + k * NU + i, -rhs[i]);
-              t += vec[cv::Qu + i] * (-rhs[i]);
-#ifdef QMPC_COOP_P_KFORM
-              vec[cv::vu + i] = -rhs[i];                            // d
-#endif
-            }
-            scal[0] += t;
-          }
-        }
-      }
-      COOP_SYNC();
-      if (!bp_ok) COOP_KNOT_LEAVE;
-#else
-      // ---- Cholesky of Quu.  Device: lane i keeps row i in registers, right-looking, the pivot and the
-      //      finished column travel by warp shuffles: 12 dependent steps of (shuffle, rsqrt, mul,
-      //      shuffle, fma), no shared-memory round trips and no barriers inside the factorisation.
-      //      Every entry sees exactly the same sequence of fused multiply-adds as in the left-looking
-      //      shared-memory variant below (kept for the host emulation), so the two are bit-identical.
-#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_CHOL_SHFL)
-      {
-        // a[l] is the current value of entry (row, j + l): the register window slides with the
-        // column, so the loop body has fixed register indices and stays ROLLED (the kernel is
-        // instruction-cache bound: the fully unrolled form cost 40 KB of SASS and ran slower).
-        const int row = lane_id < NU ? lane_id : NU - 1;   // spare lanes shadow the last row
-        double a[NU];
-#pragma unroll
-        for (int l = 0; l < NU; ++l) a[l] = Quu[NU * row + l];
-        auto column = [&](int j, auto lmax_tag) {
-          constexpr int LMAX = decltype(lmax_tag)::value;
-          const double sjj = __shfl_sync(lane_mask, a[0], j, G);
-          if (!(sjj > 0.0)) return false;                   // uniform over the problem's lanes
-          const double rdg = qmpc_rsqrt(sjj);
-          const double lj = (row == j) ? sjj * rdg : a[0] * rdg;   // L(row, j)
-          if (lane_id < NU && j <= lane_id) Quu[NU * lane_id + j] = lj;
-          if (lane_id == j) vec[cv::rdiag + j] = rdg;
-#pragma unroll
-          for (int l = 1; l <= LMAX; ++l) {
-            const double cl = __shfl_sync(lane_mask, lj, j + l, G);   // L(j + l, j); wraps harmlessly past NU
-            a[l - 1] = a[l] - lj * cl;
-          }
-          return true;
-        };
-        constexpr int H = NU / 2;
-#pragma unroll 1
-        for (int j = 0; j < H && bp_ok; ++j) bp_ok = column(j, IntTag<NU - 1>{});
-#pragma unroll 1
-        for (int j = H; j < NU && bp_ok; ++j) bp_ok = column(j, IntTag<NU - 1 - H>{});
-        COOP_SYNC();
-      }
-#else
-      // (left-looking, one row per lane).  One sync per column: the column is
-      //      exchanged through a double-buffered tcol, and the only not-yet-visible factor entry a
-      //      lane needs, L(j, j-1), is recomputed from the previous tcol (bit-identical to what the
-      //      owning lane stored).  1/sqrt via one rsqrt instead of sqrt + reciprocal.
-      {
-        double rdg_prev = 0.0;
-#ifdef QMPC_COOP_CHOL_UNROLL
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-        for (int j = 0; j < NU && bp_ok; ++j) {
-          double* tc = vec + cv::tcol + (j & 1) * NU;
-          const double* tp = vec + cv::tcol + ((j & 1) ^ 1) * NU;
-          COOP_PHASE {
-            for (int i = j + lane; i < NU; i += G) {
-              double t = Quu[NU * i + j];
-#ifdef QMPC_COOP_CHOL_UNROLL
-#pragma unroll
-#else
-#pragma unroll 4
-#endif
-              for (int l = 0; l + 1 < j; ++l) t -= Quu[NU * i + l] * Quu[NU * j + l];
-              if (j > 0) t -= Quu[NU * i + j - 1] * (i == j ? Quu[NU * j + j - 1] : tp[j] * rdg_prev);
-              tc[i] = t;
-            }
-          }
-          COOP_SYNC();
-          const double sjj = tc[j];
-          if (!(sjj > 0.0)) {
-            bp_ok = false;
-          } else {
-            const double rdg = qmpc_rsqrt(sjj);
-            const double dg = sjj * rdg;
-            COOP_PHASE {
-              for (int i = j + lane; i < NU; i += G) {
-                if (i == j) { Quu[NU * i + j] = dg; vec[cv::rdiag + j] = rdg; }
-                else Quu[NU * i + j] = tc[i] * rdg;
-              }
-            }
-            rdg_prev = rdg;
-          }
-        }
-        COOP_SYNC();
-      }
-#endif
-      if (!bp_ok) COOP_KNOT_LEAVE;
-      // ---- solves: lane c <- right-hand side c (12 columns of Qux, then Qu); register-resident,
-      //      fully unrolled (the rolled shared-memory variant was measured slower: +40 % instructions)
-      COOP_PHASE {
-        for (int c = lane; c <= 12; c += G) {
-          double rhs[NU];
-#pragma unroll
-          for (int i = 0; i < NU; ++i) rhs[i] = c < 12 ? Qux[12 * i + c] : vec[cv::Qu + i];
-          // column-oriented ("right-looking") substitutions: after x_i is final, every remaining
-          // entry is updated independently -> 12-deep critical path instead of 78 dependent FMAs
-#pragma unroll
-          for (int i = 0; i < NU; ++i) {
-            rhs[i] = rhs[i] * vec[cv::rdiag + i];
-#pragma unroll
-            for (int l = i + 1; l < NU; ++l) rhs[l] -= Quu[NU * l + i] * rhs[i];
-          }
-          if (c < 12) {
-#pragma unroll
-            for (int i = 0; i < NU; ++i) Qux[12 * i + c] = rhs[i];   // V = L^-1 Qux
-          } else {
-#pragma unroll
-            for (int i = 0; i < NU; ++i) vec[cv::vu + i] = rhs[i];
-          }
-#pragma unroll
-          for (int i = NU - 1; i >= 0; --i) {
-            rhs[i] = rhs[i] * vec[cv::rdiag + i];
-#pragma unroll
-            for (int l = 0; l < i; ++l) rhs[l] -= Quu[NU * i + l] * rhs[i];
-          }
-          if (c < 12) {
-#pragma unroll
-            for (int i = 0; i < NU; ++i) st_keep(gK + ((size_t)k * NU + i) * 12 + c, -rhs[i]);
           } else {
             double t = 0;
 #pragma unroll
@@ -1393,44 +956,9 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
         }
       }
       COOP_SYNC();
-#endif
+      if (!bp_ok) COOP_KNOT_LEAVE;
       // ---- phase F: new P = sym(P) - V^T V (16 blocks, written to the work buffer: no race with the
       //      transposed reads of Pc), pv <- Qx - V^T vu ; then swap the two buffers
-#ifdef QMPC_COOP_P_KFORM
-      // reference-order variant: P <- sym(Qxx + Qux^T K), p <- Qx + Qux^T d (the oracle's / srb kernel's update; with
-      // cond(Quu) ~ 1e14 its rounding differs from the V^T V form at the 1e-4 N level in ~1 of 50 000 solves)
-      COOP_PHASE {
-        const int br = lane >> 2, bc = lane & 3;
-        const double* Ks = T;
-        double t1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, o[9];
-#pragma unroll 1
-        for (int l = 0; l < NU; ++l) {
-          const double *Qr = Qux + 12 * l + 3 * br, *Qc = Qux + 12 * l + 3 * bc;
-          const double *Kr = Ks + 12 * l + 3 * br, *Kc = Ks + 12 * l + 3 * bc;
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) { t1[3 * a + b] += Qr[a] * Kc[b]; t2[3 * a + b] += Qc[b] * Kr[a]; }
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int b = 0; b < 3; ++b)
-            o[3 * a + b] = 0.5 * ((Pc[12 * (3 * br + a) + 3 * bc + b] + t1[3 * a + b]) +
-                                  (Pc[12 * (3 * bc + b) + 3 * br + a] + t2[3 * a + b]));
-        blk_store(Pw + 36 * br + 3 * bc, 12, o);
-        blk_store_keep(gP + (size_t)k * 144 + 36 * br + 3 * bc, 12, o);
-        if (lane < 12) {
-          const int a = lane;
-          double t = 0;
-#pragma unroll 4
-          for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * vec[cv::vu + l];
-          const double v = vec[cv::Qx + a] + t;
-          vec[cv::pv + a] = v;
-          st_keep(gpv + k * 12 + a, v);
-        }
-      }
-#else
       COOP_PHASE {
         const int br = lane >> 2, bc = lane & 3;
         double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1464,7 +992,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
           st_keep(gpv + k * 12 + a, v);
         }
       }
-#endif
       COOP_SYNC();
       { double* t = Pc; Pc = Pw; Pw = t; }
     }
@@ -1476,29 +1003,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
     // consecutive step lengths alpha = decrease^j at once (feet roll-out: NF lanes per step length, 4 per
     // round for the quadruped; lane roll-out: one lane each, 16 per round); the first one passing the
     // Armijo test wins - the result is identical to the sequential search.
-#ifdef QMPC_COOP_FEET_ROLLOUT
-    int acc_j = -1;
-    double phin = 0, violn = 0, alpha_acc = 0;
-    double alpha_round = 1.0;   // decrease^(round * NCAND), by repeated multiplication like the sequential search
-#pragma unroll 1
-    for (int round = 0; round * NCAND < o.ls_iters_max && acc_j < 0; ++round) {
-      coop_rollout_feet<NF, G>(m, cfg, wr, N, h, X, U, gK, gd, gmu, rho, alpha_round, o.ls_decrease, 1, gTX, gTU, exA, exB, xs,
-                               vls, red, P, lane_id, lane_mask, nullptr);
-      double alpha = alpha_round;
-      for (int l = 0; l < NCAND && acc_j < 0; ++l) {
-        const double pl = red[l];
-        if (round * NCAND + l < o.ls_iters_max && isfinite(pl) && pl <= phi + o.ls_c1 * alpha * dphi0) {
-          acc_j = round * NCAND + l;
-          phin = pl;
-          violn = red[NCAND + l];
-          alpha_acc = alpha;
-        }
-        alpha *= o.ls_decrease;
-      }
-      alpha_round = alpha;   // after NCAND multiplications (only used when nothing was accepted)
-      COOP_SYNC();
-    }
-#else
     int acc_j = -1;
     double phin = 0, violn = 0, alpha_acc = 0;
 #pragma unroll 1
@@ -1530,7 +1034,6 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
       }
       COOP_SYNC();
     }
-#endif
     iters = it + 1;
     if (acc_j < 0) { status = QMPC_STATUS_LINESEARCH_FAILED; COOP_ITER_LEAVE; }
     // ---------------- accepted step: the winning lane's trial trajectory is already in the scratch.
