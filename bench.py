@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_KNOT_ITER = 65.8e3   # dense reference-equivalent AL-iLQR, ne=12, m=12, p=24
 IN_BYTES, OUT_BYTES = 296, 240  # sizeof(QmpcProblem), sizeof(QmpcResult)
-NCU_DRAM_BYTES_PER_SOLVE = (2.825775e9 + 9.770318e9) / 16384   # profiles/r01_s3_ncu_coop_B16384.txt
+NCU_DRAM_BYTES_PER_SOLVE = (2.834063e9 + 9.771933e9) / 16384   # profiles/r01_s4_ncu_coop_B16384.txt
 
 
 def parse():
@@ -320,7 +320,7 @@ def main():
         "bound": "fp64_fma", "achieved": achieved_tflops, "peak": f64.value, "unit": "TFLOP/s",
         "frac": achieved_tflops / f64.value if f64.value > 0 else None,
         # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
-        # this kernel (profiles/r01_s3_ncu_coop_B16384.txt: 2.83 + 9.76 GB for 16384 solves = 769 kB per solve,
+        # this kernel (profiles/r01_s4_ncu_coop_B16384.txt: 2.83 + 9.77 GB for 16384 solves = 769 kB per solve,
         # the L2-overflowing scratch of the trial trajectories / gains), scaled to this launch's batch
         "traffic": NCU_DRAM_BYTES_PER_SOLVE * B if (a.horizon == 10 and a.model == "quat") else None,
         "traffic_source": "ncu capture at batch 16384, scaled by batch; algorithmic bytes are 536 B/solve - the "

@@ -1110,7 +1110,8 @@ __global__ void __launch_bounds__(QMPC_COOP_BLOCK, QMPC_COOP_MIN_BLOCKS)
 qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in,
                  const unsigned char* __restrict__ sched, QmpcWarmStart* __restrict__ warm,
                  QmpcResult* __restrict__ out,
-                 double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot, int wide) {
+                 double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot, int wide,
+                 int active_groups) {
   extern __shared__ __align__(16) double smem_pool[];
   if (threadIdx.x < 13) smem_pool[threadIdx.x] = cfg.q_weights[threadIdx.x];
   else if (threadIdx.x < 25) smem_pool[threadIdx.x] = cfg.r_weights[threadIdx.x - 13];
@@ -1118,24 +1119,28 @@ qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ i
   const int groups_per_block = blockDim.x / G;
   const int group = threadIdx.x / G;
   const int lane_id = threadIdx.x % G;
-  const int slot = blockIdx.x * groups_per_block + group;
-  const int nslots = gridDim.x * groups_per_block;
+  // `active_groups` of the block's groups own a slot (a partial wave is spread over all SMs instead of filling
+  // some of them): even groups first, so that up to half occupancy every problem has a warp of its own
+  const int rank = (group & 1) * ((groups_per_block + 1) / 2) + (group >> 1);
+  const bool idle = rank >= active_groups;
+  const int slot = blockIdx.x * active_groups + rank;
+  const int nslots = gridDim.x * active_groups;
   const unsigned lane_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
   double* sm = smem_pool + kCoopBlockShared + (size_t)group * smem_per_problem;
-  double* gs = scratch + (size_t)slot * scratch_per_slot;
+  double* gs = scratch + (size_t)(idle ? 0 : slot) * scratch_per_slot;
 #ifdef QMPC_COOP_BLOCK_SYNC
   // problem waves: all slots of the block run the same number of waves and barriers; a slot without a
   // problem in the last wave only passes the barriers
   for (int base = 0; base < batch; base += nslots) {
     const int pid = base + slot;
-    if (pid < batch) {
+    if (!idle && pid < batch) {
       coop_solve_one<NF, G>(cfg, o, in, sched, warm, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
     } else {
       for (int it = 0; it < o.iterations_max; ++it) { COOP_BLOCK_SYNC(); COOP_KNOT_SYNC_ALL(o.N); COOP_BLOCK_SYNC_MID(); }
     }
   }
 #else
-  for (int pid = slot; pid < batch; pid += nslots) {
+  for (int pid = slot; !idle && pid < batch; pid += nslots) {
     coop_solve_one<NF, G>(cfg, o, in, sched, warm, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
   }
 #endif

@@ -181,6 +181,24 @@ def test_edge_cases_nonfinite_zero_contacts_and_odd_batches(oracle):
         assert r.tobytes() == res[20:20 + b].tobytes()
 
 
+@pytest.mark.parametrize("B", [1, 7, 149, 300, 1185, 2500])
+def test_launch_geometry_does_not_change_results(oracle, monkeypatch, B):
+    """launch_coop spreads a partial wave of problems over the resident blocks (one block per SM first, `active`
+    groups per block); which slot solves a problem must not matter: bit-identical to the packed launch, and
+    within tolerance of the oracle, at batch sizes on either side of every branch of the geometry."""
+    from quaternion_mpc_b200 import QuatMpc
+    probs = random_batch(B, seed=11, gait="trot")
+    mpc = QuatMpc(horizon=10, max_batch=4096)       # handle larger than the batch: the geometry is per launch
+    monkeypatch.delenv("QMPC_COOP_NO_SPREAD", raising=False)
+    spread = _solve_dev(mpc, probs)
+    assert f"_x_" in mpc.describe()
+    monkeypatch.setenv("QMPC_COOP_NO_SPREAD", "1")
+    packed = _solve_dev(mpc, probs)
+    for f in ("grf_body", "grf_world", "iterations", "status"):
+        assert np.array_equal(spread[f], packed[f]), f
+    _check(spread, oracle.solve_batch(mpc.cfg, probs, nthreads=NT))
+
+
 @pytest.mark.parametrize("N", [1, 2, 25, 32])
 def test_horizon_extremes(oracle, N):
     from quaternion_mpc_b200 import QuatMpc
