@@ -188,6 +188,8 @@ int qmpc_solve_batch_convex_sched(QmpcHandle* h, const QmpcConvexProblem* d_in,
                                   void* cuda_stream);
 int qmpc_solve_batch_sched_host(QmpcHandle* h, const QmpcProblem* in, const QmpcContactSchedule* sched,
                                 int32_t batch, QmpcResult* out);
+int qmpc_solve_batch_convex_sched_host(QmpcHandle* h, const QmpcConvexProblem* in,
+                                       const QmpcContactSchedule* sched, int32_t batch, QmpcResult* out);
 
 /* ---- N2: leg kinematics in, joint torques out ---------------------------------------------------
  * Producer of the solve's foot_pos_body and consumer of its GRFs:

@@ -86,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "qmpc_solve_batch_host", "qmpc_solve_batch_convex_host", "qmpc_destroy", "qmpc_launch_count",
     "qmpc_last_error", "qmpc_status_string", "qmpc_abi_version", "qmpc_measure_fma_peak",
     "qmpc_predict_contact_schedule", "qmpc_solve_batch_sched", "qmpc_solve_batch_convex_sched",
-    "qmpc_solve_batch_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques", "qmpc_describe", "qmpc_solve_batch_warm", "qmpc_goal_state_bytes", "qmpc_goal_update",
+    "qmpc_solve_batch_sched_host", "qmpc_solve_batch_convex_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques", "qmpc_describe", "qmpc_solve_batch_warm", "qmpc_goal_state_bytes", "qmpc_goal_update",
     "qmpc_default_raibert_params", "qmpc_raibert_targets",
 ]
 
@@ -129,8 +129,10 @@ def load_library():
         f.restype = C.c_int
     lib.qmpc_solve_batch_warm.argtypes = [vp, vp, vp, vp, i32, vp, vp]
     lib.qmpc_solve_batch_warm.restype = C.c_int
-    lib.qmpc_solve_batch_sched_host.argtypes = [vp, vp, vp, i32, vp]
-    lib.qmpc_solve_batch_sched_host.restype = C.c_int
+    for name in ("qmpc_solve_batch_sched_host", "qmpc_solve_batch_convex_sched_host"):
+        f = getattr(lib, name)
+        f.argtypes = [vp, vp, vp, i32, vp]
+        f.restype = C.c_int
     lib.qmpc_predict_contact_schedule.argtypes = [vp, vp, i32, vp, vp]
     lib.qmpc_predict_contact_schedule.restype = C.c_int
     lib.qmpc_default_leg_params.argtypes = [C.POINTER(QmpcLegParams)]

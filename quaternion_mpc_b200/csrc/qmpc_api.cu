@@ -377,6 +377,10 @@ extern "C" int qmpc_solve_batch_convex_host(QmpcHandle* h, const QmpcConvexProbl
                                             QmpcResult* out) {
   return solve_host_any(h, in, nullptr, batch, out, true);
 }
+extern "C" int qmpc_solve_batch_convex_sched_host(QmpcHandle* h, const QmpcConvexProblem* in,
+                                                  const QmpcContactSchedule* sched, int32_t batch, QmpcResult* out) {
+  return solve_host_any(h, in, sched, batch, out, true);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Rows N1 / N2 of the scope table: streaming kernels either side of the solve (qmpc_periph.cuh)

@@ -44,16 +44,17 @@ using VectorXd = stubeig::Vec<13>;
 namespace legged {
 struct LeggedFeedback {
   Eigen::Vector3d torso_pos_world, torso_lin_vel_world, torso_lin_vel_body, torso_ang_vel_body;
+  Eigen::Vector3d torso_euler, torso_ang_vel_world;   // ConvexMpc only
   Eigen::Quaterniond torso_quat;
   Eigen::Matrix3d torso_rot_mat, torso_rot_mat_z;
-  stubeig::Mat<3, 4> foot_pos_body, foot_pos_world;
+  stubeig::Mat<3, 4> foot_pos_body, foot_pos_world, foot_pos_abs_com;
   Eigen::Vector4d foot_contact_flag;
   double mpc_time = 0;
 };
 struct LeggedCtrl {
   Eigen::Vector4d gait_counter;
   Eigen::Vector3d torso_pos_d_world, torso_pos_d_body, torso_lin_vel_d_body, torso_lin_vel_d_rel,
-      torso_lin_vel_d_world, torso_ang_vel_d_body;
+      torso_lin_vel_d_world, torso_ang_vel_d_body, torso_euler_d;
   Eigen::Quaterniond torso_quat_d;
   stubeig::Mat<3, 4> foot_pos_target_world;
   bool plan_contacts[NUM_LEG] = {true, true, true, true};
@@ -63,7 +64,7 @@ struct LeggedCtrl {
   stubeig::Vec<12> mpc_grf_world;
 };
 struct LeggedJoyCmd {
-  double velx = 0, vely = 0, roll_rate = 0, pitch_rate = 0, yaw_rate = 0, body_height = 0.3;
+  double velx = 0, vely = 0, roll_rate = 0, pitch_rate = 0, yaw_rate = 0, body_height = 0.3, body_x = 0, body_y = 0;
 };
 struct LeggedParam {
   double mpc_update_period = 10.0;
@@ -72,6 +73,7 @@ struct LeggedParam {
   stubeig::Vec<12> r_weights;
   double w = 50.0, mu = 0.7, fz_max = 100.0, robot_mass = 12.84, gait_freq = 2.2;
   Eigen::Matrix3d trunk_inertia;
+  int terrain_adpt_state = 0;
 };
 struct LeggedState {
   LeggedFeedback fbk;

@@ -4,6 +4,7 @@
 #include <memory>
 #include <stdexcept>
 
+#include "CudaConvexMpc.h"
 #include "CudaQuatMpc.h"
 
 extern "C" int shim_construct_only(int device, char* err, int errlen) {
@@ -84,4 +85,65 @@ extern "C" int shim_run(const QmpcProblem* in, int horizon, int ticks, QmpcProbl
 extern "C" int shim_run_sched(const QmpcProblem* in, int horizon, int ticks, double gait_phase, QmpcProblem* out_problem,
                               unsigned char* out_sched, double* out_grf_body, double* out_grf_world, int* status_iters) {
   return shim_run_impl(in, horizon, ticks, out_problem, out_grf_body, out_grf_world, status_iters, gait_phase, out_sched);
+}
+
+// ---- CudaConvexMpc: same idea.  `in` carries the measured state; desired quantities come from the joystick
+// through the shim's own goal_update.  out_problem: what the shim packed on the last tick.
+extern "C" int shim_convex_construct_only(int device, char* err, int errlen) {
+  legged::LeggedState st;
+  try {
+    legged::CudaConvexMpc mpc(st, device);
+  } catch (const std::exception& e) {
+    std::strncpy(err, e.what(), errlen - 1);
+    err[errlen - 1] = 0;
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" int shim_convex_run(const QmpcConvexProblem* in, int horizon, int ticks, int walking, double gait_phase,
+                               QmpcConvexProblem* out_problem, unsigned char* out_sched, double* out_grf_body,
+                               double* out_state6, int* status_iters) {
+  using namespace legged;
+  LeggedState st;
+  st.param.mpc_horizon = horizon;
+  st.param.mpc_update_period = 5.0;   // gazebo_go1_convex_mpc.yaml:36
+  const double Q[12] = {3.0, 3.0, 3.0, 1.0, 1.0, 20.0, 0.0, 0.0, 3.0, 2.0, 3.0, 2.0};
+  for (int i = 0; i < 12; ++i) st.param.q_weights[i] = Q[i];
+  for (int i = 0; i < 12; ++i) st.param.r_weights[i] = 1e-6;
+  st.param.mu = 0.6;
+  st.param.fz_max = 200.0;
+  for (int i = 0; i < 3; ++i) {
+    st.fbk.torso_euler[i] = in->torso_euler[i];
+    st.fbk.torso_pos_world[i] = in->torso_pos_world[i];
+    st.fbk.torso_ang_vel_world[i] = in->torso_ang_vel_world[i];
+    st.fbk.torso_lin_vel_world[i] = in->torso_lin_vel_world[i];
+    for (int j = 0; j < 3; ++j) st.fbk.torso_rot_mat(i, j) = in->torso_rot_mat[3 * i + j];
+    st.fbk.torso_rot_mat_z(i, i) = 1.0;
+    st.ctrl.torso_euler_d[i] = 0.01 * (i + 1);
+  }
+  for (int leg = 0; leg < 4; ++leg)
+    for (int i = 0; i < 3; ++i) st.fbk.foot_pos_abs_com(i, leg) = in->foot_pos_abs_com[3 * leg + i];
+  st.joy.velx = 0.3; st.joy.vely = -0.05; st.joy.yaw_rate = 0.2; st.joy.body_height = 0.29;
+  st.joy.body_x = in->torso_pos_world[0] + 0.01; st.joy.body_y = in->torso_pos_world[1] - 0.01;
+  st.ctrl.movement_mode = walking ? 1 : 0;
+  std::unique_ptr<LeggedMpc> mpc_ptr;
+  try {
+    mpc_ptr = std::make_unique<CudaConvexMpc>(st, 0);
+  } catch (const std::exception&) {
+    return 1;
+  }
+  auto* c = static_cast<CudaConvexMpc*>(mpc_ptr.get());
+  if (walking) {
+    c->enable_contact_schedule(true);
+    for (int leg = 0; leg < 4; ++leg) c->leg_fsm(leg).gait_phase = gait_phase;
+  }
+  for (int t = 0; t < ticks; ++t) mpc_ptr->update(st);
+  if (out_sched) std::memcpy(out_sched, c->last_schedule().mask, QMPC_MAX_HORIZON);
+  *out_problem = c->last_problem();
+  for (int i = 0; i < 12; ++i) out_grf_body[i] = st.ctrl.optimized_input[i];
+  for (int i = 0; i < 6; ++i) out_state6[i] = st.ctrl.optimized_state[i];
+  status_iters[0] = c->last_status();
+  status_iters[1] = c->last_iterations();
+  return 0;
 }

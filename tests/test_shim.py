@@ -19,8 +19,11 @@ def shim():
     import __graft_entry__ as g
     g.build()
     pkg = os.path.join(ROOT, "quaternion_mpc_b200")
-    srcs = [os.path.join(pkg, "shim", "CudaQuatMpc.cpp"), os.path.join(ROOT, "tests", "stubs", "shim_driver.cpp")]
-    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+    srcs = [os.path.join(pkg, "shim", "CudaQuatMpc.cpp"), os.path.join(pkg, "shim", "CudaConvexMpc.cpp"),
+            os.path.join(ROOT, "tests", "stubs", "shim_driver.cpp")]
+    deps = srcs + [os.path.join(pkg, "shim", "CudaQuatMpc.h"), os.path.join(pkg, "shim", "CudaConvexMpc.h"),
+                   os.path.join(ROOT, "tests", "stubs", "mpc", "LeggedMpc.h"), os.path.join(ROOT, "include", "qmpc.h")]
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + srcs + [
             "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"),
             "-I", os.path.join(pkg, "shim"), "-L", pkg, "-lqmpc_b200", f"-Wl,-rpath,{pkg}"])
@@ -35,6 +38,48 @@ def test_shim_builds_and_fails_loudly_without_gpu(shim):
         assert rc == 0
     else:
         assert rc == 1 and b"qmpc_create failed" in err.value
+
+
+def test_convex_shim_builds_and_fails_loudly_without_gpu(shim):
+    import torch
+    err = C.create_string_buffer(256)
+    rc = shim.shim_convex_construct_only(0, err, 256)
+    if torch.cuda.is_available():
+        assert rc == 0
+    else:
+        assert rc == 1 and b"CudaConvexMpc: qmpc_create failed" in err.value
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("walking", [0, 1])
+def test_convex_shim_tick_matches_oracle(shim, oracle, walking):
+    """CudaConvexMpc::update through the LeggedMpc pointer: the problem it packs solves to what it wrote back;
+    walking = the per-knot schedule option (the TODO at ConvexMpc.cpp:82) through the FSM stub."""
+    from quaternion_mpc_b200.workloads import random_convex_batch
+    p = random_convex_batch(1, seed=31, gait="stand")
+    out_p = np.zeros(1, dtype=abi.CONVEX_PROBLEM_DTYPE)
+    sched = np.zeros((1, abi.QMPC_MAX_HORIZON), dtype=np.uint8)
+    gb, st6, si = np.zeros(12), np.zeros(6), np.zeros(2, dtype=np.int32)
+    shim.shim_convex_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = shim.shim_convex_run(p.ctypes.data, 10, 3, walking, 0.43, out_p.ctypes.data, sched.ctypes.data,
+                              gb.ctypes.data, st6.ctypes.data, si.ctypes.data)
+    assert rc == 0
+    assert np.allclose(out_p["torso_euler"], p["torso_euler"]) and np.allclose(out_p["foot_pos_abs_com"], p["foot_pos_abs_com"])
+    assert abs(out_p["torso_lin_vel_d_world"][0, 0] - 3 * 0.005) < 1e-12      # 1 m/s^2 ramp, three 5 ms ticks
+    assert out_p["torso_lin_vel_d_world"][0, 1] == -0.05 and out_p["yaw_rate_d"][0] == 0.2
+    assert out_p["torso_pos_d_world"][0, 2] == 0.29
+    assert np.allclose(st6[:3], out_p["torso_pos_d_world"][0]) and np.allclose(st6[3:], [0.01, 0.02, 0.03])
+    cfg = default_config(2, 10)
+    if walking:
+        # FSM stub: trot from phase 0.43 at 2.2 Hz, 5 ms knots: FL+RR (1001b) until the phase passes 0.5, then FR+RL
+        assert sched[0, :10].tolist() == [9] * 7 + [6] * 3 and (sched[0, 10:] == 0).all()
+        ref = oracle.solve_batch_convex_sched(cfg, out_p, sched)
+    else:
+        assert (out_p["plan_contacts"] == 1).all()
+        ref = oracle.solve_batch_convex(cfg, out_p)
+    assert np.abs(ref["grf_body"][0] - gb).max() < 1e-4
+    assert si[1] == ref["iterations"][0]
 
 
 @pytest.mark.gpu
