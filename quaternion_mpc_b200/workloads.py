@@ -151,3 +151,28 @@ def predict_schedule_numpy(gait_states, horizon, dt):
                 m |= stance << leg
             out[b, k] = m
     return out
+
+
+def mirror_problems(p):
+    """Reflection y -> -y of the whole scene (a symmetry of the single-rigid-body problem when cfg.com_offset[1]
+    is negated too): vectors flip y, pseudo-vectors flip x and z, quaternions (w, x, y, z) flip x and z, left and
+    right feet swap (FL<->FR, RL<->RR).  Used by the size-independent parity-by-property tests."""
+    m = p.copy()
+    vec = np.array([1.0, -1.0, 1.0])
+    axial = np.array([-1.0, 1.0, -1.0])
+    quat = np.array([1.0, -1.0, 1.0, -1.0])
+    for f in ("torso_lin_vel_world", "torso_pos_d_body", "torso_lin_vel_d_body"):
+        m[f] = p[f] * vec
+    for f in ("torso_ang_vel_body", "torso_ang_vel_d_body"):
+        m[f] = p[f] * axial
+    for f in ("torso_quat", "torso_quat_d"):
+        m[f] = p[f] * quat
+    swap = [1, 0, 3, 2]
+    m["foot_pos_body"] = (p["foot_pos_body"].reshape(-1, 4, 3)[:, swap, :] * vec).reshape(-1, 12)
+    m["plan_contacts"] = p["plan_contacts"][:, swap]
+    return m
+
+
+def mirror_grf(g):
+    """The reflection of mirror_problems() applied to a [B, 12] array of per-foot forces."""
+    return (np.asarray(g).reshape(-1, 4, 3)[:, [1, 0, 3, 2], :] * np.array([1.0, -1.0, 1.0])).reshape(-1, 12)

@@ -10,7 +10,7 @@ import pytest
 
 from quaternion_mpc_b200 import abi
 from quaternion_mpc_b200.config import default_config
-from quaternion_mpc_b200.workloads import random_batch, random_convex_batch, stand_problem
+from quaternion_mpc_b200.workloads import mirror_grf, mirror_problems, random_batch, random_convex_batch, stand_problem
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -160,6 +160,28 @@ def test_properties_at_full_size():
     assert np.abs(np.linalg.norm(r["grf_world"].reshape(B, 4, 3), axis=2) - np.linalg.norm(f, axis=2)).max() < 1e-9
     r2 = _solve_dev(mpc, probs)
     assert r.tobytes() == r2.tobytes()
+
+
+def test_mirror_symmetry_at_full_size():
+    """Size-independent property at BASELINE size (no oracle): reflecting the scene left-right (state, references,
+    feet and contact masks swapped, COM offset negated) must reflect the returned GRFs, with the same iteration
+    count - the solver has no preferred side.  Same tolerance and flagged-solve policy as the oracle parity."""
+    from quaternion_mpc_b200 import QuatMpc
+    B = 65536
+    cfg, cfgm = default_config(0, 10), default_config(0, 10)
+    cfgm.com_offset[1] = -cfg.com_offset[1]
+    probs = random_batch(B, seed=5, gait="trot")
+    r = _solve_dev(QuatMpc(horizon=10, max_batch=B, cfg=cfg), probs)
+    rm = _solve_dev(QuatMpc(horizon=10, max_batch=B, cfg=cfgm), mirror_problems(probs))
+    flagged = (r["status"] >= 2) | (rm["status"] >= 2)
+    err = np.maximum(np.abs(mirror_grf(rm["grf_body"]) - r["grf_body"]).max(axis=1),
+                     np.abs(mirror_grf(rm["grf_world"]) - r["grf_world"]).max(axis=1))
+    ok = ~flagged
+    assert flagged.mean() < 0.05
+    assert (r["iterations"][ok] == rm["iterations"][ok]).mean() > 0.999
+    bad = ok & (err >= TOL)
+    print(f"[mirror: max {float(err[ok & ~bad].max()):.2e} N, {int(bad.sum())}/{B} above tolerance]", end=" ")
+    assert bad.sum() <= B // 10000, (int(bad.sum()), float(err[ok].max()))
 
 
 def test_edge_cases_nonfinite_zero_contacts_and_odd_batches(oracle):

@@ -147,3 +147,23 @@ def test_c_oracle_matches_numpy_restatement(oracle):
         r = A.solve(P, [uref] * N, dict(iterations_max=4, penalty_scaling=20.0, stat_mode="riccati"))
         assert r["iters"] == out["iterations"][i]
         assert np.abs(np.array(r["U"][0]) - out["grf_body"][i]).max() < 1e-8
+
+
+def test_oracle_mirror_symmetry():
+    """Independent check of the restatement as a whole: the single-rigid-body problem is symmetric under a left-right
+    reflection (COM offset negated with it), so the oracle's GRFs must reflect too.  Nothing in the oracle's source
+    is written symmetrically (feet are looped in order, the quaternion algebra is explicit), so a sign or index slip in
+    the dynamics, the Jacobians or the cone rows breaks this."""
+    from oracle import binding as oracle
+    from quaternion_mpc_b200.config import default_config
+    from quaternion_mpc_b200.workloads import mirror_grf, mirror_problems, random_batch
+    cfg, cfgm = default_config(0, 10), default_config(0, 10)
+    cfgm.com_offset[1] = -cfg.com_offset[1]
+    p = random_batch(192, seed=5, gait="mixed")
+    r = oracle.solve_batch(cfg, p, nthreads=os.cpu_count() or 1)
+    rm = oracle.solve_batch(cfgm, mirror_problems(p), nthreads=os.cpu_count() or 1)
+    ok = (r["status"] < 2) & (rm["status"] < 2)
+    assert ok.mean() > 0.9
+    assert (r["iterations"][ok] == rm["iterations"][ok]).all()
+    assert np.abs(mirror_grf(rm["grf_body"]) - r["grf_body"])[ok].max() < 1e-4
+    assert np.abs(mirror_grf(rm["grf_world"]) - r["grf_world"])[ok].max() < 1e-4
