@@ -27,7 +27,10 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_KNOT_ITER = 65.8e3   # dense reference-equivalent AL-iLQR, ne=12, m=12, p=24
 IN_BYTES, OUT_BYTES = 296, 240  # sizeof(QmpcProblem), sizeof(QmpcResult)
-NCU_DRAM_BYTES_PER_SOLVE = (2.834063e9 + 9.771933e9) / 16384   # profiles/r01_s4_ncu_coop_B16384.txt
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # written by tools/ncu_traffic.py from an ncu capture
+ORACLE_PIN = ("oracle pinned on the reference's inactive-cone goldens (quat_mpc_test.json u0 to 5e-7 N, trot_quat_mpc_test.json) "
+              "+ ALTRO's 3/5-iteration toy KATs + an independent SLSQP fixed point; the capped active-cone iterate of the real "
+              "ALTRO fork is unpinned (no reference vector exists)")
 
 
 def parse():
@@ -44,6 +47,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the streaming kernels either side of the solve")
+    ap.add_argument("--no-config1", action="store_true", help="skip the BASELINE config-1 latency block")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "coop", "phased", "srb", "dense"],
+                    help="QmpcCreateOptions.kernel (auto = the product default)")
     return ap.parse_args()
 
 
@@ -156,54 +162,129 @@ def aux_kernels(device, cfg, hbm_peak, robots=1 << 20, reps=20):
     return out
 
 
+def workload_of(a, world):
+    """Model config, problem generator, workload name and the `config` dict - IDENTICAL in both arms."""
+    from quaternion_mpc_b200 import abi, workloads
+    from quaternion_mpc_b200.config import default_config
+    flops, in_bytes = FLOPS_PER_KNOT_ITER, 296
+    if a.model == "quat":
+        cfg = default_config(abi.QMPC_MODEL_QUAT_4FOOT, a.horizon)
+        gen = workloads.random_batch
+        name = f"go1_quat_mpc_N{a.horizon}_{a.gait}_batch{a.batch}_per_gpu_seed0"
+    elif a.model == "quat2":   # BASELINE config 4: 2-contact model (ct_srb_trot_quat_*), m = 6, 12 cone rows
+        cfg = default_config(abi.QMPC_MODEL_QUAT_2FOOT, a.horizon)
+        gen = lambda n, seed=0, gait=None: workloads.random_batch(n, seed=seed, gait="stand", max_angle=0.2, nfeet=2)
+        name = f"two_contact_quat_mpc_N{a.horizon}_batch{a.batch}_per_gpu_seed0"
+        flops = 38e3           # SURVEY.md 8d, m = 6, p = 12
+    else:                      # ConvexMpc (row A8)
+        cfg = default_config(abi.QMPC_MODEL_EULER_CONVEX, a.horizon)
+        gen = lambda n, seed=0, gait="trot": workloads.random_convex_batch(n, seed=seed, gait=gait)
+        name = f"go1_convex_mpc_N{a.horizon}_{a.gait}_batch{a.batch}_per_gpu_seed0"
+        in_bytes = 344
+    config = {"workload": name, "model": a.model, "horizon": a.horizon, "gait": a.gait, "batch_per_gpu": a.batch,
+              "global_batch": a.batch * world, "iterations_max": cfg.iterations_max,
+              "problems": "rank r solves random_batch(batch_per_gpu, seed=r); the CPU arm solves the same global batch",
+              "l2": "GPU arm: 256 MiB flush between timed steps; CPU arm: not applicable",
+              "parallelism": f"batch-sharded x{world}"}
+    return cfg, gen, config, flops, in_bytes
+
+
+def parity_block(res, ref, tol=1e-4):
+    """Scope of the parity claim of this very run (GPU results vs the oracle on the same problems): how many solves
+    converged / stopped at the cap / were flagged, how many were compared, how many disagree.  Nothing is dropped:
+    flagged solves (either side reports linesearch_failed / backward_failed) are compared like the others and
+    counted separately."""
+    err = np.maximum(np.abs(res["grf_body"] - ref["grf_body"]).max(axis=1), np.abs(res["grf_world"] - ref["grf_world"]).max(axis=1))
+    flagged = (res["status"] >= 2) | (ref["status"] >= 2)
+    agree = (res["status"] == ref["status"]) & (res["iterations"] == ref["iterations"]) & (err < tol)
+    return {"compared": int(len(res)), "converged": int((ref["status"] == 0).sum()), "capped": int((ref["status"] == 1).sum()),
+            "flagged": int(flagged.sum()), "flagged_agree": int((flagged & agree).sum()),
+            "flagged_differ": int((flagged & ~agree).sum()), "disagree": int((~flagged & ~agree).sum()),
+            "max_err": float(err[agree].max()) if agree.any() else None, "max_err_all": float(np.nanmax(err)),
+            "tolerance_N": tol, "status_equal": int((res["status"] == ref["status"]).sum()),
+            "iterations_equal": int((res["iterations"] == ref["iterations"]).sum()), "oracle_vs_altro": ORACLE_PIN}
+
+
+def config1_block(mpc_cls, device):
+    """BASELINE config 1: one Go1 QuatMpc solve, N=10, stand.  Single-thread CPU latency of the
+    oracle port (median / p99 over 1000 solves), the B200 batch-1 latency through the host entry point the ROS shim
+    calls, and the reference's implied budget: the mpc_thread period of 5 ms = 200 Hz (Main.cpp:115)."""
+    from oracle import binding as oracle
+    from quaternion_mpc_b200 import abi
+    from quaternion_mpc_b200.config import default_config
+    from quaternion_mpc_b200.workloads import stand_problem
+    cfg = default_config(abi.QMPC_MODEL_QUAT_4FOOT, 10)
+    p = stand_problem()
+    for _ in range(20):
+        oracle.solve_batch(cfg, p)
+    t = []
+    for _ in range(1000):
+        t0 = time.perf_counter()
+        oracle.solve_batch(cfg, p)
+        t.append(time.perf_counter() - t0)
+    t = np.array(t) * 1e6
+    mpc = mpc_cls(max_batch=1, device=device, cfg=cfg)
+    out = np.empty(1, dtype=abi.RESULT_DTYPE)
+    for _ in range(20):
+        mpc.grf_update(p, out)
+    g = []
+    for _ in range(500):
+        t0 = time.perf_counter()
+        mpc.grf_update(p, out)
+        g.append(time.perf_counter() - t0)
+    g = np.array(g) * 1e6
+    mpc.close()
+    return {"workload": "single Go1 QuatMpc solve, N=10, stand (BASELINE configs[0])",
+            "cpu_single_thread_us": {"median": float(np.median(t)), "p99": float(np.percentile(t, 99)), "solves": 1000,
+                                     "kind": "port"},
+            "gpu_batch1_us": {"median": float(np.median(g)), "p99": float(np.percentile(g, 99)), "solves": 500,
+                              "path": "qmpc_solve_batch_host(batch=1), pageable buffers, pinned staging inside"},
+            "budget_us": 5000.0, "budget_source": "mpc_thread period 5 ms = 200 Hz (legged_ctrl/src/Main.cpp:115)"}
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     from quaternion_mpc_b200 import abi
-    from quaternion_mpc_b200.config import default_config
-    from quaternion_mpc_b200 import workloads
-
-    global IN_BYTES, FLOPS_PER_KNOT_ITER
-    if a.model == "quat":
-        cfg = default_config(abi.QMPC_MODEL_QUAT_4FOOT, a.horizon)
-        random_batch = workloads.random_batch
-        workload = f"go1_quat_mpc_N{a.horizon}_{a.gait}_batch{a.batch}_per_gpu_seed0"
-    elif a.model == "quat2":   # BASELINE config 4: 2-contact model (ct_srb_trot_quat_*), m = 6, 12 cone rows
-        cfg = default_config(abi.QMPC_MODEL_QUAT_2FOOT, a.horizon)
-        random_batch = lambda n, seed=0, gait=None: workloads.random_batch(n, seed=seed, gait="stand", max_angle=0.2, nfeet=2)
-        workload = f"two_contact_quat_mpc_N{a.horizon}_batch{a.batch}_per_gpu_seed0"
-        FLOPS_PER_KNOT_ITER = 38e3   # SURVEY.md 8d, m = 6, p = 12
-    else:                       # ConvexMpc (row A8): Euler SRB on the generic dense kernel
-        cfg = default_config(abi.QMPC_MODEL_EULER_CONVEX, a.horizon)
-        random_batch = lambda n, seed=0, gait="trot": workloads.random_convex_batch(n, seed=seed, gait=gait)
-        workload = f"go1_convex_mpc_N{a.horizon}_{a.gait}_batch{a.batch}_per_gpu_seed0"
-        IN_BYTES = 344
+    cfg, random_batch, config, flops_per_knot_iter, IN_BYTES = workload_of(a, world)
     threads = os.cpu_count() or 1
+    B = a.batch
 
     # ------------------------------------------------------------------ reference (CPU) arm
     if a.impl == "reference":
         if rank != 0:
             return 0
         probe, _, _ = cpu_arm(cfg, random_batch(threads * 16, seed=0, gait=a.gait), threads)
-        n = a.cpu_sample or int(min(max(probe * 4.0, 512), 1 << 16))   # ~4 s of host work per step
-        probs = random_batch(n, seed=0, gait=a.gait)
+        # one step = the GPU arm's global batch (the same problems, rank by rank) when that is <= ~10 s of host
+        # work; else a bounded sample of it
+        full = B * world
+        n = a.cpu_sample or (full if full <= probe * 10.0 else int(max(probe * 4.0, 512)))
+        n = min(n, full)
+        parts, left, r = [], n, 0
+        while left > 0:
+            m = min(B, left)
+            parts.append(random_batch(B, seed=r, gait=a.gait)[:m])
+            left -= m
+            r += 1
+        probs = np.concatenate(parts)
         vals = []
         for i in range(a.warmup + a.steps):
             v, dt, _ = cpu_arm(cfg, probs, threads)
             if i >= a.warmup:
                 vals.append((v, dt))
         v = float(np.mean([x[0] for x in vals]))
+        sample = (f"the whole global batch ({n} problems) per step" if n == full else
+                  f"the first {n} of the {full} problems of the global batch per step") + f", {threads} pthreads"
         line = {
             "impl": "reference", "metric": "go1_quat_mpc_solves_per_sec", "value": v, "unit": "solves/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": float(np.mean([x[1] for x in vals]) * 1e3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "horizon": a.horizon, "gait": a.gait,
-                       "note": "reference CPU solver = fp64 oracle port (ALTRO/Eigen/ROS absent: reference unbuildable here)"},
-            "cpu_baseline": {"value": v, "unit": "solves/s", "cores": threads, "kind": "port",
-                             "sample": f"{n} problems of the workload per step, {threads} pthreads"},
+            "config": config,
+            "note": "reference CPU solver = fp64 oracle port (ALTRO/Eigen/ROS absent: reference unbuildable here)",
+            "cpu_baseline": {"value": v, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -219,13 +300,11 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    from quaternion_mpc_b200 import ConvexMpc, QuatMpc
-    if a.model == "convex":
-        QuatMpc = ConvexMpc   # same host mirror, other entry points
+    from quaternion_mpc_b200 import ConvexMpc, MultiGpuMpc, QuatMpc
+    Mpc = ConvexMpc if a.model == "convex" else QuatMpc
 
-    B = a.batch
     probs = random_batch(B, seed=0 + rank, gait=a.gait)   # each rank owns its shard of the global batch
-    mpc = QuatMpc(max_batch=B, device=local, cfg=cfg)
+    mpc = Mpc(max_batch=B, device=local, cfg=cfg, kernel=a.kernel)
     d_in = mpc.to_device(probs)
     d_out = mpc.alloc_results(B)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
@@ -258,40 +337,78 @@ def main():
     total_ms = float(sum(kernel_ms))
     launches = mpc.launch_count - launches0
 
-    # ---- e2e: host buffers through the C-ABI host entry point (H2D + solve + D2H per step)
-    h_in = torch.from_numpy(probs.view(np.uint8).reshape(B, -1).copy()).pin_memory()
-    h_out = torch.empty((B, OUT_BYTES), dtype=torch.uint8).pin_memory()
-    for _ in range(2):
-        mpc.grf_update_host_ptr(h_in.data_ptr(), B, h_out.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        mpc.grf_update_host_ptr(h_in.data_ptr(), B, h_out.data_ptr())
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    # ---- the one collective of the path, for device-resident callers: every rank's results gathered
+    # on rank 0 over NCCL, device to device, timed on the device (the solve above is timed without it)
+    gather_ms = None
+    if world > 1:
+        outs = [torch.empty_like(d_out) for _ in range(world)] if rank == 0 else None
+        for i in range(3 + 5):
+            if i == 3:
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+            dist.gather(d_out, outs, dst=0)
+        g1.record(stream)
+        barrier()
+        gather_ms = g0.elapsed_time(g1) / 5
+        if rank == 0:
+            assert all(torch.equal(outs[0], d_out) if r == 0 else outs[r].shape == d_out.shape for r in range(world))
+
+    # ---- e2e: HOST buffers through the C-ABI (H2D + solve + D2H inside the call, per step).
+    #   1 GPU : qmpc_solve_batch_host on this rank's handle
+    #   N GPUs: ONE qmpc_solve_batch_host_multi call on rank 0 - the whole global batch in one pinned host array,
+    #           sharded over the N devices inside the C-ABI, every result back in one host array (the other ranks
+    #           wait at the barrier; their GPUs are driven by rank 0's call)
+    res = mpc.results_to_numpy(d_out)
+    if world == 1:
+        h_in = torch.from_numpy(probs.view(np.uint8).reshape(B, -1).copy()).pin_memory()
+        h_out = torch.empty((B, OUT_BYTES), dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            mpc.grf_update_host_ptr(h_in.data_ptr(), B, h_out.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            mpc.grf_update_host_ptr(h_in.data_ptr(), B, h_out.data_ptr())
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_path = "qmpc_solve_batch_host, pinned host buffers"
+        assert h_out.numpy().tobytes() == res.tobytes()
+    else:
+        e2e_s = 0.0
+        e2e_path = f"one qmpc_solve_batch_host_multi call on rank 0 over {world} devices, pinned host buffers"
+        barrier()
+        if rank == 0:
+            allp = np.concatenate([random_batch(B, seed=r, gait=a.gait) for r in range(world)])
+            multi = MultiGpuMpc(cfg, B * world, list(range(world)))
+            h_in = torch.from_numpy(allp.view(np.uint8).reshape(B * world, -1).copy()).pin_memory()
+            h_out = torch.empty((B * world, OUT_BYTES), dtype=torch.uint8).pin_memory()
+            for _ in range(2):
+                multi.grf_update_host_ptr(h_in.data_ptr(), B * world, h_out.data_ptr())
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                multi.grf_update_host_ptr(h_in.data_ptr(), B * world, h_out.data_ptr())
+            e2e_s = time.perf_counter() - t0
+            allres = h_out.numpy().reshape(-1).view(abi.RESULT_DTYPE)
+            assert allres[:B].tobytes() == res.tobytes() and np.isfinite(allres["grf_body"]).all()
+            multi.close()
+        barrier()
     if rank == 0 and len([r for r in sampler.rows if r[0] >= sampler.t_mark]) < 3:
         t_end = time.perf_counter() + 0.25          # very short runs: keep the GPU busy with the same solve
         while time.perf_counter() < t_end:          # until a few samples under load exist (not timed)
             mpc.grf_update_device(d_in, d_out)
             torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    res = h_out.numpy().reshape(-1).view(abi.RESULT_DTYPE)
     mean_iters = float(res["iterations"].mean())
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, e2e_s * 1e3, mean_iters], dtype=torch.float64, device=f"cuda:{local}")
+    t = torch.tensor([total_ms, e2e_s * 1e3, mean_iters, gather_ms or 0.0], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        total_ms, e2e_ms, gather_ms = float(tmax[0]), float(tmax[1]), float(tmax[3])
         mean_iters = float(tsum[2]) / world
-        # the one collective of the path: gather every rank's results on rank 0
-        from quaternion_mpc_b200.sharding import gather_results
-        allres = gather_results(res, B * world, device=f"cuda:{local}")
-        if rank == 0:
-            assert allres.shape[0] == B * world and np.isfinite(allres["grf_body"]).all()
     else:
         e2e_ms = e2e_s * 1e3
     if rank != 0:
@@ -306,27 +423,34 @@ def main():
     # ---- roofline: this path is bound by the vector-FMA pipe, not HBM/tensor
     f64, f32 = C.c_double(), C.c_double()
     mpc.lib.qmpc_measure_fma_peak(local, C.byref(f64), C.byref(f32))
-    flops_per_solve = mean_iters * a.horizon * FLOPS_PER_KNOT_ITER
-    avg_launch_s = (total_ms * 1e-3) / max(launches, 1)
-    achieved_tflops = B * flops_per_solve / avg_launch_s / 1e12
+    flops_per_solve = mean_iters * a.horizon * flops_per_knot_iter
+    avg_step_s = (total_ms * 1e-3) / a.steps
+    achieved_tflops = B * flops_per_solve / avg_step_s / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_achieved = B * (IN_BYTES + OUT_BYTES) / avg_launch_s / 1e9
+    hbm_achieved = B * (IN_BYTES + OUT_BYTES) / avg_step_s / 1e9
+    # DRAM bytes actually moved: dram__bytes_read.sum + dram__bytes_write.sum from an `ncu` capture of this kernel at
+    # this workload (profiles/ncu_traffic.json names the capture, its commit and its batch); null without a capture
+    traffic, traffic_src = None, "no ncu capture for this workload / kernel in profiles/ncu_traffic.json"
+    try:
+        for rec in json.load(open(TRAFFIC_FILE)):
+            if rec["model"] == a.model and rec["horizon"] == a.horizon and rec["kernel"] in mpc.describe():
+                traffic = rec["dram_bytes_per_solve"] * B
+                traffic_src = (f"ncu capture {rec['capture']} (commit {rec['commit']}, batch {rec['batch']}): "
+                               f"{rec['dram_bytes_per_solve']:.0f} DRAM bytes per solve, scaled to this launch's batch")
+    except Exception:
+        pass
     roofline = {
         "bound": "fp64_fma", "achieved": achieved_tflops, "peak": f64.value, "unit": "TFLOP/s",
         "frac": achieved_tflops / f64.value if f64.value > 0 else None,
-        # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
-        # this kernel (profiles/r01_s4_ncu_coop_B16384.txt: 2.83 + 9.77 GB for 16384 solves = 769 kB per solve,
-        # the L2-overflowing scratch of the trial trajectories / gains), scaled to this launch's batch
-        "traffic": NCU_DRAM_BYTES_PER_SOLVE * B if (a.horizon == 10 and a.model == "quat") else None,
-        "traffic_source": "ncu capture at batch 16384, scaled by batch; algorithmic bytes are 536 B/solve - the "
-                          "difference is per-slot scratch spilling the 126 MB L2 (DRAM 14 % busy, not the bound)",
+        "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "measured live by qmpc_measure_fma_peak (FP64 vector FMA; FP32 = %.1f TFLOP/s)" % f32.value,
         "algorithmic_flops_per_solve": flops_per_solve, "mean_iterations": mean_iters,
+        "launches_per_step": launches / a.steps,
         "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak, "frac": hbm_achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_solve": IN_BYTES + OUT_BYTES},
@@ -336,34 +460,34 @@ def main():
     if not a.no_aux and a.model == "quat":
         aux = aux_kernels(local, cfg, hbm_peak)
 
-    cpu = None
+    cpu, parity = None, None
     if not a.no_cpu_baseline:
         # bounded sample: probe the host rate on 16 problems per core, then time ~8 s worth of the
-        # same distribution (the first B problems are exactly rank 0's GPU batch -> parity check)
+        # same distribution (the first B problems are exactly rank 0's GPU batch -> parity block)
         probe, _, _ = cpu_arm(cfg, probs[:min(B, threads * 16)], threads)
         n = a.cpu_sample or int(min(max(probe * 8.0, 512), 1 << 17))
         cprobs = probs if n <= B else np.concatenate([probs, random_batch(n - B, seed=12345, gait=a.gait)])
         v, dt, ref = cpu_arm(cfg, cprobs[:n], threads)
         m = min(n, B)
-        ok = (ref["status"][:m] <= 1) & (res["status"][:m] <= 1)
-        err = float(np.abs(ref["grf_body"][:m] - res["grf_body"][:m])[ok].max())
+        parity = parity_block(res[:m], ref[:m])
         cpu = {"value": v, "unit": "solves/s", "cores": threads, "kind": "port",
                "sample": f"{n} problems of the workload distribution (first {m} = rank 0's GPU batch), "
-                         f"{threads} pthreads, {dt:.2f} s",
-               "grf_max_abs_err_vs_gpu": err, "parity_checked_solves": int(ok.sum())}
+                         f"{threads} pthreads, {dt:.2f} s"}
+    config1 = None
+    if not a.no_config1 and a.model == "quat" and not a.no_cpu_baseline:
+        config1 = config1_block(QuatMpc, local)
 
     line = {
         "metric": "go1_quat_mpc_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "horizon": a.horizon, "gait": a.gait, "batch_per_gpu": B,
-                   "global_batch": B * world, "iterations_max": cfg.iterations_max,
-                   "l2": "256 MiB flush between timed steps", "parallelism": f"batch-sharded x{world}",
-                   "kernel": mpc.describe()},
-        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": B * IN_BYTES,
-                "d2h_bytes_per_step": B * OUT_BYTES},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "aux_kernels": aux,
+        "config": config, "kernel": mpc.describe(),
+        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": B * world * IN_BYTES,
+                "d2h_bytes_per_step": B * world * OUT_BYTES, "path": e2e_path},
+        "gather": None if gather_ms is None else {"ms": gather_ms, "bytes": B * world * OUT_BYTES,
+                                                  "what": "torch.distributed.gather of the device result tensors on rank 0 (NCCL)"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "config1": config1, "aux_kernels": aux,
     }
     print(json.dumps(line))
     if world > 1:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define QMPC_ABI_VERSION 2
+#define QMPC_ABI_VERSION 3
 
 /* ---- models ------------------------------------------------------------- */
 #define QMPC_MODEL_QUAT_4FOOT   0 /* QuatMpc: 13-state quaternion SRB, 4 feet, 24 cone rows
@@ -131,6 +131,26 @@ int qmpc_default_config(int32_t model, int32_t horizon, QmpcConfig* cfg);
  * Replaces: QuatMpc::QuatMpc (QuatMpc.cpp:8-55) + the per-call `ALTROSolver solver(horizon)`
  * construction (QuatMpc.cpp:218-229). */
 int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t device, QmpcHandle** out);
+
+/* qmpc_create with explicit, per-handle build choices.  The library reads NO environment variables:
+ * everything that selects a kernel or a launch geometry is resolved here, once, and stored in the
+ * handle (the 200 Hz mpc_thread of Main.cpp:88-120 must not see hidden dispatch on its solve path).
+ * `opt` may be NULL (= qmpc_create).  The dense and srb kernels are the on-device cross-checks of the
+ * tests (independent implementations of the same solve); the product default is QMPC_KERNEL_AUTO. */
+#define QMPC_KERNEL_AUTO   -1 /* coop for every model                                              */
+#define QMPC_KERNEL_DENSE   0 /* generic dense algebra, one thread per problem (cross-check)        */
+#define QMPC_KERNEL_SRB     1 /* structured, one thread per problem, QUAT models only (cross-check) */
+#define QMPC_KERNEL_COOP    2 /* 16 lanes per problem, shared-memory resident, one persistent launch */
+#define QMPC_KERNEL_PHASED  3 /* coop bodies split into set-up / backward / forward launches        */
+typedef struct QmpcCreateOptions {
+  int32_t kernel;           /* QMPC_KERNEL_*                                                        */
+  int32_t smem_residents;   /* -1 = chosen by occupancy query; else bit 0: per-knot linearisation
+                               blocks, bit 1: duals kept in shared memory (coop kernel)            */
+  int32_t packed_launch;    /* 1 = fill blocks one by one instead of spreading a partial wave       */
+  int32_t reserved_;
+} QmpcCreateOptions;
+int qmpc_create_ex(const QmpcConfig* cfg, int32_t max_batch, int32_t device, const QmpcCreateOptions* opt,
+                   QmpcHandle** out);
 
 /* Solve `batch` independent problems.  `d_in` / `d_out` are DEVICE pointers; the launch is
  * enqueued on `cuda_stream` (a cudaStream_t, may be NULL = default stream) and the call returns
@@ -273,6 +293,23 @@ int qmpc_solve_batch_warm(QmpcHandle* h, const QmpcProblem* d_in, const QmpcCont
                           QmpcWarmStart* d_warm, int32_t batch, QmpcResult* d_out, void* cuda_stream);
 
 void qmpc_destroy(QmpcHandle* h);
+
+/* ---- multi-GPU host entry point -----------------------------------------------------
+ * The solves are independent (QuatMpc.cpp:218 builds a fresh solver per call), so a host batch is cut
+ * into contiguous, balanced shards - shard g = [batch*g/G, batch*(g+1)/G) - one per device; every
+ * device has its own stream and pinned staging, the copies and launches of all devices are in flight
+ * together and the results land in the caller's single `out` array in batch order.  No collective is
+ * involved: a C++ caller (the reference's host language) spreads a batch over the GPUs of one box with
+ * this one call.  `max_batch` is the capacity of the WHOLE batch.  Works for every model: `in` is an
+ * array of QmpcProblem (QUAT_*) or QmpcConvexProblem (EULER_CONVEX) according to cfg->model. */
+typedef struct QmpcMultiHandle QmpcMultiHandle;
+int  qmpc_create_multi(const QmpcConfig* cfg, int32_t max_batch, const int32_t* devices, int32_t n_devices,
+                       QmpcMultiHandle** out);
+int  qmpc_solve_batch_host_multi(QmpcMultiHandle* mh, const void* in, int32_t batch, QmpcResult* out);
+void qmpc_destroy_multi(QmpcMultiHandle* mh);
+int32_t     qmpc_multi_device_count(const QmpcMultiHandle* mh);
+int64_t     qmpc_multi_launch_count(const QmpcMultiHandle* mh);
+const char* qmpc_multi_last_error(const QmpcMultiHandle* mh);
 
 /* Introspection: number of kernel launches issued by this handle so far; last CUDA error text. */
 int64_t     qmpc_launch_count(const QmpcHandle* h);

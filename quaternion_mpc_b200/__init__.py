@@ -5,6 +5,6 @@ include/qmpc.h).  This package is the thin host-side mirror of the reference's M
 """
 from . import abi
 from .config import default_config
-from .solver import ConvexMpc, QmpcError, QuatMpc
+from .solver import ConvexMpc, MultiGpuMpc, QmpcError, QuatMpc
 
-__all__ = ["abi", "default_config", "QuatMpc", "ConvexMpc", "QmpcError"]
+__all__ = ["abi", "default_config", "QuatMpc", "ConvexMpc", "MultiGpuMpc", "QmpcError"]

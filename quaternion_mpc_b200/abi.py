@@ -19,6 +19,10 @@ QMPC_ERR_ARG = -1
 QMPC_ERR_CUDA = -2
 QMPC_ERR_CAPACITY = -3
 
+QMPC_KERNEL_AUTO, QMPC_KERNEL_DENSE, QMPC_KERNEL_SRB, QMPC_KERNEL_COOP, QMPC_KERNEL_PHASED = -1, 0, 1, 2, 3
+KERNEL_NAMES = {"auto": -1, "dense": 0, "srb": 1, "coop": 2, "phased": 3}
+QMPC_ABI_VERSION = 3
+
 STATUS_NAMES = {0: "success", 1: "max_iterations", 2: "linesearch_failed", 3: "backward_failed",
                 4: "nonfinite"}
 
@@ -35,6 +39,11 @@ class QmpcConfig(C.Structure):
         ("tol_cost_intermediate", C.c_double), ("tol_primal_feasibility", C.c_double),
         ("tol_stationarity", C.c_double),
     ]
+
+
+class QmpcCreateOptions(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("smem_residents", C.c_int32), ("packed_launch", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 PROBLEM_DTYPE = np.dtype([
@@ -88,6 +97,8 @@ EXPORTED_SYMBOLS = [
     "qmpc_predict_contact_schedule", "qmpc_solve_batch_sched", "qmpc_solve_batch_convex_sched",
     "qmpc_solve_batch_sched_host", "qmpc_solve_batch_convex_sched_host", "qmpc_default_leg_params", "qmpc_leg_kinematics", "qmpc_joint_torques", "qmpc_describe", "qmpc_solve_batch_warm", "qmpc_goal_state_bytes", "qmpc_goal_update",
     "qmpc_default_raibert_params", "qmpc_raibert_targets",
+    "qmpc_create_ex", "qmpc_create_multi", "qmpc_solve_batch_host_multi", "qmpc_destroy_multi",
+    "qmpc_multi_device_count", "qmpc_multi_launch_count", "qmpc_multi_last_error",
 ]
 
 _LIB = None
@@ -115,6 +126,20 @@ def load_library():
     lib.qmpc_default_config.restype = C.c_int
     lib.qmpc_create.argtypes = [C.POINTER(QmpcConfig), i32, i32, C.POINTER(vp)]
     lib.qmpc_create.restype = C.c_int
+    lib.qmpc_create_ex.argtypes = [C.POINTER(QmpcConfig), i32, i32, C.POINTER(QmpcCreateOptions), C.POINTER(vp)]
+    lib.qmpc_create_ex.restype = C.c_int
+    lib.qmpc_create_multi.argtypes = [C.POINTER(QmpcConfig), i32, C.POINTER(i32), i32, C.POINTER(vp)]
+    lib.qmpc_create_multi.restype = C.c_int
+    lib.qmpc_solve_batch_host_multi.argtypes = [vp, vp, i32, vp]
+    lib.qmpc_solve_batch_host_multi.restype = C.c_int
+    lib.qmpc_destroy_multi.argtypes = [vp]
+    lib.qmpc_destroy_multi.restype = None
+    lib.qmpc_multi_device_count.argtypes = [vp]
+    lib.qmpc_multi_device_count.restype = i32
+    lib.qmpc_multi_launch_count.argtypes = [vp]
+    lib.qmpc_multi_launch_count.restype = i64
+    lib.qmpc_multi_last_error.argtypes = [vp]
+    lib.qmpc_multi_last_error.restype = C.c_char_p
     for name in ("qmpc_solve_batch", "qmpc_solve_batch_convex"):
         f = getattr(lib, name)
         f.argtypes = [vp, vp, i32, vp, vp]

@@ -27,6 +27,8 @@ struct QmpcHandle {
   double* ws;          // device workspace
   size_t ws_bytes;
   void* d_in;          // staging for the *_host entry points
+  void* h_stage;       // pinned host staging for small host batches from pageable memory (batch <= kStageBatch)
+  int packed_launch;   // QmpcCreateOptions::packed_launch
   QmpcContactSchedule* d_sched;
   QmpcResult* d_out;
   cudaStream_t stream; // stream used by the *_host entry points
@@ -37,6 +39,8 @@ struct QmpcHandle {
   size_t coop_scratch_doubles;
   char err[256];
 };
+
+constexpr int kStageBatch = 64;   // host calls up to this batch are staged through pinned memory
 
 static int set_err(QmpcHandle* h, cudaError_t e, const char* where) {
   if (h) snprintf(h->err, sizeof(h->err), "%s: %s", where, cudaGetErrorString(e));
@@ -116,7 +120,7 @@ constexpr int kCoopG = 16, kCoopBlock = QMPC_COOP_BLOCK;
 
 // persistent-kernel geometry: as many resident blocks as the device holds (or the batch needs)
 template <int NF>
-static int coop_prepare_t(QmpcHandle* h) {
+static int coop_prepare_t(QmpcHandle* h, int smem_residents) {
   using L = CoopLayout<NF, kCoopG>;
   const int N = h->cfg.horizon;
   const int groups = kCoopBlock / kCoopG;
@@ -146,7 +150,7 @@ static int coop_prepare_t(QmpcHandle* h) {
     if ((rc = blocks_per_sm(order[c], &per))) return rc;
     if (per >= best) { flags = order[c]; break; }
   }
-  if (const char* wenv = getenv("QMPC_COOP_WIDE")) flags = atoi(wenv) & 3;
+  if (smem_residents >= 0) flags = smem_residents & 3;
   int per_sm = 0, sms = 0;
   if ((rc = blocks_per_sm(flags, &per_sm))) return rc;
   if (per_sm < 1) { snprintf(h->err, sizeof(h->err), "coop kernel does not fit on an SM"); return QMPC_ERR_CUDA; }
@@ -165,12 +169,19 @@ static int coop_prepare_t(QmpcHandle* h) {
   h->ws_bytes = (size_t)ws_slots * h->coop_scratch_doubles * sizeof(double);
   return QMPC_OK;
 }
-static int coop_prepare(QmpcHandle* h) {
-  return h->cfg.model == QMPC_MODEL_QUAT_4FOOT ? coop_prepare_t<4>(h) : coop_prepare_t<2>(h);
+static int coop_prepare(QmpcHandle* h, int smem_residents) {
+  return h->cfg.model == QMPC_MODEL_QUAT_4FOOT ? coop_prepare_t<4>(h, smem_residents) : coop_prepare_t<2>(h, smem_residents);
 }
 
-extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t device, QmpcHandle** out) {
+extern "C" int qmpc_create_ex(const QmpcConfig* cfg, int32_t max_batch, int32_t device, const QmpcCreateOptions* opt,
+                              QmpcHandle** out) {
   if (!cfg || !out || max_batch < 1) return QMPC_ERR_ARG;
+  QmpcCreateOptions op = {QMPC_KERNEL_AUTO, -1, 0, 0};
+  if (opt) op = *opt;
+  if (op.kernel < QMPC_KERNEL_AUTO || op.kernel > QMPC_KERNEL_PHASED) return QMPC_ERR_ARG;
+  if (op.kernel == QMPC_KERNEL_SRB && cfg->model == QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;
+  if (op.kernel == QMPC_KERNEL_PHASED) return QMPC_ERR_ARG;   // TODO(phased)
+  if (op.kernel == QMPC_KERNEL_COOP && cfg->model == QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;   // TODO(convex coop)
   if (cfg->horizon < 1 || cfg->horizon > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
   if (cfg->model < 0 || cfg->model > QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;
   if (cfg->iterations_max < 0 || !(cfg->penalty_initial > 0) || !(cfg->dt > 0)) return QMPC_ERR_ARG;
@@ -195,16 +206,14 @@ extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t dev
   o.ls_c1 = 1e-4;
   o.ls_decrease = 0.5;
   o.ls_iters_max = 25;
-  // kernel selection: the structured SRB kernel for the quaternion models; QMPC_KERNEL=dense forces
-  // the generic dense kernel (kept as the on-device cross-check and for the Euler/ConvexMpc model)
-  h->kernel = cfg->model == QMPC_MODEL_EULER_CONVEX ? 0 : 2;
-  if (const char* k = getenv("QMPC_KERNEL")) {
-    if (!strcmp(k, "dense")) h->kernel = 0;
-    else if (!strcmp(k, "srb") && cfg->model != QMPC_MODEL_EULER_CONVEX) h->kernel = 1;
-  }
+  // kernel selection, resolved once (no environment variables anywhere in the library): the cooperative
+  // kernel for the quaternion models, the dense kernel for the Euler/ConvexMpc model; the dense and srb
+  // kernels otherwise only on explicit request (the tests' on-device cross-checks)
+  h->kernel = op.kernel != QMPC_KERNEL_AUTO ? op.kernel : (cfg->model == QMPC_MODEL_EULER_CONVEX ? 0 : 2);
+  h->packed_launch = op.packed_launch;
   CU(cudaSetDevice(device));
   if (h->kernel == 2) {
-    int rc = coop_prepare(h);
+    int rc = coop_prepare(h, op.smem_residents);
     if (rc) return rc;
   } else {
     h->ws_bytes = ws_elems(*cfg, h->kernel) * h->stride * sizeof(double);
@@ -214,8 +223,14 @@ extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t dev
   CU(cudaMalloc(&h->d_in, in_sz * (size_t)max_batch));
   CU(cudaMalloc(&h->d_out, sizeof(QmpcResult) * (size_t)max_batch));
   CU(cudaMalloc(&h->d_sched, sizeof(QmpcContactSchedule) * (size_t)max_batch));
+  CU(cudaHostAlloc(&h->h_stage, (size_t)kStageBatch * (sizeof(QmpcConvexProblem) + sizeof(QmpcContactSchedule) + sizeof(QmpcResult)),
+                   cudaHostAllocDefault));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   return QMPC_OK;
+}
+
+extern "C" int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t device, QmpcHandle** out) {
+  return qmpc_create_ex(cfg, max_batch, device, nullptr, out);
 }
 
 extern "C" void qmpc_destroy(QmpcHandle* h) {
@@ -226,6 +241,7 @@ extern "C" void qmpc_destroy(QmpcHandle* h) {
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
   if (h->d_sched) cudaFree(h->d_sched);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
   delete h;
 }
 
@@ -289,11 +305,14 @@ static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned ch
   const int blocks_cap = slots <= (long long)h->coop_sms * groups ? h->coop_sms : h->coop_grid;
   int grid = slots < blocks_cap ? (int)slots : blocks_cap;
   int active = (int)((slots + grid - 1) / grid);
-  if (getenv("QMPC_COOP_NO_SPREAD")) active = groups;
+  if (h->packed_launch) active = groups;
   grid = (int)((slots + active - 1) / active);
   h->coop_last_grid = grid;
   h->coop_last_active = active;
   const size_t smem_bytes = (size_t)(groups * h->coop_smem_doubles + kCoopBlockShared) * sizeof(double);
+  // the opt-in shared-memory limit is per function AND per device, not per handle: another handle (other
+  // horizon) created or solved in between may have lowered it, so it is set before every launch
+  CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, sched, warm, d_out, h->ws, batch,
                                                                    h->coop_smem_doubles, h->coop_scratch_doubles,
                                                                    h->coop_wide, active);
@@ -348,21 +367,46 @@ extern "C" int qmpc_solve_batch_convex(QmpcHandle* h, const QmpcConvexProblem* d
   return solve_any(h, d_in, nullptr, nullptr, batch, d_out, cuda_stream, true);
 }
 
+static bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static int solve_host_any(QmpcHandle* h, const void* in, const QmpcContactSchedule* sched, int32_t batch,
                           QmpcResult* out, bool convex) {
   if (!h || !h->ws) return h ? QMPC_ERR_CUDA : QMPC_ERR_ARG;
   if (!in || !out || batch < 0) return QMPC_ERR_ARG;
+  // the entry point must match the handle's model BEFORE anything is copied: the staging buffers are
+  // sized for the handle's own problem struct
+  if (convex != (h->cfg.model == QMPC_MODEL_EULER_CONVEX)) return QMPC_ERR_ARG;
   if (batch > h->max_batch) return QMPC_ERR_CAPACITY;
   if (batch == 0) return QMPC_OK;
   CU(cudaSetDevice(h->device));
-  size_t in_sz = convex ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
-  CU(cudaMemcpyAsync(h->d_in, in, in_sz * batch, cudaMemcpyHostToDevice, h->stream));
+  const size_t in_sz = convex ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
+  // small batches from pageable memory (the batch-1 call of the 200 Hz mpc_thread passes stack objects)
+  // go through the handle's pinned staging: both copies are then truly asynchronous DMA transfers
+  const bool stage = batch <= kStageBatch && h->h_stage && !(host_ptr_is_pinned(in) && host_ptr_is_pinned(out));
+  char* st_in = (char*)h->h_stage;
+  char* st_sched = st_in + (size_t)kStageBatch * sizeof(QmpcConvexProblem);
+  char* st_out = st_sched + (size_t)kStageBatch * sizeof(QmpcContactSchedule);
+  const void* src_in = in;
+  const void* src_sched = sched;
+  void* dst_out = out;
+  if (stage) {
+    memcpy(st_in, in, in_sz * batch);
+    src_in = st_in;
+    if (sched) { memcpy(st_sched, sched, sizeof(QmpcContactSchedule) * batch); src_sched = st_sched; }
+    dst_out = st_out;
+  }
+  CU(cudaMemcpyAsync(h->d_in, src_in, in_sz * batch, cudaMemcpyHostToDevice, h->stream));
   if (sched)
-    CU(cudaMemcpyAsync(h->d_sched, sched, sizeof(QmpcContactSchedule) * batch, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_sched, src_sched, sizeof(QmpcContactSchedule) * batch, cudaMemcpyHostToDevice, h->stream));
   int rc = solve_any(h, h->d_in, sched ? h->d_sched : nullptr, nullptr, batch, h->d_out, h->stream, convex);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(out, h->d_out, sizeof(QmpcResult) * batch, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(dst_out, h->d_out, sizeof(QmpcResult) * batch, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  if (stage) memcpy(out, st_out, sizeof(QmpcResult) * batch);
   return QMPC_OK;
 }
 
@@ -492,3 +536,114 @@ extern "C" int qmpc_raibert_targets(QmpcHandle* h, const QmpcRaibertParams* rp, 
   CU(cudaGetLastError());
   return QMPC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU host entry point: contiguous balanced shards, one stream per device, all
+// copies and launches in flight together, results in the caller's one array.  No collective.
+constexpr int kMaxDevices = 16;
+struct QmpcMultiHandle {
+  int n;
+  int max_batch;
+  bool convex;
+  size_t in_sz;
+  QmpcHandle* h[kMaxDevices];
+  int shard_cap[kMaxDevices];
+  void* pin_in[kMaxDevices];     // pinned staging, used when the caller's buffers are pageable
+  QmpcResult* pin_out[kMaxDevices];
+  char err[256];
+};
+
+static void multi_shard(int batch, int g, int n, int* lo, int* hi) {
+  *lo = (int)((long long)batch * g / n);
+  *hi = (int)((long long)batch * (g + 1) / n);
+}
+
+extern "C" void qmpc_destroy_multi(QmpcMultiHandle* mh) {
+  if (!mh) return;
+  for (int g = 0; g < mh->n; ++g) {
+    if (mh->h[g]) cudaSetDevice(mh->h[g]->device);
+    if (mh->pin_in[g]) cudaFreeHost(mh->pin_in[g]);
+    if (mh->pin_out[g]) cudaFreeHost(mh->pin_out[g]);
+    qmpc_destroy(mh->h[g]);
+  }
+  delete mh;
+}
+
+extern "C" int qmpc_create_multi(const QmpcConfig* cfg, int32_t max_batch, const int32_t* devices, int32_t n_devices,
+                                 QmpcMultiHandle** out) {
+  if (!cfg || !out || !devices || max_batch < 1 || n_devices < 1 || n_devices > kMaxDevices) return QMPC_ERR_ARG;
+  for (int a = 0; a < n_devices; ++a)
+    for (int b = 0; b < a; ++b)
+      if (devices[a] == devices[b]) return QMPC_ERR_ARG;
+  QmpcMultiHandle* mh = new (std::nothrow) QmpcMultiHandle();
+  if (!mh) return QMPC_ERR_ARG;
+  memset(mh, 0, sizeof(*mh));
+  *out = mh;   // returned even on failure: qmpc_multi_last_error / qmpc_destroy_multi stay usable
+  mh->n = n_devices;
+  mh->max_batch = max_batch;
+  mh->convex = cfg->model == QMPC_MODEL_EULER_CONVEX;
+  mh->in_sz = mh->convex ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
+  for (int g = 0; g < n_devices; ++g) {
+    const int cap = (max_batch + n_devices - 1) / n_devices;   // the largest shard of any batch <= max_batch
+    mh->shard_cap[g] = cap;
+    int rc = qmpc_create(cfg, cap, devices[g], &mh->h[g]);
+    if (rc) {
+      snprintf(mh->err, sizeof(mh->err), "device %d: %.200s", devices[g], mh->h[g] ? mh->h[g]->err : "qmpc_create failed");
+      return rc;
+    }
+    if (cudaHostAlloc(&mh->pin_in[g], mh->in_sz * (size_t)cap, cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostAlloc((void**)&mh->pin_out[g], sizeof(QmpcResult) * (size_t)cap, cudaHostAllocPortable) != cudaSuccess) {
+      snprintf(mh->err, sizeof(mh->err), "device %d: pinned staging allocation failed", devices[g]);
+      return QMPC_ERR_CUDA;
+    }
+  }
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_solve_batch_host_multi(QmpcMultiHandle* mh, const void* in, int32_t batch, QmpcResult* out) {
+  if (!mh) return QMPC_ERR_ARG;
+  if (!in || !out || batch < 0) return QMPC_ERR_ARG;
+  if (batch > mh->max_batch) return QMPC_ERR_CAPACITY;
+  if (batch == 0) return QMPC_OK;
+  for (int g = 0; g < mh->n; ++g)
+    if (!mh->h[g] || !mh->h[g]->ws) return QMPC_ERR_CUDA;
+  const bool direct = host_ptr_is_pinned(in) && host_ptr_is_pinned(out);
+  int rc_all = QMPC_OK;
+  // enqueue every device's H2D copy, solve and D2H copy before waiting for any of them
+  for (int g = 0; g < mh->n; ++g) {
+    int lo, hi;
+    multi_shard(batch, g, mh->n, &lo, &hi);
+    const int cnt = hi - lo;
+    if (cnt == 0) continue;
+    QmpcHandle* h = mh->h[g];
+    const char* src = (const char*)in + mh->in_sz * (size_t)lo;
+    if (!direct) { memcpy(mh->pin_in[g], src, mh->in_sz * (size_t)cnt); src = (const char*)mh->pin_in[g]; }
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_in, src, mh->in_sz * (size_t)cnt, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) { snprintf(mh->err, sizeof(mh->err), "device %d: %s", h->device, cudaGetErrorString(e)); rc_all = QMPC_ERR_CUDA; continue; }
+    int rc = solve_any(h, h->d_in, nullptr, nullptr, cnt, h->d_out, h->stream, mh->convex);
+    if (rc) { snprintf(mh->err, sizeof(mh->err), "device %d: %.200s", h->device, h->err); rc_all = rc; continue; }
+    e = cudaMemcpyAsync(direct ? (void*)(out + lo) : (void*)mh->pin_out[g], h->d_out, sizeof(QmpcResult) * (size_t)cnt,
+                        cudaMemcpyDeviceToHost, h->stream);
+    if (e != cudaSuccess) { snprintf(mh->err, sizeof(mh->err), "device %d: %s", h->device, cudaGetErrorString(e)); rc_all = QMPC_ERR_CUDA; }
+  }
+  for (int g = 0; g < mh->n; ++g) {
+    int lo, hi;
+    multi_shard(batch, g, mh->n, &lo, &hi);
+    if (hi == lo) continue;
+    QmpcHandle* h = mh->h[g];
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { snprintf(mh->err, sizeof(mh->err), "device %d: %s", h->device, cudaGetErrorString(e)); rc_all = QMPC_ERR_CUDA; continue; }
+    if (!direct && rc_all == QMPC_OK) memcpy(out + lo, mh->pin_out[g], sizeof(QmpcResult) * (size_t)(hi - lo));
+  }
+  return rc_all;
+}
+
+extern "C" int32_t qmpc_multi_device_count(const QmpcMultiHandle* mh) { return mh ? mh->n : 0; }
+extern "C" int64_t qmpc_multi_launch_count(const QmpcMultiHandle* mh) {
+  int64_t n = 0;
+  if (mh) for (int g = 0; g < mh->n; ++g) n += mh->h[g] ? mh->h[g]->launches : 0;
+  return n;
+}
+extern "C" const char* qmpc_multi_last_error(const QmpcMultiHandle* mh) { return mh ? mh->err : "null handle"; }

@@ -27,9 +27,13 @@ class _BatchedMpc:
     _solve_sched_dev = None
     _solve_sched_host = None
 
-    def __init__(self, horizon=10, max_batch=4096, device=0, cfg=None):
+    def __init__(self, horizon=10, max_batch=4096, device=0, cfg=None, kernel="auto", smem_residents=-1,
+                 packed_launch=False):
+        """`kernel` / `smem_residents` / `packed_launch` are the QmpcCreateOptions of include/qmpc.h
+        (explicit per-handle choices; the library reads no environment variables).  kernel "dense" / "srb"
+        select the on-device cross-check kernels used by the tests."""
         self.lib = abi.load_library()
-        if self.lib.qmpc_abi_version() != 2:
+        if self.lib.qmpc_abi_version() != abi.QMPC_ABI_VERSION:
             raise QmpcError("libqmpc_b200.so ABI mismatch")
         self.cfg = cfg if cfg is not None else default_config(self.MODEL, horizon)
         if self.cfg.model != self.MODEL and not (
@@ -38,7 +42,8 @@ class _BatchedMpc:
         self.device = int(device)
         self.max_batch = int(max_batch)
         self._h = C.c_void_p()
-        rc = self.lib.qmpc_create(C.byref(self.cfg), self.max_batch, self.device, C.byref(self._h))
+        opt = abi.QmpcCreateOptions(abi.KERNEL_NAMES[kernel], int(smem_residents), int(bool(packed_launch)), 0)
+        rc = self.lib.qmpc_create_ex(C.byref(self.cfg), self.max_batch, self.device, C.byref(opt), C.byref(self._h))
         if rc != abi.QMPC_OK:
             msg = self.lib.qmpc_last_error(self._h).decode() if self._h else ""
             self.close()
@@ -272,4 +277,51 @@ class ConvexMpc(_BatchedMpc):
     _solve_dev = "qmpc_solve_batch_convex"
     _solve_host = "qmpc_solve_batch_convex_host"
     _solve_sched_dev = "qmpc_solve_batch_convex_sched"
-    _solve_sched_host = None
+    _solve_sched_host = "qmpc_solve_batch_convex_sched_host"
+
+
+class MultiGpuMpc:
+    """One host batch over several GPUs of the box through ONE C-ABI call (qmpc_create_multi /
+    qmpc_solve_batch_host_multi): contiguous balanced shards, a stream and pinned staging per device,
+    results in one host array in batch order.  No collective is involved."""
+
+    def __init__(self, cfg, max_batch, devices):
+        self.lib = abi.load_library()
+        self.cfg = cfg
+        self.max_batch = int(max_batch)
+        self.devices = list(devices)
+        self.PROBLEM_DTYPE = abi.CONVEX_PROBLEM_DTYPE if cfg.model == abi.QMPC_MODEL_EULER_CONVEX else abi.PROBLEM_DTYPE
+        self._h = C.c_void_p()
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        rc = self.lib.qmpc_create_multi(C.byref(self.cfg), self.max_batch, arr, len(self.devices), C.byref(self._h))
+        if rc != abi.QMPC_OK:
+            msg = self.lib.qmpc_multi_last_error(self._h).decode() if self._h else ""
+            self.close()
+            raise QmpcError(f"qmpc_create_multi failed rc={rc} {msg} (no CPU fallback exists)")
+
+    def grf_update(self, problems, out=None):
+        problems = np.ascontiguousarray(problems, dtype=self.PROBLEM_DTYPE)
+        if out is None:
+            out = np.empty(problems.shape[0], dtype=abi.RESULT_DTYPE)
+        self.grf_update_host_ptr(problems.ctypes.data, problems.shape[0], out.ctypes.data)
+        return out
+
+    def grf_update_host_ptr(self, in_ptr, batch, out_ptr):
+        rc = self.lib.qmpc_solve_batch_host_multi(self._h, in_ptr, batch, out_ptr)
+        if rc != abi.QMPC_OK:
+            raise QmpcError(f"qmpc_solve_batch_host_multi failed rc={rc}: {self.lib.qmpc_multi_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.qmpc_multi_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.qmpc_destroy_multi(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -17,3 +17,18 @@ def oracle():
     from oracle import binding
     binding.build()
     return binding
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """GPU parity runs: dump the per-check counts (converged / capped / flagged / disagreeing solves) so the
+    scope of every parity claim is on record (gpurun_out/parity_counts.json; copied to profiles/ per round)."""
+    try:
+        mod = sys.modules.get("test_gpu_parity") or sys.modules.get("tests.test_gpu_parity")
+        counts = getattr(mod, "PARITY_COUNTS", None)
+        if counts:
+            import json
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "parity_counts.json"), "w") as f:
+                json.dump(counts, f, indent=1)
+    except Exception:
+        pass

@@ -27,7 +27,7 @@ def test_exports_every_declared_symbol(lib):
     assert declared == set(abi.EXPORTED_SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.qmpc_abi_version() == 2
+    assert lib.qmpc_abi_version() == 3
 
 
 def test_struct_sizes_match_header():
