@@ -14,6 +14,7 @@
 #include "qmpc_dense.cuh"
 #include "qmpc_srb.cuh"
 #include "qmpc_coop.cuh"
+#include "qmpc_phased.cuh"
 #include "qmpc_periph.cuh"
 
 using namespace qmpc;
@@ -37,6 +38,10 @@ struct QmpcHandle {
                        //     16 lanes per problem, shared-memory resident; default for the QUAT models)
   int coop_grid, coop_smem_doubles, coop_wide, coop_blocks_per_sm, coop_sms, coop_last_grid = 0, coop_last_active = 0;   // persistent launch geometry of the coop kernel
   size_t coop_scratch_doubles;
+  // phased kernels (QMPC_KERNEL_PHASED): backward launch uses coop_grid / coop_smem_doubles / coop_wide above
+  int ph_fwd_grid, ph_fwd_smem_doubles, ph_fwd_blocks_per_sm, ph_chunk;
+  size_t ph_problem_doubles, ph_trial_doubles;
+  double* ph_trial;
   char err[256];
 };
 
@@ -119,11 +124,12 @@ static size_t ws_elems(const QmpcConfig& c, int kernel) {
 constexpr int kCoopG = 16, kCoopBlock = QMPC_COOP_BLOCK;
 
 // persistent-kernel geometry: as many resident blocks as the device holds (or the batch needs)
-template <int NF>
+template <class M>
 static int coop_prepare_t(QmpcHandle* h, int smem_residents) {
-  using L = CoopLayout<NF, kCoopG>;
+  using L = CoopLayout<M, kCoopG>;
   const int N = h->cfg.horizon;
   const int groups = kCoopBlock / kCoopG;
+  const bool phased = h->kernel == QMPC_KERNEL_PHASED;
   auto smem_bytes_of = [&](int flags) {
     return (size_t)(groups * L::smem_doubles(N, flags) + kCoopBlockShared) * sizeof(double);
   };
@@ -131,26 +137,37 @@ static int coop_prepare_t(QmpcHandle* h, int smem_residents) {
     const size_t b = smem_bytes_of(flags);
     *per_sm = 0;
     if (b > 227 * 1024) return QMPC_OK;
-    CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, qmpc_coop_kernel<NF, kCoopG>, kCoopBlock, b));
+    if (phased) {
+      CU(cudaFuncSetAttribute(qmpc_phased_backward_kernel<M, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, qmpc_phased_backward_kernel<M, kCoopG>, kCoopBlock, b));
+    } else {
+      CU(cudaFuncSetAttribute(qmpc_coop_kernel<M, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, qmpc_coop_kernel<M, kCoopG>, kCoopBlock, b));
+    }
     return QMPC_OK;
   };
-  CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                          (int)cudaSharedmemCarveoutMaxShared));
+  if (phased)
+    CU(cudaFuncSetAttribute(qmpc_phased_backward_kernel<M, kCoopG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            (int)cudaSharedmemCarveoutMaxShared));
+  else
+    CU(cudaFuncSetAttribute(qmpc_coop_kernel<M, kCoopG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            (int)cudaSharedmemCarveoutMaxShared));
   // Residency is what this latency-bound kernel lives on: first find the block count the bare layout
   // reaches (registers cap it at QMPC_COOP_MIN_BLOCKS), then keep the duals / linearisation blocks in
-  // shared memory too if that does not cost a block.
+  // shared memory too if that does not cost a block.  (Phased: the duals cross launches and stay in the
+  // problem block; only the linearisation blocks can be residents.)
   int best = 0, rc;
   if ((rc = blocks_per_sm(0, &best))) return rc;
   if (best < 1) { snprintf(h->err, sizeof(h->err), "coop kernel does not fit on an SM"); return QMPC_ERR_CUDA; }
   int flags = 0;
   const int order[3] = {3, 2, 1};
   for (int c = 0; c < 3; ++c) {
+    if (phased && order[c] != 1) continue;
     int per = 0;
     if ((rc = blocks_per_sm(order[c], &per))) return rc;
     if (per >= best) { flags = order[c]; break; }
   }
-  if (smem_residents >= 0) flags = smem_residents & 3;
+  if (smem_residents >= 0) flags = smem_residents & (phased ? 1 : 3);
   int per_sm = 0, sms = 0;
   if ((rc = blocks_per_sm(flags, &per_sm))) return rc;
   if (per_sm < 1) { snprintf(h->err, sizeof(h->err), "coop kernel does not fit on an SM"); return QMPC_ERR_CUDA; }
@@ -164,13 +181,37 @@ static int coop_prepare_t(QmpcHandle* h, int smem_residents) {
   h->coop_grid = resident;
   h->coop_sms = sms;
   h->coop_blocks_per_sm = per_sm;
-  const long long slots_cap = (long long)resident * groups;
-  const long long ws_slots = (h->max_batch < slots_cap ? h->max_batch : slots_cap) + groups;
-  h->ws_bytes = (size_t)ws_slots * h->coop_scratch_doubles * sizeof(double);
+  if (!phased) {
+    const long long slots_cap = (long long)resident * groups;
+    const long long ws_slots = (h->max_batch < slots_cap ? h->max_batch : slots_cap) + groups;
+    h->ws_bytes = (size_t)ws_slots * h->coop_scratch_doubles * sizeof(double);
+    return QMPC_OK;
+  }
+  // ---- phased: forward-kernel geometry, per-problem blocks (a batch is processed in chunks so that the
+  //      workspace stays bounded: 37 KB per problem at N = 10), per-slot trial trajectories
+  h->ph_fwd_smem_doubles = L::fwd_smem_doubles(N);
+  const size_t fb = (size_t)(groups * h->ph_fwd_smem_doubles + kCoopBlockShared) * sizeof(double);
+  if (fb > 227 * 1024) { snprintf(h->err, sizeof(h->err), "forward kernel does not fit on an SM"); return QMPC_ERR_CUDA; }
+  CU(cudaFuncSetAttribute(qmpc_phased_forward_kernel<M, kCoopG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          (int)cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(qmpc_phased_forward_kernel<M, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb));
+  int fper = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fper, qmpc_phased_forward_kernel<M, kCoopG>, kCoopBlock, fb));
+  if (fper < 1) { snprintf(h->err, sizeof(h->err), "forward kernel does not fit on an SM"); return QMPC_ERR_CUDA; }
+  h->ph_fwd_blocks_per_sm = fper;
+  h->ph_fwd_grid = fper * sms;
+  h->ph_problem_doubles = L::problem_doubles(N);
+  h->ph_trial_doubles = L::trial_doubles(N);
+  h->ph_chunk = h->max_batch < 65536 ? h->max_batch : 65536;
+  h->ws_bytes = (size_t)h->ph_chunk * h->ph_problem_doubles * sizeof(double);
   return QMPC_OK;
 }
 static int coop_prepare(QmpcHandle* h, int smem_residents) {
-  return h->cfg.model == QMPC_MODEL_QUAT_4FOOT ? coop_prepare_t<4>(h, smem_residents) : coop_prepare_t<2>(h, smem_residents);
+  switch (h->cfg.model) {
+    case QMPC_MODEL_QUAT_4FOOT: return coop_prepare_t<QuatModel<4>>(h, smem_residents);
+    case QMPC_MODEL_QUAT_2FOOT: return coop_prepare_t<QuatModel<2>>(h, smem_residents);
+    default: return coop_prepare_t<ConvexModel>(h, smem_residents);
+  }
 }
 
 extern "C" int qmpc_create_ex(const QmpcConfig* cfg, int32_t max_batch, int32_t device, const QmpcCreateOptions* opt,
@@ -180,8 +221,7 @@ extern "C" int qmpc_create_ex(const QmpcConfig* cfg, int32_t max_batch, int32_t 
   if (opt) op = *opt;
   if (op.kernel < QMPC_KERNEL_AUTO || op.kernel > QMPC_KERNEL_PHASED) return QMPC_ERR_ARG;
   if (op.kernel == QMPC_KERNEL_SRB && cfg->model == QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;
-  if (op.kernel == QMPC_KERNEL_PHASED) return QMPC_ERR_ARG;   // TODO(phased)
-  if (op.kernel == QMPC_KERNEL_COOP && cfg->model == QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;   // TODO(convex coop)
+
   if (cfg->horizon < 1 || cfg->horizon > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
   if (cfg->model < 0 || cfg->model > QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;
   if (cfg->iterations_max < 0 || !(cfg->penalty_initial > 0) || !(cfg->dt > 0)) return QMPC_ERR_ARG;
@@ -207,14 +247,16 @@ extern "C" int qmpc_create_ex(const QmpcConfig* cfg, int32_t max_batch, int32_t 
   o.ls_decrease = 0.5;
   o.ls_iters_max = 25;
   // kernel selection, resolved once (no environment variables anywhere in the library): the cooperative
-  // kernel for the quaternion models, the dense kernel for the Euler/ConvexMpc model; the dense and srb
-  // kernels otherwise only on explicit request (the tests' on-device cross-checks)
-  h->kernel = op.kernel != QMPC_KERNEL_AUTO ? op.kernel : (cfg->model == QMPC_MODEL_EULER_CONVEX ? 0 : 2);
+  // kernel for every model; the dense and srb kernels only on explicit request (the tests' on-device
+  // cross-checks), the phased launches likewise
+  h->kernel = op.kernel != QMPC_KERNEL_AUTO ? op.kernel : QMPC_KERNEL_COOP;
   h->packed_launch = op.packed_launch;
   CU(cudaSetDevice(device));
-  if (h->kernel == 2) {
+  if (h->kernel == QMPC_KERNEL_COOP || h->kernel == QMPC_KERNEL_PHASED) {
     int rc = coop_prepare(h, op.smem_residents);
     if (rc) return rc;
+    if (h->kernel == QMPC_KERNEL_PHASED)
+      CU(cudaMalloc(&h->ph_trial, (size_t)h->ph_fwd_grid * (kCoopBlock / kCoopG) * h->ph_trial_doubles * sizeof(double)));
   } else {
     h->ws_bytes = ws_elems(*cfg, h->kernel) * h->stride * sizeof(double);
   }
@@ -238,6 +280,7 @@ extern "C" void qmpc_destroy(QmpcHandle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ws) cudaFree(h->ws);
+  if (h->ph_trial) cudaFree(h->ph_trial);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
   if (h->d_sched) cudaFree(h->d_sched);
@@ -251,7 +294,13 @@ extern "C" const char* qmpc_last_error(const QmpcHandle* h) { return h ? h->err 
 extern "C" int qmpc_describe(const QmpcHandle* h, char* buf, int32_t n) {
   if (!h || !buf || n < 1) return QMPC_ERR_ARG;
   const char* names[3] = {"dense", "srb", "coop"};
-  if (h->kernel == 2)
+  if (h->kernel == QMPC_KERNEL_PHASED)
+    snprintf(buf, n, "kernel=phased lanes_per_problem=%d block=%d launches_per_solve=%d backward:blocks_per_sm=%d,smem_per_problem=%dB%s "
+                     "forward:blocks_per_sm=%d,smem_per_problem=%dB problem_block=%zuB chunk=%d",
+             kCoopG, kCoopBlock, 1 + 2 * h->cfg.iterations_max, h->coop_blocks_per_sm, h->coop_smem_doubles * 8,
+             (h->coop_wide & 1) ? ",lin_resident" : "", h->ph_fwd_blocks_per_sm, h->ph_fwd_smem_doubles * 8,
+             h->ph_problem_doubles * 8, h->ph_chunk);
+  else if (h->kernel == 2)
     snprintf(buf, n, "kernel=coop lanes_per_problem=%d block=%d blocks_per_sm=%d grid=%d last_launch=%dblocks_x_%dproblems "
                      "smem_per_problem=%dB smem_residents=%s%s scratch_per_slot=%zuB",
              kCoopG, kCoopBlock, h->coop_blocks_per_sm, h->coop_grid, h->coop_last_grid, h->coop_last_active,
@@ -262,6 +311,7 @@ extern "C" int qmpc_describe(const QmpcHandle* h, char* buf, int32_t n) {
   return QMPC_OK;
 }
 
+#ifndef QMPC_NO_XCHECK   // experiment builds (-DQMPC_NO_XCHECK) leave the cross-check kernels out: faster to compile
 template <class M>
 static int launch_dense(QmpcHandle* h, const typename M::Problem* d_in, const unsigned char* sched,
                         QmpcWarmStart* warm, int batch,
@@ -286,8 +336,10 @@ static int launch_srb(QmpcHandle* h, const QmpcProblem* d_in, const unsigned cha
   return QMPC_OK;
 }
 
-template <int NF>
-static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+#endif
+
+template <class M>
+static int launch_coop(QmpcHandle* h, const typename M::Problem* d_in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
                        QmpcResult* d_out,
                        cudaStream_t s) {
   const int groups = kCoopBlock / kCoopG;
@@ -312,11 +364,52 @@ static int launch_coop(QmpcHandle* h, const QmpcProblem* d_in, const unsigned ch
   const size_t smem_bytes = (size_t)(groups * h->coop_smem_doubles + kCoopBlockShared) * sizeof(double);
   // the opt-in shared-memory limit is per function AND per device, not per handle: another handle (other
   // horizon) created or solved in between may have lowered it, so it is set before every launch
-  CU(cudaFuncSetAttribute(qmpc_coop_kernel<NF, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  qmpc_coop_kernel<NF, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, sched, warm, d_out, h->ws, batch,
-                                                                   h->coop_smem_doubles, h->coop_scratch_doubles,
-                                                                   h->coop_wide, active);
+  CU(cudaFuncSetAttribute(qmpc_coop_kernel<M, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  qmpc_coop_kernel<M, kCoopG><<<grid, kCoopBlock, smem_bytes, s>>>(h->cfg, h->opts, d_in, sched, warm, d_out, h->ws, batch,
+                                                                  h->coop_smem_doubles, h->coop_scratch_doubles,
+                                                                  h->coop_wide, active);
   h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
+// phased: set-up launch, then (backward, forward) per iteration; the batch in chunks of ph_chunk problems
+template <class M>
+static int launch_phased(QmpcHandle* h, const typename M::Problem* d_in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                         QmpcResult* d_out, cudaStream_t s) {
+  const int groups = kCoopBlock / kCoopG;
+  const size_t bsm = (size_t)(groups * h->coop_smem_doubles + kCoopBlockShared) * sizeof(double);
+  const size_t fsm = (size_t)(groups * h->ph_fwd_smem_doubles + kCoopBlockShared) * sizeof(double);
+  CU(cudaFuncSetAttribute(qmpc_phased_backward_kernel<M, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+  CU(cudaFuncSetAttribute(qmpc_phased_forward_kernel<M, kCoopG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+  auto balanced_grid = [&](int n, int resident_blocks) {
+    // w passes over the resident slots: launch ceil(n / w) slots so that every pass is equally full
+    const long long slots_max = (long long)resident_blocks * groups;
+    const long long waves = (n + slots_max - 1) / slots_max;
+    const long long slots = (n + waves - 1) / waves;
+    return (int)((slots + groups - 1) / groups);
+  };
+  for (int base = 0; base < batch; base += h->ph_chunk) {
+    const int n = batch - base < h->ph_chunk ? batch - base : h->ph_chunk;
+    const typename M::Problem* in = d_in + base;
+    const unsigned char* sc = sched ? sched + (size_t)base * QMPC_MAX_HORIZON : nullptr;
+    QmpcWarmStart* wm = warm ? warm + base : nullptr;
+    QmpcResult* out = d_out + base;
+    qmpc_phased_setup_kernel<M, kCoopG><<<(n + 127) / 128, 128, 0, s>>>(h->cfg, h->opts, in, sc, wm, out, h->ws, n,
+                                                                         h->ph_problem_doubles);
+    h->launches += 1;
+    const int bgrid = balanced_grid(n, h->coop_grid), fgrid = balanced_grid(n, h->ph_fwd_grid);
+    for (int it = 0; it < h->opts.iterations_max; ++it) {
+      qmpc_phased_backward_kernel<M, kCoopG><<<bgrid, kCoopBlock, bsm, s>>>(h->cfg, h->opts, it, wm, out, h->ws, n,
+                                                                            h->ph_problem_doubles, h->coop_smem_doubles, h->coop_wide);
+      qmpc_phased_forward_kernel<M, kCoopG><<<fgrid, kCoopBlock, fsm, s>>>(h->cfg, h->opts, it, wm, out, h->ws, h->ph_trial, n,
+                                                                           h->ph_problem_doubles, h->ph_fwd_smem_doubles,
+                                                                           h->ph_trial_doubles);
+      h->launches += 2;
+    }
+    h->coop_last_grid = bgrid;
+    h->coop_last_active = fgrid;
+  }
   CU(cudaGetLastError());
   return QMPC_OK;
 }
@@ -331,17 +424,29 @@ static int solve_any(QmpcHandle* h, const void* d_in, const QmpcContactSchedule*
   CU(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned char* sc = reinterpret_cast<const unsigned char*>(d_sched);
+#ifdef QMPC_NO_XCHECK
+  if (h->kernel < 2) return QMPC_ERR_ARG;
+#define QMPC_XCHECK(call_) QMPC_ERR_ARG
+#else
+#define QMPC_XCHECK(call_) call_
+#endif
   switch (h->cfg.model) {
     case QMPC_MODEL_QUAT_4FOOT:
-      if (h->kernel == 2) return launch_coop<4>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
-      if (h->kernel == 1) return launch_srb<4>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
-      return launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      if (h->kernel == 3) return launch_phased<QuatModel<4>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      if (h->kernel == 2) return launch_coop<QuatModel<4>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      if (h->kernel == 1) return QMPC_XCHECK(launch_srb<4>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s));
+      return QMPC_XCHECK(launch_dense<QuatModel<4>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s));
     case QMPC_MODEL_QUAT_2FOOT:
-      if (h->kernel == 2) return launch_coop<2>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
-      if (h->kernel == 1) return launch_srb<2>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
-      return launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
-    default: return launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, sc, warm, batch, d_out, s);
+      if (h->kernel == 3) return launch_phased<QuatModel<2>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      if (h->kernel == 2) return launch_coop<QuatModel<2>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s);
+      if (h->kernel == 1) return QMPC_XCHECK(launch_srb<2>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s));
+      return QMPC_XCHECK(launch_dense<QuatModel<2>>(h, (const QmpcProblem*)d_in, sc, warm, batch, d_out, s));
+    default:
+      if (h->kernel == 3) return launch_phased<ConvexModel>(h, (const QmpcConvexProblem*)d_in, sc, nullptr, batch, d_out, s);
+      if (h->kernel == 2) return launch_coop<ConvexModel>(h, (const QmpcConvexProblem*)d_in, sc, nullptr, batch, d_out, s);
+      return QMPC_XCHECK(launch_dense<ConvexModel>(h, (const QmpcConvexProblem*)d_in, sc, warm, batch, d_out, s));
   }
+#undef QMPC_XCHECK
 }
 
 extern "C" int qmpc_solve_batch(QmpcHandle* h, const QmpcProblem* d_in, int32_t batch, QmpcResult* d_out,

@@ -17,6 +17,13 @@
 //   * linearisation, stationarity residuals, dual update, Riccati duals are parallel over knots.
 // The kernel is persistent: grid = resident slots, each slot strides over the batch.
 //
+// Round 2: the solve is written as PHASE FUNCTIONS over a per-problem context (CoopCtx): set-up, pre
+// (expansions, stationarity, dual update), backward (Riccati), forward (line search + accepted step),
+// epilogue.  The fused persistent kernel calls them in sequence; the phased kernels (qmpc_phased.cuh) run
+// one phase per launch with their own register / shared-memory budgets, state through L2/HBM.  The bodies
+// are generic over the model: QuatModel<NF> (QuatMpc, 2-contact model) and ConvexModel (ConvexMpc's Euler
+// SRB: state blocks swapped pairwise, a fourth knot-dependent block Dw) - see the traits in qmpc_models.cuh.
+//
 // The body is written with COOP_PHASE / COOP_SYNC so that the very same source runs on the host
 // (tests/emul, lanes executed one after another) for GPU-less debugging.
 #pragma once
@@ -82,44 +89,62 @@ QMPC_HD inline double qmpc_rsqrt(double x) {
 // Operands that are reused across the rows are read into registers ONCE, before the first store:
 // source and destination are plain pointers into the same shared-memory pool, so the compiler must
 // otherwise assume every store clobbers them and reload (measured: 7 LDS per 4 flops; now ~3).
-// dst = X(:, 3:6) * Mt + beta * X(:, 9:12)   X: 3 rows of a row-major matrix with leading dim ld
-QMPC_HD inline void blk_right(const double* X, int ld, const double* Mt, double beta, double* dst, int ldd) {
+// Offsets: oa = first column (row) of the attitude block, ob = of the angular-velocity block for the "right" /
+// "left" helpers; of the position and linear-velocity blocks for the "even" ones (memory order depends on the
+// model: QuatModel 3, 9 / 0, 6; ConvexModel 0, 6 / 3, 9).
+// dst = X(:, oa:oa+3) * Mt + beta * X(:, ob:ob+3)   X: 3 rows of a row-major matrix with leading dim ld
+QMPC_HD inline void blk_right(const double* X, int ld, int oa, int ob, const double* Mt, double beta, double* dst, int ldd) {
   double m[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) m[i] = Mt[i];
 #pragma unroll 1
   for (int a = 0; a < 3; ++a) {
     const double* Xa = X + ld * a;
-    const double x3 = Xa[3], x4 = Xa[4], x5 = Xa[5], y0 = Xa[9], y1 = Xa[10], y2 = Xa[11];
+    const double x3 = Xa[oa], x4 = Xa[oa + 1], x5 = Xa[oa + 2], y0 = Xa[ob], y1 = Xa[ob + 1], y2 = Xa[ob + 2];
     const double r0 = x3 * m[0] + x4 * m[3] + x5 * m[6] + beta * y0;
     const double r1 = x3 * m[1] + x4 * m[4] + x5 * m[7] + beta * y1;
     const double r2 = x3 * m[2] + x4 * m[5] + x5 * m[8] + beta * y2;
     dst[ldd * a] = r0; dst[ldd * a + 1] = r1; dst[ldd * a + 2] = r2;
   }
 }
-// dst = alpha * X(:, 0:3) + beta * X(:, 6:9)
-QMPC_HD inline void blk_even(const double* X, int ld, double alpha, double beta, double* dst, int ldd) {
+// dst = X(:, oa:oa+3) * Mt + X(:, ob:ob+3) * Nt   (ConvexModel: the moment column of P M, Nt = Dw)
+QMPC_HD inline void blk_right2(const double* X, int ld, int oa, int ob, const double* Mt, const double* Nt, double* dst, int ldd) {
+  double m[9], n[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { m[i] = Mt[i]; n[i] = Nt[i]; }
 #pragma unroll 1
   for (int a = 0; a < 3; ++a) {
     const double* Xa = X + ld * a;
-    const double x0 = Xa[0], x1 = Xa[1], x2 = Xa[2], y0 = Xa[6], y1 = Xa[7], y2 = Xa[8];
+    const double x3 = Xa[oa], x4 = Xa[oa + 1], x5 = Xa[oa + 2], y0 = Xa[ob], y1 = Xa[ob + 1], y2 = Xa[ob + 2];
+    const double r0 = x3 * m[0] + x4 * m[3] + x5 * m[6] + (y0 * n[0] + y1 * n[3] + y2 * n[6]);
+    const double r1 = x3 * m[1] + x4 * m[4] + x5 * m[7] + (y0 * n[1] + y1 * n[4] + y2 * n[7]);
+    const double r2 = x3 * m[2] + x4 * m[5] + x5 * m[8] + (y0 * n[2] + y1 * n[5] + y2 * n[8]);
+    dst[ldd * a] = r0; dst[ldd * a + 1] = r1; dst[ldd * a + 2] = r2;
+  }
+}
+// dst = alpha * X(:, oa:oa+3) + beta * X(:, ob:ob+3)
+QMPC_HD inline void blk_even(const double* X, int ld, int oa, int ob, double alpha, double beta, double* dst, int ldd) {
+#pragma unroll 1
+  for (int a = 0; a < 3; ++a) {
+    const double* Xa = X + ld * a;
+    const double x0 = Xa[oa], x1 = Xa[oa + 1], x2 = Xa[oa + 2], y0 = Xa[ob], y1 = Xa[ob + 1], y2 = Xa[ob + 2];
     dst[ldd * a] = alpha * x0 + beta * y0;
     dst[ldd * a + 1] = alpha * x1 + beta * y1;
     dst[ldd * a + 2] = alpha * x2 + beta * y2;
   }
 }
-// dst = Mt^T * Y(3:6, :) + beta * Y(9:12, :)   Y: 3 columns (starting at Y) of a row-major matrix
-QMPC_HD inline void blk_left(const double* Y, int ld, const double* Mt, double beta, double* dst, int ldd) {
+// dst = Mt^T * Y(oa:oa+3, :) + beta * Y(ob:ob+3, :)   Y: 3 columns (starting at Y) of a row-major matrix
+QMPC_HD inline void blk_left(const double* Y, int ld, int oa, int ob, const double* Mt, double beta, double* dst, int ldd) {
   double m[9], y[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) m[i] = Mt[i];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int b = 0; b < 3; ++b) y[3 * i + b] = Y[ld * (3 + i) + b];
+    for (int b = 0; b < 3; ++b) y[3 * i + b] = Y[ld * (oa + i) + b];
 #pragma unroll   // unrolled: m[a] must stay a compile-time register index
   for (int a = 0; a < 3; ++a) {
-    const double* Ya = Y + ld * (9 + a);
+    const double* Ya = Y + ld * (ob + a);
     const double z0 = Ya[0], z1 = Ya[1], z2 = Ya[2];
     const double m0 = m[a], m1 = m[3 + a], m2 = m[6 + a];
     const double r0 = m0 * y[0] + m1 * y[3] + m2 * y[6] + beta * z0;
@@ -128,12 +153,30 @@ QMPC_HD inline void blk_left(const double* Y, int ld, const double* Mt, double b
     dst[ldd * a] = r0; dst[ldd * a + 1] = r1; dst[ldd * a + 2] = r2;
   }
 }
-// dst = alpha * Y(0:3, :) + beta * Y(6:9, :)
-QMPC_HD inline void blk_evenT(const double* Y, int ld, double alpha, double beta, double* dst, int ldd) {
+// dst = Mt^T * Y(oa:oa+3, :) + Nt^T * Y(ob:ob+3, :)   (ConvexModel: the moment rows of M^T Y, Nt = Dw)
+QMPC_HD inline void blk_left2(const double* Y, int ld, int oa, int ob, const double* Mt, const double* Nt, double* dst, int ldd) {
+  double m[9], n[9], y[9], z[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { m[i] = Mt[i]; n[i] = Nt[i]; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) { y[3 * i + b] = Y[ld * (oa + i) + b]; z[3 * i + b] = Y[ld * (ob + i) + b]; }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double m0 = m[a], m1 = m[3 + a], m2 = m[6 + a], n0 = n[a], n1 = n[3 + a], n2 = n[6 + a];
+    const double r0 = m0 * y[0] + m1 * y[3] + m2 * y[6] + (n0 * z[0] + n1 * z[3] + n2 * z[6]);
+    const double r1 = m0 * y[1] + m1 * y[4] + m2 * y[7] + (n0 * z[1] + n1 * z[4] + n2 * z[7]);
+    const double r2 = m0 * y[2] + m1 * y[5] + m2 * y[8] + (n0 * z[2] + n1 * z[5] + n2 * z[8]);
+    dst[ldd * a] = r0; dst[ldd * a + 1] = r1; dst[ldd * a + 2] = r2;
+  }
+}
+// dst = alpha * Y(oa:oa+3, :) + beta * Y(ob:ob+3, :)
+QMPC_HD inline void blk_evenT(const double* Y, int ld, int oa, int ob, double alpha, double beta, double* dst, int ldd) {
 #pragma unroll 1
   for (int a = 0; a < 3; ++a) {
-    const double x0 = Y[ld * a], x1 = Y[ld * a + 1], x2 = Y[ld * a + 2];
-    const double y0 = Y[ld * (6 + a)], y1 = Y[ld * (6 + a) + 1], y2 = Y[ld * (6 + a) + 2];
+    const double x0 = Y[ld * (oa + a)], x1 = Y[ld * (oa + a) + 1], x2 = Y[ld * (oa + a) + 2];
+    const double y0 = Y[ld * (ob + a)], y1 = Y[ld * (ob + a) + 1], y2 = Y[ld * (ob + a) + 2];
     dst[ldd * a] = alpha * x0 + beta * y0;
     dst[ldd * a + 1] = alpha * x1 + beta * y1;
     dst[ldd * a + 2] = alpha * x2 + beta * y2;
@@ -192,48 +235,158 @@ constexpr int kCoopBlockShared = 26;   // doubles at the head of the block's sha
 template <int V>
 struct IntTag { static constexpr int value = V; };
 
-template <int NF, int G>
+QMPC_HD constexpr int coop_even(int v) { return (v + 1) / 2 * 2; }
+
+// Per-knot row of the expansions, contiguous and 16-byte aligned so that ONE bulk copy (cp.async / TMA 1-D)
+// brings a knot's data into the shared "vec" block: cost gradient lx (12), attitude Hessian block (9), input
+// gradient g = R (u - u_ref) + J^T max(0, mu + rho c) (NU), D blocks = R + rho J_a^T J_a per foot (9 NF).
+template <class M>
+struct CoopRow {
+  static constexpr int NF = M::kFeet, NU = M::NU;
+  static constexpr int lx = 0, Hphi = 12, g = 21, Dblk = 21 + NU, kLen = 21 + NU + 9 * NF, kStride = coop_even(kLen);
+};
+
+template <class M, int G>
 struct CoopLayout {
-  static constexpr int NU = 3 * NF, NC = 6 * NF;
-  static constexpr int kModel = (int)((sizeof(QuatModel<NF>) + 7) / 8);
+  static constexpr int NF = M::kFeet, NU = M::NU, NC = M::NC, NX = M::NX, NLIN = M::NLIN;
+  static constexpr int kLinStride = coop_even(NLIN);
+  static constexpr int kRow = CoopRow<M>::kStride;
+  static constexpr int kKD = NU * 12 + NU;   // one knot's gain matrix K_k followed by its feed-forward d_k
+  static constexpr int kModel = (int)((sizeof(M) + 7) / 8);
   // ---- shared memory (doubles) per problem
-  static constexpr int kVec = 156;   // the register/shuffle Cholesky needs no column-exchange buffer (cv::tcol)
-  QMPC_HD static int sX(int N) { return kModel; }
-  QMPC_HD static int sU(int N) { return sX(N) + (N + 1) * 13; }
-  QMPC_HD static int sP(int N) { return (sU(N) + N * NU + 1) / 2 * 2; }   // 16-byte aligned: cp.async target
+  // vec block: the knot row (kRow), then Qx 12, Qu 12, s 6, Atp 12, vu 12, pv 12, scal 10
+  static constexpr int vQx = kRow, vQu = vQx + 12, vs = vQu + 12, vAtp = vs + 6, vvu = vAtp + 12, vpv = vvu + 12,
+                       vscal = vpv + 12, kVec = coop_even(vscal + 10);
+  QMPC_HD static int sX(int N) { return coop_even(kModel); }
+  QMPC_HD static int sU(int N) { return sX(N) + (N + 1) * NX; }
+  QMPC_HD static int sP(int N) { return coop_even(sU(N) + N * NU); }   // 16-byte aligned: cp.async target
   QMPC_HD static int sPA(int N) { return sP(N) + 144; }    // PA, later Quu / its Cholesky factor
   QMPC_HD static int sT(int N) { return sPA(N) + 144; }
   QMPC_HD static int sPM(int N) { return sT(N) + 72; }     // PM, later SW
   QMPC_HD static int sS(int N) { return sPM(N) + 72; }
   QMPC_HD static int sQux(int N) { return sS(N) + 36; }    // Qux, later V = L^-1 Qux
-  QMPC_HD static int sVec(int N) { return sQux(N) + NU * 12; }
+  QMPC_HD static int sVec(int N) { return coop_even(sQux(N) + NU * 12); }
   QMPC_HD static int sLin(int N) { return sVec(N) + kVec; }
-  // Optional residents (`flags`): bit 0 = the per-knot linearisation blocks (27 N), bit 1 = the duals
+  // Optional residents (`flags`): bit 0 = the per-knot linearisation blocks (kLinStride N), bit 1 = the duals
   // (NC N) also live in shared memory - used when they do not cost residency (short horizons);
   // otherwise they stay in the L2-resident scratch.  Same code either way, only the pointers differ.
-  QMPC_HD static int sLinAll(int N) { return (sLin(N) + 27 + 1) / 2 * 2; }
-  QMPC_HD static int sMu(int N, int flags) { return sLinAll(N) + ((flags & 1) ? 27 * N : 0); }
-  QMPC_HD static int smem_doubles(int N, int flags) { return (sMu(N, flags) + ((flags & 2) ? NC * N : 0) + 1) / 2 * 2; }
-  // ---- global scratch (doubles) per slot
-  QMPC_HD static size_t gK(int N) { return 0; }
-  QMPC_HD static size_t gd(int N) { return gK(N) + (size_t)N * NU * 12; }
-  QMPC_HD static size_t gP(int N) { return gd(N) + (size_t)N * NU; }
+  QMPC_HD static int sLinAll(int N) { return sLin(N) + kLinStride; }
+  QMPC_HD static int sMu(int N, int flags) { return sLinAll(N) + ((flags & 1) ? kLinStride * N : 0); }
+  QMPC_HD static int smem_doubles(int N, int flags) { return coop_even(sMu(N, flags) + ((flags & 2) ? NC * N : 0)); }
+  // shared memory of the forward-only kernel (qmpc_phased.cuh): model, X, U, the gain stage (also the dx buffer
+  // of the accepted step) and the reduction slots
+  QMPC_HD static int fStage(int N) { return coop_even(sU(N) + N * NU); }
+  QMPC_HD static int fStageLen(int N) { int a = 2 * kKD, b = (N + 1) * 12; return coop_even(a > b ? a : b); }
+  QMPC_HD static int fRed(int N) { return fStage(N) + fStageLen(N); }
+  QMPC_HD static int fwd_smem_doubles(int N) { return fRed(N) + 2 * G; }
+  // ---- global scratch (doubles) per slot (fused kernel) / per problem (phased kernels); every region starts
+  //      16-byte aligned
+  QMPC_HD static size_t gK(int N) { return 0; }                                          // N x [K_k | d_k]
+  QMPC_HD static size_t gP(int N) { return gK(N) + (size_t)N * kKD; }
   QMPC_HD static size_t gpv(int N) { return gP(N) + (size_t)(N + 1) * 144; }
   QMPC_HD static size_t gmu(int N) { return gpv(N) + (size_t)(N + 1) * 12; }
-  QMPC_HD static size_t glin(int N) { return gmu(N) + (size_t)N * NC; }
-  QMPC_HD static size_t gDX(int N) { return glin(N) + (size_t)N * 27; }
+  QMPC_HD static size_t glin(int N) { return coop_even((int)(gmu(N) + (size_t)N * NC)); }
+  QMPC_HD static size_t gDX(int N) { return glin(N) + (size_t)N * kLinStride; }
+  QMPC_HD static size_t gLX(int N) { return gDX(N) + (size_t)(N + 1) * 12; }            // (N + 1) knot rows
+  QMPC_HD static size_t gEnd(int N) { return gLX(N) + (size_t)(N + 1) * kRow; }
   // trial trajectories of the speculative line search, [element][lane] so the 16 lanes store coalesced
-  // cost expansion of every knot (gradient 12 + attitude Hessian block 9), written once per iteration
-  QMPC_HD static size_t gLX(int N) { return gDX(N) + (size_t)(N + 1) * 12; }
-  QMPC_HD static size_t gTX(int N) { return (gLX(N) + (size_t)(N + 1) * 21 + 15) / 16 * 16; }
-  QMPC_HD static size_t gTU(int N) { return gTX(N) + (size_t)(N + 1) * 13 * G; }
+  QMPC_HD static size_t gTX(int N) { return (gEnd(N) + 15) / 16 * 16; }
+  QMPC_HD static size_t gTU(int N) { return gTX(N) + (size_t)(N + 1) * NX * G; }
   QMPC_HD static size_t scratch_doubles(int N) { return (gTU(N) + (size_t)N * NU * G + 15) / 16 * 16; }
+  // phased kernels: persistent per-problem block = the regions above up to gEnd, then model, X, U, scalars
+  QMPC_HD static size_t pModel(int N) { return coop_even((int)gEnd(N)); }
+  QMPC_HD static size_t pX(int N) { return pModel(N) + coop_even(kModel); }
+  QMPC_HD static size_t pU(int N) { return pX(N) + (size_t)(N + 1) * NX; }
+  QMPC_HD static size_t pScal(int N) { return coop_even((int)(pU(N) + (size_t)N * NU)); }
+  QMPC_HD static size_t problem_doubles(int N) { return (pScal(N) + 8 + 15) / 16 * 16; }
+  // phased forward kernel: per-slot trial trajectories only
+  QMPC_HD static size_t trial_doubles(int N) { return ((size_t)(N + 1) * NX * G + (size_t)N * NU * G + 15) / 16 * 16; }
 };
 
-// offsets inside the shared "vec" block
-namespace cv {
-constexpr int lx = 0, Qx = 12, Qu = 24, s = 36, Atp = 42, g = 54, Dblk = 66, Hphi = 102, vu = 111, pv = 123,
-              scal = 135, rdiag = 144, tcol = 156;  // scal[0]=dphi0 [1]=hphi [2]=phi [3]=viol
+// the three (four) knot-dependent 3x3 blocks of the error-state linearisation
+struct KnotLin4 : KnotLin {
+  double Dw[9];
+};
+
+// ---- model dispatch: linearisation blocks of one knot
+template <int NF>
+QMPC_HD inline void coop_linearize(const QuatModel<NF>& m, const double* x, const double* u, const double* xn, double hd,
+                                   double hh, KnotLin4& L) {
+  srb_linearize(m, x, u, xn, hd, hh, L);
+}
+// Euler SRB (AltroUtils.cpp:224-359 through the midpoint chain rule :78-110): with the state blocks
+// [theta, p, omega, v], T = d(theta_dot)/d(yaw) (only column 2 non-zero), Rt = the yaw-only map omega -> rpy rates
+//   Aff = I + h T_m                      Afw = h (Rt_m + (h/2) T_m Rt)
+//   Cf  = h (h/2) Rt_m Iw(yaw)^-1        Dw  = h Iw(yaw_m)^-1
+// entry by entry as v = h (h/2 * s + Jm) like the dense chain rule (terms that are exactly zero dropped).
+QMPC_HD inline void coop_linearize(const ConvexModel& m, const double* x, const double* u, const double* /*xn*/, double hd,
+                                   double hh, KnotLin4& L) {
+  double fs0 = 0, fs1 = 0, fs2 = 0, mom0 = 0, mom1 = 0, mom2 = 0;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const double* rf = m.foot + 3 * f;
+    const double u0 = u[3 * f], u1 = u[3 * f + 1], u2 = u[3 * f + 2];
+    mom0 += rf[1] * u2 - rf[2] * u1; mom1 += rf[2] * u0 - rf[0] * u2; mom2 += rf[0] * u1 - rf[1] * u0;
+    fs0 += u0; fs1 += u1; fs2 += u2;
+  }
+  double xd[12];
+  m.wrench_dyn(x, fs0, fs1, fs2, mom0, mom1, mom2, xd);
+  const double yaw_m = xd[2] * hh + x[2], w0m = xd[6] * hh + x[6], w1m = xd[7] * hh + x[7];
+  const double sy = sin(x[2]), cy = cos(x[2]), sym = sin(yaw_m), cym = cos(yaw_m);
+  double iw[4], iwm[4];
+  ConvexModel::Iw_inv(sy, cy, iw);
+  ConvexModel::Iw_inv(sym, cym, iwm);
+  const double am = w1m * cym - w0m * sym, bm = -w0m * cym - w1m * sym;   // AltroUtils.cpp:355-356 at the midpoint
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { L.Aff[i] = 0; L.Afw[i] = 0; L.Cf[i] = 0; L.Dw[i] = 0; }
+  L.Aff[0] = 1.0; L.Aff[4] = 1.0; L.Aff[8] = 1.0;
+  L.Aff[2] = hd * am; L.Aff[5] = hd * bm;
+  const double Rt[9] = {cy, sy, 0, -sy, cy, 0, 0, 0, 1}, Rtm[9] = {cym, sym, 0, -sym, cym, 0, 0, 0, 1};
+  (void)Rt;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double s = (j == 2) ? (i == 0 ? am : (i == 1 ? bm : 0.0)) : 0.0;   // T_m(i,2) * Rt(2,j), Rt(2,:) = (0,0,1)
+      L.Afw[3 * i + j] = hd * (hh * s + Rtm[3 * i + j]);
+    }
+  const double Iw[9] = {iw[0], iw[1], 0, iw[1], iw[2], 0, 0, 0, iw[3]};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) s += Rtm[3 * i + l] * Iw[3 * l + j];
+      L.Cf[3 * i + j] = hd * (hh * s);
+    }
+  L.Dw[0] = hd * iwm[0]; L.Dw[1] = hd * iwm[1]; L.Dw[3] = hd * iwm[1]; L.Dw[4] = hd * iwm[2]; L.Dw[8] = hd * iwm[3];
+}
+
+// y = A^T v (12) and t = M^T v (6) in the model's memory order of the state blocks
+template <class M>
+QMPC_HD inline void coop_At_vec(const KnotLin4& L, double hd, const double* v, double* y) {
+  constexpr int P = 3 * (0 ^ M::kSwap), A = 3 * (1 ^ M::kSwap), V = 3 * (2 ^ M::kSwap), W = 3 * (3 ^ M::kSwap);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    y[P + i] = v[P + i];
+    y[A + i] = L.Aff[i] * v[A] + L.Aff[3 + i] * v[A + 1] + L.Aff[6 + i] * v[A + 2];
+    y[V + i] = hd * v[P + i] + v[V + i];
+    y[W + i] = L.Afw[i] * v[A] + L.Afw[3 + i] * v[A + 1] + L.Afw[6 + i] * v[A + 2] + v[W + i];
+  }
+}
+template <class M>
+QMPC_HD inline void coop_Mt_vec(const KnotLin4& L, double hd, double hh, const double* v, double* t) {
+  constexpr int P = 3 * (0 ^ M::kSwap), A = 3 * (1 ^ M::kSwap), V = 3 * (2 ^ M::kSwap), W = 3 * (3 ^ M::kSwap);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    t[i] = hd * hh * v[P + i] + hd * v[V + i];
+    if (M::kDw)
+      t[3 + i] = L.Cf[i] * v[A] + L.Cf[3 + i] * v[A + 1] + L.Cf[6 + i] * v[A + 2] +
+                 (L.Dw[i] * v[W] + L.Dw[3 + i] * v[W + 1] + L.Dw[6 + i] * v[W + 2]);
+    else
+      t[3 + i] = L.Cf[i] * v[A] + L.Cf[3 + i] * v[A + 1] + L.Cf[6 + i] * v[A + 2] + hd * v[W + i];
+  }
 }
 
 // stage cost + AL terms of one knot: same accumulation order as stage_cost() / merit() in
@@ -255,8 +408,9 @@ QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, const double* 
       Jl += 0.5 * wr[3 * f + 2] * d2 * d2;
     }
   }
-  if (cfg.w != 0.0) {
-    const double s = xr[3] * x[3] + xr[4] * x[4] + xr[5] * x[5] + xr[6] * x[6];
+  if (M::kQuat && cfg.w != 0.0) {
+    constexpr int qi = M::kQuat ? 3 : 0;
+    const double s = xr[qi] * x[qi] + xr[qi + 1] * x[qi + 1] + xr[qi + 2] * x[qi + 2] + xr[qi + 3] * x[qi + 3];
     Jl += cfg.w * (1.0 - fabs(s));
   }
   J += Jl;
@@ -281,73 +435,122 @@ QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, const double* 
   }
 }
 
-// attitude block of the cost Hessian: G^T diag(Qq) G + hphi I
+// attitude block of the cost Hessian: G^T diag(Qq) G + hphi I (quaternion models) / diag(Q_rpy) (Euler model)
+template <class M>
 QMPC_HD inline void hphi_block(const QmpcConfig& cfg, const double* x, double hphi, double* H) {
-  double Gq[12];
-  quat_G(x + 3, Gq);
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b) {
-      double s = 0;
-      for (int i = 0; i < 4; ++i) s += Gq[3 * i + a] * cfg.q_weights[3 + i] * Gq[3 * i + b];
-      H[3 * a + b] = s + (a == b ? hphi : 0.0);
-    }
+  if (M::kQuat) {
+    double Gq[12];
+    quat_G(x + 3, Gq);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        double s = 0;
+        for (int i = 0; i < 4; ++i) s += Gq[3 * i + a] * cfg.q_weights[3 + i] * Gq[3 * i + b];
+        H[3 * a + b] = s + (a == b ? hphi : 0.0);
+      }
+  } else {
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) H[3 * a + b] = (a == b) ? cfg.q_weights[a] : 0.0;
+  }
 }
 
-// 3x3 block (br, bc) of the cost Hessian in error coordinates
+// 3x3 block (br, bc) of the cost Hessian in error coordinates (memory order of the blocks)
+template <class M>
 QMPC_HD inline void lxx_block(const double* wq, const double* Hphi, int br, int bc, double* out) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) out[i] = 0.0;
   if (br != bc) return;
-  if (br == 1) {
+  if (br == (1 ^ M::kSwap)) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) out[i] = Hphi[i];
   } else {
-    const int q0 = br == 0 ? 0 : (br == 2 ? 7 : 10);
+    const int q0 = M::qoff(br);
     out[0] = wq[q0]; out[4] = wq[q0 + 1]; out[8] = wq[q0 + 2];
   }
 }
 
+#if defined(__CUDA_ARCH__)
+// 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier (cp.async.bulk; SASS UBLKCP):
+// ONE lane issues ONE instruction for a whole row instead of every lane issuing 16-byte cp.async requests.
+__device__ __forceinline__ void coop_mbar_init(double* mb, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(mb);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void coop_bulk_g2s(double* dst, const double* src, unsigned bytes, double* mb) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(mb);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void coop_mbar_wait(double* mb, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(mb);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
+}
+// 16-byte cp.async requests dealt over the `nl` lanes of the problem (SASS LDGSTS)
+__device__ __forceinline__ void coop_cp_async_row(double* dst, const double* src, int doubles, int tl, int nl) {
+  for (int c = tl; 2 * c < doubles; c += nl) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 2 * c) : "memory");
+  }
+}
+#endif
+
 // One roll-out of the whole horizon by ONE lane (kept out of line: it is used by the nominal
-// roll-out, by the 16 speculative line-search lanes and by the accepted step, and inlining it three
-// times is what pushed the SASS far past the instruction cache).
+// roll-out and by the 16 speculative line-search lanes, and inlining it twice is what pushed the SASS
+// far past the instruction cache).
 //   mode 0: open loop, u = u_ref: writes the nominal X, U; returns merit / violation
-//   mode 1: trial step `alpha` around (X, U) with gains (gK, gd): X, U untouched; the trial
+//   mode 1: trial step `alpha` around (X, U) with gains (gK: N x [K_k | d_k]): X, U untouched; the trial
 //           trajectory is recorded in the scratch (gTX/gTU, element-major, lane `tl` of `tstride`) so
 //           that the accepted one is simply copied back - no second roll-out; returns merit / violation
-//   mode 2: (unused by the kernel, kept for the host emulation tests) accepted step in place
-template <int NF>
-QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig& cfg, const double* wr, int N, float h, double* X,
-                                        double* U, double* DX, const double* gK, const double* gd,
+template <class M>
+QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const double* wr, int N, float h, double* X,
+                                        double* U, const double* gK,
                                         const double* gmu, double rho, double alpha, int mode, double* Jout,
                                         double* violout, double* gTX, double* gTU, int tl, int tstride,
                                         double* kstage, unsigned lane_mask, const QmpcWarmStart* winit) {
   // Compact by construction (instruction-fetch bound otherwise): the input never
   // exists as an array - each foot's force is formed, costed, cone-checked and folded into the net
-  // wrench inside one 4-trip loop; the wrench drives both midpoint evaluations.  Accumulation
+  // wrench inside one NF-trip loop; the wrench drives both midpoint evaluations.  Accumulation
   // orders are exactly those of stage_cost() / knot_merit() / ct_dyn() / mid_dyn().
-  using M = QuatModel<NF>;
-  constexpr int NX = 13, NE = 12, NU = M::NU, NC = M::NC;
+  constexpr int NX = M::NX, NE = 12, NU = M::NU, NC = M::NC, NF = M::kFeet;
+  constexpr int kKD = NU * 12 + NU;
   const double hd = (double)h, hh = (double)(h / 2);
   double x[NX], J = 0, vl = 0;
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = X[i];
 #if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_KSTAGE)
-  // Mode 1 runs on all `tstride` lanes of the problem in lock-step: the gain matrix of knot k+1 is
-  // copied (cp.async, 16 bytes per request, the lanes split the rows) from the L2-resident scratch
-  // into a double buffer in shared memory while knot k is being computed, so the 72 broadcast reads
-  // of K_k per lane are shared-memory reads instead of L2 round trips.  The feed-forward d_k rides along.
-  constexpr int kChunksK = NU * 12 / 2, kChunks = kChunksK + NU / 2, kStage = NU * 12 + NU;
-  auto stage_gain = [&](int k) {
-    const double* srcK = gK + (size_t)k * NU * 12;
-    const double* srcd = gd + (size_t)k * NU - 2 * kChunksK;
-    double* dst = kstage + (k & 1) * kStage;
-    for (int c = tl; c < kChunks; c += tstride) {
-      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
-      const double* src = (c < kChunksK ? srcK : srcd) + 2 * c;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+  // Mode 1 runs on all `tstride` lanes of the problem in lock-step: the gain matrix (and feed-forward) of
+  // knot k+1 is copied from the L2-resident scratch into a double buffer in shared memory while knot k is
+  // being computed, so the 72 broadcast reads of K_k per lane are shared-memory reads instead of L2 round
+  // trips.  Default: one cp.async.bulk (TMA 1-D, mbarrier completion) issued by lane 0;
+  // -DQMPC_COOP_KSTAGE_LDGSTS: 16-byte cp.async requests dealt over the lanes (the round-1 form).
+#ifndef QMPC_COOP_KSTAGE_LDGSTS
+  double* mbar = kstage + 2 * kKD;
+  if (mode == 1) {
+    if (tl == 0) {
+      coop_mbar_init(mbar, 1);
+      coop_mbar_init(mbar + 1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    __syncwarp(lane_mask);
+  }
+  auto stage_gain = [&](int k) {
+    if (tl == 0) coop_bulk_g2s(kstage + (k & 1) * kKD, gK + (size_t)k * kKD, kKD * 8u, mbar + (k & 1));
+  };
+  auto stage_wait = [&](int k) { coop_mbar_wait(mbar + (k & 1), (unsigned)((k >> 1) & 1)); };
+#else
+  auto stage_gain = [&](int k) {
+    coop_cp_async_row(kstage + (k & 1) * kKD, gK + (size_t)k * kKD, kKD, tl, tstride);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  auto stage_wait = [&](int) { asm volatile("cp.async.wait_all;" ::: "memory"); };
+#endif
   if (mode == 1) stage_gain(0);
 #else
   (void)kstage; (void)lane_mask;
@@ -360,42 +563,33 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
 #pragma unroll
       for (int i = 0; i < NX; ++i) st_stream(gTX + (size_t)(k * NX + i) * tstride + tl, x[i]);
     }
-    if (mode == 2) {
-#pragma unroll
-      for (int i = 0; i < NE; ++i) DX[k * NE + i] = dx[i];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) X[k * NX + i] = x[i];
-    }
     // ---- state part of the stage cost
     double Jl = 0, sq = 0;
-    if (mode != 2) {
+    {
       double xr[NX];
       m.xref(k, xr);
 #pragma unroll
       for (int i = 0; i < NX; ++i) { const double dxi = x[i] - xr[i]; Jl += 0.5 * cfg.q_weights[i] * dxi * dxi; }
-      sq = xr[3] * x[3] + xr[4] * x[4] + xr[5] * x[5] + xr[6] * x[6];
+      if (M::kQuat) sq = xr[3] * x[3] + xr[4] * x[4] + xr[5] * x[5] + xr[6] * x[6];
     }
     if (k == N) {
-      if (mode != 2) {
-        if (cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
-        J += Jl;
-      }
+      if (M::kQuat && cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
+      J += Jl;
       break;
     }
     // ---- per foot: force, input cost, cone rows / AL merit, wrench
     double mom0 = 0, mom1 = 0, mom2 = 0, fs0 = 0, fs1 = 0, fs2 = 0, acc = 0;
 #if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_KSTAGE)
-    const double* Kk = mode == 1 ? kstage + (k & 1) * kStage : gK;
-    const double* dk = mode == 1 ? Kk + NU * 12 : gd;
+    const double* Kk = mode == 1 ? kstage + (k & 1) * kKD : gK;
     if (mode == 1) {
-      asm volatile("cp.async.wait_all;" ::: "memory");
+      stage_wait(k);
       __syncwarp(lane_mask);              // K_k visible to all lanes; everyone is done with K_{k-1}
       if (k + 1 < N) stage_gain(k + 1);
     }
 #else
-    const double* Kk = gK + (size_t)k * NU * 12;
-    const double* dk = gd + k * NU;
+    const double* Kk = gK + (size_t)k * kKD;
 #endif
+    const double* dk = Kk + NU * 12;
 #ifndef QMPC_COOP_FOOT_UNROLL
 #define QMPC_COOP_FOOT_UNROLL 1
 #endif
@@ -414,7 +608,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
         double t0 = 0, t1 = 0, t2 = 0;
         const double* K0 = Kk + (3 * f) * 12;
 #if !defined(QMPC_COOP_NO_K128) && defined(__CUDA_ARCH__)
-        {   // three 96-byte gain rows as 18 x 16-byte loads (rows are 16-byte aligned in the scratch)
+        {   // three 96-byte gain rows as 18 x 16-byte loads (rows are 16-byte aligned)
 #ifndef QMPC_COOP_NO_KSTAGE
           const unsigned ks = (unsigned)__cvta_generic_to_shared(K0);
           auto ldk = [&](int l) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ks + 16u * l)); return v; };
@@ -446,7 +640,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
         double* tu = gTU + (size_t)(k * NU + 3 * f) * tstride + tl;
         st_stream(tu, u0); st_stream(tu + tstride, u1); st_stream(tu + 2 * tstride, u2);
       }
-      if (mode != 2) {
+      {
         const double d0 = u0, d1 = u1, d2 = u2 - m.urefz(k, f);   // u_ref = (0, 0, weight share)
         Jl += 0.5 * wr[3 * f] * d0 * d0;
         Jl += 0.5 * wr[3 * f + 1] * d1 * d1;
@@ -470,39 +664,11 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
       mom1 += c1; fs1 += u1;
       mom2 += c2; fs2 += u2;
     }
-    if (mode != 2) {
-      if (cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
-      J += Jl;
-      J += acc / (2 * rho);
-    }
-    // ---- explicit midpoint step driven by the net wrench (AltroUtils.cpp:9-22, 383-391)
-    mom0 += m.tau_g[0]; mom1 += m.tau_g[1]; mom2 += m.tau_g[2];
-    const double al0 = fs0 * m.inv_mass + m.g[0], al1 = fs1 * m.inv_mass + m.g[1], al2 = fs2 * m.inv_mass + m.g[2];
-    const double aw0 = m.Iinv[0] * mom0 + m.Iinv[1] * mom1 + m.Iinv[2] * mom2;
-    const double aw1 = m.Iinv[3] * mom0 + m.Iinv[4] * mom1 + m.Iinv[5] * mom2;
-    const double aw2 = m.Iinv[6] * mom0 + m.Iinv[7] * mom1 + m.Iinv[8] * mom2;
-    double xm[NX];
-    {
-      const double *q = x + 3, *w = x + 10;
-      xm[0] = x[7] * hh + x[0]; xm[1] = x[8] * hh + x[1]; xm[2] = x[9] * hh + x[2];
-      xm[3] = (0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2])) * hh + q[0];
-      xm[4] = (0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2])) * hh + q[1];
-      xm[5] = (0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2])) * hh + q[2];
-      xm[6] = (0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2])) * hh + q[3];
-      xm[7] = al0 * hh + x[7]; xm[8] = al1 * hh + x[8]; xm[9] = al2 * hh + x[9];
-      xm[10] = aw0 * hh + x[10]; xm[11] = aw1 * hh + x[11]; xm[12] = aw2 * hh + x[12];
-    }
-    {
-      const double *q = xm + 3, *w = xm + 10;
-      const double qd0 = 0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
-      const double qd1 = 0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
-      const double qd2 = 0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
-      const double qd3 = 0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
-      x[0] = x[0] + hd * xm[7]; x[1] = x[1] + hd * xm[8]; x[2] = x[2] + hd * xm[9];
-      x[3] = x[3] + hd * qd0; x[4] = x[4] + hd * qd1; x[5] = x[5] + hd * qd2; x[6] = x[6] + hd * qd3;
-      x[7] = x[7] + hd * al0; x[8] = x[8] + hd * al1; x[9] = x[9] + hd * al2;
-      x[10] = x[10] + hd * aw0; x[11] = x[11] + hd * aw1; x[12] = x[12] + hd * aw2;
-    }
+    if (M::kQuat && cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
+    J += Jl;
+    J += acc / (2 * rho);
+    // ---- explicit midpoint step driven by the net wrench (AltroUtils.cpp:9-22, 383-391 / 224-294)
+    m.wrench_step(x, fs0, fs1, fs2, mom0, mom1, mom2, hd, hh);
     if (mode == 0) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) X[(k + 1) * NX + i] = x[i];
@@ -512,589 +678,769 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const QuatModel<NF>& m, const QmpcConfig
   *violout = vl;
 }
 
-template <int NF, int G>
-QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const QmpcProblem* in,
-                            const unsigned char* sched, QmpcWarmStart* warm, QmpcResult* out,
-                            int pid, double* sm, double* gs, int lane_id, unsigned lane_mask, int flags,
-                            const double* wts) {
-  using M = QuatModel<NF>;
-  using L = CoopLayout<NF, G>;
-  constexpr int NX = 13, NE = 12, NU = M::NU, NC = M::NC;
+// ------------------------------------------------------------------------------------------------
+// Per-problem context of the phase functions: where every array of the problem lives (shared memory or
+// the L2-resident scratch - the phases do not care) and the solver scalars, uniform over the problem's lanes.
+template <class M, int G>
+struct CoopCtx {
+  using L = CoopLayout<M, G>;
+  M* m;
+  double *X, *U, *P, *PA, *T, *PM, *S, *Qux, *vec, *lin, *red, *kstage, *dxs;
+  double *gK, *gP, *gpv, *gmu, *glin, *DX, *gLX, *gTX, *gTU;
+  int lin_stride_is_resident;   // 1: glin rows are read in place (shared memory); 0: staged into `lin` per knot
+  const double *wq, *wr;
+  int N;
+  float h;
+  double hd, hh, c1;
+  // solver state
+  double rho, phi, viol, cost_decrease, dphi0;
+  int status, iters;
+
+  // fused kernel / backward kernel: the full shared-memory layout `sm`, scratch `gs`
+  QMPC_HD void bind(double* sm, double* gs, double* trial, int N_, float h_, int flags, const double* wts) {
+    N = N_; h = h_; hd = (double)h_; hh = (double)(h_ / 2); c1 = hd * hh;
+    wq = wts; wr = wts + 13;
+    m = reinterpret_cast<M*>(sm);
+    X = sm + L::sX(N); U = sm + L::sU(N);
+    P = sm + L::sP(N); PA = sm + L::sPA(N); T = sm + L::sT(N); PM = sm + L::sPM(N); S = sm + L::sS(N);
+    Qux = sm + L::sQux(N); vec = sm + L::sVec(N); lin = sm + L::sLin(N);
+    // 2 G reduction slots at the tail of T (only used outside the backward pass, where T is dead); the
+    // roll-out's gain stage (2 kKD doubles + 2 mbarriers) occupies P, PA and the head of T meanwhile; the
+    // accepted step's dx buffer ((N + 1) x 12 <= 396) overlays P .. Qux (612 doubles, all dead by then)
+    red = T + 72 - 2 * G;
+    kstage = P; dxs = P;
+    static_assert(2 * L::kKD + 2 <= 288 + 72 - 2 * G, "gain stage overlaps the reduction slots");
+    gK = gs + L::gK(N); gP = gs + L::gP(N); gpv = gs + L::gpv(N);
+    gmu = (flags & 2) ? sm + L::sMu(N, flags) : gs + L::gmu(N);
+    glin = (flags & 1) ? sm + L::sLinAll(N) : gs + L::glin(N);
+    lin_stride_is_resident = flags & 1;
+    DX = gs + L::gDX(N); gLX = gs + L::gLX(N);
+    gTX = trial; gTU = trial + (size_t)(N + 1) * M::NX * G;
+  }
+  // forward kernel: model, X, U, stage, reduction slots in shared memory; everything else in the problem block
+  QMPC_HD void bind_forward(double* sm, double* gs, double* trial, int N_, float h_, const double* wts) {
+    N = N_; h = h_; hd = (double)h_; hh = (double)(h_ / 2); c1 = hd * hh;
+    wq = wts; wr = wts + 13;
+    m = reinterpret_cast<M*>(sm);
+    X = sm + L::sX(N); U = sm + L::sU(N);
+    P = PA = T = PM = S = Qux = vec = lin = nullptr;
+    kstage = sm + L::fStage(N); dxs = kstage; red = sm + L::fRed(N);
+    gK = gs + L::gK(N); gP = gs + L::gP(N); gpv = gs + L::gpv(N);
+    gmu = gs + L::gmu(N); glin = gs + L::glin(N); lin_stride_is_resident = 0;
+    DX = gs + L::gDX(N); gLX = gs + L::gLX(N);
+    gTX = trial; gTU = trial + (size_t)(N + 1) * M::NX * G;
+  }
+};
+
+#define COOP_ARGS_DECL int lane_id, unsigned lane_mask
+#define COOP_ARGS lane_id, lane_mask
+
+// ------------------------------------------------------------------ set-up + nominal roll-out
+template <class M, int G>
+QMPC_HD inline void coop_phase_setup(CoopCtx<M, G>& c, const QmpcConfig& cfg, const SolverOpts& o,
+                                     const typename M::Problem* in, const unsigned char* sched, QmpcWarmStart* warm,
+                                     int pid, COOP_ARGS_DECL) {
+  constexpr int NC = M::NC;
   (void)lane_id; (void)lane_mask;
-  // weights with run-time indices come from `wts` (q[13], r[12]): a block-shared copy in shared memory on
-  // the device - an indexed read of the kernel parameter bank is an LDC that stalls like a global load
-  const double* wq = wts;
-  const double* wr = wts + 13;
-  const int N = o.N;
-  const float h = o.h;
-  const double hd = (double)h, hh = (double)(h / 2), c1 = hd * hh;
-
-  M& m = *reinterpret_cast<M*>(sm);
-  double* X = sm + L::sX(N);
-  double* U = sm + L::sU(N);
-  double* DX = gs + L::gDX(N);
-  double* gLX = gs + L::gLX(N);
-  double* gTX = gs + L::gTX(N);
-  double* gTU = gs + L::gTU(N);
-  double* P = sm + L::sP(N);
-  double* PA = sm + L::sPA(N);
-    double* T = sm + L::sT(N);
-  double* PM = sm + L::sPM(N);
-  double* SW = PM;
-  double* S = sm + L::sS(N);
-  double* Qux = sm + L::sQux(N);
-  double* vec = sm + L::sVec(N);
-  // 2 G reduction slots at the tail of T (only used outside the backward pass, where T is dead); the
-  // roll-out's gain stage (2 x (NU * 12 + NU) doubles) occupies P, PA and the head of T meanwhile
-  double* red = T + 72 - 2 * G;
-  static_assert(2 * (NU * 12 + NU) <= 288 + 72 - 2 * G, "gain stage overlaps the reduction slots");
-  double* lin = sm + L::sLin(N);
-  double* gK = gs + L::gK(N);
-  double* gd = gs + L::gd(N);
-  double* gP = gs + L::gP(N);
-  double* gpv = gs + L::gpv(N);
-  double* gmu = (flags & 2) ? sm + L::sMu(N, flags) : gs + L::gmu(N);
-  double* glin = (flags & 1) ? sm + L::sLinAll(N) : gs + L::glin(N);
-  double* scal = vec + cv::scal;
-
-  // ------------------------------------------------------------------ set-up + nominal roll-out
+  const int N = c.N;
   COOP_PHASE {
 #pragma unroll 1
-    for (int i = lane; i < N * NC; i += G) gmu[i] = 0.0;
+    for (int i = lane; i < N * NC; i += G) c.gmu[i] = 0.0;
     if (lane == 0) {
-      QmpcProblem prob = in[pid];
-      m.setup(cfg, prob, sched ? sched + (size_t)pid * QMPC_MAX_HORIZON : nullptr, X);
+      typename M::Problem prob = in[pid];
+      c.m->setup(cfg, prob, sched ? sched + (size_t)pid * QMPC_MAX_HORIZON : nullptr, c.X);
     }
   }
   COOP_SYNC();
-  double rho = o.penalty_initial;
-  constexpr int NCAND = G;
+  c.rho = o.penalty_initial;
+  double* scal = c.vec + CoopLayout<M, G>::vscal;
   COOP_PHASE {
-    if (lane == 0) coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, 0.0, 0, &scal[2], &scal[3], gTX, gTU, 0, G, P, lane_mask,
-                                     (warm && warm[pid].valid) ? warm + pid : nullptr);
+    if (lane == 0) coop_rollout<M>(*c.m, cfg, c.wr, N, c.h, c.X, c.U, c.gK, c.gmu, c.rho, 0.0, 0, &scal[2], &scal[3], c.gTX, c.gTU,
+                                   0, G, c.kstage, lane_mask, (warm && warm[pid].valid) ? warm + pid : nullptr);
   }
   COOP_SYNC();
-  double phi = scal[2], viol = scal[3];
-  int status = QMPC_STATUS_MAX_ITERATIONS, iters = 0;
-  double cost_decrease = INFINITY;
-  if (!isfinite(phi)) status = QMPC_STATUS_NONFINITE;
+  c.phi = scal[2]; c.viol = scal[3];
+  c.status = QMPC_STATUS_MAX_ITERATIONS; c.iters = 0;
+  c.cost_decrease = INFINITY; c.dphi0 = 0;
+  if (!isfinite(c.phi)) c.status = QMPC_STATUS_NONFINITE;
+}
 
-#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_BLOCK_SYNC)
-#define COOP_ITER_COND(it_) ((it_) < o.iterations_max)
-#define COOP_ITER_LEAVE continue
-#else
-#define COOP_ITER_COND(it_) ((it_) < o.iterations_max && status == QMPC_STATUS_MAX_ITERATIONS)
-#define COOP_ITER_LEAVE break
-#endif
+// ------------------------------------------------------------------ per-iteration "pre": expansions,
+// stationarity + convergence test, dual / penalty update, AL terms of every knot
+template <class M, int G>
+QMPC_HD inline void coop_phase_pre(CoopCtx<M, G>& c, const QmpcConfig& cfg, const SolverOpts& o, int it, COOP_ARGS_DECL) {
+  using L = CoopLayout<M, G>;
+  using Row = CoopRow<M>;
+  constexpr int NX = M::NX, NE = 12, NU = M::NU, NC = M::NC, NF = M::kFeet, NLIN = M::NLIN;
+  (void)lane_id; (void)lane_mask;
+  const int N = c.N;
+  const M& m = *c.m;
+  double *X = c.X, *U = c.U, *gLX = c.gLX, *glin = c.glin, *gmu = c.gmu, *DX = c.DX, *red = c.red;
+  const double* wr = c.wr;
+  const double hd = c.hd, hh = c.hh;
+  // ---------------- expansions, lane k <- knot k: cost gradient + attitude Hessian block (21 doubles) and
+  // the dynamics blocks (NLIN doubles).  The same X is used throughout the iteration: computed once,
+  // knot-parallel, reused by the stationarity test and the backward pass.
+  COOP_PHASE {
 #pragma unroll 1
-  for (int it = 0; COOP_ITER_COND(it); ++it) {
-    COOP_BLOCK_SYNC();
-#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_BLOCK_SYNC)
-    if (status != QMPC_STATUS_MAX_ITERATIONS) { COOP_KNOT_SYNC_ALL(N); COOP_BLOCK_SYNC_MID(); continue; }   // finished: keep passing the barriers
-#endif
-    // ---------------- expansions, lane k <- knot k: cost gradient + attitude Hessian block (21 doubles) and
-    // the dynamics blocks (27 doubles).  The cost expansion used to be recomputed by single lanes inside
-    // the backward pass (on its critical path, and 4 KB of code in its loop) and again for the
-    // stationarity test; it is the same X throughout the iteration.
+    for (int k = lane; k <= N; k += G) {
+      double lx[NE], Hk[9], hphi;
+      cost_expand(m, cfg, k, X + k * NX, lx, &hphi);
+      hphi_block<M>(cfg, X + k * NX, hphi, Hk);
+      for (int i = 0; i < NE; ++i) gLX[k * L::kRow + Row::lx + i] = lx[i];
+      for (int i = 0; i < 9; ++i) gLX[k * L::kRow + Row::Hphi + i] = Hk[i];
+      if (k < N) {
+        KnotLin4 Lk;
+        coop_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
+        double* gl = glin + k * L::kLinStride;
+        for (int i = 0; i < 9; ++i) {
+          gl[i] = Lk.Aff[i];
+          gl[9 + i] = Lk.Afw[i];
+          gl[18 + i] = Lk.Cf[i];
+          if (NLIN > 27) gl[(NLIN > 27 ? 27 : 0) + i] = Lk.Dw[i];
+        }
+      }
+    }
+  }
+  COOP_SYNC();
+
+  if (it > 0) {
+    // ---------------- stationarity with the Riccati duals of the accepted step (DX holds y_k)
     COOP_PHASE {
+      double rx = 0, ru = 0;
 #pragma unroll 1
       for (int k = lane; k <= N; k += G) {
-        double lx[NE], Hk[9], hphi;
-        cost_expand(m, cfg, k, X + k * NX, lx, &hphi);
-        hphi_block(cfg, X + k * NX, hphi, Hk);
-        for (int i = 0; i < NE; ++i) gLX[k * 21 + i] = lx[i];
-        for (int i = 0; i < 9; ++i) gLX[k * 21 + 12 + i] = Hk[i];
-        if (k < N) {
-          KnotLin Lk;
-          srb_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
+        double lx[NE];
+        for (int a = 0; a < NE; ++a) lx[a] = gLX[k * L::kRow + Row::lx + a];
+        if (k == N) {
+          for (int a = 0; a < NE; ++a) {
+            double v = fabs(lx[a] - DX[N * NE + a]);
+            if (v > rx) rx = v;
+          }
+        } else {
+          KnotLin4 Lk;
+          const double* gl = glin + k * L::kLinStride;
           for (int i = 0; i < 9; ++i) {
-            glin[k * 27 + i] = Lk.Aff[i];
-            glin[k * 27 + 9 + i] = Lk.Afw[i];
-            glin[k * 27 + 18 + i] = Lk.Cf[i];
+            Lk.Aff[i] = gl[i];
+            Lk.Afw[i] = gl[9 + i];
+            Lk.Cf[i] = gl[18 + i];
+            if (NLIN > 27) Lk.Dw[i] = gl[(NLIN > 27 ? 27 : 0) + i];
           }
-        }
-      }
-    }
-    COOP_SYNC();
-
-    if (it > 0) {
-      // ---------------- stationarity with the Riccati duals of the accepted step (DX holds y_k)
-      COOP_PHASE {
-        double rx = 0, ru = 0;
-#pragma unroll 1
-        for (int k = lane; k <= N; k += G) {
-          double lx[NE];
-          for (int a = 0; a < NE; ++a) lx[a] = gLX[k * 21 + a];
-          if (k == N) {
-            for (int a = 0; a < NE; ++a) {
-              double v = fabs(lx[a] - DX[N * NE + a]);
-              if (v > rx) rx = v;
-            }
-          } else {
-            KnotLin Lk;
-            for (int i = 0; i < 9; ++i) {
-              Lk.Aff[i] = glin[k * 27 + i];
-              Lk.Afw[i] = glin[k * 27 + 9 + i];
-              Lk.Cf[i] = glin[k * 27 + 18 + i];
-            }
-            const double* u = U + k * NU;
-            const double* yn = DX + (k + 1) * NE;
-            double Aty[NE], t6[6];
-            srb_At_vec(Lk, hd, yn, Aty);
-            srb_Mt_vec(Lk, hd, hh, yn, t6);
-            for (int a = 0; a < NE; ++a) {
-              double v = fabs(lx[a] + Aty[a] - DX[k * NE + a]);
-              if (v > rx) rx = v;
-            }
-            // input residual per foot, rolled (once per iteration: compact code beats unrolled speed):
-            // R (u - u_ref) + J^T max(0, mu + rho c) + W^T M^T y   (same accumulation order as al_terms)
-#pragma unroll 1
-            for (int f = 0; f < NF; ++f) {
-              const double* uf = u + 3 * f;
-              const double* IS = m.IS + 9 * f;
-              const double fzc_f = m.fzc(k, f);
-              double g0 = 0, g1 = 0, g2 = 0;
-#pragma unroll 1
-              for (int r = 0; r < 6; ++r) {
-                const double j0 = m.CR[3 * r], j1 = m.CR[3 * r + 1], j2 = m.CR[3 * r + 2];
-                double c = j0 * uf[0] + j1 * uf[1] + j2 * uf[2];
-                if (r == 4) c += -fzc_f;
-                const double est = gmu[k * NC + 6 * f + r] + rho * c;
-                if (est > 0) { g0 += j0 * est; g1 += j1 * est; g2 += j2 * est; }
-              }
-              const double b0 = m.inv_mass * t6[0] + IS[0] * t6[3] + IS[3] * t6[4] + IS[6] * t6[5];
-              const double b1 = m.inv_mass * t6[1] + IS[1] * t6[3] + IS[4] * t6[4] + IS[7] * t6[5];
-              const double b2 = m.inv_mass * t6[2] + IS[2] * t6[3] + IS[5] * t6[4] + IS[8] * t6[5];
-              const double v0 = fabs(wr[3 * f] * uf[0] + g0 + b0);
-              const double v1 = fabs(wr[3 * f + 1] * uf[1] + g1 + b1);
-              const double v2 = fabs(wr[3 * f + 2] * (uf[2] - m.urefz(k, f)) + g2 + b2);
-              if (v0 > ru) ru = v0;
-              if (v1 > ru) ru = v1;
-              if (v2 > ru) ru = v2;
-            }
+          const double* u = U + k * NU;
+          const double* yn = DX + (k + 1) * NE;
+          double Aty[NE], t6[6];
+          coop_At_vec<M>(Lk, hd, yn, Aty);
+          coop_Mt_vec<M>(Lk, hd, hh, yn, t6);
+          for (int a = 0; a < NE; ++a) {
+            double v = fabs(lx[a] + Aty[a] - DX[k * NE + a]);
+            if (v > rx) rx = v;
           }
-        }
-        red[lane] = rx > ru ? rx : ru;
-      }
-      COOP_SYNC();
-      double stat = 0;
-      for (int l = 0; l < G; ++l) stat = red[l] > stat ? red[l] : stat;
-      COOP_SYNC();
-      if (stat < o.tol_stationarity && viol < o.tol_primal_feasibility) {
-        status = QMPC_STATUS_SUCCESS;
-        COOP_KNOT_SYNC_ALL(N);
-        COOP_BLOCK_SYNC_MID();
-        COOP_ITER_LEAVE;
-      }
-      if (fabs(cost_decrease) < o.tol_cost_intermediate || stat < o.tol_stationarity) {
-        // dual update (row-parallel), penalty update, merit refresh (knot-parallel)
-        COOP_PHASE {
+          // input residual per foot, rolled (once per iteration: compact code beats unrolled speed):
+          // R (u - u_ref) + J^T max(0, mu + rho c) + W^T M^T y   (same accumulation order as al_terms)
 #pragma unroll 1
-          for (int idx = lane; idx < N * NC; idx += G) {
-            const int k = idx / NC, r = idx % NC, f = r / 6, rr = r % 6;
-            const double* u = U + k * NU + 3 * f;
-            double c = m.CR[3 * rr] * u[0] + m.CR[3 * rr + 1] * u[1] + m.CR[3 * rr + 2] * u[2];
-            if (rr == 4) c += -m.fzc(k, f);
-            const double est = gmu[idx] + rho * c;
-            gmu[idx] = est > 0 ? est : 0;
-          }
-        }
-        COOP_SYNC();
-        {
-          const double r = rho * o.penalty_scaling;
-          rho = r < o.penalty_max ? r : o.penalty_max;
-        }
-        COOP_PHASE {
-          double J = 0, vl = 0;
+          for (int f = 0; f < NF; ++f) {
+            const double* uf = u + 3 * f;
+            const double* IS = m.IS + 9 * f;
+            const double fzc_f = m.fzc(k, f);
+            double g0 = 0, g1 = 0, g2 = 0;
 #pragma unroll 1
-          for (int k = lane; k <= N; k += G) knot_merit(m, cfg, wr, k, N, X + k * NX, U + k * NU, gmu + k * NC, rho, J, vl);
-          red[lane] = J;
-          red[G + lane] = vl;
-        }
-        COOP_SYNC();
-        phi = 0;
-        viol = 0;
-        for (int l = 0; l < G; ++l) {
-          phi += red[l];
-          viol = red[G + l] > viol ? red[G + l] : viol;
-        }
-        COOP_SYNC();
-      }
-    }
-
-    // ---------------- Riccati backward pass.  Lane (br, bc) = (lane / 4, lane % 4) owns the 3x3 block
-    // (br, bc) of every 12x12 quantity; all inner indices are compile-time.
-    static_assert(G == 16, "block-per-lane mapping assumes 16 lanes per problem");
-    bool bp_ok = true;
-    double* Pc = P;   // value-function Hessian of knot k+1 (then the not-yet-corrected one of knot k)
-    double* Pw = PA;  // work buffer: P A, then Quu and its Cholesky factor, then the new P (ping-pong)
-    COOP_PHASE {
-#pragma unroll 1
-      for (int e = lane; e < 21; e += G) vec[(e < 12 ? cv::pv : cv::Hphi - 12) + e] = gLX[N * 21 + e];
-      if (lane == 0) scal[0] = 0.0;
-    }
-    COOP_SYNC();
-    COOP_PHASE {
-      const int br = lane >> 2, bc = lane & 3;
-      double o[9];
-      lxx_block(wq, vec + cv::Hphi, br, bc, o);
-      blk_store(Pc + 36 * br + 3 * bc, 12, o);
-      blk_store_keep(gP + (size_t)N * 144 + 36 * br + 3 * bc, 12, o);
-      if (lane < 12) st_keep(gpv + N * 12 + lane, vec[cv::pv + lane]);
-    }
-    COOP_SYNC();
-
-#pragma unroll 1
-#define COOP_KNOT_LEAVE break
-    for (int k = N - 1; k >= 0 && bp_ok; --k) {
-      // ---- phase A: stage the knot's 3x3 blocks; per-foot AL terms; cost expansion
-      COOP_PHASE {
-#pragma unroll 1
-        for (int e = lane; e < 27 + 21; e += G) {   // the knot's dynamics blocks and cost expansion
-          if (e < 27) lin[e] = glin[k * 27 + e];
-          else vec[(e < 27 + 12 ? cv::lx - 27 : cv::Hphi - 39) + e] = gLX[k * 21 + e - 27];
-        }
-        if (lane < NF) {
-          const int f = lane;
-          const double* u = U + k * NU + 3 * f;
-          double g0 = 0, g1 = 0, g2 = 0, hb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-          for (int r = 0; r < 6; ++r) {
-            double c = m.CR[3 * r] * u[0] + m.CR[3 * r + 1] * u[1] + m.CR[3 * r + 2] * u[2];
-            if (r == 4) c += -m.fzc(k, f);
-            const double est = gmu[k * NC + 6 * f + r] + rho * c;
-            if (est > 0) {
+            for (int r = 0; r < 6; ++r) {
               const double j0 = m.CR[3 * r], j1 = m.CR[3 * r + 1], j2 = m.CR[3 * r + 2];
-              g0 += j0 * est; g1 += j1 * est; g2 += j2 * est;
-              hb[0] += rho * j0 * j0; hb[1] += rho * j0 * j1; hb[2] += rho * j0 * j2;
-              hb[3] += rho * j1 * j0; hb[4] += rho * j1 * j1; hb[5] += rho * j1 * j2;
-              hb[6] += rho * j2 * j0; hb[7] += rho * j2 * j1; hb[8] += rho * j2 * j2;
+              double cc = j0 * uf[0] + j1 * uf[1] + j2 * uf[2];
+              if (r == 4) cc += -fzc_f;
+              const double est = gmu[k * NC + 6 * f + r] + c.rho * cc;
+              if (est > 0) { g0 += j0 * est; g1 += j1 * est; g2 += j2 * est; }
             }
-          }
-          hb[0] += wr[3 * f]; hb[4] += wr[3 * f + 1]; hb[8] += wr[3 * f + 2];
-#pragma unroll
-          for (int a = 0; a < 9; ++a) vec[cv::Dblk + 9 * f + a] = hb[a];
-          vec[cv::g + 3 * f] = wr[3 * f] * u[0] + g0;
-          vec[cv::g + 3 * f + 1] = wr[3 * f + 1] * u[1] + g1;
-          vec[cv::g + 3 * f + 2] = wr[3 * f + 2] * (u[2] - m.urefz(k, f)) + g2;
-        }
-      }
-      COOP_SYNC();
-      const double* Aff = lin;
-      const double* Afw = lin + 9;
-      const double* Cf = lin + 18;
-      const double* pv = vec + cv::pv;
-      // ---- phase B: PA = P A (16 blocks), PM = P M (8 blocks), s = M^T p, Atp = A^T p
-      COOP_PHASE {
-        const int br = lane >> 2, bc = lane & 3;
-        const double* Pr = Pc + 36 * br;
-        if (bc & 1) blk_right(Pr, 12, bc == 1 ? Aff : Afw, bc == 1 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
-        else blk_even(Pr, 12, bc == 0 ? 1.0 : hd, bc == 0 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
-        if (bc < 2) {
-          if (bc == 1) blk_right(Pr, 12, Cf, hd, PM + 18 * br + 3 * bc, 6);
-          else blk_even(Pr, 12, c1, hd, PM + 18 * br + 3 * bc, 6);
-        }
-        if (lane < 6) {
-          const int e = lane;
-          vec[cv::s + e] = e < 3 ? hd * hh * pv[e] + hd * pv[6 + e]
-                                 : Cf[e - 3] * pv[3] + Cf[e] * pv[4] + Cf[3 + e] * pv[5] + hd * pv[6 + e];
-        }
-        if (lane < 12) {
-          const int a = lane, ab = a / 3, aa = a % 3;
-          double v;
-          if (ab == 0) v = pv[a];
-          else if (ab == 1) v = Aff[aa] * pv[3] + Aff[3 + aa] * pv[4] + Aff[6 + aa] * pv[5];
-          else if (ab == 2) v = hd * pv[aa] + pv[6 + aa];
-          else v = Afw[aa] * pv[3] + Afw[3 + aa] * pv[4] + Afw[6 + aa] * pv[5] + pv[9 + aa];
-          vec[cv::Atp + a] = v;
-        }
-      }
-      COOP_SYNC();
-      // ---- phase C: P <- A^T PA + lxx (16 blocks), T = M^T PA (8 blocks), S = M^T PM (4 blocks), Qx
-      COOP_PHASE {
-        const int br = lane >> 2, bc = lane & 3;
-        const double* Yc = Pw + 3 * bc;
-        double* Pd = Pc + 36 * br + 3 * bc;
-        if (br & 1) blk_left(Yc, 12, br == 1 ? Aff : Afw, br == 1 ? 0.0 : 1.0, Pd, 12);
-        else blk_evenT(Yc, 12, br == 0 ? 1.0 : hd, br == 0 ? 0.0 : 1.0, Pd, 12);
-        if (br == bc) {   // + lxx on the diagonal blocks (the same lane just wrote the block)
-          if (br == 1) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int j = 0; j < 3; ++j) Pd[12 * i + j] += vec[cv::Hphi + 3 * i + j];
-          } else {
-            const int q0 = br == 0 ? 0 : (br == 2 ? 7 : 10);
-            Pd[0] += wq[q0]; Pd[13] += wq[q0 + 1]; Pd[26] += wq[q0 + 2];
-          }
-        }
-        if (br < 2) {
-          if (br == 1) blk_left(Yc, 12, Cf, hd, T + 36 * br + 3 * bc, 12);
-          else blk_evenT(Yc, 12, c1, hd, T + 36 * br + 3 * bc, 12);
-        }
-        if (lane >= 8 && lane < 12) {
-          const int r = (lane >> 1) & 1, c = lane & 1;
-          const double* Ym = PM + 3 * c;
-          if (r == 1) blk_left(Ym, 6, Cf, hd, S + 18 * r + 3 * c, 6);
-          else blk_evenT(Ym, 6, c1, hd, S + 18 * r + 3 * c, 6);
-        }
-        if (lane < 12) vec[cv::Qx + lane] = vec[cv::Atp + lane] + vec[cv::lx + lane];
-      }
-      COOP_SYNC();
-      // ---- phase D: Qux = W^T T (NF x 4 blocks), SW = S W (2 x NF blocks), Qu = g + W^T s
-      COOP_PHASE {
-        const int br = lane >> 2, bc = lane & 3;
-        if (br < NF) blk_wt(T + 3 * bc, 12, m.inv_mass, m.IS + 9 * br, Qux + 36 * br + 3 * bc, 12, nullptr);
-        if (br < 2 && bc < NF) blk_w(S + 18 * br, 6, m.inv_mass, m.IS + 9 * bc, SW + 3 * NU * br + 3 * bc, NU);
-        if (lane < NU) {
-          const int f = lane / 3, a = lane % 3;
-          const double* IS = m.IS + 9 * f;
-          const double* s = vec + cv::s;
-          vec[cv::Qu + lane] = (m.inv_mass * s[a] + IS[a] * s[3] + IS[3 + a] * s[4] + IS[6 + a] * s[5]) + vec[cv::g + lane];
-        }
-      }
-      COOP_SYNC();
-      // ---- phase E: Quu = D + W^T (S W)  (NF x NF blocks, into the work buffer)
-      double* Quu = Pw;
-      COOP_PHASE {
-        const int br = lane >> 2, bc = lane & 3;
-        if (br < NF && bc < NF)
-          blk_wt(SW + 3 * bc, NU, m.inv_mass, m.IS + 9 * br, Quu + 3 * NU * br + 3 * bc, NU,
-                 br == bc ? vec + cv::Dblk + 9 * br : nullptr);
-      }
-      COOP_SYNC();
-      // ---- Cholesky + both triangular solves, fused, per lane, entirely in registers.  Every lane
-      //      factors the 12x12 Quu redundantly (the kernel is latency- and shared-memory-bound, not
-      //      FLOP-bound: 16 lanes doing the same 364 flops cost the same issue slots as one) and then
-      //      solves for its own right-hand side (column `lane` of Qux; lane 12: Qu) with L still in
-      //      registers: no column exchange, no barrier, no shared-memory traffic for L (this replaced
-      //      ~300 LDS/STS and 24 barriers per knot).  Straight-line code; a non-positive pivot poisons
-      //      the lane's result and is reported through `ok`.  Same operation order per entry as the
-      //      variants below, so the results are bit-identical.
-      COOP_PHASE {
-        const int c = lane < 12 ? lane : 12;   // lanes 13..15 shadow the Qu column and store nothing
-        constexpr int NT = NU * (NU + 1) / 2;
-#define QMPC_TRI(i_, l_) ((i_) * ((i_) + 1) / 2 + (l_))
-        double Lr[NT], rd[NU], rhs[NU];
-#define QMPC_DIVD(x_, i_) { (x_) = (x_) * rd[i_]; }
-#pragma unroll
-        for (int i = 0; i < NU; ++i)
-#pragma unroll
-          for (int l = 0; l <= i; ++l) Lr[QMPC_TRI(i, l)] = Quu[NU * i + l];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) rhs[i] = c < 12 ? Qux[12 * i + c] : vec[cv::Qu + i];
-        bool ok = true;
-#pragma unroll
-        for (int j = 0; j < NU; ++j) {
-          const double sjj = Lr[QMPC_TRI(j, j)];
-          ok = ok && (sjj > 0.0);
-#ifdef QMPC_COOP_FAST_RECIP
-          const double rdg = qmpc_rsqrt(sjj);   // L(i,j) = a * rsqrt: 1-2 ulp from a / sqrt(sjj)
-          rd[j] = rdg;
-#pragma unroll
-          for (int i = j + 1; i < NU; ++i) Lr[QMPC_TRI(i, j)] *= rdg;
-#else
-          // sqrt and the divisions of the reference Cholesky, built from rsqrt + FMA corrections (Markstein): the
-          // quotients come out correctly rounded, i.e. equal to a / sqrt(sjj), at 2 extra FMAs each instead of a
-          // ~25-instruction IEEE division.  The plain reciprocal form was 1-2 ulp off and, with cond(Quu) up to
-          // 1e14, moved 1 solve in 65 536 by 3e-4 N against the oracle (division-based kernels: 4e-5 N there).
-          // Only the factor's quotients matter; the substitutions below keep the plain reciprocal (measured).
-          const double r0 = qmpc_rsqrt(sjj);
-          double dg = sjj * r0;
-          dg = fma(0.5 * fma(-dg, dg, sjj), r0, dg);          // sqrt(sjj), correctly rounded
-          const double rdg = fma(fma(-dg, r0, 1.0), r0, r0);  // 1 / dg
-          rd[j] = rdg;
-#pragma unroll
-          for (int i = j + 1; i < NU; ++i) {
-            const double a = Lr[QMPC_TRI(i, j)], q = a * rdg;
-            Lr[QMPC_TRI(i, j)] = fma(fma(-q, dg, a), rdg, q);   // a / dg
-          }
-#endif
-#pragma unroll
-          for (int i = j + 1; i < NU; ++i)
-#pragma unroll
-            for (int l = j + 1; l <= i; ++l) Lr[QMPC_TRI(i, l)] -= Lr[QMPC_TRI(i, j)] * Lr[QMPC_TRI(l, j)];
-        }
-        if (!ok) bp_ok = false;
-        // forward substitution, column oriented: after y_i is final every remaining entry updates independently
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-          QMPC_DIVD(rhs[i], i);
-#pragma unroll
-          for (int l = i + 1; l < NU; ++l) rhs[l] -= Lr[QMPC_TRI(l, i)] * rhs[i];
-        }
-        if (ok && lane <= 12) {
-          if (c < 12) {
-#pragma unroll
-            for (int i = 0; i < NU; ++i) Qux[12 * i + c] = rhs[i];   // V = L^-1 Qux
-          } else {
-#pragma unroll
-            for (int i = 0; i < NU; ++i) vec[cv::vu + i] = rhs[i];
-          }
-        }
-#pragma unroll
-        for (int i = NU - 1; i >= 0; --i) {
-          QMPC_DIVD(rhs[i], i);
-#pragma unroll
-          for (int l = 0; l < i; ++l) rhs[l] -= Lr[QMPC_TRI(i, l)] * rhs[i];
-        }
-#undef QMPC_TRI
-#undef QMPC_DIVD
-        if (ok && lane <= 12) {
-          if (c < 12) {
-#pragma unroll
-            for (int i = 0; i < NU; ++i) st_keep(gK + ((size_t)k * NU + i) * 12 + c, -rhs[i]);
-          } else {
-            double t = 0;
-#pragma unroll
-            for (int i = 0; i < NU; ++i) {
-              st_keep(gd + k * NU + i, -rhs[i]);
-              t += vec[cv::Qu + i] * (-rhs[i]);
-            }
-            scal[0] += t;
+            const double b0 = m.inv_mass * t6[0] + IS[0] * t6[3] + IS[3] * t6[4] + IS[6] * t6[5];
+            const double b1 = m.inv_mass * t6[1] + IS[1] * t6[3] + IS[4] * t6[4] + IS[7] * t6[5];
+            const double b2 = m.inv_mass * t6[2] + IS[2] * t6[3] + IS[5] * t6[4] + IS[8] * t6[5];
+            const double v0 = fabs(wr[3 * f] * uf[0] + g0 + b0);
+            const double v1 = fabs(wr[3 * f + 1] * uf[1] + g1 + b1);
+            const double v2 = fabs(wr[3 * f + 2] * (uf[2] - m.urefz(k, f)) + g2 + b2);
+            if (v0 > ru) ru = v0;
+            if (v1 > ru) ru = v1;
+            if (v2 > ru) ru = v2;
           }
         }
       }
-      COOP_SYNC();
-      if (!bp_ok) COOP_KNOT_LEAVE;
-      // ---- phase F: new P = sym(P) - V^T V (16 blocks, written to the work buffer: no race with the
-      //      transposed reads of Pc), pv <- Qx - V^T vu ; then swap the two buffers
-      COOP_PHASE {
-        const int br = lane >> 2, bc = lane & 3;
-        double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#ifndef QMPC_COOP_F_UNROLL
-#define QMPC_COOP_F_UNROLL 1
-#endif
-        constexpr int kFUnroll = QMPC_COOP_F_UNROLL;
-#pragma unroll(kFUnroll)
-        for (int l = 0; l < NU; ++l) {
-          const double* Vr = Qux + 12 * l + 3 * br;
-          const double* Vc = Qux + 12 * l + 3 * bc;
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) o[3 * a + b] += Vr[a] * Vc[b];
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int b = 0; b < 3; ++b)
-            o[3 * a + b] = 0.5 * (Pc[12 * (3 * br + a) + 3 * bc + b] + Pc[12 * (3 * bc + b) + 3 * br + a]) - o[3 * a + b];
-        blk_store(Pw + 36 * br + 3 * bc, 12, o);
-        blk_store_keep(gP + (size_t)k * 144 + 36 * br + 3 * bc, 12, o);
-        if (lane < 12) {
-          const int a = lane;
-          double t = 0;
-#pragma unroll 4
-          for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * vec[cv::vu + l];
-          const double v = vec[cv::Qx + a] - t;
-          vec[cv::pv + a] = v;
-          st_keep(gpv + k * 12 + a, v);
-        }
-      }
-      COOP_SYNC();
-      { double* t = Pc; Pc = Pw; Pw = t; }
+      red[lane] = rx > ru ? rx : ru;
     }
-    if (!bp_ok) { status = QMPC_STATUS_BACKWARD_FAILED; COOP_BLOCK_SYNC_MID(); COOP_ITER_LEAVE; }
-    COOP_BLOCK_SYNC_MID();
-    const double dphi0 = scal[0];
-
-    // ---------------- forward pass: speculative back-tracking line search.  Each round evaluates NCAND
-    // consecutive step lengths alpha = decrease^j at once (feet roll-out: NF lanes per step length, 4 per
-    // round for the quadruped; lane roll-out: one lane each, 16 per round); the first one passing the
-    // Armijo test wins - the result is identical to the sequential search.
-    int acc_j = -1;
-    double phin = 0, violn = 0, alpha_acc = 0;
-#pragma unroll 1
-    for (int round = 0; round * G < o.ls_iters_max && acc_j < 0; ++round) {
+    COOP_SYNC();
+    double stat = 0;
+    for (int l = 0; l < G; ++l) stat = red[l] > stat ? red[l] : stat;
+    COOP_SYNC();
+    if (stat < o.tol_stationarity && c.viol < o.tol_primal_feasibility) {
+      c.status = QMPC_STATUS_SUCCESS;
+      return;
+    }
+    if (fabs(c.cost_decrease) < o.tol_cost_intermediate || stat < o.tol_stationarity) {
+      // dual update (row-parallel), penalty update, merit refresh (knot-parallel)
       COOP_PHASE {
-        const int j = round * G + lane;
-        // every lane rolls out (lanes past ls_iters_max too: the roll-out stages the gains
-        // cooperatively); their result is discarded below
-        double J = NAN, vl = 0, alpha = 1.0;
-        for (int q = 0; q < j; ++q) alpha *= o.ls_decrease;
-        coop_rollout<NF>(m, cfg, wr, N, h, X, U, DX, gK, gd, gmu, rho, alpha, 1, &J, &vl, gTX, gTU, lane, G, P, lane_mask, nullptr);
-        red[lane] = j < o.ls_iters_max ? J : NAN;
-        red[G + lane] = vl;
+#pragma unroll 1
+        for (int idx = lane; idx < N * NC; idx += G) {
+          const int k = idx / NC, r = idx % NC, f = r / 6, rr = r % 6;
+          const double* u = U + k * NU + 3 * f;
+          double cc = m.CR[3 * rr] * u[0] + m.CR[3 * rr + 1] * u[1] + m.CR[3 * rr + 2] * u[2];
+          if (rr == 4) cc += -m.fzc(k, f);
+          const double est = gmu[idx] + c.rho * cc;
+          gmu[idx] = est > 0 ? est : 0;
+        }
       }
       COOP_SYNC();
       {
-        double alpha = 1.0;
-        for (int q = 0; q < round * G; ++q) alpha *= o.ls_decrease;
-        for (int l = 0; l < G && acc_j < 0; ++l) {
-          const double pl = red[l];
-          if (round * G + l < o.ls_iters_max && isfinite(pl) && pl <= phi + o.ls_c1 * alpha * dphi0) {
-            acc_j = round * G + l;
-            phin = pl;
-            violn = red[G + l];
-            alpha_acc = alpha;
-          }
-          alpha *= o.ls_decrease;
-        }
+        const double r = c.rho * o.penalty_scaling;
+        c.rho = r < o.penalty_max ? r : o.penalty_max;
+      }
+      COOP_PHASE {
+        double J = 0, vl = 0;
+#pragma unroll 1
+        for (int k = lane; k <= N; k += G) knot_merit(m, cfg, wr, k, N, X + k * NX, U + k * NU, gmu + k * NC, c.rho, J, vl);
+        red[lane] = J;
+        red[G + lane] = vl;
+      }
+      COOP_SYNC();
+      c.phi = 0;
+      c.viol = 0;
+      for (int l = 0; l < G; ++l) {
+        c.phi += red[l];
+        c.viol = red[G + l] > c.viol ? red[G + l] : c.viol;
       }
       COOP_SYNC();
     }
-    iters = it + 1;
-    if (acc_j < 0) { status = QMPC_STATUS_LINESEARCH_FAILED; COOP_ITER_LEAVE; }
-    // ---------------- accepted step: the winning lane's trial trajectory is already in the scratch.
-    // lane k <- knot k: dx_k = x_new (-) x_old, Riccati dual y_k = P_k dx_k + p_k (stored in DX) ...
-    const int acc_lane = acc_j % NCAND;
+  }
+  // ---------------- AL terms of every (knot, foot) with the duals / penalty now in force: input gradient
+  // g = R (u - u_ref) + J^T max(0, mu + rho c) and D block = R + rho J_a^T J_a.  (knot, foot)-parallel over the
+  // 16 lanes - off the critical path of the Riccati recursion, where 4 lanes used to compute them knot by knot.
+  COOP_PHASE {
+#pragma unroll 1
+    for (int idx = lane; idx < N * NF; idx += G) {
+      const int k = idx / NF, f = idx % NF;
+      const double* u = U + k * NU + 3 * f;
+      double g0 = 0, g1 = 0, g2 = 0, hb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+      for (int r = 0; r < 6; ++r) {
+        double cc = m.CR[3 * r] * u[0] + m.CR[3 * r + 1] * u[1] + m.CR[3 * r + 2] * u[2];
+        if (r == 4) cc += -m.fzc(k, f);
+        const double est = gmu[k * NC + 6 * f + r] + c.rho * cc;
+        if (est > 0) {
+          const double j0 = m.CR[3 * r], j1 = m.CR[3 * r + 1], j2 = m.CR[3 * r + 2];
+          g0 += j0 * est; g1 += j1 * est; g2 += j2 * est;
+          hb[0] += c.rho * j0 * j0; hb[1] += c.rho * j0 * j1; hb[2] += c.rho * j0 * j2;
+          hb[3] += c.rho * j1 * j0; hb[4] += c.rho * j1 * j1; hb[5] += c.rho * j1 * j2;
+          hb[6] += c.rho * j2 * j0; hb[7] += c.rho * j2 * j1; hb[8] += c.rho * j2 * j2;
+        }
+      }
+      hb[0] += wr[3 * f]; hb[4] += wr[3 * f + 1]; hb[8] += wr[3 * f + 2];
+      double* row = gLX + k * L::kRow;
+#pragma unroll
+      for (int a = 0; a < 9; ++a) row[Row::Dblk + 9 * f + a] = hb[a];
+      row[Row::g + 3 * f] = wr[3 * f] * u[0] + g0;
+      row[Row::g + 3 * f + 1] = wr[3 * f + 1] * u[1] + g1;
+      row[Row::g + 3 * f + 2] = wr[3 * f + 2] * (u[2] - m.urefz(k, f)) + g2;
+    }
+  }
+  COOP_SYNC();
+}
+
+// ------------------------------------------------------------------ Riccati backward pass.  Lane (br, bc) =
+// (lane / 4, lane % 4) owns the 3x3 block (br, bc) of every 12x12 quantity; all inner indices are compile-time.
+// Sets c.dphi0; on a non-positive pivot c.status = BACKWARD_FAILED.
+template <class M, int G>
+QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
+  using L = CoopLayout<M, G>;
+  using Row = CoopRow<M>;
+  constexpr int NU = M::NU, NF = M::kFeet, NLIN = M::NLIN;
+  // memory offsets of the state blocks by role (position, attitude, linear velocity, angular velocity)
+  constexpr int oP = 3 * (0 ^ M::kSwap), oA = 3 * (1 ^ M::kSwap), oV = 3 * (2 ^ M::kSwap), oW = 3 * (3 ^ M::kSwap);
+  static_assert(G == 16, "block-per-lane mapping assumes 16 lanes per problem");
+  (void)lane_id; (void)lane_mask;
+  const int N = c.N;
+  const M& m = *c.m;
+  double *P = c.P, *PA = c.PA, *T = c.T, *PM = c.PM, *S = c.S, *Qux = c.Qux, *vec = c.vec, *gLX = c.gLX;
+  double *gK = c.gK, *gP = c.gP, *gpv = c.gpv;
+  const double* wq = c.wq;
+  const double hd = c.hd, hh = c.hh, c1 = c.c1;
+  double* SW = PM;
+  double* scal = vec + L::vscal;
+  double* row = vec;                     // the knot row [lx | Hphi | g | Dblk] staged here
+  double* pvv = vec + L::vpv;
+  bool bp_ok = true;
+  double* Pc = P;   // value-function Hessian of knot k+1 (then the not-yet-corrected one of knot k)
+  double* Pw = PA;  // work buffer: P A, then Quu and its Cholesky factor, then the new P (ping-pong)
+  // knot row + (when they are not shared-memory residents) the linearisation blocks of knot k: copied into
+  // `vec` / `lin` with 16-byte cp.async requests, issued one knot AHEAD (after phase E of knot k+1, when the
+  // row of knot k+1 is dead) so that the L2 round trip hides behind the Cholesky and phase F
+  auto stage_row = [&](int k) {
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_ROW_PREFETCH)
+    coop_cp_async_row(row, gLX + (size_t)k * L::kRow, L::kRow, lane_id, G);
+    if (!c.lin_stride_is_resident) coop_cp_async_row(c.lin, c.glin + (size_t)k * L::kLinStride, L::kLinStride, lane_id, G);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#else
     COOP_PHASE {
 #pragma unroll 1
-      for (int k = lane; k <= N; k += G) {
-        double xn[NX], dx[NE];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) xn[i] = ld_stream(gTX + (size_t)(k * NX + i) * NCAND + acc_lane);
-        state_diff<M>(xn, X + k * NX, dx);
-        const double* Pk = gP + (size_t)k * 144;
-#ifndef QMPC_COOP_ACCEPT_UNROLL
-#define QMPC_COOP_ACCEPT_UNROLL 3
+      for (int e = lane; e < L::kRow; e += G) row[e] = gLX[(size_t)k * L::kRow + e];
+      if (!c.lin_stride_is_resident) {
+#pragma unroll 1
+        for (int e = lane; e < NLIN; e += G) c.lin[e] = c.glin[(size_t)k * L::kLinStride + e];
+      }
+    }
 #endif
-        // nearly rolled (once per iteration; the kernel is instruction-cache sensitive) yet several rows of
-        // P_k - 12 L2 loads each - are in flight per trip
-        constexpr int kAcceptUnroll = QMPC_COOP_ACCEPT_UNROLL;
-#pragma unroll(kAcceptUnroll)
-        for (int a = 0; a < NE; ++a) {
-          double t = ld_keep(gpv + k * 12 + a);
+  };
+  auto stage_wait = [&]() {
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_ROW_PREFETCH)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+    COOP_SYNC();
+  };
+  COOP_PHASE {
+#pragma unroll 1
+    for (int e = lane; e < 21; e += G) {
+      const double v = gLX[(size_t)N * L::kRow + e];
+      if (e < 12) pvv[e] = v; else row[Row::Hphi + e - 12] = v;
+    }
+    if (lane == 0) scal[0] = 0.0;
+  }
+  COOP_SYNC();
+  COOP_PHASE {
+    const int br = lane >> 2, bc = lane & 3;
+    double o[9];
+    lxx_block<M>(wq, row + Row::Hphi, br, bc, o);
+    blk_store(Pc + 36 * br + 3 * bc, 12, o);
+    blk_store_keep(gP + (size_t)N * 144 + 36 * br + 3 * bc, 12, o);
+    if (lane < 12) st_keep(gpv + N * 12 + lane, pvv[lane]);
+  }
+  COOP_SYNC();
+  stage_row(N - 1);
+
+#pragma unroll 1
+  for (int k = N - 1; k >= 0 && bp_ok; --k) {
+    stage_wait();   // the row of knot k (and its linearisation blocks) are in shared memory
+    const double* lin = c.lin_stride_is_resident ? c.glin + (size_t)k * L::kLinStride : c.lin;
+    const double* Aff = lin;
+    const double* Afw = lin + 9;
+    const double* Cf = lin + 18;
+    const double* Dw = lin + (NLIN > 27 ? 27 : 0);
+    (void)Dw;
+    const double* pv = pvv;
+    // ---- phase B: PA = P A (16 blocks), PM = P M (8 blocks), s = M^T p, Atp = A^T p
+    COOP_PHASE {
+      const int br = lane >> 2, bc = lane & 3, rc = bc ^ M::kSwap;   // rc: role of this lane's block column
+      const double* Pr = Pc + 36 * br;
+      if (rc & 1) blk_right(Pr, 12, oA, oW, rc == 1 ? Aff : Afw, rc == 1 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
+      else blk_even(Pr, 12, oP, oV, rc == 0 ? 1.0 : hd, rc == 0 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
+      if (bc < 2) {
+        if (bc == 1) {
+          if (M::kDw) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);
+          else blk_right(Pr, 12, oA, oW, Cf, hd, PM + 18 * br + 3 * bc, 6);
+        } else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
+      }
+      if (lane < 6) {
+        const int e = lane;
+        double v;
+        if (e < 3) v = hd * hh * pv[oP + e] + hd * pv[oV + e];
+        else if (M::kDw) v = Cf[e - 3] * pv[oA] + Cf[e] * pv[oA + 1] + Cf[3 + e] * pv[oA + 2] +
+                             (Dw[e - 3] * pv[oW] + Dw[e] * pv[oW + 1] + Dw[3 + e] * pv[oW + 2]);
+        else v = Cf[e - 3] * pv[oA] + Cf[e] * pv[oA + 1] + Cf[3 + e] * pv[oA + 2] + hd * pv[oW + e - 3];
+        vec[L::vs + e] = v;
+      }
+      if (lane < 12) {
+        const int a = lane, ab = (a / 3) ^ M::kSwap, aa = a % 3;   // ab: role of row a
+        double v;
+        if (ab == 0) v = pv[a];
+        else if (ab == 1) v = Aff[aa] * pv[oA] + Aff[3 + aa] * pv[oA + 1] + Aff[6 + aa] * pv[oA + 2];
+        else if (ab == 2) v = hd * pv[oP + aa] + pv[a];
+        else v = Afw[aa] * pv[oA] + Afw[3 + aa] * pv[oA + 1] + Afw[6 + aa] * pv[oA + 2] + pv[a];
+        vec[L::vAtp + a] = v;
+      }
+    }
+    COOP_SYNC();
+    // ---- phase C: P <- A^T PA + lxx (16 blocks), T = M^T PA (8 blocks), S = M^T PM (4 blocks), Qx
+    COOP_PHASE {
+      const int br = lane >> 2, bc = lane & 3, rr = br ^ M::kSwap;   // rr: role of this lane's block row
+      const double* Yc = Pw + 3 * bc;
+      double* Pd = Pc + 36 * br + 3 * bc;
+      if (rr & 1) blk_left(Yc, 12, oA, oW, rr == 1 ? Aff : Afw, rr == 1 ? 0.0 : 1.0, Pd, 12);
+      else blk_evenT(Yc, 12, oP, oV, rr == 0 ? 1.0 : hd, rr == 0 ? 0.0 : 1.0, Pd, 12);
+      if (br == bc) {   // + lxx on the diagonal blocks (the same lane just wrote the block)
+        if (rr == 1) {
 #pragma unroll
-          for (int b = 0; b < NE; ++b) t += ld_keep(Pk + 12 * a + b) * dx[b];
-          DX[k * NE + a] = t;
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Pd[12 * i + j] += row[Row::Hphi + 3 * i + j];
+        } else {
+          const int q0 = M::qoff(br);
+          Pd[0] += wq[q0]; Pd[13] += wq[q0 + 1]; Pd[26] += wq[q0 + 2];
+        }
+      }
+      if (br < 2) {
+        if (br == 1) {
+          if (M::kDw) blk_left2(Yc, 12, oA, oW, Cf, Dw, T + 36 * br + 3 * bc, 12);
+          else blk_left(Yc, 12, oA, oW, Cf, hd, T + 36 * br + 3 * bc, 12);
+        } else blk_evenT(Yc, 12, oP, oV, c1, hd, T + 36 * br + 3 * bc, 12);
+      }
+      if (lane >= 8 && lane < 12) {
+        const int r = (lane >> 1) & 1, cc = lane & 1;
+        const double* Ym = PM + 3 * cc;
+        if (r == 1) {
+          if (M::kDw) blk_left2(Ym, 6, oA, oW, Cf, Dw, S + 18 * r + 3 * cc, 6);
+          else blk_left(Ym, 6, oA, oW, Cf, hd, S + 18 * r + 3 * cc, 6);
+        } else blk_evenT(Ym, 6, oP, oV, c1, hd, S + 18 * r + 3 * cc, 6);
+      }
+      if (lane < 12) vec[L::vQx + lane] = vec[L::vAtp + lane] + row[Row::lx + lane];
+    }
+    COOP_SYNC();
+    // ---- phase D: Qux = W^T T (NF x 4 blocks), SW = S W (2 x NF blocks), Qu = g + W^T s
+    COOP_PHASE {
+      const int br = lane >> 2, bc = lane & 3;
+      if (br < NF) blk_wt(T + 3 * bc, 12, m.inv_mass, m.IS + 9 * br, Qux + 36 * br + 3 * bc, 12, nullptr);
+      if (br < 2 && bc < NF) blk_w(S + 18 * br, 6, m.inv_mass, m.IS + 9 * bc, SW + 3 * NU * br + 3 * bc, NU);
+      if (lane < NU) {
+        const int f = lane / 3, a = lane % 3;
+        const double* IS = m.IS + 9 * f;
+        const double* s = vec + L::vs;
+        vec[L::vQu + lane] = (m.inv_mass * s[a] + IS[a] * s[3] + IS[3 + a] * s[4] + IS[6 + a] * s[5]) + row[Row::g + lane];
+      }
+    }
+    COOP_SYNC();
+    // ---- phase E: Quu = D + W^T (S W)  (NF x NF blocks, into the work buffer)
+    double* Quu = Pw;
+    COOP_PHASE {
+      const int br = lane >> 2, bc = lane & 3;
+      if (br < NF && bc < NF)
+        blk_wt(SW + 3 * bc, NU, m.inv_mass, m.IS + 9 * br, Quu + 3 * NU * br + 3 * bc, NU,
+               br == bc ? row + Row::Dblk + 9 * br : nullptr);
+    }
+    COOP_SYNC();
+    if (k > 0) stage_row(k - 1);   // the row of knot k is dead from here on: bring the next one in meanwhile
+    // ---- Cholesky + both triangular solves, fused, per lane, entirely in registers.  Every lane
+    //      factors the NU x NU Quu redundantly (the kernel is latency- and shared-memory-bound, not
+    //      FLOP-bound: 16 lanes doing the same flops cost the same issue slots as one) and then
+    //      solves for its own right-hand side (column `lane` of Qux; lane 12: Qu) with L still in
+    //      registers: no column exchange, no barrier, no shared-memory traffic for L.  Straight-line code; a
+    //      non-positive pivot poisons the lane's result and is reported through `ok`.
+    COOP_PHASE {
+      const int cix = lane < 12 ? lane : 12;   // lanes 13..15 shadow the Qu column and store nothing
+      constexpr int NT = NU * (NU + 1) / 2;
+#define QMPC_TRI(i_, l_) ((i_) * ((i_) + 1) / 2 + (l_))
+      double Lr[NT], rd[NU], rhs[NU];
+#define QMPC_DIVD(x_, i_) { (x_) = (x_) * rd[i_]; }
+#pragma unroll
+      for (int i = 0; i < NU; ++i)
+#pragma unroll
+        for (int l = 0; l <= i; ++l) Lr[QMPC_TRI(i, l)] = Quu[NU * i + l];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) rhs[i] = cix < 12 ? Qux[12 * i + cix] : vec[L::vQu + i];
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        const double sjj = Lr[QMPC_TRI(j, j)];
+        ok = ok && (sjj > 0.0);
+#ifdef QMPC_COOP_FAST_RECIP
+        const double rdg = qmpc_rsqrt(sjj);   // L(i,j) = a * rsqrt: 1-2 ulp from a / sqrt(sjj)
+        rd[j] = rdg;
+#pragma unroll
+        for (int i = j + 1; i < NU; ++i) Lr[QMPC_TRI(i, j)] *= rdg;
+#else
+        // sqrt and the divisions of the reference Cholesky, built from rsqrt + FMA corrections (Markstein): the
+        // quotients come out correctly rounded, i.e. equal to a / sqrt(sjj), at 2 extra FMAs each instead of a
+        // ~25-instruction IEEE division.  The plain reciprocal form was 1-2 ulp off and, with cond(Quu) up to
+        // 1e14, moved 1 solve in 65 536 by 3e-4 N against the oracle (division-based kernels: 4e-5 N there).
+        // Only the factor's quotients matter; the substitutions below keep the plain reciprocal (measured).
+        const double r0 = qmpc_rsqrt(sjj);
+        double dg = sjj * r0;
+        dg = fma(0.5 * fma(-dg, dg, sjj), r0, dg);          // sqrt(sjj), correctly rounded
+        const double rdg = fma(fma(-dg, r0, 1.0), r0, r0);  // 1 / dg
+        rd[j] = rdg;
+#pragma unroll
+        for (int i = j + 1; i < NU; ++i) {
+          const double a = Lr[QMPC_TRI(i, j)], q = a * rdg;
+          Lr[QMPC_TRI(i, j)] = fma(fma(-q, dg, a), rdg, q);   // a / dg
+        }
+#endif
+#pragma unroll
+        for (int i = j + 1; i < NU; ++i)
+#pragma unroll
+          for (int l = j + 1; l <= i; ++l) Lr[QMPC_TRI(i, l)] -= Lr[QMPC_TRI(i, j)] * Lr[QMPC_TRI(l, j)];
+      }
+      if (!ok) bp_ok = false;
+      // forward substitution, column oriented: after y_i is final every remaining entry updates independently
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        QMPC_DIVD(rhs[i], i);
+#pragma unroll
+        for (int l = i + 1; l < NU; ++l) rhs[l] -= Lr[QMPC_TRI(l, i)] * rhs[i];
+      }
+      if (ok && lane <= 12) {
+        if (cix < 12) {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) Qux[12 * i + cix] = rhs[i];   // V = L^-1 Qux
+        } else {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) vec[L::vvu + i] = rhs[i];
+        }
+      }
+#pragma unroll
+      for (int i = NU - 1; i >= 0; --i) {
+        QMPC_DIVD(rhs[i], i);
+#pragma unroll
+        for (int l = 0; l < i; ++l) rhs[l] -= Lr[QMPC_TRI(i, l)] * rhs[i];
+      }
+#undef QMPC_TRI
+#undef QMPC_DIVD
+      if (ok && lane <= 12) {
+        double* gKk = gK + (size_t)k * L::kKD;
+        if (cix < 12) {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) st_keep(gKk + i * 12 + cix, -rhs[i]);
+        } else {
+          double t = 0;
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            st_keep(gKk + NU * 12 + i, -rhs[i]);
+            t += vec[L::vQu + i] * (-rhs[i]);
+          }
+          scal[0] += t;
         }
       }
     }
     COOP_SYNC();
-    // ... then X, U <- accepted trajectory (cooperative strided copy)
+    if (!bp_ok) break;
+    // ---- phase F: new P = sym(P) - V^T V (16 blocks, written to the work buffer: no race with the
+    //      transposed reads of Pc), pv <- Qx - V^T vu ; then swap the two buffers
     COOP_PHASE {
-#pragma unroll 1
-      for (int e = lane; e < (N + 1) * NX; e += G) X[e] = ld_stream(gTX + (size_t)e * NCAND + acc_lane);
-#pragma unroll 1
-      for (int e = lane; e < N * NU; e += G) U[e] = ld_stream(gTU + (size_t)e * NCAND + acc_lane);
+      const int br = lane >> 2, bc = lane & 3;
+      double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#ifndef QMPC_COOP_F_UNROLL
+#define QMPC_COOP_F_UNROLL 1
+#endif
+      constexpr int kFUnroll = QMPC_COOP_F_UNROLL;
+#pragma unroll(kFUnroll)
+      for (int l = 0; l < NU; ++l) {
+        const double* Vr = Qux + 12 * l + 3 * br;
+        const double* Vc = Qux + 12 * l + 3 * bc;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) o[3 * a + b] += Vr[a] * Vc[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+          o[3 * a + b] = 0.5 * (Pc[12 * (3 * br + a) + 3 * bc + b] + Pc[12 * (3 * bc + b) + 3 * br + a]) - o[3 * a + b];
+      blk_store(Pw + 36 * br + 3 * bc, 12, o);
+      blk_store_keep(gP + (size_t)k * 144 + 36 * br + 3 * bc, 12, o);
+      if (lane < 12) {
+        const int a = lane;
+        double t = 0;
+#pragma unroll 4
+        for (int l = 0; l < NU; ++l) t += Qux[12 * l + a] * vec[L::vvu + l];
+        const double v = vec[L::vQx + a] - t;
+        pvv[a] = v;
+        st_keep(gpv + k * 12 + a, v);
+      }
     }
     COOP_SYNC();
-    cost_decrease = phi - phin;
-    phi = phin;
-    viol = violn;
+    { double* t = Pc; Pc = Pw; Pw = t; }
   }
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_ROW_PREFETCH)
+  if (!bp_ok) asm volatile("cp.async.wait_all;" ::: "memory");   // a failed knot leaves its successor's row in flight
+#endif
+  if (!bp_ok) c.status = QMPC_STATUS_BACKWARD_FAILED;
+  c.dphi0 = scal[0];
+}
 
-  COOP_PHASE {
-    if (lane == 0) {
-      QmpcResult r;
-      m.write_result(U, r);
-      r.max_violation = viol;
-      r.iterations = iters;
-      r.status = status;
-      out[pid] = r;
-      if (warm) warm[pid].valid = status != QMPC_STATUS_NONFINITE;
-    }
-    if (warm) {
+// ------------------------------------------------------------------ forward pass: speculative back-tracking
+// line search (lane l rolls out alpha = decrease^(round*G + l); the first lane passing the Armijo test wins -
+// identical to the sequential search), then the accepted step.
+template <class M, int G>
+QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, const SolverOpts& o, int it, COOP_ARGS_DECL) {
+  constexpr int NX = M::NX, NE = 12, NU = M::NU, NCAND = G;
+  (void)lane_id; (void)lane_mask;
+  const int N = c.N;
+  const M& m = *c.m;
+  double *X = c.X, *U = c.U, *red = c.red, *DX = c.DX, *gTX = c.gTX, *gTU = c.gTU;
+  int acc_j = -1;
+  double phin = 0, violn = 0;
 #pragma unroll 1
-      for (int e = lane; e < N * 12; e += G) {
-        const int k = e / 12, i = e % 12;
-        warm[pid].u[k][i] = i < NU ? U[k * NU + i] : 0.0;
+  for (int round = 0; round * G < o.ls_iters_max && acc_j < 0; ++round) {
+    COOP_PHASE {
+      const int j = round * G + lane;
+      // every lane rolls out (lanes past ls_iters_max too: the roll-out stages the gains
+      // cooperatively); their result is discarded below
+      double J = NAN, vl = 0, alpha = 1.0;
+      for (int q = 0; q < j; ++q) alpha *= o.ls_decrease;
+      coop_rollout<M>(m, cfg, c.wr, N, c.h, X, U, c.gK, c.gmu, c.rho, alpha, 1, &J, &vl, gTX, gTU, lane, G, c.kstage, lane_mask, nullptr);
+      red[lane] = j < o.ls_iters_max ? J : NAN;
+      red[G + lane] = vl;
+    }
+    COOP_SYNC();
+    {
+      double alpha = 1.0;
+      for (int q = 0; q < round * G; ++q) alpha *= o.ls_decrease;
+      for (int l = 0; l < G && acc_j < 0; ++l) {
+        const double pl = red[l];
+        if (round * G + l < o.ls_iters_max && isfinite(pl) && pl <= c.phi + o.ls_c1 * alpha * c.dphi0) {
+          acc_j = round * G + l;
+          phin = pl;
+          violn = red[G + l];
+        }
+        alpha *= o.ls_decrease;
+      }
+    }
+    COOP_SYNC();
+  }
+  c.iters = it + 1;
+  if (acc_j < 0) { c.status = QMPC_STATUS_LINESEARCH_FAILED; return; }
+  // ---------------- accepted step: the winning lane's trial trajectory is already in the scratch.
+  const int acc_lane = acc_j % NCAND;
+#ifndef QMPC_COOP_ACCEPT_OLD
+  // (1) lane k <- knot k: dx_k = x_new (-) x_old into the shared dx buffer; (2) Riccati duals y_k = P_k dx_k + p_k
+  // with lane a <- ROW a of every knot: the 12 active lanes read 12 consecutive rows of P_k (1152 contiguous
+  // bytes per knot, 16-byte loads), four knots' loads in flight before the first FMA - three L2 round trips for
+  // the whole horizon where lane-per-knot needed a dozen (the accept step was 12.8 % of the solve's time for 4 %
+  // of its instructions, long-scoreboard 8.6).  Row sums run b = 0..11 as before: bit-identical.
+  double* dxs = c.dxs;
+  COOP_PHASE {
+#pragma unroll 1
+    for (int k = lane; k <= N; k += G) {
+      double xn[NX], dx[NE];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xn[i] = ld_stream(gTX + (size_t)(k * NX + i) * NCAND + acc_lane);
+      state_diff<M>(xn, X + k * NX, dx);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) dxs[k * NE + i] = dx[i];
+    }
+  }
+  COOP_SYNC();
+  COOP_PHASE {
+    if (lane < NE) {
+      const int a = lane;
+      constexpr int KB = 4;
+#pragma unroll 1
+      for (int k0 = 0; k0 <= N; k0 += KB) {
+        double2 pr[KB][6];
+        double t[KB];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          const int k = k0 + q <= N ? k0 + q : N;   // clamped: a redundant load instead of a branch
+          const double2* rowp = reinterpret_cast<const double2*>(c.gP + (size_t)k * 144 + 12 * a);
+#pragma unroll
+          for (int b = 0; b < 6; ++b) pr[q][b] = rowp[b];
+          t[q] = ld_keep(c.gpv + k * 12 + a);
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          const int k = k0 + q <= N ? k0 + q : N;
+          const double* dx = dxs + k * NE;
+#pragma unroll
+          for (int b = 0; b < 6; ++b) { t[q] += pr[q][b].x * dx[2 * b]; t[q] += pr[q][b].y * dx[2 * b + 1]; }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q)
+          if (k0 + q <= N) DX[(k0 + q) * NE + a] = t[q];
       }
     }
   }
   COOP_SYNC();
+#else
+  COOP_PHASE {
+#pragma unroll 1
+    for (int k = lane; k <= N; k += G) {
+      double xn[NX], dx[NE];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xn[i] = ld_stream(gTX + (size_t)(k * NX + i) * NCAND + acc_lane);
+      state_diff<M>(xn, X + k * NX, dx);
+      const double* Pk = c.gP + (size_t)k * 144;
+#pragma unroll 3
+      for (int a = 0; a < NE; ++a) {
+        double t = ld_keep(c.gpv + k * 12 + a);
+#pragma unroll
+        for (int b = 0; b < NE; ++b) t += ld_keep(Pk + 12 * a + b) * dx[b];
+        DX[k * NE + a] = t;
+      }
+    }
+  }
+  COOP_SYNC();
+#endif
+  // ... then X, U <- accepted trajectory (cooperative strided copy)
+  COOP_PHASE {
+#pragma unroll 1
+    for (int e = lane; e < (N + 1) * NX; e += G) X[e] = ld_stream(gTX + (size_t)e * NCAND + acc_lane);
+#pragma unroll 1
+    for (int e = lane; e < N * NU; e += G) U[e] = ld_stream(gTU + (size_t)e * NCAND + acc_lane);
+  }
+  COOP_SYNC();
+  c.cost_decrease = c.phi - phin;
+  c.phi = phin;
+  c.viol = violn;
+}
+
+// ------------------------------------------------------------------ result + warm-start buffer
+template <class M, int G>
+QMPC_HD inline void coop_phase_epilogue(CoopCtx<M, G>& c, QmpcResult* out, QmpcWarmStart* warm, int pid, double* stage30,
+                                        COOP_ARGS_DECL) {
+  constexpr int NU = M::NU;
+  (void)lane_id; (void)lane_mask;
+  const int N = c.N;
+  // lane 0 assembles the 240-byte result in shared memory, the 16 lanes store it as 30 coalesced 8-byte words
+  // (one lane issuing 30 dependent global stores sat at 4 % of the solve's time in round 1's profile)
+  COOP_PHASE {
+    if (lane == 0) {
+      QmpcResult& r = *reinterpret_cast<QmpcResult*>(stage30);
+      c.m->write_result(c.U, r);
+      r.max_violation = c.viol;
+      r.iterations = c.iters;
+      r.status = c.status;
+    }
+  }
+  COOP_SYNC();
+  COOP_PHASE {
+    static_assert(sizeof(QmpcResult) % 8 == 0, "QmpcResult is copied as 8-byte words");
+    double* dst = reinterpret_cast<double*>(out + pid);
+#pragma unroll 1
+    for (int e = lane; e < (int)(sizeof(QmpcResult) / 8); e += G) dst[e] = stage30[e];
+    if (warm) {
+      if (lane == 0) warm[pid].valid = c.status != QMPC_STATUS_NONFINITE;
+#pragma unroll 1
+      for (int e = lane; e < N * 12; e += G) {
+        const int k = e / 12, i = e % 12;
+        warm[pid].u[k][i] = i < NU ? c.U[k * NU + i] : 0.0;
+      }
+    }
+  }
+  COOP_SYNC();
+}
+
+// ------------------------------------------------------------------ the whole solve, fused (one persistent kernel)
+template <class M, int G>
+QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const typename M::Problem* in,
+                            const unsigned char* sched, QmpcWarmStart* warm, QmpcResult* out,
+                            int pid, double* sm, double* gs, int lane_id, unsigned lane_mask, int flags,
+                            const double* wts) {
+  using L = CoopLayout<M, G>;
+  CoopCtx<M, G> c;
+  c.bind(sm, gs, gs + L::gTX(o.N), o.N, o.h, flags, wts);
+  coop_phase_setup<M, G>(c, cfg, o, in, sched, warm, pid, COOP_ARGS);
+#pragma unroll 1
+  for (int it = 0; it < o.iterations_max; ++it) {
+    // block-level phase alignment: every thread of the block passes this barrier exactly iterations_max times
+    // per problem wave, finished slots included (see the header comment)
+    COOP_BLOCK_SYNC();
+    if (c.status != QMPC_STATUS_MAX_ITERATIONS) {
+#if defined(__CUDA_ARCH__) && defined(QMPC_COOP_BLOCK_SYNC)
+      continue;   // finished: keep passing the barriers
+#else
+      break;
+#endif
+    }
+    coop_phase_pre<M, G>(c, cfg, o, it, COOP_ARGS);
+    if (c.status != QMPC_STATUS_MAX_ITERATIONS) continue;
+    coop_phase_backward<M, G>(c, COOP_ARGS);
+    if (c.status != QMPC_STATUS_MAX_ITERATIONS) continue;
+    coop_phase_forward<M, G>(c, cfg, o, it, COOP_ARGS);
+  }
+  coop_phase_epilogue<M, G>(c, out, warm, pid, c.P, COOP_ARGS);
 }
 
 #ifdef __CUDACC__
@@ -1105,9 +1451,9 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const Qm
 #ifndef QMPC_COOP_MIN_BLOCKS
 #define QMPC_COOP_MIN_BLOCKS (256 / QMPC_COOP_BLOCK)   // 8 warps per SM at 255 registers
 #endif
-template <int NF, int G>
+template <class M, int G>
 __global__ void __launch_bounds__(QMPC_COOP_BLOCK, QMPC_COOP_MIN_BLOCKS)
-qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ in,
+qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const typename M::Problem* __restrict__ in,
                  const unsigned char* __restrict__ sched, QmpcWarmStart* __restrict__ warm,
                  QmpcResult* __restrict__ out,
                  double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot, int wide,
@@ -1134,14 +1480,14 @@ qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const QmpcProblem* __restrict__ i
   for (int base = 0; base < batch; base += nslots) {
     const int pid = base + slot;
     if (!idle && pid < batch) {
-      coop_solve_one<NF, G>(cfg, o, in, sched, warm, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
+      coop_solve_one<M, G>(cfg, o, in, sched, warm, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
     } else {
-      for (int it = 0; it < o.iterations_max; ++it) { COOP_BLOCK_SYNC(); COOP_KNOT_SYNC_ALL(o.N); COOP_BLOCK_SYNC_MID(); }
+      for (int it = 0; it < o.iterations_max; ++it) { COOP_BLOCK_SYNC(); }
     }
   }
 #else
   for (int pid = slot; !idle && pid < batch; pid += nslots) {
-    coop_solve_one<NF, G>(cfg, o, in, sched, warm, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
+    coop_solve_one<M, G>(cfg, o, in, sched, warm, out, pid, sm, gs, lane_id, lane_mask, wide, smem_pool);
   }
 #endif
 }

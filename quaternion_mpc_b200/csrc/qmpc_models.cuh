@@ -17,6 +17,7 @@
 // host-only translation units (tests/emul: runs the very same solver bodies on the CPU so they can
 // be debugged in a GPU-less container; never part of libqmpc_b200.so)
 #define QMPC_HD
+struct double2 { double x, y; };
 #endif
 
 #include "../../include/qmpc.h"
@@ -113,6 +114,13 @@ struct QuatModel {
   static constexpr int NX = 13, NE = 12, NU = 3 * NF, NC = 6 * NF, QI = 3;
   static constexpr bool kQuat = true;
   using Problem = QmpcProblem;
+  // structure seen by the cooperative kernel (qmpc_coop.cuh): error-state blocks in memory order
+  // [position, attitude, linear velocity, angular velocity] (kSwap = 0), three knot-dependent 3x3 blocks
+  // (Aff, Afw, Cf), the (angular velocity, moment) block of M is h I
+  static constexpr int kFeet = NF, kSwap = 0, NLIN = 27;
+  static constexpr bool kDw = false;
+  // index of the first weight of error-state block b in q_weights (the attitude block has its own Hessian)
+  QMPC_HD static constexpr int qoff(int b) { return b == 0 ? 0 : (b == 2 ? 7 : 10); }
 
   double foot[3 * NF];
   double IS[9 * NF];  // Iinv * skew(r_i), 3x3 row-major per foot  (AltroUtils.cpp:433)
@@ -201,6 +209,40 @@ struct QuatModel {
     for (int a = 0; a < 3; ++a) xd[10 + a] = Iinv[3 * a] * mom[0] + Iinv[3 * a + 1] * mom[1] + Iinv[3 * a + 2] * mom[2];
   }
 
+  // One explicit-midpoint step driven by the net wrench of the feet (fs = sum f_i, mom = sum r_i x f_i): the
+  // roll-outs of the cooperative kernel never form u as an array.  Same expressions, in the same order, as
+  // ct_dyn / mid_dyn (AltroUtils.cpp:9-22, 383-391).
+  QMPC_HD void wrench_step(double* x, double fs0, double fs1, double fs2, double mom0, double mom1, double mom2,
+                           double hd, double hh) const {
+    mom0 += tau_g[0]; mom1 += tau_g[1]; mom2 += tau_g[2];
+    const double al0 = fs0 * inv_mass + g[0], al1 = fs1 * inv_mass + g[1], al2 = fs2 * inv_mass + g[2];
+    const double aw0 = Iinv[0] * mom0 + Iinv[1] * mom1 + Iinv[2] * mom2;
+    const double aw1 = Iinv[3] * mom0 + Iinv[4] * mom1 + Iinv[5] * mom2;
+    const double aw2 = Iinv[6] * mom0 + Iinv[7] * mom1 + Iinv[8] * mom2;
+    double xm[NX];
+    {
+      const double *q = x + 3, *w = x + 10;
+      xm[0] = x[7] * hh + x[0]; xm[1] = x[8] * hh + x[1]; xm[2] = x[9] * hh + x[2];
+      xm[3] = (0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2])) * hh + q[0];
+      xm[4] = (0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2])) * hh + q[1];
+      xm[5] = (0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2])) * hh + q[2];
+      xm[6] = (0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2])) * hh + q[3];
+      xm[7] = al0 * hh + x[7]; xm[8] = al1 * hh + x[8]; xm[9] = al2 * hh + x[9];
+      xm[10] = aw0 * hh + x[10]; xm[11] = aw1 * hh + x[11]; xm[12] = aw2 * hh + x[12];
+    }
+    {
+      const double *q = xm + 3, *w = xm + 10;
+      const double qd0 = 0.5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
+      const double qd1 = 0.5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
+      const double qd2 = 0.5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
+      const double qd3 = 0.5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
+      x[0] = x[0] + hd * xm[7]; x[1] = x[1] + hd * xm[8]; x[2] = x[2] + hd * xm[9];
+      x[3] = x[3] + hd * qd0; x[4] = x[4] + hd * qd1; x[5] = x[5] + hd * qd2; x[6] = x[6] + hd * qd3;
+      x[7] = x[7] + hd * al0; x[8] = x[8] + hd * al1; x[9] = x[9] + hd * al2;
+      x[10] = x[10] + hd * aw0; x[11] = x[11] + hd * aw1; x[12] = x[12] + hd * aw2;
+    }
+  }
+
   // dense column-major NX x (NX+NU)
   QMPC_HD void ct_jac(const double* x, const double* u, double* J) const {
     (void)u;
@@ -244,8 +286,17 @@ struct ConvexModel {
   static constexpr int NX = 12, NE = 12, NU = 12, NC = 24, QI = -1;
   static constexpr bool kQuat = false;
   using Problem = QmpcConvexProblem;
+  // structure seen by the cooperative kernel: state blocks in memory order [attitude (rpy), position, angular
+  // velocity, linear velocity] = the quaternion model's roles with neighbours swapped (kSwap = 1); FOUR
+  // knot-dependent 3x3 blocks: Aff, Afw, Cf and Dw = h (Rz I Rz^T)^-1 at the midpoint yaw, the (angular
+  // velocity, moment) block of M (the inertia is yaw-dependent here, so it cannot be folded into W)
+  static constexpr int kFeet = 4, kSwap = 1, NLIN = 36;
+  static constexpr bool kDw = true;
+  QMPC_HD static constexpr int qoff(int b) { return 3 * b; }
 
   double foot[12];
+  double IS[36];   // skew(r_i), 3x3 row-major per foot: the moment rows of W
+  double inv_mass;
   double CR[18];
   ContactPlan cp;
   double xr0[12], yaw_rate, dtk;
@@ -257,6 +308,12 @@ struct ConvexModel {
 
   QMPC_HD void setup(const QmpcConfig& cfg, const QmpcConvexProblem& in, const unsigned char* sched, double* x0) {
     for (int i = 0; i < 12; ++i) foot[i] = in.foot_pos_abs_com[i];
+    for (int i = 0; i < 4; ++i) {
+      const double* r = foot + 3 * i;
+      const double S[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+      for (int a = 0; a < 9; ++a) IS[9 * i + a] = S[a];
+    }
+    inv_mass = 1.0 / 12.84;   // hard-coded mass of ct_srb_dynamics, AltroUtils.cpp:239
     for (int i = 0; i < 9; ++i) R0[i] = in.torso_rot_mat[i];
     fill_cone(cfg.mu, nullptr, CR);
     cp.fill(4, cfg.horizon, in.plan_contacts, sched, cfg.robot_mass * cfg.gravity, cfg.fz_max, true);
@@ -303,6 +360,41 @@ struct ConvexModel {
           BS[9 * i + 3 * a + b] = s;
         }
     }
+  }
+
+  // (Rz I_t Rz^T)^-1 = Rz I_t^-1 Rz^T in closed form (I_t diagonal, AltroUtils.cpp:268-270): symmetric, block
+  // diagonal; returns i00, i01, i11, i22.  Used by the cooperative kernel's roll-outs and linearisation.
+  QMPC_HD static void Iw_inv(double sy, double cy, double* iw) {
+    const double ia = 1.0 / 0.0168128557, ib = 1.0 / 0.063009565, ic = 1.0 / 0.0716547275;
+    iw[0] = ia * cy * cy + ib * sy * sy;
+    iw[1] = (ia - ib) * sy * cy;
+    iw[2] = ia * sy * sy + ib * cy * cy;
+    iw[3] = ic;
+  }
+  // continuous dynamics from the net wrench (world frame): xd = f(x, fs, mom)
+  QMPC_HD void wrench_dyn(const double* x, double fs0, double fs1, double fs2, double mom0, double mom1, double mom2,
+                          double* xd) const {
+    double sy, cy, iw[4];
+    sy = sin(x[2]); cy = cos(x[2]);
+    Iw_inv(sy, cy, iw);
+    xd[0] = cy * x[6] + sy * x[7];
+    xd[1] = -sy * x[6] + cy * x[7];
+    xd[2] = x[8];
+    xd[3] = x[9]; xd[4] = x[10]; xd[5] = x[11];
+    xd[6] = iw[0] * mom0 + iw[1] * mom1;
+    xd[7] = iw[1] * mom0 + iw[2] * mom1;
+    xd[8] = iw[3] * mom2;
+    xd[9] = fs0 * inv_mass; xd[10] = fs1 * inv_mass; xd[11] = fs2 * inv_mass + -9.81;
+  }
+  QMPC_HD void wrench_step(double* x, double fs0, double fs1, double fs2, double mom0, double mom1, double mom2,
+                           double hd, double hh) const {
+    double xd[NX], xm[NX];
+    wrench_dyn(x, fs0, fs1, fs2, mom0, mom1, mom2, xd);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xm[i] = xd[i] * hh + x[i];
+    wrench_dyn(xm, fs0, fs1, fs2, mom0, mom1, mom2, xd);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = x[i] + hd * xd[i];
   }
 
   QMPC_HD void ct_dyn(const double* x, const double* u, double* xd) const {

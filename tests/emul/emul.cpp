@@ -13,6 +13,7 @@
 #ifdef QMPC_EMUL_SRB
 #include "../../quaternion_mpc_b200/csrc/qmpc_srb.cuh"
 #include "../../quaternion_mpc_b200/csrc/qmpc_coop.cuh"
+#include "../../quaternion_mpc_b200/csrc/qmpc_phased.cuh"
 #endif
 
 using namespace qmpc;
@@ -63,26 +64,58 @@ extern "C" int emul_solve_srb(const QmpcConfig* cfg, const QmpcProblem* in, cons
   return -1;
 }
 
-template <int NF, int G>
-static int run_coop(const QmpcConfig& cfg, const QmpcProblem* in, const unsigned char* sched, QmpcWarmStart* warm, int batch, QmpcResult* out) {
+template <class M, int G>
+static int run_coop(const QmpcConfig& cfg, const typename M::Problem* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                    QmpcResult* out) {
   SolverOpts o = make_opts(cfg);
-  using L = CoopLayout<NF, G>;
+  using L = CoopLayout<M, G>;
   const int wide = cfg.horizon <= 10 ? 3 : (cfg.horizon <= 16 ? 2 : 0);
   std::vector<double> sm(L::smem_doubles(cfg.horizon, wide)), gs(L::scratch_doubles(cfg.horizon));
   double wts[26];
   for (int i = 0; i < 13; ++i) wts[i] = cfg.q_weights[i];
   for (int i = 0; i < 12; ++i) wts[13 + i] = cfg.r_weights[i];
-  for (int i = 0; i < batch; ++i) coop_solve_one<NF, G>(cfg, o, in, sched, warm, out, i, sm.data(), gs.data(), 0, 0u, wide, wts);
+  for (int i = 0; i < batch; ++i) coop_solve_one<M, G>(cfg, o, in, sched, warm, out, i, sm.data(), gs.data(), 0, 0u, wide, wts);
   return 0;
 }
-extern "C" int emul_solve_coop(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+// `in`: QmpcProblem (QUAT models) or QmpcConvexProblem (EULER_CONVEX) records
+extern "C" int emul_solve_coop(const QmpcConfig* cfg, const void* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
                                QmpcResult* out) {
-  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_coop<4, 16>(*cfg, in, sched, warm, batch, out);
-  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_coop<2, 16>(*cfg, in, sched, warm, batch, out);
-  return -1;
+  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_coop<QuatModel<4>, 16>(*cfg, (const QmpcProblem*)in, sched, warm, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_coop<QuatModel<2>, 16>(*cfg, (const QmpcProblem*)in, sched, warm, batch, out);
+  return run_coop<ConvexModel, 16>(*cfg, (const QmpcConvexProblem*)in, sched, nullptr, batch, out);
+}
+
+// the phased path on the host: the same phase functions, one phase per "launch", the solver state stored to and
+// reloaded from the per-problem block between them exactly as the split kernels do (qmpc_phased.cuh)
+template <class M, int G>
+static int run_phased(const QmpcConfig& cfg, const typename M::Problem* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                      QmpcResult* out) {
+  SolverOpts o = make_opts(cfg);
+  using L = CoopLayout<M, G>;
+  const int N = cfg.horizon;
+  const size_t pstride = L::problem_doubles(N);
+  std::vector<double> ws(pstride * batch), trial(L::trial_doubles(N));
+  std::vector<double> smB(L::smem_doubles(N, 1)), smF(L::fwd_smem_doubles(N));
+  double wts[26];
+  for (int i = 0; i < 13; ++i) wts[i] = cfg.q_weights[i];
+  for (int i = 0; i < 12; ++i) wts[13 + i] = cfg.r_weights[i];
+  for (int i = 0; i < batch; ++i) phased_setup_one<M, G>(cfg, o, in, sched, warm, out, i, ws.data() + pstride * i, wts);
+  for (int it = 0; it < o.iterations_max; ++it) {
+    for (int i = 0; i < batch; ++i)
+      phased_backward_one<M, G>(cfg, o, it, warm, out, i, smB.data(), ws.data() + pstride * i, 0, 0u, 1, wts);
+    for (int i = 0; i < batch; ++i)
+      phased_forward_one<M, G>(cfg, o, it, warm, out, i, smF.data(), ws.data() + pstride * i, trial.data(), 0, 0u, wts);
+  }
+  return 0;
+}
+extern "C" int emul_solve_phased(const QmpcConfig* cfg, const void* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                                 QmpcResult* out) {
+  if (cfg->model == QMPC_MODEL_QUAT_4FOOT) return run_phased<QuatModel<4>, 16>(*cfg, (const QmpcProblem*)in, sched, warm, batch, out);
+  if (cfg->model == QMPC_MODEL_QUAT_2FOOT) return run_phased<QuatModel<2>, 16>(*cfg, (const QmpcProblem*)in, sched, warm, batch, out);
+  return run_phased<ConvexModel, 16>(*cfg, (const QmpcConvexProblem*)in, sched, nullptr, batch, out);
 }
 extern "C" int emul_coop_smem_bytes(int nf, int horizon) {
-  return 8 * (nf == 4 ? CoopLayout<4, 16>::smem_doubles(horizon, 0) : CoopLayout<2, 16>::smem_doubles(horizon, 0));
+  return 8 * (nf == 4 ? CoopLayout<QuatModel<4>, 16>::smem_doubles(horizon, 0) : CoopLayout<QuatModel<2>, 16>::smem_doubles(horizon, 0));
 }
 #endif
 

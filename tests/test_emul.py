@@ -25,7 +25,7 @@ def emul(tmp_path_factory):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DQMPC_EMUL_SRB", "-ffp-contract=off",
                            "-o", so, os.path.join(HERE, "emul", "emul.cpp")])
     lib = C.CDLL(so)
-    for name in ("emul_solve_dense", "emul_solve_srb", "emul_solve_coop"):
+    for name in ("emul_solve_dense", "emul_solve_srb", "emul_solve_coop", "emul_solve_phased"):
         getattr(lib, name).argtypes = [C.POINTER(abi.QmpcConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p]
     lib.emul_predict_schedule.argtypes = [C.POINTER(abi.QmpcConfig), C.c_void_p, C.c_int, C.c_void_p]
@@ -102,6 +102,43 @@ def test_warm_start_bodies(emul, oracle, kernel):
     a1, r1 = _run(emul, kernel, cfg, p, None, w), oracle.solve_batch_warm(cfg, p, wr, nthreads=4)
     _agree(a1, r1, max_flagged=0.3)   # warm-started iterates sit closer to the line-search floor
     assert np.abs(a1["grf_body"] - a0["grf_body"]).max() > 1e-6        # the warm start changed the iterate
+
+
+@pytest.mark.parametrize("N,dt", [(10, 0.005), (20, 0.005), (30, 0.008)])
+def test_convex_cooperative_body(emul, oracle, N, dt):
+    """Row A8 on the cooperative design: ConvexMpc's Euler SRB through the same phase functions (state blocks
+    swapped pairwise, fourth knot block Dw) against the oracle and the generic dense body, at the shipped
+    horizons / steps (config/gazebo_go1_convex_mpc.yaml:36-37, hardware_go1_convex_mpc.yaml:36-37)."""
+    cfg = default_config(abi.QMPC_MODEL_EULER_CONVEX, N)
+    cfg.dt = dt
+    p = random_convex_batch(16, seed=30 + N)
+    ref = oracle.solve_batch_convex(cfg, p, nthreads=4)
+    a = _run(emul, "emul_solve_coop", cfg, p)
+    e = _agree(a, ref)
+    b = _run(emul, "emul_solve_phased", cfg, p)
+    assert a.tobytes() == b.tobytes()
+    sched = predict_schedule_numpy(random_gait_states(16, seed=31), N, cfg.dt)
+    _agree(_run(emul, "emul_solve_coop", cfg, p, sched), oracle.solve_batch_convex_sched(cfg, p, sched, nthreads=4))
+    print(f"convex coop N={N}: max|dGRF| = {e:.2e}")
+
+
+@pytest.mark.parametrize("model,N,gait", [(0, 10, "trot"), (0, 16, "mixed"), (1, 20, "stand"), (0, 1, "trot"), (0, 32, "trot")])
+def test_phased_path_is_bit_identical_to_fused(emul, oracle, model, N, gait):
+    """The split launches (set-up / backward / forward, solver state stored to and reloaded from the per-problem
+    block between them) run the very phase functions of the fused kernel: identical results, bit for bit -
+    including schedules, warm starts and a problem that stops early."""
+    cfg = default_config(model, N)
+    p = random_batch(24, seed=50 + N, gait=gait, **({"nfeet": 2, "max_angle": 0.2} if model == 1 else {}))
+    p["torso_lin_vel_world"][3, 0] = np.nan       # non-finite: finishes in the set-up launch
+    a, b = _run(emul, "emul_solve_coop", cfg, p), _run(emul, "emul_solve_phased", cfg, p)
+    assert a.tobytes() == b.tobytes()
+    sched = predict_schedule_numpy(random_gait_states(24, seed=51), N, cfg.dt)
+    wa, wb = np.zeros(24, dtype=abi.WARM_DTYPE), np.zeros(24, dtype=abi.WARM_DTYPE)
+    for tick in range(2):
+        a, b = _run(emul, "emul_solve_coop", cfg, p, sched, wa), _run(emul, "emul_solve_phased", cfg, p, sched, wb)
+        assert a.tobytes() == b.tobytes() and wa.tobytes() == wb.tobytes()
+    cfg.iterations_max = 0
+    assert _run(emul, "emul_solve_coop", cfg, p).tobytes() == _run(emul, "emul_solve_phased", cfg, p).tobytes()
 
 
 def test_two_foot_model_body(emul, oracle):

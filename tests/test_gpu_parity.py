@@ -451,7 +451,7 @@ def _golden_problem():
     return cfg, p
 
 
-@pytest.mark.parametrize("kernel", ["coop", "srb", "dense"])
+@pytest.mark.parametrize("kernel", ["coop", "phased", "srb", "dense"])
 def test_reference_golden_vector_through_the_cuda_path(kernel):
     """quat_mpc_test.json is the output of the REAL ALTRO fork on TestAltroQuatMpc.cpp (the only reference-held
     vector the C-ABI can express).  The CUDA path itself - not only the oracle - must reproduce its first-step GRFs
@@ -473,6 +473,54 @@ def test_reference_golden_vector_through_the_cuda_path(kernel):
     print(f"[golden via {kernel}: |u0 - golden| = {e0:.2e} N, |U - golden| = {eU:.2e} N, {res['iterations'][0]} iterations]", end=" ")
     assert e0 < 2e-6 and eU < 1e-5
     assert np.abs(res["grf_world"][0] - res["grf_body"][0]).max() == 0.0     # identity attitude
+
+
+@pytest.mark.parametrize("model,N,B,gait", [(0, 10, 4096, "trot"), (0, 16, 3000, "mixed"), (1, 20, 1000, "stand"), (2, 10, 2048, "trot"),
+                                              (0, 32, 200, "trot"), (0, 1, 77, "trot")])
+def test_phased_launches_bit_identical_to_fused_kernel(oracle, model, N, B, gait):
+    """QMPC_KERNEL_PHASED (set-up / backward / forward launches, solver state through L2/HBM) runs the very phase
+    functions of the fused persistent kernel: bit-identical results for every model, with schedules and warm
+    starts, ragged batches and early finishers."""
+    import torch
+    from quaternion_mpc_b200 import ConvexMpc, QuatMpc
+    cfg = default_config(model, N)
+    Mpc = ConvexMpc if model == 2 else QuatMpc
+    probs = random_convex_batch(B, seed=90 + N) if model == 2 else \
+        random_batch(B, seed=90 + N, gait=gait, **({"nfeet": 2, "max_angle": 0.2} if model == 1 else {}))
+    if model != 2:
+        probs["torso_lin_vel_world"][B // 2, 0] = np.nan      # finishes in the set-up launch
+    fused, phased = Mpc(max_batch=B, cfg=cfg), Mpc(max_batch=B, cfg=cfg, kernel="phased")
+    assert "kernel=phased" in phased.describe()
+    a, b = _solve_dev(fused, probs), _solve_dev(phased, probs)
+    assert a.tobytes() == b.tobytes()
+    assert phased.launch_count == 1 + 2 * cfg.iterations_max
+    from quaternion_mpc_b200.workloads import predict_schedule_numpy, random_gait_states
+    sched = predict_schedule_numpy(random_gait_states(B, seed=7), N, cfg.dt)
+    assert _solve_sched_dev(fused, probs, sched).tobytes() == _solve_sched_dev(phased, probs, sched).tobytes()
+    assert _solve_dev(phased, probs[:B // 3]).tobytes() == a[:B // 3].tobytes()
+    if model != 2:
+        wa, wb = fused.alloc_warm(B), phased.alloc_warm(B)
+        for tick in range(2):
+            ra = fused.results_to_numpy(fused.grf_update_warm_device(fused.to_device(probs), wa))
+            rb = phased.results_to_numpy(phased.grf_update_warm_device(phased.to_device(probs), wb))
+            torch.cuda.synchronize()
+            assert ra.tobytes() == rb.tobytes() and torch.equal(wa, wb)
+
+
+def test_convex_mpc_cooperative_kernel_against_dense_cross_check(oracle):
+    """Row A8 on the cooperative design (state blocks swapped pairwise, fourth knot block Dw): against the oracle
+    and against the generic dense kernel (the independent on-device cross-check), N=20 / h=5 ms as shipped."""
+    from quaternion_mpc_b200 import ConvexMpc
+    cfg = default_config(abi.QMPC_MODEL_EULER_CONVEX, 20)
+    B = 4096
+    probs = random_convex_batch(B, seed=77)
+    coop, dense = ConvexMpc(max_batch=B, cfg=cfg), ConvexMpc(max_batch=B, cfg=cfg, kernel="dense")
+    assert "kernel=coop" in coop.describe() and "kernel=dense" in dense.describe()
+    a, b = _solve_dev(coop, probs), _solve_dev(dense, probs)
+    ref = oracle.solve_batch_convex(cfg, probs, nthreads=NT)
+    ea, eb = _check(a, ref, label="convex coop"), _check(b, ref, label="convex dense")
+    _check(a, b, label="convex coop-vs-dense")
+    print(f"convex coop max|dGRF| = {ea:.3e} N, dense {eb:.3e} N")
 
 
 def test_handles_with_different_horizons_interleaved(oracle):
