@@ -273,6 +273,41 @@ int qmpc_goal_update(QmpcHandle* h, void* d_goal_state, const QmpcGoalInput* d_i
 int qmpc_raibert_targets(QmpcHandle* h, const QmpcRaibertParams* rp, const QmpcGoalInput* d_in, int32_t batch,
                          double* d_foot_pos_target_world, double* d_foot_pos_target_rel, void* cuda_stream);
 
+/* ---- N3, gait-FSM half: QuatMpc::foot_update (QuatMpc.cpp:278-305) --------------------------------------
+ * One tick of the four LeggedContactFSM objects of every robot (LeggedContactFSM.cpp:10-78, 208-260): phase
+ * advance, stance -> swing at the pattern's switch time, swing -> stance at the end of the swing or on early
+ * contact (more than 90 % through the swing and the foot-force flag set), swing-foot targets from the quintic
+ * curve (Utils.cpp:236-293), stance feet hold the touch-down position.  The per-leg state (contact state, gait
+ * phase, pattern index, swing start / end, targets) is resident on the device; the outputs are what the reference
+ * writes into the LeggedState: ctrl.plan_contacts, ctrl.gait_counter and the FSM targets passed through by
+ * grf_update (QuatMpc.cpp:270-272).  movement_mode == 0 resets the FSMs and plans all feet in contact (:283-289). */
+typedef struct QmpcFootUpdateInput {
+  double  foot_pos_world[12];         /* fbk.foot_pos_world, 3x4 column-major          QuatMpc.cpp:293 */
+  double  foot_pos_target_world[12];  /* ctrl.foot_pos_target_world (Raibert targets)  QuatMpc.cpp:294 */
+  int32_t foot_contact_flag[4];       /* fbk.foot_contact_flag                         QuatMpc.cpp:295 */
+  int32_t movement_mode;              /* ctrl.movement_mode                            QuatMpc.cpp:283 */
+  int32_t pad_[3];
+} QmpcFootUpdateInput;
+typedef struct QmpcFootUpdateOutput {
+  double  foot_pos_target[12];   /* FSM_foot_pos_target_world -> ctrl.optimized_state[6 + 3 i]   QuatMpc.cpp:270 */
+  double  foot_vel_target[12];   /* FSM_foot_vel_target_world -> ctrl.optimized_input[12 + 3 i]  QuatMpc.cpp:271 */
+  double  foot_acc_target[12];   /* FSM_foot_acc_target_world -> ctrl.optimized_input[24 + 3 i]  QuatMpc.cpp:272 */
+  double  gait_counter[4];       /* ctrl.gait_counter = the leg's gait phase                     QuatMpc.cpp:292 */
+  int32_t plan_contacts[4];      /* ctrl.plan_contacts (1 = STANCE)                              QuatMpc.cpp:300 */
+} QmpcFootUpdateOutput;
+/* Bytes of device memory holding the four leg FSMs of max_batch robots. */
+int64_t qmpc_leg_fsm_state_bytes(const QmpcHandle* h);
+/* reset_params + reset for `batch` robots (LeggedContactFSM.cpp:4-31): robot i gets the gait pattern d_gait[i]
+ * (QMPC_GAIT_*; NULL = the default trot of reset_params). */
+int qmpc_leg_fsm_init(QmpcHandle* h, void* d_fsm_state, const int32_t* d_gait, int32_t batch, void* cuda_stream);
+/* One foot_update tick: dt = the FSM step (5 ms in QuatMpc.cpp:292, h in ConvexMpc.cpp:208), gait_freq =
+ * param.gait_freq.  d_problems (may be NULL): plan_contacts of the solve inputs are written in place;
+ * d_gait_out (may be NULL): the gait states qmpc_predict_contact_schedule reads - so that a tick
+ * goal_update -> foot_update -> predict schedule -> solve -> torques never leaves the device. */
+int qmpc_foot_update(QmpcHandle* h, void* d_fsm_state, const QmpcFootUpdateInput* d_in, double dt, double gait_freq,
+                     int32_t batch, QmpcFootUpdateOutput* d_out, QmpcProblem* d_problems, QmpcGaitState* d_gait_out,
+                     void* cuda_stream);
+
 /* ---- N4: warm start (trajectory shift) ------------------------------------------------------------
  * legged_ctrl builds a fresh ALTROSolver every tick and starts from u_ref (QuatMpc.cpp:218,253); the
  * ALTRO API offers ShiftTrajectory() for receding-horizon use (pattern shown in

@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from quaternion_mpc_b200.abi import (CONVEX_PROBLEM_DTYPE, GAIT_STATE_DTYPE, GOAL_INPUT_DTYPE, QmpcRaibertParams, PROBLEM_DTYPE, QMPC_MAX_HORIZON,
+from quaternion_mpc_b200.abi import (FOOT_UPDATE_INPUT_DTYPE, FOOT_UPDATE_OUTPUT_DTYPE, CONVEX_PROBLEM_DTYPE, GAIT_STATE_DTYPE, GOAL_INPUT_DTYPE, QmpcRaibertParams, PROBLEM_DTYPE, QMPC_MAX_HORIZON,
                                      RESULT_DTYPE, WARM_DTYPE, QmpcConfig, QmpcLegParams)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -44,6 +44,8 @@ def lib():
         _LIB.qmpc_ref_predict_schedule.argtypes = [C.POINTER(QmpcConfig), vp, C.c_int, vp]
         _LIB.qmpc_ref_leg_kinematics.argtypes = [C.POINTER(QmpcLegParams), vp, C.c_int, vp, vp]
         _LIB.qmpc_ref_joint_torques.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+        _LIB.qmpc_ref_leg_fsm_init.argtypes = [vp, vp, C.c_double, C.c_int]
+        _LIB.qmpc_ref_foot_update.argtypes = [vp, vp, C.c_double, C.c_double, C.c_int, vp]
         _LIB.kat_double_integrator.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.POINTER(Stats)]
         _LIB.kat_pendulum.argtypes = [C.c_int, dp, dp, C.POINTER(Stats)]
         _LIB.kat_quat_golden.argtypes = [C.c_int, dp, dp, C.POINTER(Stats)]
@@ -139,6 +141,22 @@ def raibert_targets(rp, goal_inputs):
     rc = lib().qmpc_ref_raibert_targets(C.byref(rp), g.ctypes.data, g.shape[0], tw.ctypes.data, tr.ctypes.data)
     assert rc == 0
     return tw, tr
+
+
+def new_leg_fsm(batch, gait=None, gait_freq=2.2):
+    """Per-robot state of the four LeggedContactFSM objects after reset_params + reset (opaque bytes)."""
+    st = np.zeros((batch, lib().qmpc_ref_leg_fsm_state_bytes()), dtype=np.uint8)
+    g = None if gait is None else np.ascontiguousarray(gait, dtype=np.int32)
+    assert lib().qmpc_ref_leg_fsm_init(st.ctypes.data, g.ctypes.data if g is not None else None, gait_freq, batch) == 0
+    return st
+
+
+def foot_update(state, inputs, dt=5.0 / 1000.0, gait_freq=2.2):
+    """One QuatMpc::foot_update tick; `state` (from new_leg_fsm) is updated IN PLACE."""
+    i = np.ascontiguousarray(inputs, dtype=FOOT_UPDATE_INPUT_DTYPE)
+    out = np.zeros(i.shape[0], dtype=FOOT_UPDATE_OUTPUT_DTYPE)
+    assert lib().qmpc_ref_foot_update(state.ctypes.data, i.ctypes.data, dt, gait_freq, i.shape[0], out.ctypes.data) == 0
+    return out
 
 
 def predict_schedule(cfg, gait_states):

@@ -274,3 +274,209 @@ int qmpc_ref_raibert_targets(const QmpcRaibertParams* rp, const QmpcGoalInput* i
   }
   return QMPC_OK;
 }
+
+/* ---------------------------------------------------------------- N3, gait-FSM half
+ * LeggedContactFSM as an object with the reference's members and methods
+ * (legged_ctrl/include/utils/LeggedContactFSM.h:66-107, src/utils/LeggedContactFSM.cpp:4-78, 208-270),
+ * QuinticCurve::get_foot_swing_target (src/utils/Utils.cpp:236-293) and QuatMpc::foot_update
+ * (src/mpc/QuatMpc.cpp:278-305).  Eigen's C.inverse() for a dynamic 6x6 is PartialPivLU solved against the
+ * identity; restated as such. */
+typedef struct RefLegFsm {
+  int leg_id, s;
+  double gait_phase, gait_freq;
+  int gait_freeze, gait_freeze_counter;
+  LegFsm pat; /* gait_state_pattern / gait_switch_time / gait_pattern_size */
+  int gait_pattern_index, prev_gait_pattern_index;
+  double cur_state_start_time, cur_state_end_time;
+  int not_first_call;
+  double swing_start_foot_pos_world[3], swing_end_foot_pos_world[3], swing_extend_foot_pos_world[3];
+  double terrain_height;
+  double FSM_foot_pos_target_world[3], FSM_foot_vel_target_world[3], FSM_foot_acc_target_world[3];
+  int gait;
+} RefLegFsm;
+typedef struct QmpcRefFsmState { RefLegFsm leg[4]; } QmpcRefFsmState;
+int qmpc_ref_leg_fsm_state_bytes(void) { return (int)sizeof(QmpcRefFsmState); }
+
+static void fsm_set_pattern(RefLegFsm* f, int gait) {
+  set_pattern(&f->pat, gait, f->leg_id);
+  f->gait = gait;
+  f->gait_pattern_index = 0;
+  f->prev_gait_pattern_index = f->pat.gait_pattern_size - 1;
+  f->cur_state_start_time = 0.0;
+  f->cur_state_end_time = f->pat.gait_switch_time[f->gait_pattern_index];
+}
+static void fsm_reset_params(RefLegFsm* f, double gait_freq, int leg_id, int gait) { /* :4-9 (+ optional set_*_pattern) */
+  memset(f, 0, sizeof(*f));
+  f->leg_id = leg_id;
+  f->gait_freq = gait_freq;
+  f->s = STANCE;
+  fsm_set_pattern(f, gait);
+}
+static void fsm_reset(RefLegFsm* f) { /* :10-31 */
+  f->gait_phase = 0;
+  f->gait_freeze = 0;
+  f->gait_freeze_counter = 0;
+  f->gait_pattern_index = 0;
+  f->prev_gait_pattern_index = f->pat.gait_pattern_size - 1;
+  f->cur_state_start_time = 0;
+  f->cur_state_end_time = f->pat.gait_switch_time[f->gait_pattern_index];
+  if (f->s == SWING) {
+    memcpy(f->FSM_foot_pos_target_world, f->swing_end_foot_pos_world, sizeof(double) * 3);
+    memset(f->FSM_foot_vel_target_world, 0, sizeof(double) * 3);
+  }
+  f->s = f->pat.gait_state_pattern[f->gait_pattern_index];
+  f->not_first_call = 0;
+}
+static double fsm_percent_in_state(const RefLegFsm* f) { /* :261-270 */
+  double percent = (f->gait_phase - f->cur_state_start_time) / (f->cur_state_end_time - f->cur_state_start_time);
+  if (percent < 0.0) percent = 0.0;
+  else if (percent > 1.0) percent = 1.0;
+  return percent;
+}
+static void fsm_common_enter(RefLegFsm* f) { /* :208-223 */
+  f->prev_gait_pattern_index = f->gait_pattern_index;
+  f->gait_pattern_index = (f->gait_pattern_index + 1) % f->pat.gait_pattern_size;
+  if (f->gait_pattern_index < f->prev_gait_pattern_index) f->gait_phase -= 1.0;
+  f->cur_state_start_time = f->gait_phase;
+  f->cur_state_end_time = f->pat.gait_switch_time[f->gait_pattern_index];
+  f->gait_freeze = 0;
+  f->gait_freeze_counter = 0;
+}
+/* Eigen PartialPivLU of the 6x6 C, then inverse = solve(Identity) */
+static void quintic_C_inverse_ref(float T, double* Cinv) {
+  double A[36] = {1, 0, 0, 0, 0, 0,
+                  1, T, T * T, T * T * T, T * T * T * T, T * T * T * T * T,
+                  0, 1, 0, 0, 0, 0,
+                  0, 1, 2 * T, 3 * T * T, 4 * T * T * T, 5 * T * T * T * T,
+                  1, T / 2, T * T / 4, T * T * T / 8, T * T * T * T / 16, T * T * T * T * T / 32,
+                  0, 1, T, 3 * T * T / 4, 4 * T * T * T / 8, 5 * T * T * T * T / 16};
+  int perm[6] = {0, 1, 2, 3, 4, 5};
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double best = fabs(A[6 * k + k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (fabs(A[6 * i + k]) > best) { best = fabs(A[6 * i + k]); piv = i; }
+    if (piv != k) {
+      for (int j = 0; j < 6; ++j) { double t = A[6 * k + j]; A[6 * k + j] = A[6 * piv + j]; A[6 * piv + j] = t; }
+      int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+    }
+    for (int i = k + 1; i < 6; ++i) {
+      A[6 * i + k] /= A[6 * k + k];
+      for (int j = k + 1; j < 6; ++j) A[6 * i + j] -= A[6 * i + k] * A[6 * k + j];
+    }
+  }
+  for (int c = 0; c < 6; ++c) {
+    double x[6];
+    for (int i = 0; i < 6; ++i) x[i] = perm[i] == c ? 1.0 : 0.0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < i; ++j) x[i] -= A[6 * i + j] * x[j];
+    for (int i = 5; i >= 0; --i) {
+      for (int j = i + 1; j < 6; ++j) x[i] -= A[6 * i + j] * x[j];
+      x[i] /= A[6 * i + i];
+    }
+    for (int i = 0; i < 6; ++i) Cinv[6 * i + c] = x[i];
+  }
+}
+/* QuinticCurve::get_foot_swing_target (Utils.cpp:236-293); out = [pos(3), vel(3), acc(3)] */
+static void get_foot_swing_target(float t, float T, const double* foot_pos_start, const double* foot_pos_final, double* out) {
+  double Cinv[36];
+  quintic_C_inverse_ref(T, Cinv);
+  double dx = foot_pos_final[0] - foot_pos_start[0];
+  double dy = foot_pos_final[1] - foot_pos_start[1];
+  double k = 1.26 / T;
+  double v_xy_mid = k * sqrt(dx * dx + dy * dy);
+  double theta = atan2(fabs(dy), fabs(dx));
+  double v_x_mid = (dx >= 0 ? 1 : -1) * v_xy_mid * cos(theta);
+  double v_y_mid = (dy >= 0 ? 1 : -1) * v_xy_mid * sin(theta);
+  const double con[3][6] = {
+      {foot_pos_start[0], foot_pos_final[0], 0.0, 0.0, (foot_pos_start[0] + foot_pos_final[0]) / 2, v_x_mid},
+      {foot_pos_start[1], foot_pos_final[1], 0.0, 0.0, (foot_pos_start[1] + foot_pos_final[1]) / 2, v_y_mid},
+      {foot_pos_start[2], foot_pos_final[2], 0.1, -0.1, 0.1, 0.0}};
+  for (int ax = 0; ax < 3; ++ax) {
+    double a[6];
+    for (int i = 0; i < 6; ++i) {
+      double s = 0;
+      for (int j = 0; j < 6; ++j) s += Cinv[6 * i + j] * con[ax][j];
+      a[i] = s;
+    }
+    out[ax] = a[0] + a[1] * t + a[2] * t * t + a[3] * t * t * t + a[4] * t * t * t * t + a[5] * t * t * t * t * t;
+    out[3 + ax] = a[1] + 2 * a[2] * t + 3 * a[3] * t * t + 4 * a[4] * t * t * t + 5 * a[5] * t * t * t * t;
+    out[6 + ax] = 2 * a[2] + 6 * a[3] * t + 12 * a[4] * t * t + 20 * a[5] * t * t * t;
+  }
+}
+/* LeggedContactFSM::update (:33-78) */
+static double fsm_update(RefLegFsm* f, double dt, double gait_freq, const double* foot_pos_cur_world,
+                         const double* foot_pos_target_world, int foot_force_flag) {
+  if (!f->not_first_call) {
+    memcpy(f->swing_start_foot_pos_world, foot_pos_cur_world, sizeof(double) * 3);
+    memcpy(f->swing_end_foot_pos_world, foot_pos_target_world, sizeof(double) * 3);
+    memcpy(f->FSM_foot_pos_target_world, foot_pos_target_world, sizeof(double) * 3);
+    memset(f->FSM_foot_vel_target_world, 0, sizeof(double) * 3);
+    f->not_first_call = 1;
+  }
+  f->gait_phase += gait_freq * dt;
+  if (f->s == STANCE) {
+    if (f->gait_phase >= f->cur_state_end_time) {
+      f->terrain_height = foot_pos_cur_world[2]; /* stance_exit */
+      fsm_common_enter(f);                       /* swing_enter */
+      memcpy(f->swing_start_foot_pos_world, foot_pos_cur_world, sizeof(double) * 3);
+      memset(f->swing_extend_foot_pos_world, 0, sizeof(double) * 3);
+      f->s = SWING;
+    }
+  } else if (f->s == SWING) {
+    if (fsm_percent_in_state(f) > 0.9 && foot_force_flag) {
+      f->s = STANCE;
+      fsm_common_enter(f); /* stance_enter */
+      memcpy(f->FSM_foot_pos_target_world, foot_pos_cur_world, sizeof(double) * 3);
+      memset(f->FSM_foot_vel_target_world, 0, sizeof(double) * 3);
+    } else if (fsm_percent_in_state(f) >= 1.0) {
+      f->s = STANCE;
+      fsm_common_enter(f);
+      memcpy(f->FSM_foot_pos_target_world, foot_pos_cur_world, sizeof(double) * 3);
+      memset(f->FSM_foot_vel_target_world, 0, sizeof(double) * 3);
+    }
+  }
+  if (f->s == SWING) { /* swing_update :237-246 ; stance_update is commented out in the reference */
+    double t = fsm_percent_in_state(f);
+    double fin[3], out[9];
+    for (int a = 0; a < 3; ++a) fin[a] = foot_pos_target_world[a] + f->swing_extend_foot_pos_world[a];
+    get_foot_swing_target((float)(0.5 * t / gait_freq), (float)(0.5 / gait_freq), f->swing_start_foot_pos_world, fin, out);
+    memcpy(f->FSM_foot_pos_target_world, out, sizeof(double) * 3);
+    memcpy(f->FSM_foot_vel_target_world, out + 3, sizeof(double) * 3);
+    memcpy(f->FSM_foot_acc_target_world, out + 6, sizeof(double) * 3);
+  }
+  return f->gait_phase;
+}
+
+int qmpc_ref_leg_fsm_init(QmpcRefFsmState* st, const int32_t* gait, double gait_freq, int batch) {
+  for (int b = 0; b < batch; ++b)
+    for (int i = 0; i < 4; ++i) {
+      fsm_reset_params(&st[b].leg[i], gait_freq, i, gait ? gait[b] : QMPC_GAIT_TROT);
+      fsm_reset(&st[b].leg[i]);
+    }
+  return 0;
+}
+/* QuatMpc::foot_update (QuatMpc.cpp:278-305) + the FSM passthrough of grf_update (:270-272) */
+int qmpc_ref_foot_update(QmpcRefFsmState* st, const QmpcFootUpdateInput* in, double dt, double gait_freq, int batch,
+                         QmpcFootUpdateOutput* out) {
+  for (int b = 0; b < batch; ++b) {
+    if (in[b].movement_mode == 0) {
+      for (int i = 0; i < 4; ++i) {
+        fsm_reset(&st[b].leg[i]);
+        out[b].plan_contacts[i] = 1;
+        out[b].gait_counter[i] = st[b].leg[i].gait_phase;
+      }
+    } else {
+      for (int i = 0; i < 4; ++i)
+        out[b].gait_counter[i] = fsm_update(&st[b].leg[i], dt, gait_freq, in[b].foot_pos_world + 3 * i,
+                                            in[b].foot_pos_target_world + 3 * i, in[b].foot_contact_flag[i]);
+      for (int i = 0; i < 4; ++i) out[b].plan_contacts[i] = st[b].leg[i].s;
+    }
+    for (int i = 0; i < 4; ++i) {
+      memcpy(out[b].foot_pos_target + 3 * i, st[b].leg[i].FSM_foot_pos_target_world, sizeof(double) * 3);
+      memcpy(out[b].foot_vel_target + 3 * i, st[b].leg[i].FSM_foot_vel_target_world, sizeof(double) * 3);
+      memcpy(out[b].foot_acc_target + 3 * i, st[b].leg[i].FSM_foot_acc_target_world, sizeof(double) * 3);
+    }
+  }
+  return 0;
+}

@@ -250,21 +250,46 @@ static void opts_from_cfg(const QmpcConfig* cfg, AltroRefOptions* o) {
  * a knot with no contact has u_ref = 0; SetInput(u_traj_ref.at(0)) is kept verbatim. */
 /* `warm` (nullable): the trajectory-shift warm start of include/qmpc.h (extension; ALTRO's
  * ShiftTrajectory pattern of TestBicycle.cpp:181-199, which legged_ctrl never calls). */
-int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched,
-                            QmpcWarmStart* warm, QmpcResult* out) {
+typedef struct QuatAssembly {
+  Model M;
+  double R0[9], qd[4], uref[12], x0[13];
+  double Q[(QMPC_MAX_HORIZON + 1) * 13], R[(QMPC_MAX_HORIZON + 1) * 12], xref[(QMPC_MAX_HORIZON + 1) * 13],
+      ur[(QMPC_MAX_HORIZON + 1) * 12], wq[QMPC_MAX_HORIZON + 1];
+  int p[QMPC_MAX_HORIZON + 1], ct[QMPC_MAX_HORIZON + 1];
+  double fzk[(QMPC_MAX_HORIZON + 1) * 4];
+  AltroRefProblem P;
+  int n, m, nf, N;
+} QuatAssembly;
+
+/* problem assembly of QuatMpc::grf_update (QuatMpc.cpp:118-253) into the ALTRO-shaped problem */
+static int quat_assemble(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, QuatAssembly* A) {
+  memset(A, 0, sizeof(*A));
+#define M (A->M)
+#define R0 (A->R0)
+#define qd (A->qd)
+#define uref (A->uref)
+#define x0 (A->x0)
+#define Q (A->Q)
+#define R (A->R)
+#define xref (A->xref)
+#define ur (A->ur)
+#define wq (A->wq)
+#define p (A->p)
+#define ct (A->ct)
+#define fzk (A->fzk)
+#define P (A->P)
+
   const int N = cfg->horizon;
   const int nf = cfg->model == QMPC_MODEL_QUAT_2FOOT ? 2 : 4;
   const int n = 13, m = 3 * nf;
   if (N < 1 || N > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
-  Model M;
-  memset(&M, 0, sizeof(M));
+  A->n = n; A->m = m; A->nf = nf; A->N = N;
   M.n = n; M.m = m; M.nf = nf;
   M.f = qref_quat_ct_dyn; M.df = qref_quat_ct_jac;
   memcpy(M.foot, in->foot_pos_body, sizeof(double) * 3 * nf);
   qref_inv3(cfg->inertia, M.Iinv);
   M.mass = cfg->robot_mass;
 
-  double R0[9];
   quat_to_rot(in->torso_quat, R0);
   double gw[3] = {0, 0, -cfg->gravity};
   if (cfg->model == QMPC_MODEL_QUAT_4FOOT) {
@@ -275,18 +300,18 @@ int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const 
   }
   double mg[3] = {cfg->com_mass * M.g_vec[0], cfg->com_mass * M.g_vec[1], cfg->com_mass * M.g_vec[2]};
   cross3(cfg->com_offset, mg, M.tau_g);
-  qref_fill_cone(&M, cfg->mu, R0);
+  /* QuatMpc: cone rows C_mat R0 (QuatMpc.cpp:194-215); two-contact problem: C_mat unrotated
+     (TestAltroTrotQuatMpc.cpp:101-110) */
+  qref_fill_cone(&M, cfg->mu, cfg->model == QMPC_MODEL_QUAT_4FOOT ? R0 : NULL);
 
   /* references (QuatMpc.cpp:118-176) */
   int num_contacts = 0;
   for (int i = 0; i < nf; ++i) num_contacts += in->plan_contacts[i] ? 1 : 0;
-  double uref[12] = {0};
   for (int i = 0; i < nf; ++i) {
     uref[3 * i + 2] = (in->plan_contacts[i] ? 1.0 : 0.0) * cfg->robot_mass * cfg->gravity / num_contacts;
     M.fzmax_c[i] = cfg->fz_max * (in->plan_contacts[i] ? 1.0 : 0.0);
   }
   /* torso_quat_d += 0.5 G(q_d) w_d * 5 ms ; renormalise (QuatMpc.cpp:128-137) */
-  double qd[4];
   {
     const double *q = in->torso_quat_d, *w = in->torso_ang_vel_d_body;
     double s = 0.5 * cfg->quat_d_dt;
@@ -297,10 +322,6 @@ int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const 
     double nrm = sqrt(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
     for (int i = 0; i < 4; ++i) qd[i] /= nrm;
   }
-  double Q[(QMPC_MAX_HORIZON + 1) * 13], R[(QMPC_MAX_HORIZON + 1) * 12], xref[(QMPC_MAX_HORIZON + 1) * 13],
-      ur[(QMPC_MAX_HORIZON + 1) * 12], wq[QMPC_MAX_HORIZON + 1];
-  int p[QMPC_MAX_HORIZON + 1], ct[QMPC_MAX_HORIZON + 1];
-  double fzk[(QMPC_MAX_HORIZON + 1) * 4] = {0};
   if (sched) {
     M.fzmax_ck = fzk;
     for (int k = 0; k < N; ++k) {
@@ -334,19 +355,41 @@ int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const 
     ct[k] = ALTRO_REF_INEQUALITY;
   }
   /* x_init (QuatMpc.cpp:231-245): omega dropped by the reference's `;` at :242 */
-  double x0[13] = {0};
   memcpy(x0 + 3, in->torso_quat, sizeof(double) * 4);
   for (int i = 0; i < 3; ++i)
     x0[7 + i] = R0[i] * in->torso_lin_vel_world[0] + R0[3 + i] * in->torso_lin_vel_world[1] +
                 R0[6 + i] * in->torso_lin_vel_world[2];
   if (!cfg->drop_omega0) memcpy(x0 + 10, in->torso_ang_vel_body, sizeof(double) * 3);
 
-  AltroRefProblem P;
-  memset(&P, 0, sizeof(P));
-  P.N = N; P.n = n; P.m = m; P.h = (float)cfg->dt; P.ctx = &M;
-  P.dyn = qref_mid_dyn; P.jac = qref_mid_jac;
-  P.Q = Q; P.R = R; P.xref = xref; P.uref = ur; P.w = wq;
-  P.p = p; P.ctype = ct; P.con = qref_cone_con; P.conjac = qref_cone_jac; P.x0 = x0;
+#undef M
+#undef R0
+#undef qd
+#undef uref
+#undef x0
+#undef Q
+#undef R
+#undef xref
+#undef ur
+#undef wq
+#undef p
+#undef ct
+#undef fzk
+#undef P
+  A->P.N = N; A->P.n = n; A->P.m = m; A->P.h = (float)cfg->dt; A->P.ctx = &A->M;
+  A->P.dyn = qref_mid_dyn; A->P.jac = qref_mid_jac;
+  A->P.Q = A->Q; A->P.R = A->R; A->P.xref = A->xref; A->P.uref = A->ur; A->P.w = A->wq;
+  A->P.p = A->p; A->P.ctype = A->ct; A->P.con = qref_cone_con; A->P.conjac = qref_cone_jac; A->P.x0 = A->x0;
+  return QMPC_OK;
+}
+
+int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched,
+                            QmpcWarmStart* warm, QmpcResult* out) {
+  QuatAssembly* A = (QuatAssembly*)malloc(sizeof(QuatAssembly));
+  if (!A) return QMPC_ERR_ARG;
+  int rc = quat_assemble(cfg, in, sched, A);
+  if (rc) { free(A); return rc; }
+  const int N = A->N, nf = A->nf, m = A->m;
+  const double *R0 = A->R0, *qd = A->qd, *uref = A->uref;
   AltroRefOptions o;
   opts_from_cfg(cfg, &o);
   o.use_quaternion = 1;
@@ -357,14 +400,14 @@ int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const 
   if (warm && warm->valid)
     for (int k = 0; k < N; ++k) memcpy(U + k * m, warm->u[k + 1 < N ? k + 1 : N - 1], sizeof(double) * m);
   AltroRefStats st;
-  if (altro_ref_solve(&P, &o, X, U, &st)) return QMPC_ERR_ARG;
+  if (altro_ref_solve(&A->P, &o, X, U, &st)) { free(A); return QMPC_ERR_ARG; }
 
   memset(out, 0, sizeof(*out));
   for (int i = 0; i < nf; ++i) {
     mat3v(R0, U + 3 * i, out->grf_world + 3 * i);            /* QuatMpc.cpp:268 */
     memcpy(out->grf_body + 3 * i, U + 3 * i, sizeof(double) * 3); /* QuatMpc.cpp:269 */
   }
-  memcpy(out->torso_quat_d, qd, sizeof(qd));
+  memcpy(out->torso_quat_d, qd, sizeof(double) * 4);
   out->max_violation = st.max_violation;
   out->iterations = st.iterations;
   out->status = st.status;
@@ -373,6 +416,70 @@ int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const 
       for (int i = 0; i < 12; ++i) warm->u[k][i] = i < m ? U[k * m + i] : 0.0;
     warm->valid = st.status != QMPC_STATUS_NONFINITE;
   }
+  free(A);
+  return QMPC_OK;
+}
+
+
+/* ---- the restated NLP itself, for solver-independent checks (tests/test_oracle_fixed_point.py): plain cost
+ * (no augmented-Lagrangian terms) of the input trajectory U by single shooting, its gradient by the adjoint
+ * recursion with the full-state midpoint Jacobians, and the linear cone rows  cone_A u_k + cone_b_k <= 0.
+ * cone_A: (6 nf) x m row-major (the same for every knot), cone_b: N x (6 nf). */
+int qmpc_ref_nlp_eval(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, const double* U, double* cost,
+                      double* grad, double* X, double* cone_A, double* cone_b) {
+  QuatAssembly* A = (QuatAssembly*)malloc(sizeof(QuatAssembly));
+  if (!A) return QMPC_ERR_ARG;
+  int rc = quat_assemble(cfg, in, sched, A);
+  if (rc) { free(A); return rc; }
+  const int N = A->N, n = A->n, m = A->m, nf = A->nf;
+  const AltroRefProblem* P = &A->P;
+  double Xl[(QMPC_MAX_HORIZON + 1) * 13];
+  memcpy(Xl, A->x0, sizeof(double) * n);
+  for (int k = 0; k < N; ++k) P->dyn(P->ctx, Xl + (k + 1) * n, Xl + k * n, U + k * m, P->h);
+  double J = 0, lam[13], lx[13];
+  for (int k = N; k >= 0; --k) {
+    const double *x = Xl + k * n, *xr = P->xref + k * n, *Qk = P->Q + k * n;
+    for (int i = 0; i < n; ++i) { double d = x[i] - xr[i]; J += 0.5 * Qk[i] * d * d; lx[i] = Qk[i] * d; }
+    if (P->w[k] != 0.0) {
+      double sdot = xr[3] * x[3] + xr[4] * x[4] + xr[5] * x[5] + xr[6] * x[6];
+      J += P->w[k] * (1.0 - fabs(sdot));
+      double sg = sdot >= 0 ? 1.0 : -1.0;
+      for (int i = 0; i < 4; ++i) lx[3 + i] += -P->w[k] * sg * xr[3 + i];
+    }
+    if (k == N) { memcpy(lam, lx, sizeof(double) * n); continue; }
+    const double *u = U + k * m, *urk = P->uref + k * m, *Rk = P->R + k * m;
+    double Jd[13 * 25], nl[13];
+    memset(Jd, 0, sizeof(Jd));
+    P->jac(P->ctx, Jd, x, u, P->h); /* column-major n x (n + m) */
+    for (int j = 0; j < m; ++j) {
+      double d = u[j] - urk[j], g = Rk[j] * d;
+      J += 0.5 * Rk[j] * d * d;
+      for (int i = 0; i < n; ++i) g += Jd[(n + j) * n + i] * lam[i];
+      if (grad) grad[k * m + j] = g;
+    }
+    for (int j = 0; j < n; ++j) {
+      double sacc = lx[j];
+      for (int i = 0; i < n; ++i) sacc += Jd[j * n + i] * lam[i];
+      nl[j] = sacc;
+    }
+    memcpy(lam, nl, sizeof(double) * n);
+  }
+  if (cost) *cost = J;
+  if (X) memcpy(X, Xl, sizeof(double) * (N + 1) * n);
+  if (cone_A) {
+    memset(cone_A, 0, sizeof(double) * 6 * nf * m);
+    for (int i = 0; i < nf; ++i)
+      for (int r = 0; r < 6; ++r)
+        for (int b = 0; b < 3; ++b) cone_A[(6 * i + r) * m + 3 * i + b] = A->M.CR[3 * r + b];
+  }
+  if (cone_b) {
+    double zero_u[12] = {0}, c[24];
+    for (int k = 0; k < N; ++k) {
+      P->con(P->ctx, k, c, Xl + k * n, zero_u);
+      memcpy(cone_b + k * 6 * nf, c, sizeof(double) * 6 * nf);
+    }
+  }
+  free(A);
   return QMPC_OK;
 }
 

@@ -71,6 +71,11 @@ GAIT_STATE_DTYPE = np.dtype([("gait_phase", "f8", 4), ("gait_freq", "f8"), ("gai
 GOAL_INPUT_DTYPE = np.dtype([("joy_vel", "f8", 2), ("joy_ang_rate", "f8", 3), ("joy_body_height", "f8"),
                              ("torso_pos_world", "f8", 3), ("torso_quat", "f8", 4), ("torso_lin_vel_world", "f8", 3)],
                             align=True)
+FOOT_UPDATE_INPUT_DTYPE = np.dtype([("foot_pos_world", "f8", 12), ("foot_pos_target_world", "f8", 12),
+                                    ("foot_contact_flag", "i4", 4), ("movement_mode", "i4"), ("pad_", "i4", 3)], align=True)
+FOOT_UPDATE_OUTPUT_DTYPE = np.dtype([("foot_pos_target", "f8", 12), ("foot_vel_target", "f8", 12), ("foot_acc_target", "f8", 12),
+                                     ("gait_counter", "f8", 4), ("plan_contacts", "i4", 4)], align=True)
+assert FOOT_UPDATE_INPUT_DTYPE.itemsize == 224 and FOOT_UPDATE_OUTPUT_DTYPE.itemsize == 336
 QMPC_GAIT_TROT, QMPC_GAIT_TROT_WITH_STAND, QMPC_GAIT_CRAWL, QMPC_GAIT_STAND = 0, 1, 2, 3
 
 
@@ -99,6 +104,7 @@ EXPORTED_SYMBOLS = [
     "qmpc_default_raibert_params", "qmpc_raibert_targets",
     "qmpc_create_ex", "qmpc_create_multi", "qmpc_solve_batch_host_multi", "qmpc_destroy_multi",
     "qmpc_multi_device_count", "qmpc_multi_launch_count", "qmpc_multi_last_error",
+    "qmpc_leg_fsm_state_bytes", "qmpc_leg_fsm_init", "qmpc_foot_update",
 ]
 
 _LIB = None
@@ -170,6 +176,12 @@ def load_library():
     lib.qmpc_goal_state_bytes.restype = i64
     lib.qmpc_goal_update.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.qmpc_goal_update.restype = C.c_int
+    lib.qmpc_leg_fsm_state_bytes.argtypes = [vp]
+    lib.qmpc_leg_fsm_state_bytes.restype = i64
+    lib.qmpc_leg_fsm_init.argtypes = [vp, vp, vp, i32, vp]
+    lib.qmpc_leg_fsm_init.restype = C.c_int
+    lib.qmpc_foot_update.argtypes = [vp, vp, vp, C.c_double, C.c_double, i32, vp, vp, vp, vp]
+    lib.qmpc_foot_update.restype = C.c_int
     lib.qmpc_default_raibert_params.argtypes = [C.POINTER(QmpcRaibertParams)]
     lib.qmpc_default_raibert_params.restype = C.c_int
     lib.qmpc_raibert_targets.argtypes = [vp, C.POINTER(QmpcRaibertParams), vp, i32, vp, vp, vp]

@@ -617,6 +617,42 @@ extern "C" int qmpc_goal_update(QmpcHandle* h, void* d_goal_state, const QmpcGoa
   return QMPC_OK;
 }
 
+// ---- row N3, gait-FSM half
+extern "C" int64_t qmpc_leg_fsm_state_bytes(const QmpcHandle* h) {
+  return h ? (int64_t)kFsmFields * (int64_t)sizeof(double) * 4 * h->max_batch : 0;
+}
+
+extern "C" int qmpc_leg_fsm_init(QmpcHandle* h, void* d_fsm_state, const int32_t* d_gait, int32_t batch, void* cuda_stream) {
+  int rc = periph_check(h, batch);
+  if (rc) return rc;
+  if (!d_fsm_state) return QMPC_ERR_ARG;
+  if (batch == 0) return QMPC_OK;
+  CU(cudaSetDevice(h->device));
+  qmpc_leg_fsm_init_kernel<<<(4 * batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>((double*)d_fsm_state,
+                                                                                         (size_t)4 * h->max_batch, d_gait, batch);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
+extern "C" int qmpc_foot_update(QmpcHandle* h, void* d_fsm_state, const QmpcFootUpdateInput* d_in, double dt, double gait_freq,
+                                int32_t batch, QmpcFootUpdateOutput* d_out, QmpcProblem* d_problems, QmpcGaitState* d_gait_out,
+                                void* cuda_stream) {
+  int rc = periph_check(h, batch);
+  if (rc) return rc;
+  if (!d_fsm_state || !d_in || !d_out || !(gait_freq > 0) || !(dt > 0)) return QMPC_ERR_ARG;
+  if (batch == 0) return QMPC_OK;
+  // C^-1 of the quintic swing curve depends on the gait frequency only: once per launch, on the host
+  QuinticInv ci;
+  if (!quintic_C_inverse((float)(0.5 / gait_freq), ci.m)) return QMPC_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  qmpc_foot_update_kernel<<<(4 * batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(
+      (double*)d_fsm_state, (size_t)4 * h->max_batch, ci, d_in, dt, gait_freq, batch, d_out, d_problems, d_gait_out);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return QMPC_OK;
+}
+
 extern "C" int qmpc_default_raibert_params(QmpcRaibertParams* rp) {
   if (!rp) return QMPC_ERR_ARG;
   memset(rp, 0, sizeof(*rp));

@@ -276,7 +276,7 @@ struct CoopLayout {
   // shared memory of the forward-only kernel (qmpc_phased.cuh): model, X, U, the gain stage (also the dx buffer
   // of the accepted step) and the reduction slots
   QMPC_HD static int fStage(int N) { return coop_even(sU(N) + N * NU); }
-  QMPC_HD static int fStageLen(int N) { int a = 2 * kKD, b = (N + 1) * 12; return coop_even(a > b ? a : b); }
+  QMPC_HD static int fStageLen(int N) { int a = 2 * kKD + 2, b = (N + 1) * 12; return coop_even(a > b ? a : b); }   // + 2 mbarriers
   QMPC_HD static int fRed(int N) { return fStage(N) + fStageLen(N); }
   QMPC_HD static int fwd_smem_doubles(int N) { return fRed(N) + 2 * G; }
   // ---- global scratch (doubles) per slot (fused kernel) / per problem (phased kernels); every region starts

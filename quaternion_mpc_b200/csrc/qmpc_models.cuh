@@ -149,7 +149,9 @@ struct QuatModel {
     }
     double mg[3] = {cfg.com_mass * g[0], cfg.com_mass * g[1], cfg.com_mass * g[2]};
     cross3(cfg.com_offset, mg, tau_g);
-    fill_cone(cfg.mu, R0, CR);
+    // QuatMpc rotates the cone rows into the body frame, C_mat R0 (QuatMpc.cpp:194-215); the reference's
+    // two-contact problem uses C_mat as it is (TestAltroTrotQuatMpc.cpp:101-110)
+    fill_cone(cfg.mu, NF == 4 ? R0 : nullptr, CR);
     for (int i = 0; i < NF; ++i) {
       const double* r = foot + 3 * i;
       const double S[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};

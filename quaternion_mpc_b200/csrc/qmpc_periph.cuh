@@ -86,7 +86,15 @@ QMPC_HD inline GaitLegPattern gait_pattern(int gait, int leg) {
 // predict_contact_state(dt) of one leg (LeggedContactFSM.cpp:272-286); falls through to STANCE
 QMPC_HD inline int predict_contact(const GaitLegPattern& p, double gait_phase, double gait_freq, double dt) {
   double ph = add_rn(gait_phase, mul_rn(gait_freq, dt));
-  while (ph > 1.0) ph = add_rn(ph, -1.0);
+  // the reference wraps with `while (ph > 1.0) ph -= 1.0` (LeggedContactFSM.cpp:275-277): for ph < 2^53 every
+  // subtraction is exact, so the loop ends at ph - floor(ph), or at 1.0 when ph is a whole number >= 1 - computed
+  // here in closed form (bit-identical), because one robot record with an Inf / NaN / 1e12 phase must not hang the
+  // launch (and every later solve on the stream); non-finite and absurd phases fall through to STANCE
+  if (ph > 1.0) {
+    if (!(ph < 9.0e15)) return 1;
+    const double r = ph - floor(ph);
+    ph = (r == 0.0) ? 1.0 : r;
+  }
   for (int i = 0; i < p.n; ++i)
     if (ph <= p.sw[i]) return p.stance[i];
   return 1;
@@ -260,7 +268,230 @@ QMPC_HD inline void raibert_one(const QmpcRaibertParams& rp, const QmpcGoalInput
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Row N3, gait-FSM half: LeggedContactFSM::update / reset for the four legs of every robot
+// (LeggedContactFSM.cpp:10-78, 208-260) as driven by QuatMpc::foot_update (QuatMpc.cpp:278-305), and the quintic
+// swing curve (Utils.cpp:236-293).  Per-leg state lives on the device, element-major [field][4 robot + leg].
+constexpr int kFsmFields = 27;
+namespace fsm {
+constexpr int s = 0, phase = 1, idx = 2, prev = 3, start = 4, end = 5, called = 6, swing_start = 7, swing_end = 10,
+              swing_extend = 13, pos = 16, vel = 19, acc = 22, terrain = 25, gait = 26;
+}
+struct FsmRef {
+  double* p;
+  size_t stride;
+  QMPC_HD double& at(int f) const { return p[(size_t)f * stride]; }
+};
+
+// C matrix of QuinticCurve::get_foot_swing_target (Utils.cpp:238-244): T is a FLOAT there, its powers are
+// float products, each entry is then stored as double.  Row-major 6x6.
+QMPC_HD inline void quintic_C(float T, double* C) {
+  const double c[36] = {1, 0, 0, 0, 0, 0,
+                        1, T, T * T, T * T * T, T * T * T * T, T * T * T * T * T,
+                        0, 1, 0, 0, 0, 0,
+                        0, 1, 2 * T, 3 * T * T, 4 * T * T * T, 5 * T * T * T * T,
+                        1, T / 2, T * T / 4, T * T * T / 8, T * T * T * T / 16, T * T * T * T * T / 32,
+                        0, 1, T, 3 * T * T / 4, 4 * T * T * T / 8, 5 * T * T * T * T / 16};
+  for (int i = 0; i < 36; ++i) C[i] = c[i];
+}
+// C.inverse() (Eigen: PartialPivLU, then solve against the identity): host-side helper, evaluated once per launch
+// - C depends on the gait frequency only
+inline bool quintic_C_inverse(float T, double* Cinv) {
+  double A[36];
+  int perm[6];
+  quintic_C(T, A);
+  for (int i = 0; i < 6; ++i) perm[i] = i;
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double best = fabs(A[6 * k + k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (fabs(A[6 * i + k]) > best) { best = fabs(A[6 * i + k]); piv = i; }
+    if (best == 0.0) return false;
+    if (piv != k) {
+      for (int j = 0; j < 6; ++j) { const double t = A[6 * k + j]; A[6 * k + j] = A[6 * piv + j]; A[6 * piv + j] = t; }
+      const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+    }
+    for (int i = k + 1; i < 6; ++i) {
+      A[6 * i + k] /= A[6 * k + k];
+      for (int j = k + 1; j < 6; ++j) A[6 * i + j] -= A[6 * i + k] * A[6 * k + j];
+    }
+  }
+  for (int c = 0; c < 6; ++c) {
+    double x[6];
+    for (int i = 0; i < 6; ++i) x[i] = perm[i] == c ? 1.0 : 0.0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < i; ++j) x[i] -= A[6 * i + j] * x[j];
+    for (int i = 5; i >= 0; --i) {
+      for (int j = i + 1; j < 6; ++j) x[i] -= A[6 * i + j] * x[j];
+      x[i] /= A[6 * i + i];
+    }
+    for (int i = 0; i < 6; ++i) Cinv[6 * i + c] = x[i];
+  }
+  return true;
+}
+struct QuinticInv { double m[36]; };
+
+// position / velocity / acceleration of one axis: a = Cinv con, then the three polynomials exactly as written
+// at Utils.cpp:262-264 (no FMA: the products and sums of the reference, one rounding each)
+QMPC_HD inline void quintic_axis(const QuinticInv& ci, const double* con, double t, double* p, double* v, double* a) {
+  double c[6];
+  for (int i = 0; i < 6; ++i) {
+    double acc = 0.0;
+    for (int j = 0; j < 6; ++j) acc = add_rn(acc, mul_rn(ci.m[6 * i + j], con[j]));
+    c[i] = acc;
+  }
+  const double t2 = mul_rn(t, t);   // the reference evaluates a*t*t*... left to right: ((a t) t) t
+  (void)t2;
+  auto pw = [&](double coef, int n) { double r = coef; for (int i = 0; i < n; ++i) r = mul_rn(r, t); return r; };
+  *p = add_rn(add_rn(add_rn(add_rn(add_rn(c[0], pw(c[1], 1)), pw(c[2], 2)), pw(c[3], 3)), pw(c[4], 4)), pw(c[5], 5));
+  *v = add_rn(add_rn(add_rn(add_rn(c[1], pw(mul_rn(2, c[2]), 1)), pw(mul_rn(3, c[3]), 2)), pw(mul_rn(4, c[4]), 3)), pw(mul_rn(5, c[5]), 4));
+  *a = add_rn(add_rn(add_rn(mul_rn(2, c[2]), pw(mul_rn(6, c[3]), 1)), pw(mul_rn(12, c[4]), 2)), pw(mul_rn(20, c[5]), 3));
+}
+
+// QuinticCurve::get_foot_swing_target(t, T, start, final) -> pos[3], vel[3], acc[3]
+QMPC_HD inline void quintic_swing_target(const QuinticInv& ci, float tf, float T, const double* p0, const double* pT,
+                                         double* pos, double* vel, double* acc) {
+  const double t = (double)tf;
+  const double dx = pT[0] - p0[0], dy = pT[1] - p0[1];
+  const double k = 1.26 / (double)T;
+  const double v_xy_mid = mul_rn(k, sqrt(add_rn(mul_rn(dx, dx), mul_rn(dy, dy))));
+  const double theta = atan2(fabs(dy), fabs(dx));
+  const double v_x_mid = mul_rn(mul_rn((dx >= 0 ? 1.0 : -1.0), v_xy_mid), cos(theta));
+  const double v_y_mid = mul_rn(mul_rn((dy >= 0 ? 1.0 : -1.0), v_xy_mid), sin(theta));
+  const double zc[6] = {p0[2], pT[2], 0.1, -0.1, 0.1, 0.0};
+  const double xc[6] = {p0[0], pT[0], 0.0, 0.0, add_rn(p0[0], pT[0]) / 2, v_x_mid};
+  const double yc[6] = {p0[1], pT[1], 0.0, 0.0, add_rn(p0[1], pT[1]) / 2, v_y_mid};
+  quintic_axis(ci, xc, t, pos + 0, vel + 0, acc + 0);
+  quintic_axis(ci, yc, t, pos + 1, vel + 1, acc + 1);
+  quintic_axis(ci, zc, t, pos + 2, vel + 2, acc + 2);
+}
+
+QMPC_HD inline double fsm_percent(double phase, double start, double end) {
+  double pct = add_rn(phase, -start) / add_rn(end, -start);
+  if (pct < 0.0) pct = 0.0;
+  else if (pct > 1.0) pct = 1.0;
+  return pct;
+}
+
+// reset_params (trot unless `gait` says otherwise) + reset: a freshly constructed controller
+QMPC_HD inline void leg_fsm_init_one(const FsmRef& st, int leg, int gait) {
+  const GaitLegPattern pat = gait_pattern(gait, leg);
+  for (int f = 0; f < kFsmFields; ++f) st.at(f) = 0.0;
+  st.at(fsm::gait) = (double)gait;
+  st.at(fsm::prev) = (double)(pat.n - 1);
+  st.at(fsm::end) = pat.sw[0];
+  st.at(fsm::s) = (double)pat.stance[0];
+}
+
+// One tick of QuatMpc::foot_update for one leg (QuatMpc.cpp:278-305): movement_mode 0 -> reset() and
+// plan_contact = true; else update(dt, gait_freq, cur, target, foot_force_flag).
+QMPC_HD inline void leg_fsm_tick_one(const FsmRef& st, const QuinticInv& ci, int leg, int movement_mode, double dt, double gait_freq,
+                                     const double* cur, const double* tgt, bool flag, double* pos, double* vel, double* acc,
+                                     double* gait_counter, int* contact) {
+  const GaitLegPattern pat = gait_pattern((int)st.at(fsm::gait), leg);
+  int s = (int)st.at(fsm::s), idx = (int)st.at(fsm::idx), prev = (int)st.at(fsm::prev);
+  double phase = st.at(fsm::phase), start = st.at(fsm::start), end = st.at(fsm::end);
+  bool called = st.at(fsm::called) != 0.0;
+  double sw0[3], sw1[3], ext[3], P[3], V[3], A[3];
+  for (int a = 0; a < 3; ++a) {
+    sw0[a] = st.at(fsm::swing_start + a); sw1[a] = st.at(fsm::swing_end + a); ext[a] = st.at(fsm::swing_extend + a);
+    P[a] = st.at(fsm::pos + a); V[a] = st.at(fsm::vel + a); A[a] = st.at(fsm::acc + a);
+  }
+  double terrain = st.at(fsm::terrain);
+  if (movement_mode == 0) {
+    // LeggedContactFSM::reset (LeggedContactFSM.cpp:10-31)
+    phase = 0; idx = 0; prev = pat.n - 1; start = 0; end = pat.sw[0];
+    if (s == 0) { for (int a = 0; a < 3; ++a) { P[a] = sw1[a]; V[a] = 0.0; } }
+    s = pat.stance[0];
+    called = false;
+    *gait_counter = phase;      // ctrl.gait_counter is not written in this branch; reported as the reset phase
+    *contact = 1;               // QuatMpc.cpp:288
+  } else {
+    // LeggedContactFSM::update (LeggedContactFSM.cpp:33-78)
+    if (!called) {
+      for (int a = 0; a < 3; ++a) { sw0[a] = cur[a]; sw1[a] = tgt[a]; P[a] = tgt[a]; V[a] = 0.0; }
+      called = true;
+    }
+    phase = add_rn(phase, mul_rn(gait_freq, dt));
+    auto common_enter = [&]() {   // :208-223
+      prev = idx;
+      idx = (idx + 1) % pat.n;
+      if (idx < prev) phase = add_rn(phase, -1.0);
+      start = phase;
+      end = pat.sw[idx];
+    };
+    if (s == 1) {
+      if (phase >= end) {
+        terrain = cur[2];                                            // stance_exit :80-84
+        common_enter();                                              // swing_enter :225-229
+        for (int a = 0; a < 3; ++a) { sw0[a] = cur[a]; ext[a] = 0.0; }
+        s = 0;
+      }
+    } else {
+      const double pct = fsm_percent(phase, start, end);
+      if ((pct > 0.9 && flag) || pct >= 1.0) {                       // early contact / end of swing :53-64
+        s = 1;
+        common_enter();                                              // stance_enter :231-235
+        for (int a = 0; a < 3; ++a) { P[a] = cur[a]; V[a] = 0.0; }
+      }
+    }
+    if (s == 0) {                                                    // swing_update :237-246
+      const double t = fsm_percent(phase, start, end);
+      const double fin[3] = {add_rn(tgt[0], ext[0]), add_rn(tgt[1], ext[1]), add_rn(tgt[2], ext[2])};
+      quintic_swing_target(ci, (float)(mul_rn(0.5, t) / gait_freq), (float)(0.5 / gait_freq), sw0, fin, P, V, A);
+    }                                                                // stance_update is empty (:248-259)
+    *gait_counter = phase;
+    *contact = s;
+  }
+  for (int a = 0; a < 3; ++a) { pos[a] = P[a]; vel[a] = V[a]; acc[a] = A[a]; }
+  st.at(fsm::s) = (double)s; st.at(fsm::idx) = (double)idx; st.at(fsm::prev) = (double)prev;
+  st.at(fsm::phase) = phase; st.at(fsm::start) = start; st.at(fsm::end) = end; st.at(fsm::called) = called ? 1.0 : 0.0;
+  for (int a = 0; a < 3; ++a) {
+    st.at(fsm::swing_start + a) = sw0[a]; st.at(fsm::swing_end + a) = sw1[a]; st.at(fsm::swing_extend + a) = ext[a];
+    st.at(fsm::pos + a) = P[a]; st.at(fsm::vel + a) = V[a]; st.at(fsm::acc + a) = A[a];
+  }
+  st.at(fsm::terrain) = terrain;
+}
+
 #ifdef __CUDACC__
+// one thread per (robot, leg)
+__global__ void __launch_bounds__(256)
+qmpc_leg_fsm_init_kernel(double* __restrict__ state, size_t stride, const int32_t* __restrict__ gait, int batch) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * batch) return;
+  leg_fsm_init_one(FsmRef{state + t, stride}, t & 3, gait ? gait[t >> 2] : QMPC_GAIT_TROT);
+}
+
+__global__ void __launch_bounds__(256)
+qmpc_foot_update_kernel(double* __restrict__ state, size_t stride, QuinticInv ci, const QmpcFootUpdateInput* __restrict__ in,
+                        double dt, double gait_freq, int batch, QmpcFootUpdateOutput* __restrict__ out,
+                        QmpcProblem* __restrict__ problems, QmpcGaitState* __restrict__ gait_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * batch) return;
+  const int b = t >> 2, leg = t & 3;
+  const QmpcFootUpdateInput* r = in + b;
+  double cur[3], tgt[3], pos[3], vel[3], acc[3], gc;
+  int contact;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { cur[a] = r->foot_pos_world[3 * leg + a]; tgt[a] = r->foot_pos_target_world[3 * leg + a]; }
+  const FsmRef st{state + t, stride};
+  leg_fsm_tick_one(st, ci, leg, r->movement_mode, dt, gait_freq, cur, tgt, r->foot_contact_flag[leg] != 0, pos, vel, acc, &gc,
+                   &contact);
+  QmpcFootUpdateOutput* o = out + b;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    o->foot_pos_target[3 * leg + a] = pos[a]; o->foot_vel_target[3 * leg + a] = vel[a]; o->foot_acc_target[3 * leg + a] = acc[a];
+  }
+  o->gait_counter[leg] = gc;
+  o->plan_contacts[leg] = contact;
+  if (problems) problems[b].plan_contacts[leg] = contact;
+  if (gait_out) {
+    gait_out[b].gait_phase[leg] = gc;
+    if (leg == 0) { gait_out[b].gait_freq = gait_freq; gait_out[b].gait = (int32_t)st.at(fsm::gait); gait_out[b].pad_ = 0; }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 qmpc_goal_update_kernel(double* __restrict__ state, size_t stride, const QmpcGoalInput* __restrict__ in, int batch,
                         QmpcProblem* __restrict__ problems) {

@@ -1,6 +1,7 @@
 // CudaConvexMpc.cpp — see CudaConvexMpc.h.  Host-side packing only; no solver arithmetic here.
 #include "CudaConvexMpc.h"
 
+#include <cstdio>
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
@@ -121,7 +122,18 @@ bool CudaConvexMpc::grf_update(LeggedState& state) {
   } else {
     rc = qmpc_solve_batch_convex_host(handle_, &p, 1, &r);
   }
-  if (rc != QMPC_OK) return true;  // drop-in: the reference never reports failure; outputs left untouched
+  const bool bad = rc != QMPC_OK || r.status == QMPC_STATUS_NONFINITE || r.status == QMPC_STATUS_BACKWARD_FAILED;
+  last_rc_ = rc;
+  last_tick_failed_ = bad;
+  if (bad) {   // update() keeps returning true (the reference's contract), but the failure is counted and reported
+    ++failure_count_;
+    if (rc != QMPC_OK) std::snprintf(last_error_, sizeof(last_error_), "qmpc rc=%d: %s", rc, qmpc_last_error(handle_));
+    else std::snprintf(last_error_, sizeof(last_error_), "solver status %d (%s)", r.status, qmpc_status_string(r.status));
+    if (failure_count_ == 1) std::fprintf(stderr, "[CudaConvexMpc] solve failed: %s (further failures are counted)\n", last_error_);
+    if (zero_on_failure_) for (int i = 0; i < 12; ++i) state.ctrl.optimized_input[i] = 0.0;
+    if (rc == QMPC_OK) last_ = r;
+    return true;
+  }
   last_ = r;
   // ---- unpack what ConvexMpc::grf_update writes (ConvexMpc.cpp:190-195)
   for (int i = 0; i < 12; ++i) state.ctrl.optimized_input[i] = r.grf_body[i];   // R^T u per leg

@@ -39,7 +39,19 @@ class CudaConvexMpc : public LeggedMpc {
   int last_iterations() const { return last_.iterations; }
   const QmpcConvexProblem& last_problem() const { return prob_; }
 
+  // failed solves are never silent (see CudaQuatMpc.h): counted, last error kept, first one logged; on failure
+  // the previous tick's forces are held unless zero_on_failure is set
+  void set_zero_on_failure(bool z) { zero_on_failure_ = z; }
+  long failure_count() const { return failure_count_; }
+  int last_return_code() const { return last_rc_; }
+  const char* last_error() const { return last_error_; }
+  bool last_tick_failed() const { return last_tick_failed_; }
+
  private:
+  bool zero_on_failure_ = false, last_tick_failed_ = false;
+  long failure_count_ = 0;
+  int last_rc_ = QMPC_OK;
+  char last_error_[256] = {0};
   QmpcHandle* handle_ = nullptr;
   QmpcConfig cfg_;
   QmpcConvexProblem prob_;

@@ -3,6 +3,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -114,6 +115,46 @@ bool CudaQuatMpc::foot_update(LeggedState& state) {
   return true;
 }
 
+// A failed solve (see FailurePolicy in the header): count it, keep the error text, log the first one, write the
+// GRF outputs the policy asks for, and keep the desired attitude integrating (QuatMpc.cpp:128-137 runs before
+// the solve in the reference, so it must not stall with it).
+void CudaQuatMpc::on_failure(LeggedState& state, int rc, int status) {
+  ++failure_count_;
+  last_rc_ = rc;
+  last_tick_failed_ = true;
+  if (rc != QMPC_OK) std::snprintf(last_error_, sizeof(last_error_), "qmpc rc=%d: %s", rc, qmpc_last_error(handle_));
+  else std::snprintf(last_error_, sizeof(last_error_), "solver status %d (%s)", status, qmpc_status_string(status));
+  if (failure_count_ == 1) std::fprintf(stderr, "[CudaQuatMpc] solve failed: %s (policy %d; further failures are counted)\n",
+                                        last_error_, (int)failure_policy_);
+  if (failure_policy_ != FailurePolicy::kHoldLast) {
+    int nc = 0;
+    for (int leg = 0; leg < NUM_LEG; ++leg) nc += state.ctrl.plan_contacts[leg] ? 1 : 0;
+    for (int leg = 0; leg < NUM_LEG; ++leg)
+      for (int i = 0; i < 3; ++i) {
+        double f = 0.0;
+        if (failure_policy_ == FailurePolicy::kWeightShare && i == 2 && nc > 0 && state.ctrl.plan_contacts[leg])
+          f = state.param.robot_mass * 9.81 / nc;
+        state.ctrl.optimized_input[3 * leg + i] = f;     // body frame; the weight share is along body z as in u_ref
+      }
+    for (int leg = 0; leg < NUM_LEG; ++leg) {             // mpc_grf_world = R0 u (QuatMpc.cpp:268)
+      const double fz = state.ctrl.optimized_input[3 * leg + 2];
+      for (int i = 0; i < 3; ++i) state.ctrl.mpc_grf_world[3 * leg + i] = state.fbk.torso_rot_mat(i, 2) * fz;
+    }
+  }
+  if (rc != QMPC_OK) {   // no result came back: integrate the desired attitude here (QuatMpc.cpp:128-137)
+    const double q[4] = {prob_.torso_quat_d[0], prob_.torso_quat_d[1], prob_.torso_quat_d[2], prob_.torso_quat_d[3]};
+    const double* w = prob_.torso_ang_vel_d_body;
+    const double sc = 0.5 * cfg_.quat_d_dt;
+    double qd[4] = {q[0] + sc * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]), q[1] + sc * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]),
+                    q[2] + sc * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]), q[3] + sc * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2])};
+    const double nrm = std::sqrt(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
+    if (nrm > 0 && std::isfinite(nrm)) {
+      state.ctrl.torso_quat_d.w() = qd[0] / nrm; state.ctrl.torso_quat_d.x() = qd[1] / nrm;
+      state.ctrl.torso_quat_d.y() = qd[2] / nrm; state.ctrl.torso_quat_d.z() = qd[3] / nrm;
+    }
+  }
+}
+
 bool CudaQuatMpc::grf_update(LeggedState& state) {
   const auto t0 = std::chrono::high_resolution_clock::now();
   // ---- pack exactly the fields QuatMpc::grf_update reads (QuatMpc.cpp:118-246)
@@ -137,6 +178,20 @@ bool CudaQuatMpc::grf_update(LeggedState& state) {
     for (int i = 0; i < 3; ++i) p.foot_pos_body[3 * leg + i] = state.fbk.foot_pos_body(i, leg);
     p.plan_contacts[leg] = state.ctrl.plan_contacts[leg] ? 1 : 0;
   }
+  // "sin ang vel test" (QuatMpc.cpp:139-146): after the integration step the reference REPLACES torso_quat_d by
+  // euler_to_quat of a sine Euler trajectory (Utils.cpp:76-99).  Reproduced by handing the solve that quaternion
+  // with a zero desired rate: its own integration + renormalisation (QuatMpc.cpp:132-133) is then the identity.
+  if (state.joy.sin_ang_vel) {
+    const double e = 3.14 / 8 * std::sin(2 * 3.14 / 900 * attitude_traj_count_);
+    state.ctrl.torso_euler_d[0] = e; state.ctrl.torso_euler_d[1] = e; state.ctrl.torso_euler_d[2] = e;
+    attitude_traj_count_ += 1;
+    const double cr = std::cos(e / 2), sr = std::sin(e / 2);   // roll = pitch = yaw = e
+    p.torso_quat_d[0] = cr * cr * cr + sr * sr * sr;
+    p.torso_quat_d[1] = cr * cr * sr - sr * sr * cr;
+    p.torso_quat_d[2] = cr * sr * cr + sr * cr * sr;
+    p.torso_quat_d[3] = sr * cr * cr - cr * sr * sr;
+    for (int i = 0; i < 3; ++i) p.torso_ang_vel_d_body[i] = 0.0;
+  }
   // ---- solve on the GPU (batch = 1; H2D, kernel, D2H, sync inside the call)
   QmpcResult r;
   int rc;
@@ -149,8 +204,22 @@ bool CudaQuatMpc::grf_update(LeggedState& state) {
   } else {
     rc = qmpc_solve_batch_host(handle_, &p, 1, &r);
   }
-  if (rc != QMPC_OK) return true;  // drop-in: the reference never reports failure; outputs left untouched
+  if (rc != QMPC_OK) {               // the reference's contract: update() returns true whatever happens (Main.cpp:107)
+    on_failure(state, rc, -1);
+    return true;
+  }
   last_ = r;
+  last_rc_ = QMPC_OK;
+  last_tick_failed_ = false;
+  if (r.status == QMPC_STATUS_NONFINITE || r.status == QMPC_STATUS_BACKWARD_FAILED) {
+    on_failure(state, QMPC_OK, r.status);   // GRFs by policy; torso_quat_d below is still the solver's (valid) one
+    // what is unpacked below: the policy's forces (hold-last: the state's current values, i.e. unchanged)
+    for (int i = 0; i < 12; ++i) { r.grf_body[i] = state.ctrl.optimized_input[i]; r.grf_world[i] = state.ctrl.mpc_grf_world[i]; }
+    if (!std::isfinite(r.torso_quat_d[0] + r.torso_quat_d[1] + r.torso_quat_d[2] + r.torso_quat_d[3])) {
+      r.torso_quat_d[0] = p.torso_quat_d[0]; r.torso_quat_d[1] = p.torso_quat_d[1];
+      r.torso_quat_d[2] = p.torso_quat_d[2]; r.torso_quat_d[3] = p.torso_quat_d[3];
+    }
+  }
   // ---- unpack what QuatMpc::grf_update writes (QuatMpc.cpp:133-137, 231, 261-272)
   state.ctrl.torso_quat_d.w() = r.torso_quat_d[0];
   state.ctrl.torso_quat_d.x() = r.torso_quat_d[1];

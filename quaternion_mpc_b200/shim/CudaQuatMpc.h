@@ -45,6 +45,22 @@ class CudaQuatMpc : public LeggedMpc {
   int last_iterations() const { return last_.iterations; }
   const QmpcProblem& last_problem() const { return prob_; }
 
+  // What grf_update writes when the solve FAILED - the C-ABI call returned an error (CUDA fault, lost device)
+  // or the solver reported a non-finite / non-positive-definite problem.  update() keeps returning true (the
+  // reference's contract, Main.cpp:107 ignores the value), but the failure is never silent: it is counted,
+  // the last error text is kept, the first occurrence is logged to stderr, and the GRF outputs follow an
+  // explicit policy instead of silently staying at the previous tick's values.
+  enum class FailurePolicy {
+    kHoldLast,     // keep the previous tick's GRFs (what "outputs left untouched" amounts to), default
+    kWeightShare,  // u_ref: the robot's weight shared by the feet planned in contact (QuatMpc.cpp:118-125)
+    kZero          // zero forces
+  };
+  void set_failure_policy(FailurePolicy p) { failure_policy_ = p; }
+  long failure_count() const { return failure_count_; }        // ticks whose solve failed, since construction
+  int last_return_code() const { return last_rc_; }            // QMPC_OK or the error of the last tick
+  const char* last_error() const { return last_error_; }       // sticky: text of the most recent failure
+  bool last_tick_failed() const { return last_tick_failed_; }
+
  private:
   // 100-sample moving average with Neumaier-compensated running sum, same arithmetic as
   // utils/MovingWindowFilter.hpp:26-62 (kept local so the shim has no dependency on that header)
@@ -62,6 +78,13 @@ class CudaQuatMpc : public LeggedMpc {
   QmpcResult last_;
   bool use_schedule_ = false;
   QmpcContactSchedule sched_{};
+  double attitude_traj_count_ = 0;   // QuatMpc.h:33, the sine attitude test trajectory (QuatMpc.cpp:139-146)
+  FailurePolicy failure_policy_ = FailurePolicy::kHoldLast;
+  long failure_count_ = 0;
+  int last_rc_ = QMPC_OK;
+  bool last_tick_failed_ = false;
+  char last_error_[256] = {0};
+  void on_failure(LeggedState& state, int rc, int status);
 };
 
 }  // namespace legged

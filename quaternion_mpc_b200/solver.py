@@ -146,6 +146,35 @@ class _BatchedMpc:
                                                   tw.data_ptr(), tr.data_ptr(), s))
         return tw, tr
 
+    # -- gait FSM (second half): QuatMpc::foot_update --------------------------------
+    def alloc_leg_fsm(self, d_gait=None):
+        """Device state of the four LeggedContactFSM objects of max_batch robots, initialised like
+        reset_params + reset (LeggedContactFSM.cpp:4-31); d_gait: int32 (max_batch,) QMPC_GAIT_* or None = trot."""
+        import torch
+        n = int(self.lib.qmpc_leg_fsm_state_bytes(self._h))
+        st = torch.zeros(n, dtype=torch.uint8, device=f"cuda:{self.device}")
+        if d_gait is not None:
+            assert d_gait.dtype == torch.int32 and d_gait.is_cuda and d_gait.shape[0] == self.max_batch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.qmpc_leg_fsm_init(self._h, st.data_ptr(), d_gait.data_ptr() if d_gait is not None else None,
+                                               self.max_batch, s))
+        return st
+
+    def foot_update(self, d_fsm_state, d_inputs, gait_freq=2.2, dt=5.0 / 1000.0, d_problems=None, d_gait_out=None, stream=None):
+        """One batched QuatMpc::foot_update tick (QuatMpc.cpp:278-305): FOOT_UPDATE_INPUT_DTYPE records in,
+        FOOT_UPDATE_OUTPUT_DTYPE records out; optionally writes plan_contacts into d_problems and the gait
+        states predict_contact_schedule reads into d_gait_out."""
+        import torch
+        batch = d_inputs.shape[0]
+        assert d_inputs.is_cuda and d_inputs.dtype == torch.uint8 and d_inputs.shape[1] == abi.FOOT_UPDATE_INPUT_DTYPE.itemsize
+        out = torch.empty((batch, abi.FOOT_UPDATE_OUTPUT_DTYPE.itemsize), dtype=torch.uint8, device=d_inputs.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.qmpc_foot_update(self._h, d_fsm_state.data_ptr(), d_inputs.data_ptr(), float(dt), float(gait_freq),
+                                              batch, out.data_ptr(),
+                                              d_problems.data_ptr() if d_problems is not None else None,
+                                              d_gait_out.data_ptr() if d_gait_out is not None else None, s))
+        return out
+
     # -- warm start / trajectory shift (SURVEY 8f N4) ---------------------------------------------
     def alloc_warm(self, batch):
         """Device buffer of `batch` QmpcWarmStart records, all invalid (first solve starts cold)."""

@@ -139,3 +139,24 @@ extern "C" int emul_raibert(const QmpcRaibertParams* rp, const QmpcGoalInput* in
   for (int i = 0; i < batch; ++i) raibert_one(*rp, in[i], tw + 12 * i, tr + 12 * i);
   return 0;
 }
+
+// ---- row N3, gait-FSM half: the foot_update body on the host (state: element-major doubles, stride = 4 * capacity)
+extern "C" int emul_fsm_state_doubles(void) { return kFsmFields; }
+extern "C" int emul_leg_fsm_init(double* state, int capacity, const int32_t* gait, int batch) {
+  for (int t = 0; t < 4 * batch; ++t) leg_fsm_init_one(FsmRef{state + t, (size_t)4 * capacity}, t & 3, gait ? gait[t >> 2] : QMPC_GAIT_TROT);
+  return 0;
+}
+extern "C" int emul_foot_update(double* state, int capacity, const QmpcFootUpdateInput* in, double dt, double gait_freq, int batch,
+                                QmpcFootUpdateOutput* out) {
+  QuinticInv ci;
+  if (!quintic_C_inverse((float)(0.5 / gait_freq), ci.m)) return -1;
+  for (int t = 0; t < 4 * batch; ++t) {
+    const int b = t >> 2, leg = t & 3;
+    int contact;
+    leg_fsm_tick_one(FsmRef{state + t, (size_t)4 * capacity}, ci, leg, in[b].movement_mode, dt, gait_freq, in[b].foot_pos_world + 3 * leg,
+                     in[b].foot_pos_target_world + 3 * leg, in[b].foot_contact_flag[leg] != 0, out[b].foot_pos_target + 3 * leg,
+                     out[b].foot_vel_target + 3 * leg, out[b].foot_acc_target + 3 * leg, &out[b].gait_counter[leg], &contact);
+    out[b].plan_contacts[leg] = contact;
+  }
+  return 0;
+}

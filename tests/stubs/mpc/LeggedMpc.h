@@ -65,6 +65,7 @@ struct LeggedCtrl {
 };
 struct LeggedJoyCmd {
   double velx = 0, vely = 0, roll_rate = 0, pitch_rate = 0, yaw_rate = 0, body_height = 0.3, body_x = 0, body_y = 0;
+  bool sin_ang_vel = false;   // LeggedState.h:157
 };
 struct LeggedParam {
   double mpc_update_period = 10.0;

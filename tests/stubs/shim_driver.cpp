@@ -147,3 +147,69 @@ extern "C" int shim_convex_run(const QmpcConvexProblem* in, int horizon, int tic
   status_iters[1] = c->last_iterations();
   return 0;
 }
+
+// ---- failure policy and the sine attitude trajectory of CudaQuatMpc
+static void fill_state(legged::LeggedState& st, const QmpcProblem* in) {
+  const double Q[13] = {2.5, 2.5, 10.0, 0, 0, 0, 0, 0.1, 0.1, 0.1, 0.15, 0.15, 0.15};
+  st.param.mpc_horizon = 10;
+  for (int i = 0; i < 13; ++i) st.param.q_weights[i] = Q[i];
+  for (int i = 0; i < 12; ++i) st.param.r_weights[i] = 1e-6;
+  st.param.trunk_inertia(0, 0) = 0.0168128557; st.param.trunk_inertia(1, 1) = 0.063009565; st.param.trunk_inertia(2, 2) = 0.0716547275;
+  st.fbk.torso_quat.w() = in->torso_quat[0]; st.fbk.torso_quat.x() = in->torso_quat[1];
+  st.fbk.torso_quat.y() = in->torso_quat[2]; st.fbk.torso_quat.z() = in->torso_quat[3];
+  double w = in->torso_quat[0], x = in->torso_quat[1], y = in->torso_quat[2], z = in->torso_quat[3];
+  auto& R = st.fbk.torso_rot_mat;
+  R(0, 0) = 1 - 2 * (y * y + z * z); R(0, 1) = 2 * (x * y - w * z); R(0, 2) = 2 * (x * z + w * y);
+  R(1, 0) = 2 * (x * y + w * z); R(1, 1) = 1 - 2 * (x * x + z * z); R(1, 2) = 2 * (y * z - w * x);
+  R(2, 0) = 2 * (x * z - w * y); R(2, 1) = 2 * (y * z + w * x); R(2, 2) = 1 - 2 * (x * x + y * y);
+  for (int i = 0; i < 3; ++i) st.fbk.torso_rot_mat_z(i, i) = 1.0;
+  st.fbk.torso_pos_world[2] = 0.3;
+  for (int i = 0; i < 3; ++i) st.fbk.torso_lin_vel_world[i] = in->torso_lin_vel_world[i];
+  for (int leg = 0; leg < 4; ++leg)
+    for (int i = 0; i < 3; ++i) st.fbk.foot_pos_body(i, leg) = in->foot_pos_body[3 * leg + i];
+  st.ctrl.torso_quat_d.w() = 1.0;
+  st.joy.body_height = 0.3;
+  st.ctrl.movement_mode = 0;
+}
+
+// tick 1: a normal solve; tick 2: a NaN velocity -> the solver reports NONFINITE.  policy: 0 hold-last, 1 weight share, 2 zero.
+// out: grf_body after tick 1 (12) and after tick 2 (12); info = {failure_count, last_tick_failed, last_status, update() return}
+extern "C" int shim_failure_policy(const QmpcProblem* in, int policy, double* grf_tick1, double* grf_tick2, int* info, char* err,
+                                   int errlen) {
+  using namespace legged;
+  LeggedState st;
+  fill_state(st, in);
+  std::unique_ptr<LeggedMpc> mpc_ptr;
+  try { mpc_ptr = std::make_unique<CudaQuatMpc>(st, 0); } catch (const std::exception&) { return 1; }
+  auto* q = static_cast<CudaQuatMpc*>(mpc_ptr.get());
+  q->set_failure_policy(policy == 0 ? CudaQuatMpc::FailurePolicy::kHoldLast
+                                    : (policy == 1 ? CudaQuatMpc::FailurePolicy::kWeightShare : CudaQuatMpc::FailurePolicy::kZero));
+  bool ok = mpc_ptr->update(st);
+  for (int i = 0; i < 12; ++i) grf_tick1[i] = st.ctrl.optimized_input[i];
+  if (q->failure_count() != 0 || q->last_tick_failed()) return 2;
+  st.fbk.torso_lin_vel_world[1] = std::nan("");
+  ok = mpc_ptr->update(st) && ok;
+  for (int i = 0; i < 12; ++i) grf_tick2[i] = st.ctrl.optimized_input[i];
+  info[0] = (int)q->failure_count(); info[1] = q->last_tick_failed(); info[2] = q->last_status(); info[3] = ok;
+  std::strncpy(err, q->last_error(), errlen - 1);
+  err[errlen - 1] = 0;
+  return 0;
+}
+
+// joy.sin_ang_vel: `ticks` updates; returns the torso_quat_d the shim packed on the last tick and the one it wrote back
+extern "C" int shim_sin_ang_vel(const QmpcProblem* in, int ticks, double* packed_quat_d, double* state_quat_d, double* euler_d) {
+  using namespace legged;
+  LeggedState st;
+  fill_state(st, in);
+  st.joy.sin_ang_vel = true;
+  st.joy.yaw_rate = 0.4;   // must NOT move the desired attitude in this mode: the sine trajectory replaces it
+  std::unique_ptr<LeggedMpc> mpc_ptr;
+  try { mpc_ptr = std::make_unique<CudaQuatMpc>(st, 0); } catch (const std::exception&) { return 1; }
+  auto* q = static_cast<CudaQuatMpc*>(mpc_ptr.get());
+  for (int t = 0; t < ticks; ++t) mpc_ptr->update(st);
+  for (int i = 0; i < 4; ++i) packed_quat_d[i] = q->last_problem().torso_quat_d[i];
+  state_quat_d[0] = st.ctrl.torso_quat_d.w(); state_quat_d[1] = st.ctrl.torso_quat_d.x();
+  state_quat_d[2] = st.ctrl.torso_quat_d.y(); state_quat_d[3] = st.ctrl.torso_quat_d.z();
+  for (int i = 0; i < 3; ++i) euler_d[i] = st.ctrl.torso_euler_d[i];
+  return 0;
+}

@@ -273,3 +273,197 @@ def test_gpu_goal_update_and_raibert(oracle):
     mpc.lib.qmpc_default_raibert_params(C.byref(rp))
     rw, rr = oracle.raibert_targets(rp, g)
     assert np.abs(tw.cpu().numpy() - rw).max() < 1e-11 and np.abs(tr.cpu().numpy() - rr).max() < 1e-11
+
+
+# ------------------------------------------------------------------------------------------ row N3, gait-FSM half
+def _foot_inputs(n, seed, tick, mode=1, flag_prob=0.3):
+    """Feet under a slowly walking torso, Raibert-like targets ahead of them, random foot-force flags."""
+    rng = np.random.default_rng(seed * 7919 + tick)
+    i = np.zeros(n, dtype=abi.FOOT_UPDATE_INPUT_DTYPE)
+    base = np.array([0.20, 0.14, 0.0, 0.20, -0.14, 0.0, -0.20, 0.14, 0.0, -0.20, -0.14, 0.0])[None]
+    drift = 0.001 * tick
+    i["foot_pos_world"] = base + drift + rng.uniform(-0.02, 0.02, (n, 12))
+    i["foot_pos_target_world"] = base + drift + 0.05 + rng.uniform(-0.03, 0.03, (n, 12))
+    i["foot_contact_flag"] = rng.uniform(size=(n, 4)) < flag_prob
+    i["movement_mode"] = mode
+    return i
+
+
+def _quintic_numpy(t, T, p0, pT):
+    """Independent statement of QuinticCurve::get_foot_swing_target (Utils.cpp:236-293): the unique quintic through
+    the six conditions per axis, solved with numpy (float T and t as in the reference's signature)."""
+    t, T = float(np.float32(t)), float(np.float32(T))
+    rows = lambda s: (np.array([1, s, s**2, s**3, s**4, s**5]), np.array([0, 1, 2 * s, 3 * s**2, 4 * s**3, 5 * s**4]))
+    Cm = np.stack([rows(0)[0], rows(T)[0], rows(0)[1], rows(T)[1], rows(T / 2)[0], rows(T / 2)[1]])
+    d = pT[:2] - p0[:2]
+    vmid = 1.26 / T * d            # k |d| (cos, sin)(theta) with the signs restored = k d
+    out = np.zeros(9)
+    for ax in range(3):
+        con = [p0[ax], pT[ax], 0, 0, (p0[ax] + pT[ax]) / 2, vmid[ax]] if ax < 2 else [p0[2], pT[2], 0.1, -0.1, 0.1, 0.0]
+        a = np.linalg.solve(Cm, np.array(con, float))
+        out[ax] = np.polyval(a[::-1], t)
+        out[3 + ax] = np.polyval(np.polyder(a[::-1]), t)
+        out[6 + ax] = np.polyval(np.polyder(a[::-1], 2), t)
+    return out
+
+
+def test_oracle_leg_fsm_follows_the_gait_tables_and_the_quintic(oracle):
+    """LeggedContactFSM restated (oracle) against independent statements: contact states of an undisturbed trot
+    follow the pattern table tick by tick; swing targets equal the numpy quintic; stance feet hold the touch-down
+    position; early contact (> 90 % of the swing + foot-force flag) switches to stance; movement_mode 0 resets."""
+    n, freq, dt = 4, 2.2, 5.0 / 1000.0
+    st = oracle.new_leg_fsm(n, gait_freq=freq)
+    phase = np.zeros(4)
+    swing_start = {}
+    for tick in range(260):                                   # > 2.8 gait cycles
+        inp = _foot_inputs(n, 1, tick, flag_prob=0.0)
+        out = oracle.foot_update(st, inp, dt, freq)
+        phase = phase + freq * dt                             # every leg of a robot runs the same clock in a trot
+        cyc = phase[0] % 1.0 if phase[0] % 1.0 != 0 else 1.0
+        # trot table (LeggedContactFSM.cpp:87-108): FL/RR stance for phase < 0.5, FR/RL swing first
+        if abs(cyc - 0.5) > 2 * freq * dt and min(cyc, 1 - cyc) > 2 * freq * dt:
+            want = np.array([1, 0, 0, 1]) if cyc < 0.5 else np.array([0, 1, 1, 0])
+            assert (out["plan_contacts"] == want).all(), (tick, cyc, out["plan_contacts"][0])
+        for leg in range(4):
+            sw = out["plan_contacts"][0, leg] == 0
+            if sw and (leg not in swing_start):
+                # a leg that begins in swing at reset starts its state at phase 0 (reset(), :16); one entered through
+                # a transition starts it at the phase of the entering tick (common_enter, :217)
+                swing_start[leg] = (inp["foot_pos_world"][0, 3 * leg:3 * leg + 3].copy(),
+                                    0.0 if tick == 0 else out["gait_counter"][0, leg])
+            if not sw:
+                swing_start.pop(leg, None)
+        # swing feet: the oracle's target equals the independent quintic evaluated at the same state percent
+        pat_end = {0: 1.0, 3: 1.0, 1: 0.5, 2: 0.5}
+        for leg, (p0, ph0) in list(swing_start.items()):
+            if out["plan_contacts"][0, leg] != 0:
+                continue
+            start = ph0
+            pct = min(max((out["gait_counter"][0, leg] - start) / (pat_end[leg] - start), 0.0), 1.0)
+            want = _quintic_numpy(0.5 * pct / freq, 0.5 / freq, p0, inp["foot_pos_target_world"][0, 3 * leg:3 * leg + 3])
+            got = np.concatenate([out[f][0, 3 * leg:3 * leg + 3] for f in ("foot_pos_target", "foot_vel_target", "foot_acc_target")])
+            # the reference builds C from FLOAT powers of T (Utils.cpp:236-244): ~1e-7 relative off the exact quintic
+            assert np.abs(got[:6] - want[:6]).max() < 1e-5 and np.abs(got[6:] - want[6:]).max() < 1e-3, (tick, leg)
+    # swing-curve end points: t = 0 -> start with z velocity 0.1; t = T -> target; apex 0.1 at T / 2
+    T = 0.5 / freq
+    p0, pT = np.array([0.1, -0.05, 0.0]), np.array([0.25, 0.02, 0.01])
+    a, m, b = _quintic_numpy(0, T, p0, pT), _quintic_numpy(T / 2, T, p0, pT), _quintic_numpy(T, T, p0, pT)
+    assert np.abs(a[:3] - p0).max() < 1e-9 and abs(a[5] - 0.1) < 1e-9
+    assert np.abs(b[:3] - pT).max() < 1e-6 and abs(m[2] - 0.1) < 1e-9
+    # early contact: a flagged swing foot past 90 % of its swing lands at once and holds its position
+    st = oracle.new_leg_fsm(1, gait_freq=freq)
+    landed = None
+    for tick in range(200):
+        inp = _foot_inputs(1, 2, tick, flag_prob=0.0)
+        pct_fr = (tick * freq * dt % 1.0) / 0.5                # FR swings over phase 0 .. 0.5
+        if 0.92 < pct_fr < 1.0 and landed is None:
+            inp["foot_contact_flag"][0, 1] = 1
+        out = oracle.foot_update(st, inp, dt, freq)
+        if inp["foot_contact_flag"][0, 1] and landed is None:
+            assert out["plan_contacts"][0, 1] == 1              # before the table's switch time
+            landed = inp["foot_pos_world"][0, 3:6].copy()
+            assert np.array_equal(out["foot_pos_target"][0, 3:6], landed) and (out["foot_vel_target"][0, 3:6] == 0).all()
+    assert landed is not None
+    # movement_mode 0: reset, every foot planned in contact, phase 0
+    out = oracle.foot_update(st, _foot_inputs(1, 2, 500, mode=0), dt, freq)
+    assert (out["plan_contacts"] == 1).all() and (out["gait_counter"] == 0).all()
+
+
+def _emul_lib(tmp_path):
+    import os
+    import subprocess
+    so = str(tmp_path / "libqmpc_emul.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so,
+                           os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul", "emul.cpp")])
+    return C.CDLL(so)
+
+
+def test_emulated_leg_fsm_body_matches_oracle(oracle, tmp_path):
+    """The kernel body (tests/emul) against the oracle over 400 ticks, all four gait patterns, random foot-force
+    flags, mode switches: contact states and gait counters bit-exact, swing targets to 1e-12."""
+    em = _emul_lib(tmp_path)
+    n, cap, freq, dt = 64, 70, 2.2, 5.0 / 1000.0
+    gait = (np.arange(n) % 4).astype(np.int32)
+    state = np.zeros(em.emul_fsm_state_doubles() * 4 * cap)
+    em.emul_leg_fsm_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    em.emul_foot_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    assert em.emul_leg_fsm_init(state.ctypes.data, cap, gait.ctypes.data, n) == 0
+    st = oracle.new_leg_fsm(n, gait=gait, gait_freq=freq)
+    seen = set()
+    for tick in range(400):
+        inp = _foot_inputs(n, 3, tick, mode=0 if tick in (0, 1, 250) else 1)
+        got = np.zeros(n, dtype=abi.FOOT_UPDATE_OUTPUT_DTYPE)
+        assert em.emul_foot_update(state.ctypes.data, cap, inp.ctypes.data, dt, freq, n, got.ctypes.data) == 0
+        ref = oracle.foot_update(st, inp, dt, freq)
+        assert np.array_equal(got["plan_contacts"], ref["plan_contacts"]), tick
+        assert np.array_equal(got["gait_counter"], ref["gait_counter"]), tick
+        for f in ("foot_pos_target", "foot_vel_target", "foot_acc_target"):
+            assert np.abs(got[f] - ref[f]).max() < 1e-12, (tick, f)
+        seen |= set(map(tuple, ref["plan_contacts"]))
+    assert len(seen) >= 6          # trot, trot-with-stand, crawl and stand masks all occurred
+
+
+@pytest.mark.gpu
+def test_gpu_foot_update_matches_oracle_and_closes_the_loop(oracle):
+    """Batched QuatMpc::foot_update on the device against the oracle (contact states / gait counters bit-exact,
+    swing targets 1e-12), then one whole controller tick without leaving the device:
+    goal_update -> foot_update (writes plan_contacts + gait states) -> predict schedule -> scheduled solve -> torques."""
+    import torch
+    from quaternion_mpc_b200 import QuatMpc
+    B, freq, dt = 3000, 2.2, 5.0 / 1000.0
+    mpc = QuatMpc(horizon=10, max_batch=B)
+    gait = (np.arange(B) % 4).astype(np.int32)
+    d_fsm = mpc.alloc_leg_fsm(torch.from_numpy(gait).cuda())
+    st = oracle.new_leg_fsm(B, gait=gait, gait_freq=freq)
+    d_probs = mpc.to_device(random_batch(B, seed=8, gait="trot"))
+    d_gait = torch.zeros((B, abi.GAIT_STATE_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    for tick in range(150):
+        inp = _foot_inputs(B, 4, tick, mode=0 if tick == 0 else 1)
+        d_out = mpc.foot_update(d_fsm, torch.from_numpy(inp.view(np.uint8).reshape(B, -1)).cuda(), freq, dt, d_probs, d_gait)
+        ref = oracle.foot_update(st, inp, dt, freq)
+        if tick % 10 == 0 or tick > 140:
+            got = d_out.cpu().numpy().reshape(-1).view(abi.FOOT_UPDATE_OUTPUT_DTYPE)
+            assert np.array_equal(got["plan_contacts"], ref["plan_contacts"]) and np.array_equal(got["gait_counter"], ref["gait_counter"])
+            for f in ("foot_pos_target", "foot_vel_target", "foot_acc_target"):
+                assert np.abs(got[f] - ref[f]).max() < 1e-12, (tick, f)
+    probs = d_probs.cpu().numpy().reshape(-1).view(abi.PROBLEM_DTYPE)
+    assert np.array_equal(probs["plan_contacts"], ref["plan_contacts"])
+    g = d_gait.cpu().numpy().reshape(-1).view(abi.GAIT_STATE_DTYPE)
+    assert np.array_equal(g["gait_phase"], ref["gait_counter"]) and (g["gait"] == gait).all() and (g["gait_freq"] == freq).all()
+    # the rest of the tick on the device: schedule from the FSM's own gait states, solve, torques
+    d_sched = mpc.predict_contact_schedule(d_gait)
+    d_res = mpc.grf_update_sched_device(d_probs, d_sched)
+    q = np.array([0.0, 0.8, -1.6] * 4)[None] + np.random.default_rng(1).uniform(-0.1, 0.1, (B, 12))
+    _, jac = mpc.leg_kinematics(torch.from_numpy(q).cuda())
+    pc = torch.from_numpy(ref["plan_contacts"].astype(np.int32)).cuda()
+    tau = mpc.joint_torques(d_res, jac, pc, movement_mode=1).cpu().numpy()
+    sched = oracle.predict_schedule(mpc.cfg, g)
+    assert np.array_equal(d_sched.cpu().numpy(), sched)
+    rr = oracle.solve_batch_sched(mpc.cfg, probs, sched, nthreads=8)
+    res = mpc.results_to_numpy(d_res)
+    ok = (res["status"] < 2) & (rr["status"] < 2)
+    # stand-pattern robots plan four feet; others whatever the FSM says; flight phases cannot occur in these tables
+    assert ok.mean() > 0.8 and np.abs(res["grf_body"][ok] - rr["grf_body"][ok]).max() < 1e-4
+    rtau = oracle.joint_torques(rr, oracle.leg_kinematics(_leg_params(), q)[1], ref["plan_contacts"].astype(np.int32), 1)
+    assert np.abs(tau[ok] - rtau[ok]).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_schedule_predictor_survives_non_finite_and_huge_phases():
+    """One bad robot record (Inf / NaN / 1e12 gait phase or frequency) must not hang the launch: the reference's
+    `while (ph > 1.0) ph -= 1.0` is evaluated in closed form and absurd phases fall through to STANCE."""
+    import torch
+    from quaternion_mpc_b200 import QuatMpc
+    mpc = QuatMpc(horizon=16, max_batch=64)
+    g = random_gait_states(64, seed=3)
+    g["gait_phase"][1] = np.inf
+    g["gait_phase"][2] = np.nan
+    g["gait_phase"][3] = 1e12 + 0.25
+    g["gait_freq"][4] = np.inf
+    g["gait_phase"][5] = 7.0          # a whole number wraps to 1.0, not 0.0
+    out = mpc.predict_contact_schedule(torch.from_numpy(g.view(np.uint8).reshape(64, -1)).cuda()).cpu().numpy()
+    want = predict_schedule_numpy(g[6:], 16, mpc.cfg.dt)
+    assert np.array_equal(out[6:], want)
+    assert (out[1, :16] == 15).all() and (out[2, 0] == 15) and (out[4, 1:16] == 15).all()
+    g5 = g[5:6].copy(); g5["gait_phase"] = 1.0
+    assert np.array_equal(out[5], predict_schedule_numpy(g5, 16, mpc.cfg.dt)[0])

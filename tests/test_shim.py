@@ -117,3 +117,42 @@ def test_shim_contact_schedule_mode(shim, oracle):
     assert sched[0, :4].tolist() == [9, 9, 9, 9] and sched[0, 4:10].tolist() == [6] * 6 and (sched[0, 10:] == 0).all()
     ref = oracle.solve_batch_sched(default_config(0, 10), out_p, sched)
     assert np.abs(ref["grf_body"][0] - gb).max() < 1e-4 and si[1] == ref["iterations"][0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("policy", [0, 1, 2])
+def test_shim_failed_solve_is_reported_and_follows_the_policy(shim, policy):
+    """A solve the solver cannot do (NaN state -> status NONFINITE) is counted, flagged and described; update() still
+    returns true (the reference's contract) and the GRFs follow the explicit policy: hold the last tick's values,
+    the weight share u_ref, or zero."""
+    p = random_batch(1, seed=23, gait="stand")
+    g1, g2, info = np.zeros(12), np.zeros(12), np.zeros(4, dtype=np.int32)
+    err = C.create_string_buffer(256)
+    shim.shim_failure_policy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    assert shim.shim_failure_policy(p.ctypes.data, policy, g1.ctypes.data, g2.ctypes.data, info.ctypes.data, err, 256) == 0
+    assert info.tolist() == [1, 1, 4, 1]
+    assert b"nonfinite" in err.value
+    assert np.isfinite(g1).all() and abs(g1[2::3].sum() - 12.84 * 9.81) < 5.0
+    if policy == 0:
+        assert np.array_equal(g2, g1)
+    elif policy == 1:
+        want = np.zeros(12); want[2::3] = 12.84 * 9.81 / 4
+        assert np.allclose(g2, want, atol=1e-12)
+    else:
+        assert (g2 == 0).all()
+
+
+@pytest.mark.gpu
+def test_shim_sine_attitude_trajectory(shim):
+    """joy.sin_ang_vel (QuatMpc.cpp:139-146): the desired attitude is euler_to_quat of the sine Euler trajectory,
+    not the integrated joystick rate."""
+    p = random_batch(1, seed=24, gait="stand")
+    packed, state_q, eul = np.zeros(4), np.zeros(4), np.zeros(3)
+    ticks = 37
+    assert shim.shim_sin_ang_vel(C.c_void_p(p.ctypes.data), ticks, C.c_void_p(packed.ctypes.data), C.c_void_p(state_q.ctypes.data),
+                                 C.c_void_p(eul.ctypes.data)) == 0
+    e = 3.14 / 8 * np.sin(2 * 3.14 / 900 * (ticks - 1))
+    assert np.allclose(eul, e, atol=1e-15)
+    c, s_ = np.cos(e / 2), np.sin(e / 2)
+    want = np.array([c * c * c + s_ * s_ * s_, c * c * s_ - s_ * s_ * c, c * s_ * c + s_ * c * s_, s_ * c * c - c * s_ * s_])   # Utils.cpp:94-97
+    assert np.abs(packed - want).max() < 1e-15 and np.abs(state_q - want).max() < 1e-12
