@@ -527,9 +527,9 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
   // Mode 1 runs on all `tstride` lanes of the problem in lock-step: the gain matrix (and feed-forward) of
   // knot k+1 is copied from the L2-resident scratch into a double buffer in shared memory while knot k is
   // being computed, so the 72 broadcast reads of K_k per lane are shared-memory reads instead of L2 round
-  // trips.  Default: one cp.async.bulk (TMA 1-D, mbarrier completion) issued by lane 0;
-  // -DQMPC_COOP_KSTAGE_LDGSTS: 16-byte cp.async requests dealt over the lanes (the round-1 form).
-#ifndef QMPC_COOP_KSTAGE_LDGSTS
+  // trips.  Default: 16-byte cp.async requests dealt over the lanes (LDGSTS); -DQMPC_COOP_KSTAGE_BULK: one
+  // cp.async.bulk (TMA 1-D, mbarrier completion) issued by lane 0 (measured, see profiles/r02_experiments.md).
+#ifdef QMPC_COOP_KSTAGE_BULK
   double* mbar = kstage + 2 * kKD;
   if (mode == 1) {
     if (tl == 0) {

@@ -142,3 +142,52 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert [lp.rho_fix[i][0] for i in range(4)] == [0.1881, 0.1881, -0.1881, -0.1881]      # BaseInterface.cpp:12-15
     assert [lp.rho_fix[i][2] for i in range(4)] == [0.0812, -0.0812, 0.0812, -0.0812]      # :20-23
     assert rp.gait_freq == 2.2 and rp.delta_x_limit == 0.5 and rp.delta_y_limit == 0.3
+
+
+def test_multi_gpu_entry_points_argument_errors(lib):
+    """qmpc_create_multi / qmpc_solve_batch_host_multi: null pointers, empty or duplicate device lists and
+    oversized lists are argument errors; without a GPU creation fails loudly with QMPC_ERR_CUDA (no CPU fallback)."""
+    import torch
+    cfg = default_config(0, 10)
+    h = C.c_void_p()
+    dev = (C.c_int32 * 2)(0, 0)
+    E = abi.QMPC_ERR_ARG
+    assert lib.qmpc_create_multi(None, 16, dev, 1, C.byref(h)) == E
+    assert lib.qmpc_create_multi(C.byref(cfg), 16, None, 1, C.byref(h)) == E
+    assert lib.qmpc_create_multi(C.byref(cfg), 16, dev, 0, C.byref(h)) == E
+    assert lib.qmpc_create_multi(C.byref(cfg), 16, dev, 17, C.byref(h)) == E
+    assert lib.qmpc_create_multi(C.byref(cfg), 16, dev, 2, C.byref(h)) == E          # the same device twice
+    assert lib.qmpc_create_multi(C.byref(cfg), 0, dev, 1, C.byref(h)) == E
+    assert lib.qmpc_solve_batch_host_multi(None, None, 1, None) == E
+    assert lib.qmpc_multi_device_count(None) == 0 and lib.qmpc_multi_launch_count(None) == 0
+    lib.qmpc_destroy_multi(None)
+    if not torch.cuda.is_available():
+        assert lib.qmpc_create_multi(C.byref(cfg), 16, dev, 1, C.byref(h)) == abi.QMPC_ERR_CUDA
+        assert b"device 0" in lib.qmpc_multi_last_error(h)
+        lib.qmpc_destroy_multi(h)
+
+
+def test_create_ex_options(lib):
+    """QmpcCreateOptions are validated before any CUDA call; the library reads no environment variables."""
+    cfg = default_config(0, 10)
+    h = C.c_void_p()
+    for bad in (abi.QmpcCreateOptions(4, -1, 0, 0), abi.QmpcCreateOptions(-2, -1, 0, 0)):
+        assert lib.qmpc_create_ex(C.byref(cfg), 8, 0, C.byref(bad), C.byref(h)) == abi.QMPC_ERR_ARG
+    c2 = default_config(2, 10)
+    srb = abi.QmpcCreateOptions(abi.QMPC_KERNEL_SRB, -1, 0, 0)
+    assert lib.qmpc_create_ex(C.byref(c2), 8, 0, C.byref(srb), C.byref(h)) == abi.QMPC_ERR_ARG   # srb: quaternion models only
+    src = open(os.path.join(ROOT, "quaternion_mpc_b200", "csrc", "qmpc_api.cu")).read()
+    assert "getenv" not in src
+
+
+def test_multi_shards_are_the_python_shards():
+    """The C-ABI's shard g = [batch g / G, batch (g + 1) / G) is sharding.shard_range: contiguous, balanced, ordered."""
+    from quaternion_mpc_b200.sharding import shard_range
+    for batch in (0, 1, 7, 4096, 32768, 100003):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for g in range(world):
+                lo, hi = shard_range(batch, g, world)
+                assert lo == prev and hi == (batch * (g + 1)) // world and hi - lo in (batch // world, batch // world + 1)
+                prev = hi
+            assert prev == batch

@@ -1,0 +1,96 @@
+// bulk_probe.cu — isolates the gain-staging pattern of coop_rollout (qmpc_coop.cuh): per 16-lane group a double
+// buffer in shared memory filled by ONE cp.async.bulk per knot (mbarrier completion) vs 16-byte cp.async per lane.
+// Two groups per warp with independent barriers, re-initialised per "roll-out".  Prints PASS/FAIL + timings.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <vector>
+constexpr int kKD = 156, N = 10, G = 16;
+__device__ __forceinline__ void mbar_init(double* mb, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(mb);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigned bytes, double* mb) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(mb);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(double* mb, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(mb);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
+}
+template <int MODE>   // 0 = bulk, 1 = ldgsts
+__global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ gK, double* out, int rollouts, int nprob) {
+  extern __shared__ __align__(16) double sm[];
+  const int group = threadIdx.x / G, tl = threadIdx.x % G;
+  const unsigned lane_mask = ((1u << G) - 1u) << ((threadIdx.x % 32) / G * G);
+  double* kstage = sm + (size_t)group * (2 * kKD + 2);
+  double* mbar = kstage + 2 * kKD;
+  const int pid = blockIdx.x * (blockDim.x / G) + group;
+  if (pid >= nprob) return;
+  const double* src = gK + (size_t)pid * N * kKD;
+  double acc = 0;
+  for (int r = 0; r < rollouts; ++r) {
+    if (MODE == 0) {
+      if (tl == 0) {
+        mbar_init(mbar, 1); mbar_init(mbar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      __syncwarp(lane_mask);
+    }
+    auto stage = [&](int k) {
+      if (MODE == 0) { if (tl == 0) bulk_g2s(kstage + (k & 1) * kKD, src + (size_t)k * kKD, kKD * 8u, mbar + (k & 1)); }
+      else {
+        for (int c = tl; 2 * c < kKD; c += G) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(kstage + (k & 1) * kKD + 2 * c);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)k * kKD + 2 * c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    };
+    stage(0);
+    for (int k = 0; k < N; ++k) {
+      if (MODE == 0) mbar_wait(mbar + (k & 1), (unsigned)((k >> 1) & 1));
+      else asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp(lane_mask);
+      if (k + 1 < N) stage(k + 1);
+      const double* Kk = kstage + (k & 1) * kKD;
+      for (int i = tl; i < kKD; i += G) acc += Kk[i] * (1 + k);
+    }
+    __syncwarp(lane_mask);
+  }
+  out[(size_t)pid * G + tl] = acc;
+}
+int main(int argc, char** argv) {
+  const int nprob = 2048 * 8, rollouts = 20;
+  std::vector<double> h((size_t)nprob * N * kKD);
+  for (size_t i = 0; i < h.size(); ++i) h[i] = (double)((i * 2654435761u) % 1000) * 1e-3;
+  double *d, *o0, *o1;
+  cudaMalloc(&d, h.size() * 8); cudaMalloc(&o0, (size_t)nprob * G * 8); cudaMalloc(&o1, (size_t)nprob * G * 8);
+  cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+  const size_t smem = 8 * (2 * kKD + 2) * 8;
+  cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  stage_kernel<1><<<nprob / 8, 128, smem>>>(d, o1, rollouts, nprob);
+  cudaError_t er = cudaDeviceSynchronize();
+  printf("ldgsts: %s\n", cudaGetErrorString(er));
+  cudaEventRecord(e0);
+  stage_kernel<1><<<nprob / 8, 128, smem>>>(d, o1, rollouts, nprob);
+  cudaEventRecord(e1);
+  stage_kernel<0><<<nprob / 8, 128, smem>>>(d, o0, rollouts, nprob);
+  cudaEventRecord(e2);
+  er = cudaDeviceSynchronize();
+  printf("bulk: %s\n", cudaGetErrorString(er));
+  float a, b; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+  std::vector<double> r0((size_t)nprob * G), r1((size_t)nprob * G);
+  cudaMemcpy(r0.data(), o0, r0.size() * 8, cudaMemcpyDeviceToHost); cudaMemcpy(r1.data(), o1, r1.size() * 8, cudaMemcpyDeviceToHost);
+  size_t bad = 0; for (size_t i = 0; i < r0.size(); ++i) bad += r0[i] != r1[i];
+  printf("{\"ldgsts_ms\": %.3f, \"bulk_ms\": %.3f, \"mismatches\": %zu, \"verdict\": \"%s\"}\n", a, b, bad, bad ? "FAIL" : "PASS");
+  return 0;
+}
