@@ -314,6 +314,7 @@ int altro_ref_solve(const AltroRefProblem* P, const AltroRefOptions* o, double* 
   double viol = 0;
   double phi = merit(P, &w, X, U, &viol);
   int status = ALTRO_REF_MAX_ITERATIONS, iters = 0, trials = 0;
+  double pivot_ratio = 1.0;
   double cost_decrease = INFINITY, stat = INFINITY;
   if (!isfinite(phi)) status = ALTRO_REF_NONFINITE;
 
@@ -438,6 +439,12 @@ int altro_ref_solve(const AltroRefProblem* P, const AltroRefOptions* o, double* 
       for (int i = 0; i < m * ne; ++i) Qux[i] += w.Hux[k * m * ne + i];
       memcpy(L, Quu, sizeof(double) * m * m);
       if (chol(L, m)) { bp_ok = 0; break; }
+      { /* diagnostic: ratio of the largest to the smallest Cholesky pivot of this Quu (squared diagonal of L) */
+        double dmin = L[0], dmax = L[0];
+        for (int i = 1; i < m; ++i) { double v = L[i * m + i]; if (v < dmin) dmin = v; if (v > dmax) dmax = v; }
+        double r = (dmax / dmin) * (dmax / dmin);
+        if (r > pivot_ratio) pivot_ratio = r;
+      }
       for (int i = 0; i < m; ++i) {
         for (int j = 0; j < ne; ++j) S[i * (ne + 1) + j] = Qux[i * ne + j];
         S[i * (ne + 1) + ne] = Qu[i];
@@ -518,6 +525,7 @@ int altro_ref_solve(const AltroRefProblem* P, const AltroRefOptions* o, double* 
     st->max_violation = viol;
     st->stationarity = stat;
     st->penalty = w.rho[0];
+    st->pivot_ratio = pivot_ratio;
   }
   free(base);
   return 0;

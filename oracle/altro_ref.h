@@ -70,6 +70,7 @@ typedef struct AltroRefProblem {
 typedef struct AltroRefStats {
   int iterations, status, ls_trials;
   double cost, max_violation, stationarity, penalty;
+  double pivot_ratio; /* diagnostic: largest (max pivot / min pivot) of any Quu factored during the solve */
 } AltroRefStats;
 
 void altro_ref_default_options(AltroRefOptions* o);

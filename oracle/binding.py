@@ -19,7 +19,7 @@ _LIB = None
 class Stats(C.Structure):
     _fields_ = [("iterations", C.c_int), ("status", C.c_int), ("ls_trials", C.c_int),
                 ("cost", C.c_double), ("max_violation", C.c_double), ("stationarity", C.c_double),
-                ("penalty", C.c_double)]
+                ("penalty", C.c_double), ("pivot_ratio", C.c_double)]
 
 
 def build(force=False):
@@ -76,6 +76,24 @@ def solve_batch_convex(cfg, problems, nthreads=1):
     if rc:
         raise RuntimeError(f"oracle failed rc={rc}")
     return out
+
+
+def solve_batch_diag(cfg, problems, warm=None, schedule=None, nthreads=1):
+    """solve_batch / solve_batch_warm plus a conditioning diagnostic per solve: the largest ratio of the largest to
+    the smallest Cholesky pivot of any Quu factored during the solve (an estimate of cond(Quu)).  Used by the parity
+    policy: a solve whose ratio exceeds 1e12 amplifies 1-ulp differences between two fp64 implementations past the
+    1e-4 N tolerance - it is numerically undetermined, and is reported as such instead of being hidden."""
+    problems = np.ascontiguousarray(problems, dtype=PROBLEM_DTYPE)
+    sched = None if schedule is None else _sched_bytes(schedule, problems.shape[0])
+    out = np.zeros(problems.shape[0], dtype=RESULT_DTYPE)
+    ratio = np.zeros(problems.shape[0])
+    f = lib().qmpc_ref_solve_batch_diag
+    f.argtypes = [C.POINTER(QmpcConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    rc = f(C.byref(cfg), problems.ctypes.data, sched.ctypes.data if sched is not None else None,
+           warm.ctypes.data if warm is not None else None, problems.shape[0], out.ctypes.data, ratio.ctypes.data, nthreads)
+    if rc:
+        raise RuntimeError(f"oracle failed rc={rc}")
+    return out, ratio
 
 
 def _sched_bytes(schedule, batch):

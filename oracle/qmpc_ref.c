@@ -382,6 +382,8 @@ static int quat_assemble(const QmpcConfig* cfg, const QmpcProblem* in, const uns
   return QMPC_OK;
 }
 
+static __thread double tl_last_pivot_ratio = 0.0; /* diagnostic of the calling thread's last QuatMpc solve */
+
 int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched,
                             QmpcWarmStart* warm, QmpcResult* out) {
   QuatAssembly* A = (QuatAssembly*)malloc(sizeof(QuatAssembly));
@@ -401,6 +403,7 @@ int qmpc_ref_solve_one_warm(const QmpcConfig* cfg, const QmpcProblem* in, const 
     for (int k = 0; k < N; ++k) memcpy(U + k * m, warm->u[k + 1 < N ? k + 1 : N - 1], sizeof(double) * m);
   AltroRefStats st;
   if (altro_ref_solve(&A->P, &o, X, U, &st)) { free(A); return QMPC_ERR_ARG; }
+  tl_last_pivot_ratio = st.pivot_ratio;
 
   memset(out, 0, sizeof(*out));
   for (int i = 0; i < nf; ++i) {
@@ -581,6 +584,7 @@ int qmpc_ref_solve_one_convex(const QmpcConfig* cfg, const QmpcConvexProblem* in
 
 /* ============================================================ batch drivers (one worker per core) */
 typedef struct Job {
+  double* pivot_ratio; /* NULL or batch diagnostics */
   const QmpcConfig* cfg;
   const void* in;
   const unsigned char* sched; /* NULL or batch x QMPC_MAX_HORIZON mask bytes */
@@ -596,12 +600,23 @@ static void* worker(void* arg) {
                        : qmpc_ref_solve_one_warm(j->cfg, (const QmpcProblem*)j->in + i, sc, j->warm ? j->warm + i : NULL,
                                                  j->out + i);
     if (rc) j->rc = rc;
+    if (j->pivot_ratio && !j->convex) j->pivot_ratio[i] = tl_last_pivot_ratio;
   }
   return NULL;
 }
+static int run_batch_diag(const QmpcConfig* cfg, const void* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                          QmpcResult* out, int nthreads, int convex, double* pivot_ratio);
 static int run_batch(const QmpcConfig* cfg, const void* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
                      QmpcResult* out,
                      int nthreads, int convex) {
+  return run_batch_diag(cfg, in, sched, warm, batch, out, nthreads, convex, NULL);
+}
+int qmpc_ref_solve_batch_diag(const QmpcConfig* cfg, const QmpcProblem* in, const unsigned char* sched, QmpcWarmStart* warm,
+                              int batch, QmpcResult* out, double* pivot_ratio, int nthreads) {
+  return run_batch_diag(cfg, in, sched, warm, batch, out, nthreads, 0, pivot_ratio);
+}
+static int run_batch_diag(const QmpcConfig* cfg, const void* in, const unsigned char* sched, QmpcWarmStart* warm, int batch,
+                          QmpcResult* out, int nthreads, int convex, double* pivot_ratio) {
   if (!cfg || !in || !out || batch < 0) return QMPC_ERR_ARG;
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
@@ -609,6 +624,7 @@ static int run_batch(const QmpcConfig* cfg, const void* in, const unsigned char*
   pthread_t th[256];
   Job jobs[256];
   for (int t = 0; t < nthreads; ++t) {
+    jobs[t].pivot_ratio = pivot_ratio;
     jobs[t].cfg = cfg; jobs[t].in = in; jobs[t].sched = sched; jobs[t].warm = warm; jobs[t].out = out; jobs[t].convex = convex; jobs[t].rc = 0;
     jobs[t].lo = (int)((long long)batch * t / nthreads);
     jobs[t].hi = (int)((long long)batch * (t + 1) / nthreads);

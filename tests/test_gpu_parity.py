@@ -27,11 +27,18 @@ def _solve_dev(mpc, probs):
 PARITY_COUNTS = []   # one record per _check call, printed at the end of the session (conftest.py)
 
 
-def _check(res, ref, tol=TOL, max_undetermined=5e-3, max_outliers=0.0, label=""):
+COND_LIMIT = 1e12   # largest / smallest Cholesky pivot of Quu beyond which fp64 leaves < 4 digits: 1-ulp differences
+                    # between two correct implementations then exceed the 1e-4 N tolerance (measured: warm-started
+                    # solves reach 3e14 because duals restart at 0 while the penalty escalates to 1e8 against R = 1e-6)
+
+
+def _check(res, ref, tol=TOL, max_undetermined=5e-3, label="", pivot_ratio=None, min_allow=1):
     """Parity policy, with every count printed (nothing is exempted silently).
 
     * A solve whose status is success / max_iterations on BOTH sides must agree completely: same status,
-      same iteration count, GRFs within `tol`.  Exceptions need `max_outliers` (default: none).
+      same iteration count, GRFs within `tol`.  No outlier allowance.
+    * `pivot_ratio` (oracle diagnostic, warm-start tests): a solve whose Quu reached a pivot ratio above COND_LIMIT
+      is numerically undetermined in fp64; it is treated like a flagged solve - compared, counted, reported.
     * A solve that either side flags line-search-failed / backward-failed sits at the Armijo round-off
       floor (a 1-ulp difference such as FMA contraction decides whether a 2^-24 step is accepted).  It is
       still compared: it counts as `flagged_agree` when status, iteration count and GRFs agree like any
@@ -40,19 +47,21 @@ def _check(res, ref, tol=TOL, max_undetermined=5e-3, max_outliers=0.0, label="")
     err = np.maximum(np.abs(res["grf_body"] - ref["grf_body"]).max(axis=1),
                      np.abs(res["grf_world"] - ref["grf_world"]).max(axis=1))
     flagged = (res["status"] >= 2) | (ref["status"] >= 2)
+    ill = np.zeros(len(res), bool) if pivot_ratio is None else (pivot_ratio > COND_LIMIT)
+    flagged = flagged | ill
     agree = (res["status"] == ref["status"]) & (res["iterations"] == ref["iterations"]) & (err < tol)
     bad = ~agree & ~flagged
     differ = ~agree & flagged
-    counts = {"label": label, "solves": int(len(res)), "converged": int((ref["status"] == 0).sum()),
+    counts = {"label": label, "solves": int(len(res)), "ill_conditioned": int(ill.sum()), "converged": int((ref["status"] == 0).sum()),
               "capped": int((ref["status"] == 1).sum()), "flagged": int(flagged.sum()),
               "flagged_agree": int((flagged & agree).sum()), "flagged_differ": int(differ.sum()),
               "flagged_status_mismatch": int((flagged & (res["status"] != ref["status"])).sum()),
               "disagree": int(bad.sum()), "max_err_agreeing": float(err[agree].max()) if agree.any() else 0.0}
     PARITY_COUNTS.append(counts)
     print("[parity %s]" % " ".join(f"{k}={v:.3g}" if isinstance(v, float) else f"{k}={v}" for k, v in counts.items()), end=" ")
-    if bad.sum() > int(max_outliers * len(res)):
-        raise AssertionError((int(bad.sum()), float(err[bad].max()), int(np.flatnonzero(bad)[0])))
-    assert differ.sum() <= max(1, int(max_undetermined * len(res))), counts
+    if bad.any():
+        raise AssertionError((int(bad.sum()), float(err[bad].max()), int(np.flatnonzero(bad)[0]), counts))
+    assert differ.sum() <= max(min_allow, int(max_undetermined * len(res))), counts
     assert np.abs(res["torso_quat_d"] - ref["torso_quat_d"]).max() < 1e-12
     return counts["max_err_agreeing"]
 
@@ -267,7 +276,7 @@ def test_contact_schedule_solves_match_oracle(oracle, N, B, seed):
     sched = predict_schedule_numpy(random_gait_states(B, seed=seed), N, mpc.cfg.dt)
     res = _solve_sched_dev(mpc, probs, sched)
     ref = oracle.solve_batch_sched(mpc.cfg, probs, sched, nthreads=NT)
-    worst = _check(res, ref, max_undetermined=2e-2)
+    worst = _check(res, ref, label=f"sched N={N}")
     # a swing foot at knot 0 must carry no force in converged solves
     sw0 = np.stack([((sched[:, 0] >> i) & 1) == 0 for i in range(4)], 1)
     conv = res["status"] == 0
@@ -292,7 +301,7 @@ def test_constant_schedule_bit_identical_and_flight_phase(oracle):
     res = _solve_sched_dev(mpc, probs, sched)
     ref = oracle.solve_batch_sched(mpc.cfg, probs, sched, nthreads=NT)
     assert np.isfinite(res["grf_body"]).all()
-    _check(res, ref, max_undetermined=5e-2)
+    _check(res, ref, label="flight phase")
 
 
 def test_convex_and_cross_check_kernels_with_schedule(oracle):
@@ -303,12 +312,12 @@ def test_convex_and_cross_check_kernels_with_schedule(oracle):
     cp = random_convex_batch(B, seed=12)
     sched = predict_schedule_numpy(random_gait_states(B, seed=12), 10, cmpc.cfg.dt)
     res = _solve_sched_dev(cmpc, cp, sched)
-    _check(res, oracle.solve_batch_convex_sched(cmpc.cfg, cp, sched, nthreads=NT), max_undetermined=5e-2)
+    _check(res, oracle.solve_batch_convex_sched(cmpc.cfg, cp, sched, nthreads=NT), label="convex sched")
     probs = random_batch(B, seed=13, gait="trot")
     ref = oracle.solve_batch_sched(default_config(0, 10), probs, sched, nthreads=NT)
     for k in ("dense", "srb"):
         mpc = QuatMpc(horizon=10, max_batch=B, kernel=k)
-        _check(_solve_sched_dev(mpc, probs, sched), ref, max_undetermined=5e-2)
+        _check(_solve_sched_dev(mpc, probs, sched), ref, label=f"sched {k}")
 
 
 # ---------------------------------------------------------------------------- row N4: warm start
@@ -330,10 +339,10 @@ def test_warm_start_closed_loop_matches_oracle(oracle):
         d_res = mpc.grf_update_warm_device(mpc.to_device(probs), d_warm)
         torch.cuda.synchronize()
         res = mpc.results_to_numpy(d_res)
-        ref = oracle.solve_batch_warm(mpc.cfg, probs, w_ref, nthreads=NT)
+        ref, ratio = oracle.solve_batch_diag(mpc.cfg, probs, warm=w_ref, nthreads=NT)
         if tick == 0:
             assert res.tobytes() == cold.tobytes()          # invalid buffer -> cold start, bit-identical
-        _check(res, ref, max_undetermined=5e-2, max_outliers=2e-3)
+        _check(res, ref, max_undetermined=1.9e-2, label=f"warm tick {tick}", pivot_ratio=ratio)
         w = d_warm.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE)
         ok = (res["status"] < 2) & (ref["status"] < 2) & (res["iterations"] == ref["iterations"])
         ok &= np.abs(res["grf_body"] - ref["grf_body"]).max(axis=1) < TOL
@@ -368,8 +377,8 @@ def test_schedule_and_warm_edge_cases(oracle):
         res = mpc.results_to_numpy(d)
         if tick == 0:
             assert res.tobytes() == full.tobytes()
-        _check(res, oracle.solve_batch_warm(mpc.cfg, probs, w_ref, schedule=sched, nthreads=NT), max_undetermined=0.1,
-               max_outliers=0.02)
+        ref, ratio = oracle.solve_batch_diag(mpc.cfg, probs, warm=w_ref, schedule=sched, nthreads=NT)
+        _check(res, ref, min_allow=3, label=f"warm+sched tick {tick}", pivot_ratio=ratio)
     # 2-foot model: warm buffer rows keep their 12-wide layout, entries 6..11 stay zero
     cfg2 = default_config(abi.QMPC_MODEL_QUAT_2FOOT, 12)
     m2 = QuatMpc(max_batch=64, cfg=cfg2)
@@ -379,8 +388,8 @@ def test_schedule_and_warm_edge_cases(oracle):
         w_ref = dw.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE).copy()
         d = m2.grf_update_warm_device(m2.to_device(p2), dw)
         torch.cuda.synchronize()
-        _check(m2.results_to_numpy(d), oracle.solve_batch_warm(cfg2, p2, w_ref, nthreads=NT), max_undetermined=0.1,
-               max_outliers=0.02)
+        ref, ratio = oracle.solve_batch_diag(cfg2, p2, warm=w_ref, nthreads=NT)
+        _check(m2.results_to_numpy(d), ref, min_allow=3, label=f"warm 2-foot tick {tick}", pivot_ratio=ratio)
     w = dw.cpu().numpy().reshape(-1).view(abi.WARM_DTYPE)
     assert (w["u"][:, :, 6:] == 0).all() and (w["u"][:, 12:, :] == 0).all() and (w["valid"] == 1).all()
 

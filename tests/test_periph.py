@@ -439,11 +439,18 @@ def test_gpu_foot_update_matches_oracle_and_closes_the_loop(oracle):
     tau = mpc.joint_torques(d_res, jac, pc, movement_mode=1).cpu().numpy()
     sched = oracle.predict_schedule(mpc.cfg, g)
     assert np.array_equal(d_sched.cpu().numpy(), sched)
-    rr = oracle.solve_batch_sched(mpc.cfg, probs, sched, nthreads=8)
+    rr, ratio = oracle.solve_batch_diag(mpc.cfg, probs, schedule=sched, nthreads=8)
     res = mpc.results_to_numpy(d_res)
-    ok = (res["status"] < 2) & (rr["status"] < 2)
-    # stand-pattern robots plan four feet; others whatever the FSM says; flight phases cannot occur in these tables
-    assert ok.mean() > 0.8 and np.abs(res["grf_body"][ok] - rr["grf_body"][ok]).max() < 1e-4
+    # same parity policy as tests/test_gpu_parity.py::_check: solves neither side flags and whose Quu stayed below the
+    # fp64 conditioning limit must agree in status, iteration count and GRFs (1e-4 N); the others are counted
+    err = np.abs(res["grf_body"] - rr["grf_body"]).max(axis=1)
+    exempt = (res["status"] >= 2) | (rr["status"] >= 2) | (ratio > 1e12)
+    agree = (res["status"] == rr["status"]) & (res["iterations"] == rr["iterations"]) & (err < 1e-4)
+    print(f"[pipeline parity: solves={B} exempt={int(exempt.sum())} exempt_differ={int((exempt & ~agree).sum())} "
+          f"disagree={int((~exempt & ~agree).sum())} max_err={float(err[agree].max()):.2e}]", end=" ")
+    assert not (~exempt & ~agree).any(), (int((~exempt & ~agree).sum()), float(err[~exempt & ~agree].max()))
+    assert (exempt & ~agree).sum() <= B // 100
+    ok = agree
     rtau = oracle.joint_torques(rr, oracle.leg_kinematics(_leg_params(), q)[1], ref["plan_contacts"].astype(np.int32), 1)
     assert np.abs(tau[ok] - rtau[ok]).max() < 1e-4
 

@@ -3,6 +3,7 @@
 // Two groups per warp with independent barriers, re-initialised per "roll-out".  Prints PASS/FAIL + timings.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 constexpr int kKD = 156, N = 10, G = 16;
 __device__ __forceinline__ void mbar_init(double* mb, unsigned count) {
@@ -25,7 +26,8 @@ __device__ __forceinline__ void mbar_wait(double* mb, unsigned parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
 }
-template <int MODE>   // 0 = bulk, 1 = ldgsts
+template <int MODE>   // 0 = bulk (lane 0 of BOTH half-warps in one predicated instruction), 1 = ldgsts,
+                      // 2 = bulk, the two half-warps issue from different code paths, 3 = bulk, only half-warp 0 works
 __global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ gK, double* out, int rollouts, int nprob) {
   extern __shared__ __align__(16) double sm[];
   const int group = threadIdx.x / G, tl = threadIdx.x % G;
@@ -34,10 +36,11 @@ __global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ g
   double* mbar = kstage + 2 * kKD;
   const int pid = blockIdx.x * (blockDim.x / G) + group;
   if (pid >= nprob) return;
+  if (MODE == 3 && ((threadIdx.x % 32) / G) != 0) return;
   const double* src = gK + (size_t)pid * N * kKD;
   double acc = 0;
   for (int r = 0; r < rollouts; ++r) {
-    if (MODE == 0) {
+    if (MODE != 1) {
       if (tl == 0) {
         mbar_init(mbar, 1); mbar_init(mbar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -46,8 +49,11 @@ __global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ g
       __syncwarp(lane_mask);
     }
     auto stage = [&](int k) {
-      if (MODE == 0) { if (tl == 0) bulk_g2s(kstage + (k & 1) * kKD, src + (size_t)k * kKD, kKD * 8u, mbar + (k & 1)); }
-      else {
+      if (MODE == 0 || MODE == 3) { if (tl == 0) bulk_g2s(kstage + (k & 1) * kKD, src + (size_t)k * kKD, kKD * 8u, mbar + (k & 1)); }
+      else if (MODE == 2) {
+        if (((threadIdx.x % 32) / G) == 0) { if (tl == 0) bulk_g2s(kstage + (k & 1) * kKD, src + (size_t)k * kKD, kKD * 8u, mbar + (k & 1)); }
+        else { if (tl == 0) bulk_g2s(kstage + (k & 1) * kKD, src + (size_t)k * kKD, kKD * 8u, mbar + (k & 1)); }
+      } else {
         for (int c = tl; 2 * c < kKD; c += G) {
           const unsigned sa = (unsigned)__cvta_generic_to_shared(kstage + (k & 1) * kKD + 2 * c);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)k * kKD + 2 * c) : "memory");
@@ -57,7 +63,7 @@ __global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ g
     };
     stage(0);
     for (int k = 0; k < N; ++k) {
-      if (MODE == 0) mbar_wait(mbar + (k & 1), (unsigned)((k >> 1) & 1));
+      if (MODE != 1) mbar_wait(mbar + (k & 1), (unsigned)((k >> 1) & 1));
       else asm volatile("cp.async.wait_all;" ::: "memory");
       __syncwarp(lane_mask);
       if (k + 1 < N) stage(k + 1);
@@ -68,14 +74,8 @@ __global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ g
   }
   out[(size_t)pid * G + tl] = acc;
 }
-int main(int argc, char** argv) {
-  const int nprob = 2048 * 8, rollouts = 20;
-  std::vector<double> h((size_t)nprob * N * kKD);
-  for (size_t i = 0; i < h.size(); ++i) h[i] = (double)((i * 2654435761u) % 1000) * 1e-3;
-  double *d, *o0, *o1;
-  cudaMalloc(&d, h.size() * 8); cudaMalloc(&o0, (size_t)nprob * G * 8); cudaMalloc(&o1, (size_t)nprob * G * 8);
-  cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
-  const size_t smem = 8 * (2 * kKD + 2) * 8;
+template <int MODE>
+static int run(const double* d, double* o0, double* o1, int nprob, int rollouts, size_t smem) {
   cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
   stage_kernel<1><<<nprob / 8, 128, smem>>>(d, o1, rollouts, nprob);
   cudaError_t er = cudaDeviceSynchronize();
@@ -83,14 +83,30 @@ int main(int argc, char** argv) {
   cudaEventRecord(e0);
   stage_kernel<1><<<nprob / 8, 128, smem>>>(d, o1, rollouts, nprob);
   cudaEventRecord(e1);
-  stage_kernel<0><<<nprob / 8, 128, smem>>>(d, o0, rollouts, nprob);
+  stage_kernel<MODE><<<nprob / 8, 128, smem>>>(d, o0, rollouts, nprob);
   cudaEventRecord(e2);
   er = cudaDeviceSynchronize();
-  printf("bulk: %s\n", cudaGetErrorString(er));
+  printf("bulk mode %d: %s\n", MODE, cudaGetErrorString(er));
+  if (er != cudaSuccess) return 1;
   float a, b; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
   std::vector<double> r0((size_t)nprob * G), r1((size_t)nprob * G);
   cudaMemcpy(r0.data(), o0, r0.size() * 8, cudaMemcpyDeviceToHost); cudaMemcpy(r1.data(), o1, r1.size() * 8, cudaMemcpyDeviceToHost);
-  size_t bad = 0; for (size_t i = 0; i < r0.size(); ++i) bad += r0[i] != r1[i];
-  printf("{\"ldgsts_ms\": %.3f, \"bulk_ms\": %.3f, \"mismatches\": %zu, \"verdict\": \"%s\"}\n", a, b, bad, bad ? "FAIL" : "PASS");
-  return 0;
+  size_t bad = 0, cmp = 0;
+  for (size_t i = 0; i < r0.size(); ++i) { if (MODE == 3 && ((i / G) & 1)) continue; ++cmp; bad += r0[i] != r1[i]; }
+  printf("{\"mode\": %d, \"ldgsts_ms\": %.3f, \"bulk_ms\": %.3f, \"compared\": %zu, \"mismatches\": %zu, \"verdict\": \"%s\"}\n", MODE, a, b, cmp, bad, bad ? "FAIL" : "PASS");
+  return bad != 0;
+}
+int main(int argc, char** argv) {
+  const int mode = argc > 1 ? atoi(argv[1]) : 0;
+  const int nprob = 2048 * 8, rollouts = 20;
+  std::vector<double> h((size_t)nprob * N * kKD);
+  for (size_t i = 0; i < h.size(); ++i) h[i] = (double)((i * 2654435761u) % 1000) * 1e-3;
+  double *d, *o0, *o1;
+  cudaMalloc(&d, h.size() * 8); cudaMalloc(&o0, (size_t)nprob * G * 8); cudaMalloc(&o1, (size_t)nprob * G * 8);
+  cudaMemset(o0, 0, (size_t)nprob * G * 8);
+  cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+  const size_t smem = 8 * (2 * kKD + 2) * 8;
+  if (mode == 2) return run<2>(d, o0, o1, nprob, rollouts, smem);
+  if (mode == 3) return run<3>(d, o0, o1, nprob, rollouts, smem);
+  return run<0>(d, o0, o1, nprob, rollouts, smem);
 }
