@@ -59,8 +59,14 @@
 #define COOP_KNOT_SYNC_ALL(N_) ((void)0)
 #endif
 
-#ifdef __CUDACC__
+// The roll-out is inlined at its two call sites (nominal roll-out: mode 0; line search: mode 1): each copy is
+// specialised for its mode and, above all, the call no longer spills the caller's live registers around it
+// (31 LDL / 61 STL static in the out-of-line build).  Measured +6.7 % at B = 4096, +6.5 % at B = 65 536
+// (profiles/r02_experiments.md); round 1 had three call sites and measured the opposite.
+#if defined(__CUDACC__) && defined(QMPC_COOP_ROLLOUT_NOINLINE)
 #define QMPC_NOINLINE __noinline__
+#elif defined(__CUDACC__)
+#define QMPC_NOINLINE __forceinline__
 #else
 #define QMPC_NOINLINE
 #endif
@@ -469,28 +475,6 @@ QMPC_HD inline void lxx_block(const double* wq, const double* Hphi, int br, int 
 }
 
 #if defined(__CUDA_ARCH__)
-// 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier (cp.async.bulk; SASS UBLKCP):
-// ONE lane issues ONE instruction for a whole row instead of every lane issuing 16-byte cp.async requests.
-__device__ __forceinline__ void coop_mbar_init(double* mb, unsigned count) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(mb);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-}
-__device__ __forceinline__ void coop_bulk_g2s(double* dst, const double* src, unsigned bytes, double* mb) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(mb);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
-}
-__device__ __forceinline__ void coop_mbar_wait(double* mb, unsigned parity) {
-  const unsigned b = (unsigned)__cvta_generic_to_shared(mb);
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
-}
 // 16-byte cp.async requests dealt over the `nl` lanes of the problem (SASS LDGSTS)
 __device__ __forceinline__ void coop_cp_async_row(double* dst, const double* src, int doubles, int tl, int nl) {
   for (int c = tl; 2 * c < doubles; c += nl) {
@@ -507,7 +491,7 @@ __device__ __forceinline__ void coop_cp_async_row(double* dst, const double* src
 //   mode 1: trial step `alpha` around (X, U) with gains (gK: N x [K_k | d_k]): X, U untouched; the trial
 //           trajectory is recorded in the scratch (gTX/gTU, element-major, lane `tl` of `tstride`) so
 //           that the accepted one is simply copied back - no second roll-out; returns merit / violation
-template <class M>
+template <class M, bool kSmem = true>
 QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const double* wr, int N, float h, double* X,
                                         double* U, const double* gK,
                                         const double* gmu, double rho, double alpha, int mode, double* Jout,
@@ -519,6 +503,17 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
   // orders are exactly those of stage_cost() / knot_merit() / ct_dyn() / mid_dyn().
   constexpr int NX = M::NX, NE = 12, NU = M::NU, NC = M::NC, NF = M::kFeet;
   constexpr int kKD = NU * 12 + NU;
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_ASSUME_SHARED)
+  // this function is kept out of line, so its pointers are generic: tell the compiler which ones are shared memory
+  // (model, trajectories, weights - in the fused and forward kernels) so that it emits LDS / STS instead of generic
+  // LD / ST (149 M generic loads per 16 384 solves in the roll-out otherwise, profiles/r02_ncu_coop_B16384.txt)
+  if (kSmem) {
+    __builtin_assume(__isShared(&m));
+    __builtin_assume(__isShared(X));
+    __builtin_assume(__isShared(U));
+    __builtin_assume(__isShared(wr));
+  }
+#endif
   const double hd = (double)h, hh = (double)(h / 2);
   double x[NX], J = 0, vl = 0;
 #pragma unroll
@@ -527,30 +522,15 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
   // Mode 1 runs on all `tstride` lanes of the problem in lock-step: the gain matrix (and feed-forward) of
   // knot k+1 is copied from the L2-resident scratch into a double buffer in shared memory while knot k is
   // being computed, so the 72 broadcast reads of K_k per lane are shared-memory reads instead of L2 round
-  // trips.  Default: 16-byte cp.async requests dealt over the lanes (LDGSTS); -DQMPC_COOP_KSTAGE_BULK: one
-  // cp.async.bulk (TMA 1-D, mbarrier completion) issued by lane 0 (measured, see profiles/r02_experiments.md).
-#ifdef QMPC_COOP_KSTAGE_BULK
-  double* mbar = kstage + 2 * kKD;
-  if (mode == 1) {
-    if (tl == 0) {
-      coop_mbar_init(mbar, 1);
-      coop_mbar_init(mbar + 1, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp(lane_mask);
-  }
-  auto stage_gain = [&](int k) {
-    if (tl == 0) coop_bulk_g2s(kstage + (k & 1) * kKD, gK + (size_t)k * kKD, kKD * 8u, mbar + (k & 1));
-  };
-  auto stage_wait = [&](int k) { coop_mbar_wait(mbar + (k & 1), (unsigned)((k >> 1) & 1)); };
-#else
+  // trips.  16-byte cp.async requests dealt over the lanes (LDGSTS).  One cp.async.bulk per knot (TMA 1-D, mbarrier
+  // completion, issued by lane 0) was measured in tools/probes/bulk_probe.cu: the same staging pattern runs 2.3x
+  // SLOWER (1.47 ms against 0.63 ms), and in the kernel the gain stores of the backward pass would additionally
+  // need a generic -> async proxy fence per knot (profiles/r02_experiments.md) - not adopted.
   auto stage_gain = [&](int k) {
     coop_cp_async_row(kstage + (k & 1) * kKD, gK + (size_t)k * kKD, kKD, tl, tstride);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto stage_wait = [&](int) { asm volatile("cp.async.wait_all;" ::: "memory"); };
-#endif
   if (mode == 1) stage_gain(0);
 #else
   (void)kstage; (void)lane_mask;
@@ -1211,7 +1191,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
       const int br = lane >> 2, bc = lane & 3;
       double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #ifndef QMPC_COOP_F_UNROLL
-#define QMPC_COOP_F_UNROLL 1
+#define QMPC_COOP_F_UNROLL 2   // measured +0.4 % over 1 (profiles/r02_experiments.md)
 #endif
       constexpr int kFUnroll = QMPC_COOP_F_UNROLL;
 #pragma unroll(kFUnroll)
@@ -1371,6 +1351,18 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
     for (int e = lane; e < N * NU; e += G) U[e] = ld_stream(gTU + (size_t)e * NCAND + acc_lane);
   }
   COOP_SYNC();
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_DISCARD)
+  // The 16 trial trajectories (33.7 KB per slot at N = 10) are dead from here on, and they were 78 % of the DRAM
+  // traffic of round 1's kernel (769 kB per solve against 536 B algorithmic): dirty L2 lines written back to HBM when
+  // the scratch of 2368 slots (169 MB) overflows the 126 MB L2.  discard.global.L2 drops the lines WITHOUT write-back
+  // (every line is rewritten in full by the next line search: 16 lanes x 8 bytes = one 128-byte line per element),
+  // so only the live 37 KB per slot compete for the L2.
+  {
+    const size_t nlines = ((size_t)(N + 1) * NX * G + (size_t)N * NU * G + 15) / 16;
+    for (size_t e = (size_t)lane_id; e < nlines; e += G)
+      asm volatile("discard.global.L2 [%0], 128;" ::"l"(gTX + e * 16) : "memory");
+  }
+#endif
   c.cost_decrease = c.phi - phin;
   c.phi = phin;
   c.viol = violn;

@@ -58,7 +58,7 @@ QMPC_HD void phased_setup_one(const QmpcConfig& cfg, const SolverOpts& o, const 
   c.N = N;
   c.rho = o.penalty_initial;
   double J, vl;
-  coop_rollout<M>(m, cfg, wts + 13, N, o.h, X, U, gp + L::gK(N), gmu, c.rho, 0.0, 0, &J, &vl, nullptr, nullptr, 0, G, nullptr, 0u,
+  coop_rollout<M, false>(m, cfg, wts + 13, N, o.h, X, U, gp + L::gK(N), gmu, c.rho, 0.0, 0, &J, &vl, nullptr, nullptr, 0, G, nullptr, 0u,
                   (warm && warm[pid].valid) ? warm + pid : nullptr);
   c.phi = J; c.viol = vl;
   c.status = QMPC_STATUS_MAX_ITERATIONS; c.iters = 0;

@@ -24,12 +24,18 @@ rows = list(csv.reader(io.StringIO(src)))
 # region markers from the source file itself
 lines = open("/root/repo/quaternion_mpc_b200/csrc/qmpc_coop.cuh").read().split("\n")
 marks = []
-pats = [("blk helpers", "// ---- 3x3 block kernels"), ("layout", "struct CoopLayout"), ("knot_merit/hphi", "// stage cost + AL terms of one knot"),
-        ("rollout", "// One roll-out of the whole horizon"), ("setup", "// ------------------------------------------------------------------ set-up"),
-        ("linearise", "// ---------------- linearise"), ("stationarity", "// ---------------- stationarity"), ("dual update", "// dual update (row-parallel)"),
-        ("bp init", "// ---------------- Riccati backward pass"), ("phase A", "// ---- phase A"), ("phase B", "// ---- phase B"), ("phase C", "// ---- phase C"),
-        ("phase D", "// ---- phase D"), ("phase E", "// ---- phase E"), ("chol+solves", "// ---- Cholesky + both triangular solves"), ("old chol", "// ---- Cholesky of Quu"),
-        ("phase F", "// ---- phase F"), ("linesearch", "// ---------------- forward pass"), ("accept", "// ---------------- accepted step"), ("epilogue", "  COOP_PHASE {\n    if (lane == 0) {\n      QmpcResult r;")]
+pats = [("blk helpers", "// ---- 3x3 block kernels"), ("layout", "struct CoopRow"), ("linearize/At/Mt", "// ---- model dispatch: linearisation"),
+        ("knot_merit/hphi", "// stage cost + AL terms of one knot"), ("bulk/cp.async helpers", "// 1-D bulk copy global -> shared"),
+        ("rollout", "// One roll-out of the whole horizon"), ("ctx", "// Per-problem context of the phase functions"),
+        ("setup", "// ------------------------------------------------------------------ set-up + nominal roll-out"),
+        ("expansions", "// ---------------- expansions, lane k <- knot k"), ("stationarity", "// ---------------- stationarity"),
+        ("dual update", "// dual update (row-parallel)"), ("AL terms", "// ---------------- AL terms of every (knot, foot)"),
+        ("bp init", "// ------------------------------------------------------------------ Riccati backward pass"),
+        ("phase B", "// ---- phase B"), ("phase C", "// ---- phase C"), ("phase D", "// ---- phase D"), ("phase E", "// ---- phase E"),
+        ("chol+solves", "// ---- Cholesky + both triangular solves"), ("phase F", "// ---- phase F"),
+        ("linesearch", "// ------------------------------------------------------------------ forward pass"),
+        ("accept", "// ---------------- accepted step"), ("epilogue", "// ------------------------------------------------------------------ result + warm-start buffer"),
+        ("fused loop", "// ------------------------------------------------------------------ the whole solve, fused")]
 for name, pat in pats:
     p0 = pat.split("\n")[0]
     for i, l in enumerate(lines):

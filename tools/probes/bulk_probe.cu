@@ -26,6 +26,24 @@ __device__ __forceinline__ void mbar_wait(double* mb, unsigned parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
 }
+// mode 4: the exact instruction sequence libcu++ emits for cuda::device::memcpy_async_tx + barrier_arrive_tx + wait
+// (copy first, then arrive.expect_tx returning a token, token-based try_wait, source through cvta.to.global)
+__device__ __forceinline__ unsigned long long bulk_g2s_tok(double* dst, const double* src, unsigned bytes, double* mb) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(mb);
+  const unsigned long long g = (unsigned long long)__cvta_generic_to_global(src);
+  unsigned long long tok;
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(g), "r"(bytes), "r"(b) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;" : "=l"(tok) : "r"(b), "r"(bytes) : "memory");
+  return tok;
+}
+__device__ __forceinline__ void mbar_wait_tok(double* mb, unsigned long long tok) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(mb);
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.shared.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b), "l"(tok) : "memory");
+  }
+}
 template <int MODE>   // 0 = bulk (lane 0 of BOTH half-warps in one predicated instruction), 1 = ldgsts,
                       // 2 = bulk, the two half-warps issue from different code paths, 3 = bulk, only half-warp 0 works
 __global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ gK, double* out, int rollouts, int nprob) {
@@ -36,7 +54,7 @@ __global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ g
   double* mbar = kstage + 2 * kKD;
   const int pid = blockIdx.x * (blockDim.x / G) + group;
   if (pid >= nprob) return;
-  if (MODE == 3 && ((threadIdx.x % 32) / G) != 0) return;
+  if ((MODE == 3 || MODE == 4) && ((threadIdx.x % 32) / G) != 0) return;
   const double* src = gK + (size_t)pid * N * kKD;
   double acc = 0;
   for (int r = 0; r < rollouts; ++r) {
@@ -61,6 +79,32 @@ __global__ void __launch_bounds__(128) stage_kernel(const double* __restrict__ g
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
     };
+    if (MODE == 4) {
+      for (int k = 0; k < N; ++k) {
+        if (tl == 0) {
+          const unsigned long long tok = bulk_g2s_tok(kstage + (k & 1) * kKD, src + (size_t)k * kKD, kKD * 8u, mbar + (k & 1));
+          mbar_wait_tok(mbar + (k & 1), tok);
+        }
+        __syncwarp(lane_mask);
+        const double* Kk = kstage + (k & 1) * kKD;
+        for (int i = tl; i < kKD; i += G) acc += Kk[i] * (1 + k);
+        __syncwarp(lane_mask);
+      }
+      continue;
+    }
+    if (MODE == 5) {   // mode 4's recipe, pipelined one knot ahead as the kernel does it
+      unsigned long long tok[2] = {0, 0};
+      if (tl == 0) tok[0] = bulk_g2s_tok(kstage, src, kKD * 8u, mbar);
+      for (int k = 0; k < N; ++k) {
+        if (tl == 0) mbar_wait_tok(mbar + (k & 1), tok[k & 1]);
+        __syncwarp(lane_mask);
+        if (k + 1 < N && tl == 0) tok[(k + 1) & 1] = bulk_g2s_tok(kstage + ((k + 1) & 1) * kKD, src + (size_t)(k + 1) * kKD, kKD * 8u, mbar + ((k + 1) & 1));
+        const double* Kk = kstage + (k & 1) * kKD;
+        for (int i = tl; i < kKD; i += G) acc += Kk[i] * (1 + k);
+      }
+      __syncwarp(lane_mask);
+      continue;
+    }
     stage(0);
     for (int k = 0; k < N; ++k) {
       if (MODE != 1) mbar_wait(mbar + (k & 1), (unsigned)((k >> 1) & 1));
@@ -92,7 +136,7 @@ static int run(const double* d, double* o0, double* o1, int nprob, int rollouts,
   std::vector<double> r0((size_t)nprob * G), r1((size_t)nprob * G);
   cudaMemcpy(r0.data(), o0, r0.size() * 8, cudaMemcpyDeviceToHost); cudaMemcpy(r1.data(), o1, r1.size() * 8, cudaMemcpyDeviceToHost);
   size_t bad = 0, cmp = 0;
-  for (size_t i = 0; i < r0.size(); ++i) { if (MODE == 3 && ((i / G) & 1)) continue; ++cmp; bad += r0[i] != r1[i]; }
+  for (size_t i = 0; i < r0.size(); ++i) { if ((MODE == 3 || MODE == 4) && ((i / G) & 1)) continue; ++cmp; bad += r0[i] != r1[i]; }
   printf("{\"mode\": %d, \"ldgsts_ms\": %.3f, \"bulk_ms\": %.3f, \"compared\": %zu, \"mismatches\": %zu, \"verdict\": \"%s\"}\n", MODE, a, b, cmp, bad, bad ? "FAIL" : "PASS");
   return bad != 0;
 }
@@ -108,5 +152,7 @@ int main(int argc, char** argv) {
   const size_t smem = 8 * (2 * kKD + 2) * 8;
   if (mode == 2) return run<2>(d, o0, o1, nprob, rollouts, smem);
   if (mode == 3) return run<3>(d, o0, o1, nprob, rollouts, smem);
+  if (mode == 4) return run<4>(d, o0, o1, nprob, rollouts, smem);
+  if (mode == 5) return run<5>(d, o0, o1, nprob, rollouts, smem);
   return run<0>(d, o0, o1, nprob, rollouts, smem);
 }
