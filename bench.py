@@ -136,6 +136,11 @@ def aux_kernels(device, cfg, hbm_peak, robots=1 << 20, reps=20):
     d_state = mpc.alloc_goal_state()
     foot, jac = mpc.leg_kinematics(q)
     pc = torch.ones((robots, 4), dtype=torch.int32, device=dev)
+    d_fsm = mpc.alloc_leg_fsm()
+    fin = np.zeros(robots, dtype=abi.FOOT_UPDATE_INPUT_DTYPE)
+    fin["movement_mode"] = 1
+    fin["foot_pos_target_world"] = 0.05
+    d_fin = torch.from_numpy(fin.view(np.uint8).reshape(robots, -1)).to(dev)
     cases = {
         # bytes per robot: what the kernel must read + write (struct sizes from include/qmpc.h)
         "predict_contact_schedule": (48 + 32, lambda: mpc.predict_contact_schedule(g)),
@@ -143,6 +148,8 @@ def aux_kernels(device, cfg, hbm_peak, robots=1 << 20, reps=20):
         "joint_torques": (96 + 288 + 16 + 96, lambda: mpc.joint_torques(d_res, jac, pc)),
         "goal_update": (128 + 5 * 16 + 6 * (2 * 16 + 16) + 128, lambda: mpc.goal_update(d_state, d_gin, d_probs)),
         "raibert_targets": (128 + 192, lambda: mpc.raibert_targets(d_gin)),
+        # QuatMpc::foot_update: input + output records, the 27-field FSM state of 4 legs read and written
+        "foot_update": (224 + 336 + 2 * 27 * 4 * 8, lambda: mpc.foot_update(d_fsm, d_fin)),
     }
     out = {"robots": robots}
     for name, (bpr, fn) in cases.items():

@@ -28,10 +28,11 @@ from quaternion_mpc_b200.workloads import random_convex_batch
 c = ConvexMpc(horizon=10, max_batch=B)
 rc = c.grf_update_device(c.to_device(random_convex_batch(B, seed=3))); torch.cuda.synchronize()
 ph = QuatMpc(horizon=10, max_batch=B, kernel="phased")
-rp = ph.grf_update_device(d); torch.cuda.synchronize()
+d2 = mpc.to_device(p)                             # `d` was overwritten in place by goal_update above
+rp = ph.grf_update_device(d2); torch.cuda.synchronize()
 assert ph.results_to_numpy(rp).tobytes() == mpc.results_to_numpy(r).tobytes()
 m20 = QuatMpc(horizon=20, max_batch=B)            # linearisation blocks staged per knot (not shared-memory residents)
-r20 = m20.grf_update_device(d); torch.cuda.synchronize()
+r20 = m20.grf_update_device(d2); torch.cuda.synchronize()
 fsm = mpc.alloc_leg_fsm()
 fin = np.zeros(B, dtype=abi.FOOT_UPDATE_INPUT_DTYPE); fin["movement_mode"] = 1
 for _ in range(3):
