@@ -305,8 +305,12 @@ def main():
         print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
         return 1
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # host-side barrier for the one-call multi-GPU e2e leg: the other ranks must wait WITHOUT a kernel on their
+        # GPU (an NCCL barrier spins on the device and takes SMs from the solve rank 0 launches there)
+        cpu_group = dist.new_group(backend="gloo")
     from quaternion_mpc_b200 import ConvexMpc, MultiGpuMpc, QuatMpc
     Mpc = ConvexMpc if a.model == "convex" else QuatMpc
 
@@ -384,6 +388,7 @@ def main():
         e2e_s = 0.0
         e2e_path = f"one qmpc_solve_batch_host_multi call on rank 0 over {world} devices, pinned host buffers"
         barrier()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             allp = np.concatenate([random_batch(B, seed=r, gait=a.gait) for r in range(world)])
             multi = MultiGpuMpc(cfg, B * world, list(range(world)))
@@ -398,6 +403,7 @@ def main():
             allres = h_out.numpy().reshape(-1).view(abi.RESULT_DTYPE)
             assert allres[:B].tobytes() == res.tobytes() and np.isfinite(allres["grf_body"]).all()
             multi.close()
+        dist.barrier(group=cpu_group)      # ranks != 0 wait here on the host, their GPUs idle for rank 0's call
         barrier()
     if rank == 0 and len([r for r in sampler.rows if r[0] >= sampler.t_mark]) < 3:
         t_end = time.perf_counter() + 0.25          # very short runs: keep the GPU busy with the same solve
