@@ -138,8 +138,9 @@ int qmpc_create(const QmpcConfig* cfg, int32_t max_batch, int32_t device, QmpcHa
  * `opt` may be NULL (= qmpc_create).  The dense and srb kernels are the on-device cross-checks of the
  * tests (independent implementations of the same solve); the product default is QMPC_KERNEL_AUTO. */
 #define QMPC_KERNEL_AUTO   -1 /* coop for every model                                              */
-#define QMPC_KERNEL_DENSE   0 /* generic dense algebra, one thread per problem (cross-check)        */
-#define QMPC_KERNEL_SRB     1 /* structured, one thread per problem, QUAT models only (cross-check) */
+#define QMPC_KERNEL_DENSE   0 /* generic dense algebra, one thread per problem: cross-check, compiled only
+                                 into the test-only libqmpc_b200_xcheck.so (QMPC_ERR_ARG in the product)  */
+#define QMPC_KERNEL_SRB     1 /* structured, one thread per problem, QUAT models only: cross-check, ditto    */
 #define QMPC_KERNEL_COOP    2 /* 16 lanes per problem, shared-memory resident, one persistent launch */
 #define QMPC_KERNEL_PHASED  3 /* coop bodies split into set-up / backward / forward launches        */
 typedef struct QmpcCreateOptions {

@@ -108,20 +108,27 @@ EXPORTED_SYMBOLS = [
 ]
 
 _LIB = None
+_XLIB = None
 
 
-def lib_path():
+def lib_path(xcheck=False):
     # QMPC_LIB lets an experiment point at an alternative build of the same library
+    if xcheck:
+        return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqmpc_b200_xcheck.so")
     return os.environ.get("QMPC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqmpc_b200.so")
 
 
-def load_library():
+def load_library(xcheck=False):
     """Load libqmpc_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if absent:
-    there is no Python / CPU fallback for the solve."""
-    global _LIB
-    if _LIB is not None:
+    there is no Python / CPU fallback for the solve.  xcheck=True loads the TEST-ONLY sibling
+    libqmpc_b200_xcheck.so, the same library plus the dense / srb cross-check kernels (the product
+    library does not contain them)."""
+    global _LIB, _XLIB
+    if xcheck and _XLIB is not None:
+        return _XLIB
+    if not xcheck and _LIB is not None:
         return _LIB
-    path = lib_path()
+    path = lib_path(xcheck)
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} not found: the CUDA extension is not built. Run `python -c 'import "
@@ -200,5 +207,8 @@ def load_library():
     lib.qmpc_measure_fma_peak.restype = C.c_int
     lib.qmpc_abi_version.argtypes = []
     lib.qmpc_abi_version.restype = i32
-    _LIB = lib
+    if xcheck:
+        _XLIB = lib
+    else:
+        _LIB = lib
     return lib

@@ -224,6 +224,9 @@ extern "C" int qmpc_create_ex(const QmpcConfig* cfg, int32_t max_batch, int32_t 
   if (opt) op = *opt;
   if (op.kernel < QMPC_KERNEL_AUTO || op.kernel > QMPC_KERNEL_PHASED) return QMPC_ERR_ARG;
   if (op.kernel == QMPC_KERNEL_SRB && cfg->model == QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;
+#ifdef QMPC_NO_XCHECK   // the product library: the cross-check kernels are compiled into the test-only sibling only
+  if (op.kernel == QMPC_KERNEL_DENSE || op.kernel == QMPC_KERNEL_SRB) return QMPC_ERR_ARG;
+#endif
 
   if (cfg->horizon < 1 || cfg->horizon > QMPC_MAX_HORIZON) return QMPC_ERR_ARG;
   if (cfg->model < 0 || cfg->model > QMPC_MODEL_EULER_CONVEX) return QMPC_ERR_ARG;

@@ -32,7 +32,8 @@ class _BatchedMpc:
         """`kernel` / `smem_residents` / `packed_launch` are the QmpcCreateOptions of include/qmpc.h
         (explicit per-handle choices; the library reads no environment variables).  kernel "dense" / "srb"
         select the on-device cross-check kernels used by the tests."""
-        self.lib = abi.load_library()
+        # the dense / srb cross-check kernels live in the test-only sibling library, not in the product
+        self.lib = abi.load_library(xcheck=kernel in ("dense", "srb"))
         if self.lib.qmpc_abi_version() != abi.QMPC_ABI_VERSION:
             raise QmpcError("libqmpc_b200.so ABI mismatch")
         self.cfg = cfg if cfg is not None else default_config(self.MODEL, horizon)

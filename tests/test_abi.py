@@ -191,3 +191,20 @@ def test_multi_shards_are_the_python_shards():
                 assert lo == prev and hi == (batch * (g + 1)) // world and hi - lo in (batch // world, batch // world + 1)
                 prev = hi
             assert prev == batch
+
+
+def test_product_library_has_no_cross_check_kernels(lib):
+    """The dense / srb kernels are test infrastructure (independent on-device implementations): the product
+    library answers QMPC_ERR_ARG when asked for them; the test-only sibling libqmpc_b200_xcheck.so carries them."""
+    import torch
+    cfg = default_config(0, 10)
+    h = C.c_void_p()
+    for k in (abi.QMPC_KERNEL_DENSE, abi.QMPC_KERNEL_SRB):
+        opt = abi.QmpcCreateOptions(k, -1, 0, 0)
+        assert lib.qmpc_create_ex(C.byref(cfg), 8, 0, C.byref(opt), C.byref(h)) == abi.QMPC_ERR_ARG
+    x = abi.load_library(xcheck=True)
+    assert x is not lib and x.qmpc_abi_version() == abi.QMPC_ABI_VERSION
+    opt = abi.QmpcCreateOptions(abi.QMPC_KERNEL_DENSE, -1, 0, 0)
+    rc = x.qmpc_create_ex(C.byref(cfg), 8, 0, C.byref(opt), C.byref(h))
+    assert rc == (abi.QMPC_OK if torch.cuda.is_available() else abi.QMPC_ERR_CUDA)
+    x.qmpc_destroy(h)
