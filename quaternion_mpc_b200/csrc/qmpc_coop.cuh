@@ -90,6 +90,20 @@ QMPC_HD inline double qmpc_rsqrt(double x) {
 #endif
 }
 
+// max(0, x) of the AL terms.  Written as `x > 0 ? x : 0` the compiler emits max.f64, which sm_100a has no instruction
+// for: ptxas expands it to DSETP.MAX + SEL + FSEL + LOP3 (NaN quieting) + register moves, 6-7 instructions, 24 times
+// per knot of every roll-out.  setp + selp is 3, and returns the same value for every input (NaN -> 0, -0 -> +0).
+QMPC_HD inline double pos_part(double x) {
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_POS_PART_MAX)
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, 0d0000000000000000;\n\tselp.f64 %0, %1, 0d0000000000000000, p;\n\t}"
+      : "=d"(r) : "d"(x));
+  return r;
+#else
+  return x > 0 ? x : 0;
+#endif
+}
+
 // ---- 3x3 block kernels used by the block-per-lane phases (lane = (block row, block col)) --------
 // The row loop is deliberately NOT unrolled: the kernel is instruction-fetch bound, compact code wins.
 // Operands that are reused across the rows are read into registers ONCE, before the first store:
@@ -104,6 +118,19 @@ QMPC_HD inline double qmpc_rsqrt(double x) {
                                      // over 1 = rolled, once the roll-out was inlined; round 1 measured the opposite)
 #endif
 constexpr int kBlkRowUnroll = QMPC_COOP_BLK_ROW_UNROLL;
+// Phases B / C give every lane of a problem one 3x3 block of P A, A^T (P A), P M, M^T (P A), M^T (P M).  The blocks of
+// the "odd" roles (attitude, angular velocity) are genuine 3x3 products, those of the "even" roles (position, linear
+// velocity) are alpha X_a + beta X_b.  Written as two helpers the lanes of a warp DIVERGE and every phase issues both
+// instruction streams (phase C: six helpers in sequence).  Uniform form (default; -DQMPC_COOP_DIVERGENT_BLK restores the
+// two-helper form): the even lanes call the odd lanes' helper with the constant blocks I / h I from the block's shared
+// memory and the operands exchanged - fma(beta, x_b, 1 * x_a + 0 + 0) is the very fma(alpha, x, beta y) the even helper
+// evaluates, rounding for rounding, so the results are bit-identical - and T and S share one call with per-lane
+// operands.  Not used by the Euler model (its moment blocks need the two-matrix helpers).
+#ifdef QMPC_COOP_DIVERGENT_BLK
+constexpr bool kUniformBlk = false;
+#else
+constexpr bool kUniformBlk = true;
+#endif
 QMPC_HD inline void blk_right(const double* X, int ld, int oa, int ob, const double* Mt, double beta, double* dst, int ldd) {
   double m[9];
 #pragma unroll
@@ -241,7 +268,17 @@ QMPC_HD inline void blk_store(double* dst, int ld, const double* v) {
     for (int b = 0; b < 3; ++b) dst[ld * a + b] = v[3 * a + b];
 }
 
-constexpr int kCoopBlockShared = 26;   // doubles at the head of the block's shared memory: q[13], r[12], pad
+// doubles at the head of the block's shared memory: q[13], r[12], pad, then two constant 3x3 blocks - I at 26 and
+// h I at 35 - the operands that let the "even" lanes of phases B / C run the very block product of the odd lanes
+constexpr int kCoopBlockShared = 44;
+constexpr int kCoopI3 = 26, kCoopHI3 = 35;
+QMPC_HD inline double coop_block_const(const QmpcConfig& cfg, float h, int i) {
+  if (i < 13) return cfg.q_weights[i];
+  if (i < 25) return cfg.r_weights[i - 13];
+  if (i < kCoopI3) return 0.0;
+  const int e = (i - kCoopI3) % 9;
+  return (e % 4 == 0) ? (i < kCoopHI3 ? 1.0 : (double)h) : 0.0;
+}
 
 template <int V>
 struct IntTag { static constexpr int value = V; };
@@ -437,7 +474,7 @@ QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, const double* 
         if (r == 4) c += -fzc_f;
         const double mui = mu_k[6 * f + r];
         const double est = mui + rho * c;
-        const double lh = est > 0 ? est : 0;
+        const double lh = pos_part(est);
         if (c > viol) viol = c;
         acc += lh * lh - mui * mui;
       }
@@ -638,7 +675,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
           if (r == 4) c += -fzc_f;
           const double mui = mu_f[r];
           const double est = mui + rho * c;
-          const double lh = est > 0 ? est : 0;
+          const double lh = pos_part(est);
           if (c > vl) vl = c;
           acc += lh * lh - mui * mui;
         }
@@ -673,7 +710,7 @@ struct CoopCtx {
   double *X, *U, *P, *PA, *T, *PM, *S, *Qux, *vec, *lin, *red, *kstage, *dxs;
   double *gK, *gP, *gpv, *gmu, *glin, *DX, *gLX, *gTX, *gTU;
   int lin_stride_is_resident;   // 1: glin rows are read in place (shared memory); 0: staged into `lin` per knot
-  const double *wq, *wr;
+  const double *wq, *wr, *I3, *hI3;
   int N;
   float h;
   double hd, hh, c1;
@@ -684,7 +721,7 @@ struct CoopCtx {
   // fused kernel / backward kernel: the full shared-memory layout `sm`, scratch `gs`
   QMPC_HD void bind(double* sm, double* gs, double* trial, int N_, float h_, int flags, const double* wts) {
     N = N_; h = h_; hd = (double)h_; hh = (double)(h_ / 2); c1 = hd * hh;
-    wq = wts; wr = wts + 13;
+    wq = wts; wr = wts + 13; I3 = wts + kCoopI3; hI3 = wts + kCoopHI3;
     m = reinterpret_cast<M*>(sm);
     X = sm + L::sX(N); U = sm + L::sU(N);
     P = sm + L::sP(N); PA = sm + L::sPA(N); T = sm + L::sT(N); PM = sm + L::sPM(N); S = sm + L::sS(N);
@@ -705,7 +742,7 @@ struct CoopCtx {
   // forward kernel: model, X, U, stage, reduction slots in shared memory; everything else in the problem block
   QMPC_HD void bind_forward(double* sm, double* gs, double* trial, int N_, float h_, const double* wts) {
     N = N_; h = h_; hd = (double)h_; hh = (double)(h_ / 2); c1 = hd * hh;
-    wq = wts; wr = wts + 13;
+    wq = wts; wr = wts + 13; I3 = wts + kCoopI3; hI3 = wts + kCoopHI3;
     m = reinterpret_cast<M*>(sm);
     X = sm + L::sX(N); U = sm + L::sU(N);
     P = PA = T = PM = S = Qux = vec = lin = nullptr;
@@ -868,7 +905,7 @@ QMPC_HD inline void coop_phase_pre(CoopCtx<M, G>& c, const QmpcConfig& cfg, cons
           double cc = m.CR[3 * rr] * u[0] + m.CR[3 * rr + 1] * u[1] + m.CR[3 * rr + 2] * u[2];
           if (rr == 4) cc += -m.fzc(k, f);
           const double est = gmu[idx] + c.rho * cc;
-          gmu[idx] = est > 0 ? est : 0;
+          gmu[idx] = pos_part(est);
         }
       }
       COOP_SYNC();
@@ -1011,6 +1048,16 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
     COOP_PHASE {
       const int br = lane >> 2, bc = lane & 3, rc = bc ^ M::kSwap;   // rc: role of this lane's block column
       const double* Pr = Pc + 36 * br;
+      if (kUniformBlk && !M::kDw) {
+        // ONE block product for all 16 lanes (see kUniformBlk): the even roles are the odd roles' product with the
+        // constant blocks I / h I and the two operands exchanged - same operations, same roundings
+        const bool odd = rc & 1;
+        blk_right(Pr, 12, odd ? oA : (rc == 0 ? oP : oV), odd ? oW : (rc == 0 ? oV : oP),
+                  odd ? (rc == 1 ? Aff : Afw) : c.I3, rc == 2 ? hd : (rc == 3 ? 1.0 : 0.0), Pw + 36 * br + 3 * bc, 12);
+        if (bc < 2)   // P M: moment columns X_A Cf + h X_W, force columns c1 X_P + h X_V = X_V (h I) + c1 X_P
+          blk_right(Pr, 12, bc == 1 ? oA : oV, bc == 1 ? oW : oP, bc == 1 ? Cf : c.hI3, bc == 1 ? hd : c1,
+                    PM + 18 * br + 3 * bc, 6);
+      } else {
       if (rc & 1) blk_right(Pr, 12, oA, oW, rc == 1 ? Aff : Afw, rc == 1 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
       else blk_even(Pr, 12, oP, oV, rc == 0 ? 1.0 : hd, rc == 0 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
       if (bc < 2) {
@@ -1018,6 +1065,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
           if (M::kDw) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);
           else blk_right(Pr, 12, oA, oW, Cf, hd, PM + 18 * br + 3 * bc, 6);
         } else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
+      }
       }
       if (lane < 6) {
         const int e = lane;
@@ -1044,8 +1092,14 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
       const int br = lane >> 2, bc = lane & 3, rr = br ^ M::kSwap;   // rr: role of this lane's block row
       const double* Yc = Pw + 3 * bc;
       double* Pd = Pc + 36 * br + 3 * bc;
+      if (kUniformBlk && !M::kDw) {
+        const bool odd = rr & 1;
+        blk_left(Yc, 12, odd ? oA : (rr == 0 ? oP : oV), odd ? oW : (rr == 0 ? oV : oP),
+                 odd ? (rr == 1 ? Aff : Afw) : c.I3, rr == 2 ? hd : (rr == 3 ? 1.0 : 0.0), Pd, 12);
+      } else {
       if (rr & 1) blk_left(Yc, 12, oA, oW, rr == 1 ? Aff : Afw, rr == 1 ? 0.0 : 1.0, Pd, 12);
       else blk_evenT(Yc, 12, oP, oV, rr == 0 ? 1.0 : hd, rr == 0 ? 0.0 : 1.0, Pd, 12);
+      }
       if (br == bc) {   // + lxx on the diagonal blocks (the same lane just wrote the block)
         if (rr == 1) {
 #pragma unroll
@@ -1057,6 +1111,16 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
           Pd[0] += wq[q0]; Pd[13] += wq[q0 + 1]; Pd[26] += wq[q0 + 2];
         }
       }
+      if (kUniformBlk && !M::kDw) {
+        // T = M^T (P A) on lanes 0..7 and S = M^T (P M) on lanes 8..11 as ONE block product with per-lane operands:
+        // moment rows Cf^T Y_A + h Y_W, force rows c1 Y_P + h Y_V = (h I)^T Y_V + c1 Y_P
+        if (lane < 12) {
+          const bool isS = lane >= 8;
+          const int r = isS ? (lane >> 1) & 1 : br, cc = isS ? (lane & 1) : bc, ldy = isS ? 6 : 12;
+          blk_left(isS ? PM + 3 * cc : Yc, ldy, r == 1 ? oA : oV, r == 1 ? oW : oP, r == 1 ? Cf : c.hI3, r == 1 ? hd : c1,
+                   isS ? S + 18 * r + 3 * cc : T + 36 * r + 3 * cc, ldy);
+        }
+      } else {
       if (br < 2) {
         if (br == 1) {
           if (M::kDw) blk_left2(Yc, 12, oA, oW, Cf, Dw, T + 36 * br + 3 * bc, 12);
@@ -1070,6 +1134,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
           if (M::kDw) blk_left2(Ym, 6, oA, oW, Cf, Dw, S + 18 * r + 3 * cc, 6);
           else blk_left(Ym, 6, oA, oW, Cf, hd, S + 18 * r + 3 * cc, 6);
         } else blk_evenT(Ym, 6, oP, oV, c1, hd, S + 18 * r + 3 * cc, 6);
+      }
       }
       if (lane < 12) vec[L::vQx + lane] = vec[L::vAtp + lane] + row[Row::lx + lane];
     }
@@ -1109,10 +1174,25 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
 #define QMPC_TRI(i_, l_) ((i_) * ((i_) + 1) / 2 + (l_))
       double Lr[NT], rd[NU], rhs[NU];
 #define QMPC_DIVD(x_, i_) { (x_) = (x_) * rd[i_]; }
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_CHOL_LD64)
+      {   // lower triangle of Quu with 16-byte loads (rows start 16-byte aligned: NU is even): 42 LDS.128 for 78 LDS.64
+        static_assert(NU % 2 == 0, "Quu rows must start 16-byte aligned");
+        const double2* Q2 = reinterpret_cast<const double2*>(Quu);
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+          for (int l = 0; l <= i; l += 2) {
+            const double2 v = Q2[(NU * i + l) / 2];
+            Lr[QMPC_TRI(i, l)] = v.x;
+            if (l + 1 <= i) Lr[QMPC_TRI(i, l + 1)] = v.y;
+          }
+      }
+#else
 #pragma unroll
       for (int i = 0; i < NU; ++i)
 #pragma unroll
         for (int l = 0; l <= i; ++l) Lr[QMPC_TRI(i, l)] = Quu[NU * i + l];
+#endif
 #pragma unroll
       for (int i = 0; i < NU; ++i) rhs[i] = cix < 12 ? Qux[12 * i + cix] : vec[L::vQu + i];
       bool ok = true;
@@ -1304,13 +1384,39 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
       state_diff<M>(xn, X + k * NX, dx);
 #pragma unroll
       for (int i = 0; i < NE; ++i) dxs[k * NE + i] = dx[i];
+#ifndef QMPC_COOP_ACCEPT_COPY_LAST
+      // X <- accepted states right here: the lane holds its knot's new state in registers and nobody reads the old
+      // one again (the copy loop at the end took one L2 round trip per element: `unroll 1`, load -> store)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) X[k * NX + i] = xn[i];
+#endif
     }
+#ifndef QMPC_COOP_ACCEPT_COPY_LAST
+    // U <- accepted inputs, four independent loads in flight per lane
+#pragma unroll 1
+    for (int e0 = 0; e0 < N * NU; e0 += 4 * G) {
+      double t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = e0 + q * G + lane;
+        t[q] = ld_stream(gTU + (size_t)(e < N * NU ? e : N * NU - 1) * NCAND + acc_lane);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = e0 + q * G + lane;
+        if (e < N * NU) U[e] = t[q];
+      }
+    }
+#endif
   }
   COOP_SYNC();
   COOP_PHASE {
     if (lane < NE) {
       const int a = lane;
-      constexpr int KB = 4;
+#ifndef QMPC_COOP_ACCEPT_KB
+#define QMPC_COOP_ACCEPT_KB 4
+#endif
+      constexpr int KB = QMPC_COOP_ACCEPT_KB;
 #pragma unroll 1
       for (int k0 = 0; k0 <= N; k0 += KB) {
         double2 pr[KB][6];
@@ -1357,6 +1463,7 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
   }
   COOP_SYNC();
 #endif
+#if defined(QMPC_COOP_ACCEPT_OLD) || defined(QMPC_COOP_ACCEPT_COPY_LAST)
   // ... then X, U <- accepted trajectory (cooperative strided copy)
   COOP_PHASE {
 #pragma unroll 1
@@ -1365,6 +1472,7 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
     for (int e = lane; e < N * NU; e += G) U[e] = ld_stream(gTU + (size_t)e * NCAND + acc_lane);
   }
   COOP_SYNC();
+#endif
 #if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_DISCARD)
   // The 16 trial trajectories (33.7 KB per slot at N = 10) are dead from here on, and they were 78 % of the DRAM
   // traffic of round 1's kernel (769 kB per solve against 536 B algorithmic): dirty L2 lines written back to HBM when
@@ -1465,8 +1573,7 @@ qmpc_coop_kernel(QmpcConfig cfg, SolverOpts o, const typename M::Problem* __rest
                  double* __restrict__ scratch, int batch, int smem_per_problem, size_t scratch_per_slot, int wide,
                  int active_groups) {
   extern __shared__ __align__(16) double smem_pool[];
-  if (threadIdx.x < 13) smem_pool[threadIdx.x] = cfg.q_weights[threadIdx.x];
-  else if (threadIdx.x < 25) smem_pool[threadIdx.x] = cfg.r_weights[threadIdx.x - 13];
+  if (threadIdx.x < kCoopBlockShared) smem_pool[threadIdx.x] = coop_block_const(cfg, o.h, threadIdx.x);
   __syncthreads();
   const int groups_per_block = blockDim.x / G;
   const int group = threadIdx.x / G;

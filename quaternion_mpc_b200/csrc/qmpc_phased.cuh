@@ -150,12 +150,9 @@ qmpc_phased_setup_kernel(QmpcConfig cfg, SolverOpts o, const typename M::Problem
                          QmpcResult* __restrict__ out, double* __restrict__ ws, int batch, size_t pstride) {
   const int pid = blockIdx.x * blockDim.x + threadIdx.x;
   if (pid >= batch) return;
-  double wts[26];
+  double wts[kCoopBlockShared];
 #pragma unroll
-  for (int i = 0; i < 13; ++i) wts[i] = cfg.q_weights[i];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) wts[13 + i] = cfg.r_weights[i];
-  wts[25] = 0;
+  for (int i = 0; i < kCoopBlockShared; ++i) wts[i] = coop_block_const(cfg, o.h, i);
   phased_setup_one<M, G>(cfg, o, in, sched, warm, out, pid, ws + (size_t)pid * pstride, wts);
 }
 
@@ -164,8 +161,7 @@ __global__ void __launch_bounds__(QMPC_COOP_BLOCK, QMPC_COOP_MIN_BLOCKS)
 qmpc_phased_backward_kernel(QmpcConfig cfg, SolverOpts o, int it, QmpcWarmStart* __restrict__ warm, QmpcResult* __restrict__ out,
                             double* __restrict__ ws, int batch, size_t pstride, int smem_per_problem, int flags) {
   extern __shared__ __align__(16) double smem_pool[];
-  if (threadIdx.x < 13) smem_pool[threadIdx.x] = cfg.q_weights[threadIdx.x];
-  else if (threadIdx.x < 25) smem_pool[threadIdx.x] = cfg.r_weights[threadIdx.x - 13];
+  if (threadIdx.x < kCoopBlockShared) smem_pool[threadIdx.x] = coop_block_const(cfg, o.h, threadIdx.x);
   __syncthreads();
   const int groups_per_block = blockDim.x / G, group = threadIdx.x / G, lane_id = threadIdx.x % G;
   const unsigned lane_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
@@ -184,8 +180,7 @@ qmpc_phased_forward_kernel(QmpcConfig cfg, SolverOpts o, int it, QmpcWarmStart* 
                            double* __restrict__ ws, double* __restrict__ trial, int batch, size_t pstride, int smem_per_problem,
                            size_t trial_stride) {
   extern __shared__ __align__(16) double smem_pool[];
-  if (threadIdx.x < 13) smem_pool[threadIdx.x] = cfg.q_weights[threadIdx.x];
-  else if (threadIdx.x < 25) smem_pool[threadIdx.x] = cfg.r_weights[threadIdx.x - 13];
+  if (threadIdx.x < kCoopBlockShared) smem_pool[threadIdx.x] = coop_block_const(cfg, o.h, threadIdx.x);
   __syncthreads();
   const int groups_per_block = blockDim.x / G, group = threadIdx.x / G, lane_id = threadIdx.x % G;
   const unsigned lane_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));

@@ -71,9 +71,8 @@ static int run_coop(const QmpcConfig& cfg, const typename M::Problem* in, const 
   using L = CoopLayout<M, G>;
   const int wide = cfg.horizon <= 10 ? 3 : (cfg.horizon <= 16 ? 2 : 0);
   std::vector<double> sm(L::smem_doubles(cfg.horizon, wide)), gs(L::scratch_doubles(cfg.horizon));
-  double wts[26];
-  for (int i = 0; i < 13; ++i) wts[i] = cfg.q_weights[i];
-  for (int i = 0; i < 12; ++i) wts[13 + i] = cfg.r_weights[i];
+  double wts[kCoopBlockShared];
+  for (int i = 0; i < kCoopBlockShared; ++i) wts[i] = coop_block_const(cfg, o.h, i);
   for (int i = 0; i < batch; ++i) coop_solve_one<M, G>(cfg, o, in, sched, warm, out, i, sm.data(), gs.data(), 0, 0u, wide, wts);
   return 0;
 }
@@ -96,9 +95,8 @@ static int run_phased(const QmpcConfig& cfg, const typename M::Problem* in, cons
   const size_t pstride = L::problem_doubles(N);
   std::vector<double> ws(pstride * batch), trial(L::trial_doubles(N));
   std::vector<double> smB(L::smem_doubles(N, 1)), smF(L::fwd_smem_doubles(N));
-  double wts[26];
-  for (int i = 0; i < 13; ++i) wts[i] = cfg.q_weights[i];
-  for (int i = 0; i < 12; ++i) wts[13 + i] = cfg.r_weights[i];
+  double wts[kCoopBlockShared];
+  for (int i = 0; i < kCoopBlockShared; ++i) wts[i] = coop_block_const(cfg, o.h, i);
   for (int i = 0; i < batch; ++i) phased_setup_one<M, G>(cfg, o, in, sched, warm, out, i, ws.data() + pstride * i, wts);
   for (int it = 0; it < o.iterations_max; ++it) {
     for (int i = 0; i < batch; ++i)

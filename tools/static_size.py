@@ -13,7 +13,7 @@ for line in open(sass, errors="replace"):
     if line.startswith("\t.section") or line.startswith(".section"):
         continue
     if infunc is None: continue
-    keep = ("coop_kernelILi4" in infunc) or ("ILi4E" in infunc and ("rollout" in infunc or "cost_expand" in infunc)) or "gemm3" in infunc
+    keep = ("qmpc_coop_kernelINS_9QuatModelILi4" in infunc) or ("coop_kernelILi4" in infunc) or ("ILi4E" in infunc and ("rollout" in infunc or "cost_expand" in infunc)) or "gemm3" in infunc
     if not keep: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', line)
     if m:
