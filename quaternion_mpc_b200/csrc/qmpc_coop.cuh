@@ -191,6 +191,28 @@ QMPC_HD inline void blk_left(const double* Y, int ld, int oa, int ob, const doub
     dst[ldd * a] = r0; dst[ldd * a + 1] = r1; dst[ldd * a + 2] = r2;
   }
 }
+// blk_left + a 3x3 block held in registers, added to the rounded result before the store (phase C: the cost
+// Hessian block; it used to be added by a load-add-store pass over the block the lane had just stored)
+QMPC_HD inline void blk_left_add(const double* Y, int ld, int oa, int ob, const double* Mt, double beta, const double* add,
+                                 double* dst, int ldd) {
+  double m[9], y[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] = Mt[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) y[3 * i + b] = Y[ld * (oa + i) + b];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double* Ya = Y + ld * (ob + a);
+    const double z0 = Ya[0], z1 = Ya[1], z2 = Ya[2];
+    const double m0 = m[a], m1 = m[3 + a], m2 = m[6 + a];
+    const double r0 = m0 * y[0] + m1 * y[3] + m2 * y[6] + beta * z0;
+    const double r1 = m0 * y[1] + m1 * y[4] + m2 * y[7] + beta * z1;
+    const double r2 = m0 * y[2] + m1 * y[5] + m2 * y[8] + beta * z2;
+    dst[ldd * a] = r0 + add[3 * a]; dst[ldd * a + 1] = r1 + add[3 * a + 1]; dst[ldd * a + 2] = r2 + add[3 * a + 2];
+  }
+}
 // dst = Mt^T * Y(oa:oa+3, :) + Nt^T * Y(ob:ob+3, :)   (ConvexModel: the moment rows of M^T Y, Nt = Dw)
 QMPC_HD inline void blk_left2(const double* Y, int ld, int oa, int ob, const double* Mt, const double* Nt, double* dst, int ldd) {
   double m[9], n[9], y[9], z[9];
@@ -612,6 +634,13 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
     const double* Kk = gK + (size_t)k * kKD;
 #endif
     const double* dk = Kk + NU * 12;
+#ifndef QMPC_COOP_CR_LDS
+    double cr[18];   // cone rows in registers across the foot loop (the loop re-read them per foot: 72 LDS per knot; +1.6 %)
+#pragma unroll
+    for (int i = 0; i < 18; ++i) cr[i] = m.CR[i];
+#else
+    const double* cr = m.CR;
+#endif
 #ifndef QMPC_COOP_FOOT_UNROLL
 #define QMPC_COOP_FOOT_UNROLL 1
 #endif
@@ -671,7 +700,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
         const double fzc_f = m.fzc(k, f);
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-          double c = m.CR[3 * r] * u0 + m.CR[3 * r + 1] * u1 + m.CR[3 * r + 2] * u2;
+          double c = cr[3 * r] * u0 + cr[3 * r + 1] * u1 + cr[3 * r + 2] * u2;
           if (r == 4) c += -fzc_f;
           const double mui = mu_f[r];
           const double est = mui + rho * c;
@@ -688,7 +717,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
     }
     if (M::kQuat && cfg.w != 0.0) Jl += cfg.w * (1.0 - fabs(sq));
     J += Jl;
-    J += acc / (2 * rho);
+    J += qmpc_div(acc, 2 * rho);
     // ---- explicit midpoint step driven by the net wrench (AltroUtils.cpp:9-22, 383-391 / 224-294)
     m.wrench_step(x, fs0, fs1, fs2, mom0, mom1, mom2, hd, hh);
     if (mode == 0) {
@@ -787,6 +816,58 @@ QMPC_HD inline void coop_phase_setup(CoopCtx<M, G>& c, const QmpcConfig& cfg, co
   if (!isfinite(c.phi)) c.status = QMPC_STATUS_NONFINITE;
 }
 
+// stationarity residuals of knot k with the Riccati duals y (DX): |lx + A^T y_{k+1} - y_k| and, per foot (rolled: once
+// per iteration, compact code beats unrolled speed), |R (u - u_ref) + J^T max(0, mu + rho c) + W^T M^T y_{k+1}|
+// (accumulation order of the AL terms)
+template <class M>
+QMPC_HD inline void coop_knot_residuals(const M& m, double rho, int N, int k, double hd, double hh, const double* U,
+                                               const double* DX, const double* gmu, const double* wr, const double* lx,
+                                               const KnotLin4& Lk, double& rx, double& ru) {
+  constexpr int NE = 12, NU = M::NU, NC = M::NC, NF = M::kFeet;
+  if (k == N) {
+#pragma unroll
+    for (int a = 0; a < NE; ++a) {
+      double v = fabs(lx[a] - DX[N * NE + a]);
+      if (v > rx) rx = v;
+    }
+    return;
+  }
+  const double* u = U + k * NU;
+  const double* yn = DX + (k + 1) * NE;
+  double Aty[NE], t6[6];
+  coop_At_vec<M>(Lk, hd, yn, Aty);
+  coop_Mt_vec<M>(Lk, hd, hh, yn, t6);
+#pragma unroll
+  for (int a = 0; a < NE; ++a) {
+    double v = fabs(lx[a] + Aty[a] - DX[k * NE + a]);
+    if (v > rx) rx = v;
+  }
+#pragma unroll 1
+  for (int f = 0; f < NF; ++f) {
+    const double* uf = u + 3 * f;
+    const double* IS = m.IS + 9 * f;
+    const double fzc_f = m.fzc(k, f);
+    double g0 = 0, g1 = 0, g2 = 0;
+#pragma unroll 1
+    for (int r = 0; r < 6; ++r) {
+      const double j0 = m.CR[3 * r], j1 = m.CR[3 * r + 1], j2 = m.CR[3 * r + 2];
+      double cc = j0 * uf[0] + j1 * uf[1] + j2 * uf[2];
+      if (r == 4) cc += -fzc_f;
+      const double est = gmu[k * NC + 6 * f + r] + rho * cc;
+      if (est > 0) { g0 += j0 * est; g1 += j1 * est; g2 += j2 * est; }
+    }
+    const double b0 = m.inv_mass * t6[0] + IS[0] * t6[3] + IS[3] * t6[4] + IS[6] * t6[5];
+    const double b1 = m.inv_mass * t6[1] + IS[1] * t6[3] + IS[4] * t6[4] + IS[7] * t6[5];
+    const double b2 = m.inv_mass * t6[2] + IS[2] * t6[3] + IS[5] * t6[4] + IS[8] * t6[5];
+    const double v0 = fabs(wr[3 * f] * uf[0] + g0 + b0);
+    const double v1 = fabs(wr[3 * f + 1] * uf[1] + g1 + b1);
+    const double v2 = fabs(wr[3 * f + 2] * (uf[2] - m.urefz(k, f)) + g2 + b2);
+    if (v0 > ru) ru = v0;
+    if (v1 > ru) ru = v1;
+    if (v2 > ru) ru = v2;
+  }
+}
+
 // ------------------------------------------------------------------ per-iteration "pre": expansions,
 // stationarity + convergence test, dual / penalty update, AL terms of every knot
 template <class M, int G>
@@ -803,18 +884,30 @@ QMPC_HD inline void coop_phase_pre(CoopCtx<M, G>& c, const QmpcConfig& cfg, cons
   // ---------------- expansions, lane k <- knot k: cost gradient + attitude Hessian block (21 doubles) and
   // the dynamics blocks (NLIN doubles).  The same X is used throughout the iteration: computed once,
   // knot-parallel, reused by the stationarity test and the backward pass.
+  // Fused with it (default; -DQMPC_COOP_STAT_SEPARATE restores the second pass): the stationarity residuals of
+  // knot k with the Riccati duals of the accepted step (DX holds y_k) - the lane has lx and the linearisation blocks
+  // of its knot in registers at that point; the separate pass re-read them through the L2.
+#ifdef QMPC_COOP_STAT_SEPARATE
+  constexpr bool kStatFused = false;
+#else
+  constexpr bool kStatFused = true;
+#endif
   COOP_PHASE {
+    double rx = 0, ru = 0;
 #pragma unroll 1
     for (int k = lane; k <= N; k += G) {
       double lx[NE], Hk[9], hphi;
+      KnotLin4 Lk = {};   // (an uninitialised block reaching the residuals at k = N made ptxas spill)
       cost_expand(m, cfg, k, X + k * NX, lx, &hphi);
       hphi_block<M>(cfg, X + k * NX, hphi, Hk);
+#pragma unroll
       for (int i = 0; i < NE; ++i) gLX[k * L::kRow + Row::lx + i] = lx[i];
+#pragma unroll
       for (int i = 0; i < 9; ++i) gLX[k * L::kRow + Row::Hphi + i] = Hk[i];
       if (k < N) {
-        KnotLin4 Lk;
         coop_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
         double* gl = glin + k * L::kLinStride;
+#pragma unroll
         for (int i = 0; i < 9; ++i) {
           gl[i] = Lk.Aff[i];
           gl[9 + i] = Lk.Afw[i];
@@ -822,72 +915,39 @@ QMPC_HD inline void coop_phase_pre(CoopCtx<M, G>& c, const QmpcConfig& cfg, cons
           if (NLIN > 27) gl[(NLIN > 27 ? 27 : 0) + i] = Lk.Dw[i];
         }
       }
+      if (kStatFused && it > 0) coop_knot_residuals<M>(m, c.rho, N, k, hd, hh, U, DX, gmu, wr, lx, Lk, rx, ru);
     }
+    if (kStatFused && it > 0) red[lane] = rx > ru ? rx : ru;
   }
   COOP_SYNC();
 
   if (it > 0) {
-    // ---------------- stationarity with the Riccati duals of the accepted step (DX holds y_k)
-    COOP_PHASE {
-      double rx = 0, ru = 0;
+    if (!kStatFused) {
+      // ---------------- stationarity in a pass of its own
+      COOP_PHASE {
+        double rx = 0, ru = 0;
 #pragma unroll 1
-      for (int k = lane; k <= N; k += G) {
-        double lx[NE];
-        for (int a = 0; a < NE; ++a) lx[a] = gLX[k * L::kRow + Row::lx + a];
-        if (k == N) {
-          for (int a = 0; a < NE; ++a) {
-            double v = fabs(lx[a] - DX[N * NE + a]);
-            if (v > rx) rx = v;
-          }
-        } else {
-          KnotLin4 Lk;
-          const double* gl = glin + k * L::kLinStride;
-          for (int i = 0; i < 9; ++i) {
-            Lk.Aff[i] = gl[i];
-            Lk.Afw[i] = gl[9 + i];
-            Lk.Cf[i] = gl[18 + i];
-            if (NLIN > 27) Lk.Dw[i] = gl[(NLIN > 27 ? 27 : 0) + i];
-          }
-          const double* u = U + k * NU;
-          const double* yn = DX + (k + 1) * NE;
-          double Aty[NE], t6[6];
-          coop_At_vec<M>(Lk, hd, yn, Aty);
-          coop_Mt_vec<M>(Lk, hd, hh, yn, t6);
-          for (int a = 0; a < NE; ++a) {
-            double v = fabs(lx[a] + Aty[a] - DX[k * NE + a]);
-            if (v > rx) rx = v;
-          }
-          // input residual per foot, rolled (once per iteration: compact code beats unrolled speed):
-          // R (u - u_ref) + J^T max(0, mu + rho c) + W^T M^T y   (same accumulation order as al_terms)
-#pragma unroll 1
-          for (int f = 0; f < NF; ++f) {
-            const double* uf = u + 3 * f;
-            const double* IS = m.IS + 9 * f;
-            const double fzc_f = m.fzc(k, f);
-            double g0 = 0, g1 = 0, g2 = 0;
-#pragma unroll 1
-            for (int r = 0; r < 6; ++r) {
-              const double j0 = m.CR[3 * r], j1 = m.CR[3 * r + 1], j2 = m.CR[3 * r + 2];
-              double cc = j0 * uf[0] + j1 * uf[1] + j2 * uf[2];
-              if (r == 4) cc += -fzc_f;
-              const double est = gmu[k * NC + 6 * f + r] + c.rho * cc;
-              if (est > 0) { g0 += j0 * est; g1 += j1 * est; g2 += j2 * est; }
+        for (int k = lane; k <= N; k += G) {
+          double lx[NE];
+          KnotLin4 Lk = {};
+#pragma unroll
+          for (int a = 0; a < NE; ++a) lx[a] = gLX[k * L::kRow + Row::lx + a];
+          if (k < N) {
+            const double* gl = glin + k * L::kLinStride;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+              Lk.Aff[i] = gl[i];
+              Lk.Afw[i] = gl[9 + i];
+              Lk.Cf[i] = gl[18 + i];
+              if (NLIN > 27) Lk.Dw[i] = gl[(NLIN > 27 ? 27 : 0) + i];
             }
-            const double b0 = m.inv_mass * t6[0] + IS[0] * t6[3] + IS[3] * t6[4] + IS[6] * t6[5];
-            const double b1 = m.inv_mass * t6[1] + IS[1] * t6[3] + IS[4] * t6[4] + IS[7] * t6[5];
-            const double b2 = m.inv_mass * t6[2] + IS[2] * t6[3] + IS[5] * t6[4] + IS[8] * t6[5];
-            const double v0 = fabs(wr[3 * f] * uf[0] + g0 + b0);
-            const double v1 = fabs(wr[3 * f + 1] * uf[1] + g1 + b1);
-            const double v2 = fabs(wr[3 * f + 2] * (uf[2] - m.urefz(k, f)) + g2 + b2);
-            if (v0 > ru) ru = v0;
-            if (v1 > ru) ru = v1;
-            if (v2 > ru) ru = v2;
           }
+          coop_knot_residuals<M>(m, c.rho, N, k, hd, hh, U, DX, gmu, wr, lx, Lk, rx, ru);
         }
+        red[lane] = rx > ru ? rx : ru;
       }
-      red[lane] = rx > ru ? rx : ru;
+      COOP_SYNC();
     }
-    COOP_SYNC();
     double stat = 0;
     for (int l = 0; l < G; ++l) stat = red[l] > stat ? red[l] : stat;
     COOP_SYNC();
@@ -1092,7 +1152,18 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
       const int br = lane >> 2, bc = lane & 3, rr = br ^ M::kSwap;   // rr: role of this lane's block row
       const double* Yc = Pw + 3 * bc;
       double* Pd = Pc + 36 * br + 3 * bc;
-      if (kUniformBlk && !M::kDw) {
+#ifndef QMPC_COOP_LXX_RMW
+      constexpr bool kLxxFold = kUniformBlk && !M::kDw;
+#else
+      constexpr bool kLxxFold = false;
+#endif
+      if (kLxxFold) {
+        const bool odd = rr & 1;
+        double lxx[9];
+        lxx_block<M>(wq, row + Row::Hphi, br, bc, lxx);   // zero off the diagonal
+        blk_left_add(Yc, 12, odd ? oA : (rr == 0 ? oP : oV), odd ? oW : (rr == 0 ? oV : oP),
+                     odd ? (rr == 1 ? Aff : Afw) : c.I3, rr == 2 ? hd : (rr == 3 ? 1.0 : 0.0), lxx, Pd, 12);
+      } else if (kUniformBlk && !M::kDw) {
         const bool odd = rr & 1;
         blk_left(Yc, 12, odd ? oA : (rr == 0 ? oP : oV), odd ? oW : (rr == 0 ? oV : oP),
                  odd ? (rr == 1 ? Aff : Afw) : c.I3, rr == 2 ? hd : (rr == 3 ? 1.0 : 0.0), Pd, 12);
@@ -1100,7 +1171,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
       if (rr & 1) blk_left(Yc, 12, oA, oW, rr == 1 ? Aff : Afw, rr == 1 ? 0.0 : 1.0, Pd, 12);
       else blk_evenT(Yc, 12, oP, oV, rr == 0 ? 1.0 : hd, rr == 0 ? 0.0 : 1.0, Pd, 12);
       }
-      if (br == bc) {   // + lxx on the diagonal blocks (the same lane just wrote the block)
+      if (!kLxxFold && br == bc) {   // + lxx on the diagonal blocks (the same lane just wrote the block)
         if (rr == 1) {
 #pragma unroll
           for (int i = 0; i < 3; ++i)
@@ -1218,8 +1289,15 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
         rd[j] = rdg;
 #pragma unroll
         for (int i = j + 1; i < NU; ++i) {
+#ifndef QMPC_COOP_CHOL_RDG_SCALE
+          // first guess and correction with r0 itself (within an ulp of 1 / dg): the correction step returns the
+          // correctly rounded a / dg from either reciprocal, and the pivot chain no longer waits for rdg
+          const double a = Lr[QMPC_TRI(i, j)], q = a * r0;
+          Lr[QMPC_TRI(i, j)] = fma(fma(-q, dg, a), r0, q);   // a / dg
+#else
           const double a = Lr[QMPC_TRI(i, j)], q = a * rdg;
           Lr[QMPC_TRI(i, j)] = fma(fma(-q, dg, a), rdg, q);   // a / dg
+#endif
         }
 #endif
 #pragma unroll
@@ -1285,7 +1363,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
       const int br = lane >> 2, bc = lane & 3;
       double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #ifndef QMPC_COOP_F_UNROLL
-#define QMPC_COOP_F_UNROLL 2   // measured +0.4 % over 1 (profiles/r02_experiments.md)
+#define QMPC_COOP_F_UNROLL 4   // measured +0.4 % for 2 over 1, +0.2 % for 4 over 2, 12 loses (profiles/r02_experiments.md)
 #endif
       constexpr int kFUnroll = QMPC_COOP_F_UNROLL;
 #pragma unroll(kFUnroll)
@@ -1535,6 +1613,13 @@ QMPC_HD void coop_solve_one(const QmpcConfig& cfg, const SolverOpts& o, const ty
   using L = CoopLayout<M, G>;
   CoopCtx<M, G> c;
   c.bind(sm, gs, gs + L::gTX(o.N), o.N, o.h, flags, wts);
+#ifndef QMPC_COOP_DX_GLOBAL
+  // Riccati duals y_k of the accepted step (written by the accepted step, read by the next iteration's stationarity
+  // test): for short horizons they fit behind the dx buffer in the P .. Qux region, which is dead from the end of the
+  // backward pass to the start of the next one - shared memory instead of two L2 round trips per iteration.
+  // Layout while they live: dx buffer [0, 12 (N+1)) | y [156, 156 + 12 (N+1)) | reduction slots [328, 360)
+  if (o.N <= 12) c.DX = c.P + 156;
+#endif
   coop_phase_setup<M, G>(c, cfg, o, in, sched, warm, pid, COOP_ARGS);
 #pragma unroll 1
   for (int it = 0; it < o.iterations_max; ++it) {
