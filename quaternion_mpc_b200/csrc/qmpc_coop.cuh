@@ -27,6 +27,7 @@
 // The body is written with COOP_PHASE / COOP_SYNC so that the very same source runs on the host
 // (tests/emul, lanes executed one after another) for GPU-less debugging.
 #pragma once
+#include <cstddef>
 #include "qmpc_srb.cuh"
 
 #ifdef __CUDA_ARCH__
@@ -101,6 +102,16 @@ QMPC_HD inline double pos_part(double x) {
   return r;
 #else
   return x > 0 ? x : 0;
+#endif
+}
+
+// m0 p0 + m1 p1 + m2 p2 + beta pb in the order nvcc contracts that expression - written out with fma on the device so
+// that operands which are selects of constants (beta = cond ? h : 0) cannot be folded into the products differently
+QMPC_HD inline double coop_dot4(double m0, double p0, double m1, double p1, double m2, double p2, double beta, double pb) {
+#ifdef __CUDA_ARCH__
+  return fma(beta, pb, fma(m2, p2, fma(m0, p0, __dmul_rn(m1, p1))));
+#else
+  return m0 * p0 + m1 * p1 + m2 * p2 + beta * pb;
 #endif
 }
 
@@ -293,11 +304,11 @@ QMPC_HD inline void blk_store(double* dst, int ld, const double* v) {
 // doubles at the head of the block's shared memory: q[13], r[12], pad, then two constant 3x3 blocks - I at 26 and
 // h I at 35 - the operands that let the "even" lanes of phases B / C run the very block product of the odd lanes
 constexpr int kCoopBlockShared = 44;
-constexpr int kCoopI3 = 26, kCoopHI3 = 35;
+constexpr int kCoopI3 = 26, kCoopHI3 = 35, kCoopC1 = 25;   // slot 25: c1 = h (h / 2), the (position, force) entry of M
 QMPC_HD inline double coop_block_const(const QmpcConfig& cfg, float h, int i) {
   if (i < 13) return cfg.q_weights[i];
   if (i < 25) return cfg.r_weights[i - 13];
-  if (i < kCoopI3) return 0.0;
+  if (i < kCoopI3) return (double)h * (double)(h / 2);
   const int e = (i - kCoopI3) % 9;
   return (e % 4 == 0) ? (i < kCoopHI3 ? 1.0 : (double)h) : 0.0;
 }
@@ -636,10 +647,22 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
     const double* dk = Kk + NU * 12;
 #ifndef QMPC_COOP_CR_LDS
     double cr[18];   // cone rows in registers across the foot loop (the loop re-read them per foot: 72 LDS per knot; +1.6 %)
+#if defined(__CUDA_ARCH__)
+    if (kSmem && offsetof(M, CR) % 16 == 0) {   // 9 LDS.128 (the model sits 16-byte aligned in shared memory)
+      const double2* cr2 = reinterpret_cast<const double2*>(m.CR);
 #pragma unroll
-    for (int i = 0; i < 18; ++i) cr[i] = m.CR[i];
+      for (int i = 0; i < 9; ++i) { const double2 v = cr2[i]; cr[2 * i] = v.x; cr[2 * i + 1] = v.y; }
+    } else
+#endif
+    {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) cr[i] = m.CR[i];
+    }
 #else
     const double* cr = m.CR;
+#endif
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_KSTAGE) && !defined(QMPC_COOP_NO_K128)
+    const unsigned ks0 = (unsigned)__cvta_generic_to_shared(Kk);   // shared-window address of K_k, once per knot
 #endif
 #ifndef QMPC_COOP_FOOT_UNROLL
 #define QMPC_COOP_FOOT_UNROLL 1
@@ -661,7 +684,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
 #if !defined(QMPC_COOP_NO_K128) && defined(__CUDA_ARCH__)
         {   // three 96-byte gain rows as 18 x 16-byte loads (rows are 16-byte aligned)
 #ifndef QMPC_COOP_NO_KSTAGE
-          const unsigned ks = (unsigned)__cvta_generic_to_shared(K0);
+          const unsigned ks = ks0 + (unsigned)(3 * f * 12 * sizeof(double));
           auto ldk = [&](int l) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ks + 16u * l)); return v; };
 #else
           const double2* K2 = reinterpret_cast<const double2*>(K0);
@@ -704,7 +727,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
           if (r == 4) c += -fzc_f;
           const double mui = mu_f[r];
           const double est = mui + rho * c;
-          const double lh = pos_part(est);
+          const double lh = pos_part(est);   // (a predicated fma instead of the two selects: ptxas if-converts it back)
           if (c > vl) vl = c;
           acc += lh * lh - mui * mui;
         }
@@ -884,13 +907,13 @@ QMPC_HD inline void coop_phase_pre(CoopCtx<M, G>& c, const QmpcConfig& cfg, cons
   // ---------------- expansions, lane k <- knot k: cost gradient + attitude Hessian block (21 doubles) and
   // the dynamics blocks (NLIN doubles).  The same X is used throughout the iteration: computed once,
   // knot-parallel, reused by the stationarity test and the backward pass.
-  // Fused with it (default; -DQMPC_COOP_STAT_SEPARATE restores the second pass): the stationarity residuals of
-  // knot k with the Riccati duals of the accepted step (DX holds y_k) - the lane has lx and the linearisation blocks
-  // of its knot in registers at that point; the separate pass re-read them through the L2.
-#ifdef QMPC_COOP_STAT_SEPARATE
-  constexpr bool kStatFused = false;
-#else
+  // -DQMPC_COOP_STAT_FUSED computes the stationarity residuals of knot k in the same pass (the lane has lx and the
+  // linearisation blocks of its knot in registers at that point, the separate pass re-reads them): measured no
+  // faster (1.687 M against 1.700 M solves/s at B = 4096, run 14) - the separate pass stays the default.
+#ifdef QMPC_COOP_STAT_FUSED
   constexpr bool kStatFused = true;
+#else
+  constexpr bool kStatFused = false;
 #endif
   COOP_PHASE {
     double rx = 0, ru = 0;
@@ -904,6 +927,14 @@ QMPC_HD inline void coop_phase_pre(CoopCtx<M, G>& c, const QmpcConfig& cfg, cons
       for (int i = 0; i < NE; ++i) gLX[k * L::kRow + Row::lx + i] = lx[i];
 #pragma unroll
       for (int i = 0; i < 9; ++i) gLX[k * L::kRow + Row::Hphi + i] = Hk[i];
+#ifndef QMPC_COOP_TERMINAL_FROM_L2
+      if (k == N) {   // the backward pass starts from these: hand them over in shared memory
+#pragma unroll
+        for (int i = 0; i < NE; ++i) c.vec[L::vpv + i] = lx[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) c.vec[L::vQx + i] = Hk[i];
+      }
+#endif
       if (k < N) {
         coop_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
         double* gl = glin + k * L::kLinStride;
@@ -1074,6 +1105,22 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
 #endif
     COOP_SYNC();
   };
+#ifndef QMPC_COOP_TERMINAL_FROM_L2
+  // terminal knot: its cost gradient (-> p_N) and attitude Hessian block were left in shared memory by the
+  // expansions pass of this iteration (pvv, vec + vQx: `pre` and the backward pass always run in the same kernel), so
+  // the row of knot N - 1 can be requested first and its L2 round trip overlaps the set-up of P_N
+  stage_row(N - 1);
+  COOP_PHASE {
+    const int br = lane >> 2, bc = lane & 3;
+    double o[9];
+    lxx_block<M>(wq, vec + L::vQx, br, bc, o);
+    blk_store(Pc + 36 * br + 3 * bc, 12, o);
+    blk_store_keep(gP + (size_t)N * 144 + 36 * br + 3 * bc, 12, o);
+    if (lane < 12) st_keep(gpv + N * 12 + lane, pvv[lane]);
+    if (lane == 0) scal[0] = 0.0;
+  }
+  COOP_SYNC();
+#else
   COOP_PHASE {
 #pragma unroll 1
     for (int e = lane; e < 21; e += G) {
@@ -1093,6 +1140,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
   }
   COOP_SYNC();
   stage_row(N - 1);
+#endif
 
 #pragma unroll 1
   for (int k = N - 1; k >= 0 && bp_ok; --k) {
@@ -1127,23 +1175,59 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
         } else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
       }
       }
-      if (lane < 6) {
-        const int e = lane;
-        double v;
-        if (e < 3) v = hd * hh * pv[oP + e] + hd * pv[oV + e];
-        else if (M::kDw) v = Cf[e - 3] * pv[oA] + Cf[e] * pv[oA + 1] + Cf[3 + e] * pv[oA + 2] +
-                             (Dw[e - 3] * pv[oW] + Dw[e] * pv[oW + 1] + Dw[3 + e] * pv[oW + 2]);
-        else v = Cf[e - 3] * pv[oA] + Cf[e] * pv[oA + 1] + Cf[3 + e] * pv[oA + 2] + hd * pv[oW + e - 3];
-        vec[L::vs + e] = v;
-      }
-      if (lane < 12) {
-        const int a = lane, ab = (a / 3) ^ M::kSwap, aa = a % 3;   // ab: role of row a
-        double v;
-        if (ab == 0) v = pv[a];
-        else if (ab == 1) v = Aff[aa] * pv[oA] + Aff[3 + aa] * pv[oA + 1] + Aff[6 + aa] * pv[oA + 2];
-        else if (ab == 2) v = hd * pv[oP + aa] + pv[a];
-        else v = Afw[aa] * pv[oA] + Afw[3 + aa] * pv[oA + 1] + Afw[6 + aa] * pv[oA + 2] + pv[a];
-        vec[L::vAtp + a] = v;
+#ifndef QMPC_COOP_VEC_DIVERGENT
+      constexpr bool kUniformVec = kUniformBlk && !M::kDw;
+#else
+      constexpr bool kUniformVec = false;
+#endif
+      if (kUniformVec) {
+        // s = M^T p (6 entries) and Atp = A^T p (12 entries): seven divergent one-line paths, each a dependent
+        // LDS -> FMA -> STS chain, when written per role.  Every one of them is an instance of
+        //   v = m0 p0 + m1 p1 + m2 p2 + beta pb  =  fma(beta, pb, fma(m2, p2, fma(m0, p0, m1 p1)))
+        // with operands that are matrix entries, entries of p, or the constants 0 / 1 / h / c1 of the block's table
+        // (a product by 1 or 0 is exact): one uniform evaluation for Atp (lanes 0..11), one for s (lanes 0..5),
+        // rounding for rounding what the role-specific expressions evaluate.
+        const double *zero = c.I3 + 1, *one = c.I3, *hp = c.hI3, *c1p = c.wq + kCoopC1;
+        (void)hp;
+        if (lane < 12) {
+          const int a = lane, ab = (a / 3) ^ M::kSwap, aa = a % 3;   // ab: role of row a
+          const bool odd = ab & 1;
+          const double* Mx = (ab == 1 ? Aff : Afw) + aa;
+          const double *m0 = odd ? Mx : (ab == 2 ? hp : zero), *m1 = odd ? Mx + 3 : one, *m2 = odd ? Mx + 6 : zero;
+          const double *p0 = odd ? pv + oA : pv + oP + aa, *p1 = odd ? pv + oA + 1 : pv + a, *p2 = odd ? pv + oA + 2 : pv + a;
+          const double beta = ab == 3 ? 1.0 : 0.0;
+          vec[L::vAtp + a] = coop_dot4(*m0, *p0, *m1, *p1, *m2, *p2, beta, pv[a]);
+        }
+        if (lane < 6) {
+          const int e = lane;
+          // moment rows: Cf^T p_A + h p_W; force rows: c1 p_P + h p_V, which the role-specific code evaluates as
+          // fma(h, p_V, c1 p_P) (the compiler shares the "+ h p" tail of the two branches): c1 p_P is the rounded product
+          const bool mom = e >= 3;
+          const double* Cx = Cf + (mom ? e - 3 : 0);
+          const double *m0 = mom ? Cx : zero, *m1 = mom ? Cx + 3 : c1p, *m2 = mom ? Cx + 6 : zero;
+          const double *p0 = mom ? pv + oA : pv + oP + e, *p1 = mom ? pv + oA + 1 : pv + oP + e, *p2 = mom ? pv + oA + 2 : pv + oP + e;
+          const double *pb = mom ? pv + oW + e - 3 : pv + oV + e;
+          vec[L::vs + e] = coop_dot4(*m0, *p0, *m1, *p1, *m2, *p2, hd, *pb);
+        }
+      } else {
+        if (lane < 6) {
+          const int e = lane;
+          double v;
+          if (e < 3) v = hd * hh * pv[oP + e] + hd * pv[oV + e];
+          else if (M::kDw) v = Cf[e - 3] * pv[oA] + Cf[e] * pv[oA + 1] + Cf[3 + e] * pv[oA + 2] +
+                               (Dw[e - 3] * pv[oW] + Dw[e] * pv[oW + 1] + Dw[3 + e] * pv[oW + 2]);
+          else v = Cf[e - 3] * pv[oA] + Cf[e] * pv[oA + 1] + Cf[3 + e] * pv[oA + 2] + hd * pv[oW + e - 3];
+          vec[L::vs + e] = v;
+        }
+        if (lane < 12) {
+          const int a = lane, ab = (a / 3) ^ M::kSwap, aa = a % 3;   // ab: role of row a
+          double v;
+          if (ab == 0) v = pv[a];
+          else if (ab == 1) v = Aff[aa] * pv[oA] + Aff[3 + aa] * pv[oA + 1] + Aff[6 + aa] * pv[oA + 2];
+          else if (ab == 2) v = hd * pv[oP + aa] + pv[a];
+          else v = Afw[aa] * pv[oA] + Afw[3 + aa] * pv[oA + 1] + Afw[6 + aa] * pv[oA + 2] + pv[a];
+          vec[L::vAtp + a] = v;
+        }
       }
     }
     COOP_SYNC();
@@ -1452,6 +1536,8 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
   // bytes per knot, 16-byte loads), four knots' loads in flight before the first FMA - three L2 round trips for
   // the whole horizon where lane-per-knot needed a dozen (the accept step was 12.8 % of the solve's time for 4 %
   // of its instructions, long-scoreboard 8.6).  Row sums run b = 0..11 as before: bit-identical.
+  // (Dealing the 12 (N + 1) rows over all 16 lanes, two batches with the first one's loads issued before step (1),
+  // measured 1.4 % SLOWER, run 15: not adopted.)
   double* dxs = c.dxs;
   COOP_PHASE {
 #pragma unroll 1
