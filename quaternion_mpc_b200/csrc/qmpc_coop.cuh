@@ -601,11 +601,37 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
   // completion, issued by lane 0) was measured in tools/probes/bulk_probe.cu: the same staging pattern runs 2.3x
   // SLOWER (1.47 ms against 0.63 ms), and in the kernel the gain stores of the backward pass would additionally
   // need a generic -> async proxy fence per knot (profiles/r02_experiments.md) - not adopted.
+#ifndef QMPC_COOP_KSTAGE_REGS
   auto stage_gain = [&](int k) {
     coop_cp_async_row(kstage + (k & 1) * kKD, gK + (size_t)k * kKD, kKD, tl, tstride);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto stage_wait = [&](int) { asm volatile("cp.async.wait_all;" ::: "memory"); };
+#else
+  // -DQMPC_COOP_KSTAGE_REGS: through registers instead of cp.async - the lane's 16-byte chunks of K_{k+1} | d_{k+1} are
+  // loaded (L2, ld.cg) right after the barrier of knot k and stored to the other half of the double buffer at the top
+  // of knot k + 1: 2 instructions per chunk where ptxas wraps every LDGSTS in three padding instructions plus address
+  // arithmetic (about 10).  Measured 3.5 ... 4.6 % SLOWER (run 17): the loads' scoreboard wait lands on the lane
+  // itself, cp.async's does not.  Not the default.
+  constexpr int kChunks = (kKD / 2 + 15) / 16;   // chunks per lane at 16 lanes per problem
+  double2 kreg[kChunks];
+  auto stage_gain = [&](int k) {
+    const double2* src = reinterpret_cast<const double2*>(gK + (size_t)k * kKD);
+#pragma unroll
+    for (int j = 0; j < kChunks; ++j) {
+      const int cidx = tl + tstride * j;
+      if (2 * cidx < kKD) kreg[j] = __ldcg(src + cidx);
+    }
+  };
+  auto stage_wait = [&](int k) {
+    double2* dst = reinterpret_cast<double2*>(kstage + (k & 1) * kKD);
+#pragma unroll
+    for (int j = 0; j < kChunks; ++j) {
+      const int cidx = tl + tstride * j;
+      if (2 * cidx < kKD) dst[cidx] = kreg[j];
+    }
+  };
+#endif
   if (mode == 1) stage_gain(0);
 #else
   (void)kstage; (void)lane_mask;
@@ -681,6 +707,7 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
       } else {
         double t0 = 0, t1 = 0, t2 = 0;
         const double* K0 = Kk + (3 * f) * 12;
+        (void)K0;
 #if !defined(QMPC_COOP_NO_K128) && defined(__CUDA_ARCH__)
         {   // three 96-byte gain rows as 18 x 16-byte loads (rows are 16-byte aligned)
 #ifndef QMPC_COOP_NO_KSTAGE
@@ -1156,15 +1183,19 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
     COOP_PHASE {
       const int br = lane >> 2, bc = lane & 3, rc = bc ^ M::kSwap;   // rc: role of this lane's block column
       const double* Pr = Pc + 36 * br;
-      if (kUniformBlk && !M::kDw) {
+      if (kUniformBlk) {
         // ONE block product for all 16 lanes (see kUniformBlk): the even roles are the odd roles' product with the
         // constant blocks I / h I and the two operands exchanged - same operations, same roundings
         const bool odd = rc & 1;
         blk_right(Pr, 12, odd ? oA : (rc == 0 ? oP : oV), odd ? oW : (rc == 0 ? oV : oP),
                   odd ? (rc == 1 ? Aff : Afw) : c.I3, rc == 2 ? hd : (rc == 3 ? 1.0 : 0.0), Pw + 36 * br + 3 * bc, 12);
-        if (bc < 2)   // P M: moment columns X_A Cf + h X_W, force columns c1 X_P + h X_V = X_V (h I) + c1 X_P
-          blk_right(Pr, 12, bc == 1 ? oA : oV, bc == 1 ? oW : oP, bc == 1 ? Cf : c.hI3, bc == 1 ? hd : c1,
-                    PM + 18 * br + 3 * bc, 6);
+        if (bc < 2) {   // P M: moment columns X_A Cf + h X_W, force columns c1 X_P + h X_V = X_V (h I) + c1 X_P
+          if (!M::kDw)
+            blk_right(Pr, 12, bc == 1 ? oA : oV, bc == 1 ? oW : oP, bc == 1 ? Cf : c.hI3, bc == 1 ? hd : c1,
+                      PM + 18 * br + 3 * bc, 6);
+          else if (bc == 1) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);   // Euler model: X_A Cf + X_W Dw
+          else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
+        }
       } else {
       if (rc & 1) blk_right(Pr, 12, oA, oW, rc == 1 ? Aff : Afw, rc == 1 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
       else blk_even(Pr, 12, oP, oV, rc == 0 ? 1.0 : hd, rc == 0 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
@@ -1237,7 +1268,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
       const double* Yc = Pw + 3 * bc;
       double* Pd = Pc + 36 * br + 3 * bc;
 #ifndef QMPC_COOP_LXX_RMW
-      constexpr bool kLxxFold = kUniformBlk && !M::kDw;
+      constexpr bool kLxxFold = kUniformBlk;
 #else
       constexpr bool kLxxFold = false;
 #endif
@@ -1247,7 +1278,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
         lxx_block<M>(wq, row + Row::Hphi, br, bc, lxx);   // zero off the diagonal
         blk_left_add(Yc, 12, odd ? oA : (rr == 0 ? oP : oV), odd ? oW : (rr == 0 ? oV : oP),
                      odd ? (rr == 1 ? Aff : Afw) : c.I3, rr == 2 ? hd : (rr == 3 ? 1.0 : 0.0), lxx, Pd, 12);
-      } else if (kUniformBlk && !M::kDw) {
+      } else if (kUniformBlk) {
         const bool odd = rr & 1;
         blk_left(Yc, 12, odd ? oA : (rr == 0 ? oP : oV), odd ? oW : (rr == 0 ? oV : oP),
                  odd ? (rr == 1 ? Aff : Afw) : c.I3, rr == 2 ? hd : (rr == 3 ? 1.0 : 0.0), Pd, 12);
@@ -1274,6 +1305,17 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
           const int r = isS ? (lane >> 1) & 1 : br, cc = isS ? (lane & 1) : bc, ldy = isS ? 6 : 12;
           blk_left(isS ? PM + 3 * cc : Yc, ldy, r == 1 ? oA : oV, r == 1 ? oW : oP, r == 1 ? Cf : c.hI3, r == 1 ? hd : c1,
                    isS ? S + 18 * r + 3 * cc : T + 36 * r + 3 * cc, ldy);
+        }
+      } else if (kUniformBlk) {
+        // Euler model: the moment rows need the two-matrix product (Cf^T Y_A + Dw^T Y_W), so T and S share one call
+        // per row type instead of one call each
+        if (lane < 12) {
+          const bool isS = lane >= 8;
+          const int r = isS ? (lane >> 1) & 1 : br, cc = isS ? (lane & 1) : bc, ldy = isS ? 6 : 12;
+          const double* Y = isS ? PM + 3 * cc : Yc;
+          double* dst = isS ? S + 18 * r + 3 * cc : T + 36 * r + 3 * cc;
+          if (r == 1) blk_left2(Y, ldy, oA, oW, Cf, Dw, dst, ldy);
+          else blk_evenT(Y, ldy, oP, oV, c1, hd, dst, ldy);
         }
       } else {
       if (br < 2) {
