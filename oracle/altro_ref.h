@@ -27,6 +27,7 @@ extern "C" {
 
 #define ALTRO_REF_EQUALITY 0   /* c(x,u) == 0 */
 #define ALTRO_REF_INEQUALITY 1 /* c(x,u) <= 0  (TestDoubleIntegrator.cpp:296-303) */
+#define ALTRO_REF_SOC 2        /* c(x,u) = (v, s) in the second-order cone |v| <= s, scalar last (:414-448); p <= 16 */
 
 #define ALTRO_REF_SUCCESS 0
 #define ALTRO_REF_MAX_ITERATIONS 1
@@ -50,6 +51,7 @@ typedef struct AltroRefOptions { /* altro::AltroOptions subset; defaults = altro
   int use_quaternion, quat_start_index;
   double ls_c1, ls_decrease; /* Armijo constant, back-tracking factor */
   int ls_iters_max;
+  int use_backtracking_linesearch; /* 1: back-tracking (the MPC path); 0: strong-Wolfe cubic search (ALTRO's default) */
 } AltroRefOptions;
 
 typedef struct AltroRefProblem {

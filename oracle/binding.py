@@ -48,6 +48,8 @@ def lib():
         _LIB.qmpc_ref_foot_update.argtypes = [vp, vp, C.c_double, C.c_double, C.c_int, vp]
         _LIB.kat_double_integrator.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.POINTER(Stats)]
         _LIB.kat_pendulum.argtypes = [C.c_int, dp, dp, C.POINTER(Stats)]
+        _LIB.kat_pendulum_ls.argtypes = [C.c_int, C.c_int, dp, dp, C.POINTER(Stats)]
+        _LIB.kat_double_integrator_ls.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, C.POINTER(Stats)]
         _LIB.kat_quat_golden.argtypes = [C.c_int, dp, dp, C.POINTER(Stats)]
         _LIB.kat_quat_rollout.argtypes = [C.c_int, dp, dp]
         _LIB.kat_pendulum_midpoint.argtypes = [dp, dp, C.c_float, dp, dp]
@@ -206,16 +208,19 @@ def joint_torques(results, jac_foot, plan_contacts, movement_mode):
     return tau
 
 
-def kat_double_integrator(variant, penalty_initial=0.0, penalty_scaling=0.0, iterations_max=0):
+def kat_double_integrator(variant, penalty_initial=0.0, penalty_scaling=0.0, iterations_max=0, cubic=False):
+    """variant 0..2: TestDoubleIntegrator.cpp:69-375; 3: the second-order-cone control bound (:377-491).
+    cubic: ALTRO's default (strong-Wolfe, cubic interpolation) line search instead of back-tracking."""
     X, U, st = np.zeros((11, 4)), np.zeros((10, 2)), Stats()
-    lib().kat_double_integrator(variant, penalty_initial, penalty_scaling, iterations_max, _dp(X), _dp(U), C.byref(st))
+    lib().kat_double_integrator_ls(variant, penalty_initial, penalty_scaling, iterations_max, int(cubic), _dp(X), _dp(U),
+                                   C.byref(st))
     return X, U, st
 
 
-def kat_pendulum(variant):
+def kat_pendulum(variant, cubic=False):
     N = 50 if variant == 0 else 20
     X, U, st = np.zeros((N + 1, 2)), np.zeros((N, 1)), Stats()
-    lib().kat_pendulum(variant, _dp(X), _dp(U), C.byref(st))
+    lib().kat_pendulum_ls(variant, int(cubic), _dp(X), _dp(U), C.byref(st))
     return X, U, st
 
 

@@ -38,27 +38,40 @@ void kat_di_dynamics(const double* x, const double* u, float h, double* xn, doub
   di_dyn(0, xn, x, u, h);
   di_jac(0, J, x, u, h);
 }
+/* ctx: {N, soc}.  soc = 1: the control bound is the second-order cone (u, u_bnd), TestDoubleIntegrator.cpp:414-436 */
 static void di_con(void* ctx, int k, double* c, const double* x, const double* u) {
-  int N = *(int*)ctx;
+  int N = ((int*)ctx)[0], soc = ((int*)ctx)[1];
   if (k == N) { /* goal constraint, xf = 0 */
     for (int i = 0; i < 4; ++i) c[i] = x[i];
+  } else if (soc) { /* |u|_2 <= u_bnd = 1 as (u, u_bnd) in the cone */
+    c[0] = u[0]; c[1] = u[1]; c[2] = 1.0;
   } else {      /* control bounds |u| <= 1 */
     for (int i = 0; i < 2; ++i) { c[i] = u[i] - 1.0; c[i + 2] = -1.0 - u[i]; }
   }
 }
 static void di_conjac(void* ctx, int k, double* J, const double* x, const double* u) {
   (void)x; (void)u;
-  int N = *(int*)ctx;
-  const int p = 4;
+  int N = ((int*)ctx)[0], soc = ((int*)ctx)[1];
+  const int p = (k < N && soc) ? 3 : 4;
   if (k == N) {
     for (int i = 0; i < 4; ++i) J[i * p + i] = 1.0;
+  } else if (soc) {
+    for (int i = 0; i < 2; ++i) J[(4 + i) * p + i] = 1.0;   /* 3 x 6 column-major, d c_i / d u_i = 1 */
   } else {
     for (int i = 0; i < 2; ++i) { J[(4 + i) * p + i] = 1.0; J[(4 + i) * p + i + 2] = -1.0; }
   }
 }
-/* variant: 0 unconstrained, 1 goal equality, 2 goal + control bounds */
+/* variant: 0 unconstrained, 1 goal equality, 2 goal + control bounds, 3 goal + second-order-cone control bound
+ * (TestDoubleIntegrator.cpp:377-491) */
+/* cubic != 0: ALTRO's default line search (the reference tests do not set use_backtracking_linesearch) */
+int kat_double_integrator_ls(int variant, double penalty_initial, double penalty_scaling, int iterations_max, int cubic,
+                             double* X, double* U, AltroRefStats* st);
 int kat_double_integrator(int variant, double penalty_initial, double penalty_scaling, int iterations_max,
                           double* X, double* U, AltroRefStats* st) {
+  return kat_double_integrator_ls(variant, penalty_initial, penalty_scaling, iterations_max, 0, X, U, st);
+}
+int kat_double_integrator_ls(int variant, double penalty_initial, double penalty_scaling, int iterations_max, int cubic,
+                             double* X, double* U, AltroRefStats* st) {
   enum { N = 10, n = 4, m = 2 };
   float tf = 5.0f;
   const float h = tf / (double)N;
@@ -66,14 +79,16 @@ int kat_double_integrator(int variant, double penalty_initial, double penalty_sc
   int p[N + 1] = {0}, ct[N + 1] = {0};
   for (int i = 0; i < (N + 1) * n; ++i) Q[i] = 1.0;
   for (int i = 0; i < (N + 1) * m; ++i) R[i] = 1e-2;
-  double x0[4] = {variant == 2 ? 2.0 : 1.0, 2.0, 0.0, 0.0};
-  int NN = N;
+  double x0[4] = {variant >= 2 ? 2.0 : 1.0, 2.0, 0.0, 0.0};
+  int NN[2] = {N, variant == 3};
   if (variant >= 1) { p[N] = 4; ct[N] = ALTRO_REF_EQUALITY; }
   if (variant == 2)
     for (int k = 0; k < N; ++k) { p[k] = 4; ct[k] = ALTRO_REF_INEQUALITY; }
+  if (variant == 3)
+    for (int k = 0; k < N; ++k) { p[k] = 3; ct[k] = ALTRO_REF_SOC; }
   AltroRefProblem P;
   memset(&P, 0, sizeof(P));
-  P.N = N; P.n = n; P.m = m; P.h = h; P.ctx = &NN; P.dyn = di_dyn; P.jac = di_jac;
+  P.N = N; P.n = n; P.m = m; P.h = h; P.ctx = NN; P.dyn = di_dyn; P.jac = di_jac;
   P.Q = Q; P.R = R; P.xref = xr; P.uref = ur; P.w = w; P.p = p; P.ctype = ct;
   P.con = di_con; P.conjac = di_conjac; P.x0 = x0;
   AltroRefOptions o;
@@ -81,6 +96,7 @@ int kat_double_integrator(int variant, double penalty_initial, double penalty_sc
   if (penalty_initial > 0) o.penalty_initial = penalty_initial;
   if (penalty_scaling > 0) o.penalty_scaling = penalty_scaling;
   if (iterations_max > 0) o.iterations_max = iterations_max;
+  if (cubic) o.use_backtracking_linesearch = 0;
   memset(U, 0, sizeof(double) * N * m);
   return altro_ref_solve(&P, &o, X, U, st);
 }
@@ -121,7 +137,9 @@ static void pend_conjac(void* ctx, int k, double* J, const double* x, const doub
   J[0] = -1.0; J[3] = -1.0; /* 2 x 3 column-major, -I on the state block */
 }
 /* variant 0: N=50, tf=3, unconstrained, iterations_max 20 ; variant 1: N=20, tf=2, goal equality */
-int kat_pendulum(int variant, double* X, double* U, AltroRefStats* st) {
+int kat_pendulum_ls(int variant, int cubic, double* X, double* U, AltroRefStats* st);
+int kat_pendulum(int variant, double* X, double* U, AltroRefStats* st) { return kat_pendulum_ls(variant, 0, X, U, st); }
+int kat_pendulum_ls(int variant, int cubic, double* X, double* U, AltroRefStats* st) {
   enum { NMAX = 50, n = 2, m = 1 };
   const int N = variant == 0 ? 50 : 20;
   const float tf = variant == 0 ? 3.0f : 2.0f;
@@ -144,6 +162,7 @@ int kat_pendulum(int variant, double* X, double* U, AltroRefStats* st) {
   AltroRefOptions o;
   altro_ref_default_options(&o);
   o.iterations_max = variant == 0 ? 20 : 100;
+  if (cubic) o.use_backtracking_linesearch = 0;
   for (int k = 0; k < N; ++k) U[k] = 0.1;
   return altro_ref_solve(&P, &o, X, U, st);
 }
