@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-config1", action="store_true", help="skip the BASELINE config-1 latency block")
     ap.add_argument("--kernel", default="auto", choices=["auto", "coop", "phased", "srb", "dense"],
                     help="QmpcCreateOptions.kernel (auto = the product default)")
+    ap.add_argument("--host-chunks", type=int, default=0,
+                    help="QmpcCreateOptions.host_chunks (2..4 = chunked copy / solve pipeline of the host entry points; default off)")
     return ap.parse_args()
 
 
@@ -315,7 +317,7 @@ def main():
     Mpc = ConvexMpc if a.model == "convex" else QuatMpc
 
     probs = random_batch(B, seed=0 + rank, gait=a.gait)   # each rank owns its shard of the global batch
-    mpc = Mpc(max_batch=B, device=local, cfg=cfg, kernel=a.kernel)
+    mpc = Mpc(max_batch=B, device=local, cfg=cfg, kernel=a.kernel, host_chunks=a.host_chunks)
     d_in = mpc.to_device(probs)
     d_out = mpc.alloc_results(B)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
@@ -382,7 +384,7 @@ def main():
             mpc.grf_update_host_ptr(h_in.data_ptr(), B, h_out.data_ptr())
         barrier()
         e2e_s = time.perf_counter() - t0
-        e2e_path = "qmpc_solve_batch_host, pinned host buffers"
+        e2e_path = "qmpc_solve_batch_host, pinned host buffers" + (f", up to {a.host_chunks} chunks" if a.host_chunks > 1 else "")
         assert h_out.numpy().tobytes() == res.tobytes()
     else:
         e2e_s = 0.0

@@ -148,7 +148,9 @@ typedef struct QmpcCreateOptions {
   int32_t smem_residents;   /* -1 = chosen by occupancy query; else bit 0: per-knot linearisation
                                blocks, bit 1: duals kept in shared memory (coop kernel)            */
   int32_t packed_launch;    /* 1 = fill blocks one by one instead of spreading a partial wave       */
-  int32_t reserved_;
+  int32_t host_chunks;      /* *_host entry points: 0 / 1 = one copy-solve-copy sequence (default); 2..4 = a batch of
+                               several problem waves is copied and solved in up to that many chunks of whole waves,
+                               copies overlapping the solves (measured: no gain on a B200, see qmpc_api.cu)        */
 } QmpcCreateOptions;
 int qmpc_create_ex(const QmpcConfig* cfg, int32_t max_batch, int32_t device, const QmpcCreateOptions* opt,
                    QmpcHandle** out);

@@ -43,7 +43,7 @@ class QmpcConfig(C.Structure):
 
 class QmpcCreateOptions(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("smem_residents", C.c_int32), ("packed_launch", C.c_int32),
-                ("reserved_", C.c_int32)]
+                ("host_chunks", C.c_int32)]
 
 
 PROBLEM_DTYPE = np.dtype([

@@ -28,8 +28,8 @@ class _BatchedMpc:
     _solve_sched_host = None
 
     def __init__(self, horizon=10, max_batch=4096, device=0, cfg=None, kernel="auto", smem_residents=-1,
-                 packed_launch=False):
-        """`kernel` / `smem_residents` / `packed_launch` are the QmpcCreateOptions of include/qmpc.h
+                 packed_launch=False, host_chunks=0):
+        """`kernel` / `smem_residents` / `packed_launch` / `host_chunks` are the QmpcCreateOptions of include/qmpc.h
         (explicit per-handle choices; the library reads no environment variables).  kernel "dense" / "srb"
         select the on-device cross-check kernels used by the tests."""
         # the dense / srb cross-check kernels live in the test-only sibling library, not in the product
@@ -43,7 +43,7 @@ class _BatchedMpc:
         self.device = int(device)
         self.max_batch = int(max_batch)
         self._h = C.c_void_p()
-        opt = abi.QmpcCreateOptions(abi.KERNEL_NAMES[kernel], int(smem_residents), int(bool(packed_launch)), 0)
+        opt = abi.QmpcCreateOptions(abi.KERNEL_NAMES[kernel], int(smem_residents), int(bool(packed_launch)), int(host_chunks))
         rc = self.lib.qmpc_create_ex(C.byref(self.cfg), self.max_batch, self.device, C.byref(opt), C.byref(self._h))
         if rc != abi.QMPC_OK:
             msg = self.lib.qmpc_last_error(self._h).decode() if self._h else ""

@@ -122,6 +122,26 @@ def test_host_and_device_entry_points_agree(oracle):
         mpc.grf_update(random_batch(301, seed=1))
 
 
+@pytest.mark.parametrize("B", [2369, 5001, 12000])
+def test_chunked_host_pipeline_is_bit_identical(B):
+    """Opt-in: a host batch of several problem waves copied and solved in chunks of whole waves (copies of chunk i + 1 /
+    i - 1 overlap the solve of chunk i, QmpcCreateOptions.host_chunks = 4): same bytes as the default one
+    copy-solve-copy sequence and as the device entry point, with and without a contact schedule, ragged last chunk
+    included."""
+    from quaternion_mpc_b200 import QuatMpc
+    from quaternion_mpc_b200.workloads import predict_schedule_numpy, random_gait_states
+    probs = random_batch(B, seed=21, gait="mixed")
+    a, b = QuatMpc(horizon=10, max_batch=B, host_chunks=4), QuatMpc(horizon=10, max_batch=B)
+    ref = _solve_dev(a, probs)
+    n0 = a.launch_count
+    ra, rb = a.grf_update(probs), b.grf_update(probs)
+    assert a.launch_count - n0 >= 2            # the pipeline really ran in chunks
+    assert ra.tobytes() == ref.tobytes() and rb.tobytes() == ref.tobytes()
+    sched = predict_schedule_numpy(random_gait_states(B, seed=22), 10, a.cfg.dt)
+    assert a.grf_update_sched(probs, sched).tobytes() == b.grf_update_sched(probs, sched).tobytes()
+    assert a.grf_update(probs[:2368]).tobytes() == ref[:2368].tobytes()   # one wave: the plain sequence
+
+
 def test_omega0_quirk_and_full_state(oracle):
     """drop_omega0=1 reproduces QuatMpc.cpp:232-245 (measured omega ignored); 0 uses it."""
     from quaternion_mpc_b200 import QuatMpc
