@@ -84,7 +84,16 @@ QMPC_HD inline void st_keep(double* p, double v) { *p = v; }
 QMPC_HD inline double ld_keep(const double* p) { return *p; }
 
 QMPC_HD inline double qmpc_rsqrt(double x) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_LIBM_RSQRT)
+  // rsqrt() of the CUDA math library without its range checks (zero / negative / denormal / non-finite arguments branch
+  // to a slow path there; here a non-positive pivot is reported through `ok` and poisons the lane's result anyway): the
+  // same seed (MUFU.RSQ64H, low word 0) and the same refinement y0 + (0.5 + 0.375 e) (y0 e), e = 1 - x y0^2 - the same
+  // value for every normal positive x, 6 instructions for 9 + a branch.
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(-x, y0 * y0, 1.0);
+  return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+#elif defined(__CUDA_ARCH__)
   return rsqrt(x);
 #else
   return 1.0 / sqrt(x);
@@ -413,7 +422,9 @@ QMPC_HD inline void coop_linearize(const ConvexModel& m, const double* x, const 
   double xd[12];
   m.wrench_dyn(x, fs0, fs1, fs2, mom0, mom1, mom2, xd);
   const double yaw_m = xd[2] * hh + x[2], w0m = xd[6] * hh + x[6], w1m = xd[7] * hh + x[7];
-  const double sy = sin(x[2]), cy = cos(x[2]), sym = sin(yaw_m), cym = cos(yaw_m);
+  double sy, cy, sym, cym;
+  qmpc_sincos(x[2], &sy, &cy);
+  qmpc_sincos(yaw_m, &sym, &cym);
   double iw[4], iwm[4];
   ConvexModel::Iw_inv(sy, cy, iw);
   ConvexModel::Iw_inv(sym, cym, iwm);
@@ -512,7 +523,7 @@ QMPC_HD inline void knot_merit(const M& m, const QmpcConfig& cfg, const double* 
         acc += lh * lh - mui * mui;
       }
     }
-    J += acc / (2 * rho);
+    J += qmpc_div(acc, 2 * rho);
   }
 }
 
@@ -1182,30 +1193,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
     // ---- phase B: PA = P A (16 blocks), PM = P M (8 blocks), s = M^T p, Atp = A^T p
     COOP_PHASE {
       const int br = lane >> 2, bc = lane & 3, rc = bc ^ M::kSwap;   // rc: role of this lane's block column
-      const double* Pr = Pc + 36 * br;
-      if (kUniformBlk) {
-        // ONE block product for all 16 lanes (see kUniformBlk): the even roles are the odd roles' product with the
-        // constant blocks I / h I and the two operands exchanged - same operations, same roundings
-        const bool odd = rc & 1;
-        blk_right(Pr, 12, odd ? oA : (rc == 0 ? oP : oV), odd ? oW : (rc == 0 ? oV : oP),
-                  odd ? (rc == 1 ? Aff : Afw) : c.I3, rc == 2 ? hd : (rc == 3 ? 1.0 : 0.0), Pw + 36 * br + 3 * bc, 12);
-        if (bc < 2) {   // P M: moment columns X_A Cf + h X_W, force columns c1 X_P + h X_V = X_V (h I) + c1 X_P
-          if (!M::kDw)
-            blk_right(Pr, 12, bc == 1 ? oA : oV, bc == 1 ? oW : oP, bc == 1 ? Cf : c.hI3, bc == 1 ? hd : c1,
-                      PM + 18 * br + 3 * bc, 6);
-          else if (bc == 1) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);   // Euler model: X_A Cf + X_W Dw
-          else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
-        }
-      } else {
-      if (rc & 1) blk_right(Pr, 12, oA, oW, rc == 1 ? Aff : Afw, rc == 1 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
-      else blk_even(Pr, 12, oP, oV, rc == 0 ? 1.0 : hd, rc == 0 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
-      if (bc < 2) {
-        if (bc == 1) {
-          if (M::kDw) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);
-          else blk_right(Pr, 12, oA, oW, Cf, hd, PM + 18 * br + 3 * bc, 6);
-        } else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
-      }
-      }
+      // the two small vectors first: their load -> fma -> store chains then run under the block products' loads
 #ifndef QMPC_COOP_VEC_DIVERGENT
       constexpr bool kUniformVec = kUniformBlk && !M::kDw;
 #else
@@ -1260,11 +1248,36 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
           vec[L::vAtp + a] = v;
         }
       }
+      const double* Pr = Pc + 36 * br;
+      if (kUniformBlk) {
+        // ONE block product for all 16 lanes (see kUniformBlk): the even roles are the odd roles' product with the
+        // constant blocks I / h I and the two operands exchanged - same operations, same roundings
+        const bool odd = rc & 1;
+        blk_right(Pr, 12, odd ? oA : (rc == 0 ? oP : oV), odd ? oW : (rc == 0 ? oV : oP),
+                  odd ? (rc == 1 ? Aff : Afw) : c.I3, rc == 2 ? hd : (rc == 3 ? 1.0 : 0.0), Pw + 36 * br + 3 * bc, 12);
+        if (bc < 2) {   // P M: moment columns X_A Cf + h X_W, force columns c1 X_P + h X_V = X_V (h I) + c1 X_P
+          if (!M::kDw)
+            blk_right(Pr, 12, bc == 1 ? oA : oV, bc == 1 ? oW : oP, bc == 1 ? Cf : c.hI3, bc == 1 ? hd : c1,
+                      PM + 18 * br + 3 * bc, 6);
+          else if (bc == 1) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);   // Euler model: X_A Cf + X_W Dw
+          else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
+        }
+      } else {
+      if (rc & 1) blk_right(Pr, 12, oA, oW, rc == 1 ? Aff : Afw, rc == 1 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
+      else blk_even(Pr, 12, oP, oV, rc == 0 ? 1.0 : hd, rc == 0 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
+      if (bc < 2) {
+        if (bc == 1) {
+          if (M::kDw) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);
+          else blk_right(Pr, 12, oA, oW, Cf, hd, PM + 18 * br + 3 * bc, 6);
+        } else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
+      }
+      }
     }
     COOP_SYNC();
     // ---- phase C: P <- A^T PA + lxx (16 blocks), T = M^T PA (8 blocks), S = M^T PM (4 blocks), Qx
     COOP_PHASE {
       const int br = lane >> 2, bc = lane & 3, rr = br ^ M::kSwap;   // rr: role of this lane's block row
+      if (lane < 12) vec[L::vQx + lane] = vec[L::vAtp + lane] + row[Row::lx + lane];
       const double* Yc = Pw + 3 * bc;
       double* Pd = Pc + 36 * br + 3 * bc;
 #ifndef QMPC_COOP_LXX_RMW
@@ -1333,20 +1346,19 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
         } else blk_evenT(Ym, 6, oP, oV, c1, hd, S + 18 * r + 3 * cc, 6);
       }
       }
-      if (lane < 12) vec[L::vQx + lane] = vec[L::vAtp + lane] + row[Row::lx + lane];
     }
     COOP_SYNC();
     // ---- phase D: Qux = W^T T (NF x 4 blocks), SW = S W (2 x NF blocks), Qu = g + W^T s
     COOP_PHASE {
       const int br = lane >> 2, bc = lane & 3;
-      if (br < NF) blk_wt(T + 3 * bc, 12, m.inv_mass, m.IS + 9 * br, Qux + 36 * br + 3 * bc, 12, nullptr);
-      if (br < 2 && bc < NF) blk_w(S + 18 * br, 6, m.inv_mass, m.IS + 9 * bc, SW + 3 * NU * br + 3 * bc, NU);
       if (lane < NU) {
         const int f = lane / 3, a = lane % 3;
         const double* IS = m.IS + 9 * f;
         const double* s = vec + L::vs;
         vec[L::vQu + lane] = (m.inv_mass * s[a] + IS[a] * s[3] + IS[3 + a] * s[4] + IS[6 + a] * s[5]) + row[Row::g + lane];
       }
+      if (br < NF) blk_wt(T + 3 * bc, 12, m.inv_mass, m.IS + 9 * br, Qux + 36 * br + 3 * bc, 12, nullptr);
+      if (br < 2 && bc < NF) blk_w(S + 18 * br, 6, m.inv_mass, m.IS + 9 * bc, SW + 3 * NU * br + 3 * bc, NU);
     }
     COOP_SYNC();
     // ---- phase E: Quu = D + W^T (S W)  (NF x NF blocks, into the work buffer)
@@ -1410,7 +1422,8 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
         // Only the factor's quotients matter; the substitutions below keep the plain reciprocal (measured).
         const double r0 = qmpc_rsqrt(sjj);
         double dg = sjj * r0;
-        dg = fma(0.5 * fma(-dg, dg, sjj), r0, dg);          // sqrt(sjj), correctly rounded
+        dg = fma(0.5 * fma(-dg, dg, sjj), r0, dg);          // sqrt(sjj), correctly rounded  (the exact factor 0.5 moved onto r0,
+                                                            // off the pivot chain: measured 1 % SLOWER, run 20)
         const double rdg = fma(fma(-dg, r0, 1.0), r0, r0);  // 1 / dg
         rd[j] = rdg;
 #pragma unroll

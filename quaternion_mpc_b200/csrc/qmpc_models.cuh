@@ -24,6 +24,17 @@ struct double2 { double x, y; };
 
 namespace qmpc {
 
+// sin and cos of one angle.  On the device one sincos() call: a single argument reduction for both (the Euler model's
+// roll-outs evaluate the pair twice per knot); same values as sin() / cos() of the CUDA math library (checked on the
+// device against the previous build, profiles/r02_run2*_bitcheck.log).  -DQMPC_SINCOS_SEPARATE restores the two calls.
+QMPC_HD inline void qmpc_sincos(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__) && !defined(QMPC_SINCOS_SEPARATE)
+  sincos(a, s, c);
+#else
+  *s = sin(a); *c = cos(a);
+#endif
+}
+
 QMPC_HD inline void cross3(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1];
   c[1] = a[2] * b[0] - a[0] * b[2];
@@ -377,7 +388,7 @@ struct ConvexModel {
   QMPC_HD void wrench_dyn(const double* x, double fs0, double fs1, double fs2, double mom0, double mom1, double mom2,
                           double* xd) const {
     double sy, cy, iw[4];
-    sy = sin(x[2]); cy = cos(x[2]);
+    qmpc_sincos(x[2], &sy, &cy);
     Iw_inv(sy, cy, iw);
     xd[0] = cy * x[6] + sy * x[7];
     xd[1] = -sy * x[6] + cy * x[7];

@@ -80,6 +80,11 @@ QMPC_HD inline GaitLegPattern gait_pattern(int gait, int leg) {
       p.n = 1; p.sw[0] = 1.0; p.stance[0] = 1;
       break;
   }
+  // unused entries never match (ph <= -inf is false for every ph): predict_contact tests all three without a loop
+  // over p.n, so the pattern stays in registers (the indexed loop put it in local memory: 3 LDL / 5 STL per leg)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i >= p.n) { p.sw[i] = -INFINITY; p.stance[i] = 1; }
   return p;
 }
 
@@ -95,8 +100,9 @@ QMPC_HD inline int predict_contact(const GaitLegPattern& p, double gait_phase, d
     const double r = ph - floor(ph);
     ph = (r == 0.0) ? 1.0 : r;
   }
-  for (int i = 0; i < p.n; ++i)
-    if (ph <= p.sw[i]) return p.stance[i];
+  if (ph <= p.sw[0]) return p.stance[0];
+  if (ph <= p.sw[1]) return p.stance[1];
+  if (ph <= p.sw[2]) return p.stance[2];
   return 1;
 }
 
