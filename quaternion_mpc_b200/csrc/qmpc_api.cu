@@ -677,7 +677,7 @@ extern "C" int qmpc_goal_update(QmpcHandle* h, void* d_goal_state, const QmpcGoa
   if (!d_goal_state || !d_in || !d_problems) return QMPC_ERR_ARG;
   if (batch == 0) return QMPC_OK;
   CU(cudaSetDevice(h->device));
-  qmpc_goal_update_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(
+  qmpc_goal_update_kernel<<<(batch + kGoalBlock - 1) / kGoalBlock, kGoalBlock, 0, (cudaStream_t)cuda_stream>>>(
       (double*)d_goal_state, (size_t)h->max_batch, d_in, batch, d_problems);
   h->launches += 1;
   CU(cudaGetLastError());
@@ -738,7 +738,7 @@ extern "C" int qmpc_raibert_targets(QmpcHandle* h, const QmpcRaibertParams* rp, 
   if (!rp || !d_in || (!d_foot_pos_target_world && !d_foot_pos_target_rel)) return QMPC_ERR_ARG;
   if (batch == 0) return QMPC_OK;
   CU(cudaSetDevice(h->device));
-  qmpc_raibert_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(*rp, d_in, batch, d_foot_pos_target_world,
+  qmpc_raibert_kernel<<<(batch + kRaibertBlock - 1) / kRaibertBlock, kRaibertBlock, 0, (cudaStream_t)cuda_stream>>>(*rp, d_in, batch, d_foot_pos_target_world,
                                                                                  d_foot_pos_target_rel);
   h->launches += 1;
   CU(cudaGetLastError());

@@ -10,6 +10,7 @@
 // robot (N1) or per (robot, leg) (N2), consecutive threads touch consecutive addresses, grid sized
 // to the batch.  The bodies are QMPC_HD so tests/emul can run them on the host.
 #pragma once
+#include <cstddef>
 #include "qmpc_models.cuh"
 
 namespace qmpc {
@@ -498,20 +499,84 @@ qmpc_foot_update_kernel(double* __restrict__ state, size_t stride, QuinticInv ci
   }
 }
 
-__global__ void __launch_bounds__(256)
+// One thread per robot, 128 robots per block; the filter state is element-major (consecutive threads, consecutive
+// addresses).  The array-of-structures sides go through shared memory like the Raibert kernel's: the block's 128 input
+// records come in with consecutive threads on consecutive addresses, and the 16 words goal_update writes into each
+// QmpcProblem (three runs: words 0..6, 22..27, 32..34 of the 37) go out run by run instead of field by field.
+constexpr int kGoalBlock = 128;
+__global__ void __launch_bounds__(kGoalBlock)
 qmpc_goal_update_kernel(double* __restrict__ state, size_t stride, const QmpcGoalInput* __restrict__ in, int batch,
                         QmpcProblem* __restrict__ problems) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= batch) return;
-  goal_update_one(GoalStateRef{state + i, stride}, in[i], problems[i]);
+  constexpr int kIn = (int)(sizeof(QmpcGoalInput) / 8), kInPad = kIn + 1, kOut = 16, kOutPad = 17;
+  constexpr int kProb = (int)(sizeof(QmpcProblem) / 8);
+  static_assert(sizeof(QmpcProblem) % 8 == 0 && offsetof(QmpcProblem, torso_quat) == 0 &&
+                offsetof(QmpcProblem, torso_lin_vel_world) == 32 && offsetof(QmpcProblem, torso_pos_d_body) == 176 &&
+                offsetof(QmpcProblem, torso_lin_vel_d_body) == 200 && offsetof(QmpcProblem, torso_ang_vel_d_body) == 256,
+                "QmpcProblem layout changed: update the output runs below");
+  __shared__ double s_in[kGoalBlock * kInPad];
+  __shared__ double s_out[kGoalBlock * kOutPad];
+  const size_t i0 = (size_t)blockIdx.x * kGoalBlock;
+  const int cnt = (int)((size_t)batch - i0 < (size_t)kGoalBlock ? (size_t)batch - i0 : (size_t)kGoalBlock);
+  const double* src = reinterpret_cast<const double*>(in + i0);
+  for (int e = threadIdx.x; e < cnt * kIn; e += kGoalBlock) s_in[(e / kIn) * kInPad + e % kIn] = src[e];
+  __syncthreads();
+  if ((int)threadIdx.x < cnt) {
+    QmpcGoalInput rec;
+    double* r = reinterpret_cast<double*>(&rec);
+#pragma unroll
+    for (int e = 0; e < kIn; ++e) r[e] = s_in[threadIdx.x * kInPad + e];
+    QmpcProblem tmp;
+    goal_update_one(GoalStateRef{state + i0 + threadIdx.x, stride}, rec, tmp);
+    double* o = s_out + threadIdx.x * kOutPad;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = tmp.torso_quat[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      o[4 + j] = tmp.torso_lin_vel_world[j];
+      o[7 + j] = tmp.torso_pos_d_body[j];
+      o[10 + j] = tmp.torso_lin_vel_d_body[j];
+      o[13 + j] = tmp.torso_ang_vel_d_body[j];
+    }
+  }
+  __syncthreads();
+  double* dst = reinterpret_cast<double*>(problems + i0);
+  for (int e = threadIdx.x; e < cnt * kOut; e += kGoalBlock) {
+    const int r = e / kOut, j = e % kOut;
+    const int word = j < 7 ? j : (j < 13 ? 22 + (j - 7) : 32 + (j - 13));
+    dst[(size_t)r * kProb + word] = s_out[r * kOutPad + j];
+  }
 }
 
-__global__ void __launch_bounds__(256)
+// One thread per robot, 128 robots per block.  Records in (128-byte QmpcGoalInput) and out (two 96-byte target sets) are
+// array-of-structures: read / written by the threads themselves every access scatters 32 x 8 bytes over 4 KB / 3 KB.
+// The block instead copies its 128 input records into shared memory with consecutive threads on consecutive
+// addresses (row stride padded to 17 doubles: conflict-free), every thread works on its record there, and the
+// 128 x 12 results of each output go out the same way.
+constexpr int kRaibertBlock = 128;
+__global__ void __launch_bounds__(kRaibertBlock)
 qmpc_raibert_kernel(QmpcRaibertParams rp, const QmpcGoalInput* __restrict__ in, int batch,
                     double* __restrict__ tgt_world, double* __restrict__ tgt_rel) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= batch) return;
-  raibert_one(rp, in[i], tgt_world ? tgt_world + 12 * (size_t)i : nullptr, tgt_rel ? tgt_rel + 12 * (size_t)i : nullptr);
+  constexpr int kIn = (int)(sizeof(QmpcGoalInput) / 8), kInPad = kIn + 1;
+  static_assert(sizeof(QmpcGoalInput) % 8 == 0, "QmpcGoalInput is copied as 8-byte words");
+  __shared__ double s_in[kRaibertBlock * kInPad];
+  __shared__ double s_w[kRaibertBlock * 13], s_r[kRaibertBlock * 13];
+  const size_t i0 = (size_t)blockIdx.x * kRaibertBlock;
+  const int cnt = (int)((size_t)batch - i0 < (size_t)kRaibertBlock ? (size_t)batch - i0 : (size_t)kRaibertBlock);
+  const double* src = reinterpret_cast<const double*>(in + i0);
+  for (int e = threadIdx.x; e < cnt * kIn; e += kRaibertBlock) s_in[(e / kIn) * kInPad + e % kIn] = src[e];
+  __syncthreads();
+  if ((int)threadIdx.x < cnt) {
+    QmpcGoalInput rec;
+    double* r = reinterpret_cast<double*>(&rec);
+#pragma unroll
+    for (int e = 0; e < kIn; ++e) r[e] = s_in[threadIdx.x * kInPad + e];
+    raibert_one(rp, rec, s_w + 13 * threadIdx.x, s_r + 13 * threadIdx.x);
+  }
+  __syncthreads();
+  if (tgt_world)
+    for (int e = threadIdx.x; e < cnt * 12; e += kRaibertBlock) tgt_world[12 * i0 + e] = s_w[(e / 12) * 13 + e % 12];
+  if (tgt_rel)
+    for (int e = threadIdx.x; e < cnt * 12; e += kRaibertBlock) tgt_rel[12 * i0 + e] = s_r[(e / 12) * 13 + e % 12];
 }
 
 // One thread per (robot, leg): 32 stance bits of its leg, exchanged inside the quad by shuffles; lane `leg`
@@ -541,23 +606,34 @@ qmpc_predict_schedule_kernel(const QmpcGaitState* __restrict__ g, int batch, int
   if ((t >> 2) < batch) reinterpret_cast<unsigned long long*>(out + robot)[leg] = w;
 }
 
+// One thread per (robot, leg).  The 3 + 9 results of a thread are 24- and 72-byte records: written by the threads
+// themselves every store instruction scatters 32 x 8 bytes over 768 / 2304 bytes (4 partially written sectors per
+// sector's worth of data; the kernel sat at 0.40 of the HBM roof).  They are staged in shared memory instead and the
+// block writes its 768 + 2304 contiguous doubles with consecutive threads on consecutive addresses.
 __global__ void __launch_bounds__(256)
 qmpc_leg_kinematics_kernel(QmpcLegParams lp, const double* __restrict__ joint_pos, int batch,
                            double* __restrict__ foot_pos_body, double* __restrict__ jac_foot) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // (robot, leg)
-  if (t >= batch * 4) return;
-  const int leg = t & 3;
-  const double q[3] = {joint_pos[3 * (size_t)t], joint_pos[3 * (size_t)t + 1], joint_pos[3 * (size_t)t + 2]};
-  double p[3], J[9];
-  leg_fk_jac(q, lp.rho_fix[leg], lp.rho_opt[leg], p, J);
-  if (foot_pos_body) {
+  __shared__ double sf[256 * 3];
+  __shared__ double sj[256 * 9];
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x;
+  const size_t t = t0 + threadIdx.x;   // (robot, leg)
+  const size_t total = (size_t)batch * 4;
+  const int cnt = (int)(total - t0 < blockDim.x ? total - t0 : blockDim.x);
+  if (t < total) {
+    const int leg = (int)(t & 3);
+    const double q[3] = {joint_pos[3 * t], joint_pos[3 * t + 1], joint_pos[3 * t + 2]};
+    double p[3], J[9];
+    leg_fk_jac(q, lp.rho_fix[leg], lp.rho_opt[leg], p, J);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) foot_pos_body[3 * (size_t)t + a] = p[a];
-  }
-  if (jac_foot) {
+    for (int a = 0; a < 3; ++a) sf[3 * threadIdx.x + a] = p[a];
 #pragma unroll
-    for (int a = 0; a < 9; ++a) jac_foot[9 * (size_t)t + a] = J[a];
+    for (int a = 0; a < 9; ++a) sj[9 * threadIdx.x + a] = J[a];
   }
+  __syncthreads();
+  if (foot_pos_body)
+    for (int i = threadIdx.x; i < 3 * cnt; i += blockDim.x) foot_pos_body[3 * t0 + i] = sf[i];
+  if (jac_foot)
+    for (int i = threadIdx.x; i < 9 * cnt; i += blockDim.x) jac_foot[9 * t0 + i] = sj[i];
 }
 
 __global__ void __launch_bounds__(256)
