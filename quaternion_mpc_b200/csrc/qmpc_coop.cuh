@@ -141,16 +141,12 @@ constexpr int kBlkRowUnroll = QMPC_COOP_BLK_ROW_UNROLL;
 // Phases B / C give every lane of a problem one 3x3 block of P A, A^T (P A), P M, M^T (P A), M^T (P M).  The blocks of
 // the "odd" roles (attitude, angular velocity) are genuine 3x3 products, those of the "even" roles (position, linear
 // velocity) are alpha X_a + beta X_b.  Written as two helpers the lanes of a warp DIVERGE and every phase issues both
-// instruction streams (phase C: six helpers in sequence).  Uniform form (default; -DQMPC_COOP_DIVERGENT_BLK restores the
-// two-helper form): the even lanes call the odd lanes' helper with the constant blocks I / h I from the block's shared
-// memory and the operands exchanged - fma(beta, x_b, 1 * x_a + 0 + 0) is the very fma(alpha, x, beta y) the even helper
-// evaluates, rounding for rounding, so the results are bit-identical - and T and S share one call with per-lane
-// operands.  Not used by the Euler model (its moment blocks need the two-matrix helpers).
-#ifdef QMPC_COOP_DIVERGENT_BLK
-constexpr bool kUniformBlk = false;
-#else
-constexpr bool kUniformBlk = true;
-#endif
+// instruction streams (phase C: six helpers in sequence; that form is in the history, commit 943f4b3).  Uniform form: the
+// even lanes call the odd lanes' helper with the constant blocks I / h I from the block's shared memory and the
+// operands exchanged - fma(beta, x_b, 1 * x_a + 0 + 0) is the very fma(alpha, x, beta y) the even helper evaluates,
+// rounding for rounding, so the results are bit-identical (+7 %) - and T and S share one call with per-lane operands.
+// The Euler model's moment blocks need the two-matrix helpers (blk_right2 / blk_left2) and keep blk_even / blk_evenT
+// for the force blocks next to them.
 QMPC_HD inline void blk_right(const double* X, int ld, int oa, int ob, const double* Mt, double beta, double* dst, int ldd) {
   double m[9];
 #pragma unroll
@@ -612,37 +608,11 @@ QMPC_HD QMPC_NOINLINE void coop_rollout(const M& m, const QmpcConfig& cfg, const
   // completion, issued by lane 0) was measured in tools/probes/bulk_probe.cu: the same staging pattern runs 2.3x
   // SLOWER (1.47 ms against 0.63 ms), and in the kernel the gain stores of the backward pass would additionally
   // need a generic -> async proxy fence per knot (profiles/r02_experiments.md) - not adopted.
-#ifndef QMPC_COOP_KSTAGE_REGS
   auto stage_gain = [&](int k) {
     coop_cp_async_row(kstage + (k & 1) * kKD, gK + (size_t)k * kKD, kKD, tl, tstride);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto stage_wait = [&](int) { asm volatile("cp.async.wait_all;" ::: "memory"); };
-#else
-  // -DQMPC_COOP_KSTAGE_REGS: through registers instead of cp.async - the lane's 16-byte chunks of K_{k+1} | d_{k+1} are
-  // loaded (L2, ld.cg) right after the barrier of knot k and stored to the other half of the double buffer at the top
-  // of knot k + 1: 2 instructions per chunk where ptxas wraps every LDGSTS in three padding instructions plus address
-  // arithmetic (about 10).  Measured 3.5 ... 4.6 % SLOWER (run 17): the loads' scoreboard wait lands on the lane
-  // itself, cp.async's does not.  Not the default.
-  constexpr int kChunks = (kKD / 2 + 15) / 16;   // chunks per lane at 16 lanes per problem
-  double2 kreg[kChunks];
-  auto stage_gain = [&](int k) {
-    const double2* src = reinterpret_cast<const double2*>(gK + (size_t)k * kKD);
-#pragma unroll
-    for (int j = 0; j < kChunks; ++j) {
-      const int cidx = tl + tstride * j;
-      if (2 * cidx < kKD) kreg[j] = __ldcg(src + cidx);
-    }
-  };
-  auto stage_wait = [&](int k) {
-    double2* dst = reinterpret_cast<double2*>(kstage + (k & 1) * kKD);
-#pragma unroll
-    for (int j = 0; j < kChunks; ++j) {
-      const int cidx = tl + tstride * j;
-      if (2 * cidx < kKD) dst[cidx] = kreg[j];
-    }
-  };
-#endif
   if (mode == 1) stage_gain(0);
 #else
   (void)kstage; (void)lane_mask;
@@ -945,34 +915,26 @@ QMPC_HD inline void coop_phase_pre(CoopCtx<M, G>& c, const QmpcConfig& cfg, cons
   // ---------------- expansions, lane k <- knot k: cost gradient + attitude Hessian block (21 doubles) and
   // the dynamics blocks (NLIN doubles).  The same X is used throughout the iteration: computed once,
   // knot-parallel, reused by the stationarity test and the backward pass.
-  // -DQMPC_COOP_STAT_FUSED computes the stationarity residuals of knot k in the same pass (the lane has lx and the
-  // linearisation blocks of its knot in registers at that point, the separate pass re-reads them): measured no
-  // faster (1.687 M against 1.700 M solves/s at B = 4096, run 14) - the separate pass stays the default.
-#ifdef QMPC_COOP_STAT_FUSED
-  constexpr bool kStatFused = true;
-#else
-  constexpr bool kStatFused = false;
-#endif
+  // (Computing the stationarity residuals of knot k in this same pass - lx and the linearisation blocks are in
+  // registers here, the separate pass below re-reads them - was measured no faster: 1.687 M against 1.700 M solves/s at
+  // B = 4096, run 14.)
   COOP_PHASE {
-    double rx = 0, ru = 0;
 #pragma unroll 1
     for (int k = lane; k <= N; k += G) {
       double lx[NE], Hk[9], hphi;
-      KnotLin4 Lk = {};   // (an uninitialised block reaching the residuals at k = N made ptxas spill)
+      KnotLin4 Lk = {};
       cost_expand(m, cfg, k, X + k * NX, lx, &hphi);
       hphi_block<M>(cfg, X + k * NX, hphi, Hk);
 #pragma unroll
       for (int i = 0; i < NE; ++i) gLX[k * L::kRow + Row::lx + i] = lx[i];
 #pragma unroll
       for (int i = 0; i < 9; ++i) gLX[k * L::kRow + Row::Hphi + i] = Hk[i];
-#ifndef QMPC_COOP_TERMINAL_FROM_L2
       if (k == N) {   // the backward pass starts from these: hand them over in shared memory
 #pragma unroll
         for (int i = 0; i < NE; ++i) c.vec[L::vpv + i] = lx[i];
 #pragma unroll
         for (int i = 0; i < 9; ++i) c.vec[L::vQx + i] = Hk[i];
       }
-#endif
       if (k < N) {
         coop_linearize(m, X + k * NX, U + k * NU, X + (k + 1) * NX, hd, hh, Lk);
         double* gl = glin + k * L::kLinStride;
@@ -984,21 +946,19 @@ QMPC_HD inline void coop_phase_pre(CoopCtx<M, G>& c, const QmpcConfig& cfg, cons
           if (NLIN > 27) gl[(NLIN > 27 ? 27 : 0) + i] = Lk.Dw[i];
         }
       }
-      if (kStatFused && it > 0) coop_knot_residuals<M>(m, c.rho, N, k, hd, hh, U, DX, gmu, wr, lx, Lk, rx, ru);
     }
-    if (kStatFused && it > 0) red[lane] = rx > ru ? rx : ru;
   }
   COOP_SYNC();
 
   if (it > 0) {
-    if (!kStatFused) {
-      // ---------------- stationarity in a pass of its own
+    {
+      // ---------------- stationarity with the Riccati duals of the accepted step (DX holds y_k)
       COOP_PHASE {
         double rx = 0, ru = 0;
 #pragma unroll 1
         for (int k = lane; k <= N; k += G) {
           double lx[NE];
-          KnotLin4 Lk = {};
+          KnotLin4 Lk = {};   // (an uninitialised block reaching the residuals at k = N made ptxas spill)
 #pragma unroll
           for (int a = 0; a < NE; ++a) lx[a] = gLX[k * L::kRow + Row::lx + a];
           if (k < N) {
@@ -1143,7 +1103,6 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
 #endif
     COOP_SYNC();
   };
-#ifndef QMPC_COOP_TERMINAL_FROM_L2
   // terminal knot: its cost gradient (-> p_N) and attitude Hessian block were left in shared memory by the
   // expansions pass of this iteration (pvv, vec + vQx: `pre` and the backward pass always run in the same kernel), so
   // the row of knot N - 1 can be requested first and its L2 round trip overlaps the set-up of P_N
@@ -1158,27 +1117,6 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
     if (lane == 0) scal[0] = 0.0;
   }
   COOP_SYNC();
-#else
-  COOP_PHASE {
-#pragma unroll 1
-    for (int e = lane; e < 21; e += G) {
-      const double v = gLX[(size_t)N * L::kRow + e];
-      if (e < 12) pvv[e] = v; else row[Row::Hphi + e - 12] = v;
-    }
-    if (lane == 0) scal[0] = 0.0;
-  }
-  COOP_SYNC();
-  COOP_PHASE {
-    const int br = lane >> 2, bc = lane & 3;
-    double o[9];
-    lxx_block<M>(wq, row + Row::Hphi, br, bc, o);
-    blk_store(Pc + 36 * br + 3 * bc, 12, o);
-    blk_store_keep(gP + (size_t)N * 144 + 36 * br + 3 * bc, 12, o);
-    if (lane < 12) st_keep(gpv + N * 12 + lane, pvv[lane]);
-  }
-  COOP_SYNC();
-  stage_row(N - 1);
-#endif
 
 #pragma unroll 1
   for (int k = N - 1; k >= 0 && bp_ok; --k) {
@@ -1195,7 +1133,7 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
       const int br = lane >> 2, bc = lane & 3, rc = bc ^ M::kSwap;   // rc: role of this lane's block column
       // the two small vectors first: their load -> fma -> store chains then run under the block products' loads
 #ifndef QMPC_COOP_VEC_DIVERGENT
-      constexpr bool kUniformVec = kUniformBlk && !M::kDw;
+      constexpr bool kUniformVec = !M::kDw;
 #else
       constexpr bool kUniformVec = false;
 #endif
@@ -1249,9 +1187,9 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
         }
       }
       const double* Pr = Pc + 36 * br;
-      if (kUniformBlk) {
-        // ONE block product for all 16 lanes (see kUniformBlk): the even roles are the odd roles' product with the
-        // constant blocks I / h I and the two operands exchanged - same operations, same roundings
+      {
+        // ONE block product for all 16 lanes (see the comment above blk_right): the even roles are the odd roles'
+        // product with the constant blocks I / h I and the two operands exchanged - same operations, same roundings
         const bool odd = rc & 1;
         blk_right(Pr, 12, odd ? oA : (rc == 0 ? oP : oV), odd ? oW : (rc == 0 ? oV : oP),
                   odd ? (rc == 1 ? Aff : Afw) : c.I3, rc == 2 ? hd : (rc == 3 ? 1.0 : 0.0), Pw + 36 * br + 3 * bc, 12);
@@ -1262,15 +1200,6 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
           else if (bc == 1) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);   // Euler model: X_A Cf + X_W Dw
           else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
         }
-      } else {
-      if (rc & 1) blk_right(Pr, 12, oA, oW, rc == 1 ? Aff : Afw, rc == 1 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
-      else blk_even(Pr, 12, oP, oV, rc == 0 ? 1.0 : hd, rc == 0 ? 0.0 : 1.0, Pw + 36 * br + 3 * bc, 12);
-      if (bc < 2) {
-        if (bc == 1) {
-          if (M::kDw) blk_right2(Pr, 12, oA, oW, Cf, Dw, PM + 18 * br + 3 * bc, 6);
-          else blk_right(Pr, 12, oA, oW, Cf, hd, PM + 18 * br + 3 * bc, 6);
-        } else blk_even(Pr, 12, oP, oV, c1, hd, PM + 18 * br + 3 * bc, 6);
-      }
       }
     }
     COOP_SYNC();
@@ -1280,71 +1209,27 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
       if (lane < 12) vec[L::vQx + lane] = vec[L::vAtp + lane] + row[Row::lx + lane];
       const double* Yc = Pw + 3 * bc;
       double* Pd = Pc + 36 * br + 3 * bc;
-#ifndef QMPC_COOP_LXX_RMW
-      constexpr bool kLxxFold = kUniformBlk;
-#else
-      constexpr bool kLxxFold = false;
-#endif
-      if (kLxxFold) {
+      {   // A^T (P A) + lxx: one product for all lanes, the cost Hessian block (zero off the diagonal) folded in
         const bool odd = rr & 1;
         double lxx[9];
-        lxx_block<M>(wq, row + Row::Hphi, br, bc, lxx);   // zero off the diagonal
+        lxx_block<M>(wq, row + Row::Hphi, br, bc, lxx);
         blk_left_add(Yc, 12, odd ? oA : (rr == 0 ? oP : oV), odd ? oW : (rr == 0 ? oV : oP),
                      odd ? (rr == 1 ? Aff : Afw) : c.I3, rr == 2 ? hd : (rr == 3 ? 1.0 : 0.0), lxx, Pd, 12);
-      } else if (kUniformBlk) {
-        const bool odd = rr & 1;
-        blk_left(Yc, 12, odd ? oA : (rr == 0 ? oP : oV), odd ? oW : (rr == 0 ? oV : oP),
-                 odd ? (rr == 1 ? Aff : Afw) : c.I3, rr == 2 ? hd : (rr == 3 ? 1.0 : 0.0), Pd, 12);
-      } else {
-      if (rr & 1) blk_left(Yc, 12, oA, oW, rr == 1 ? Aff : Afw, rr == 1 ? 0.0 : 1.0, Pd, 12);
-      else blk_evenT(Yc, 12, oP, oV, rr == 0 ? 1.0 : hd, rr == 0 ? 0.0 : 1.0, Pd, 12);
       }
-      if (!kLxxFold && br == bc) {   // + lxx on the diagonal blocks (the same lane just wrote the block)
-        if (rr == 1) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) Pd[12 * i + j] += row[Row::Hphi + 3 * i + j];
+      if (lane < 12) {
+        // T = M^T (P A) on lanes 0..7 and S = M^T (P M) on lanes 8..11 with per-lane operands
+        const bool isS = lane >= 8;
+        const int r = isS ? (lane >> 1) & 1 : br, cc = isS ? (lane & 1) : bc, ldy = isS ? 6 : 12;
+        const double* Y = isS ? PM + 3 * cc : Yc;
+        double* dst = isS ? S + 18 * r + 3 * cc : T + 36 * r + 3 * cc;
+        if (!M::kDw) {
+          // ONE block product: moment rows Cf^T Y_A + h Y_W, force rows c1 Y_P + h Y_V = (h I)^T Y_V + c1 Y_P
+          blk_left(Y, ldy, r == 1 ? oA : oV, r == 1 ? oW : oP, r == 1 ? Cf : c.hI3, r == 1 ? hd : c1, dst, ldy);
         } else {
-          const int q0 = M::qoff(br);
-          Pd[0] += wq[q0]; Pd[13] += wq[q0 + 1]; Pd[26] += wq[q0 + 2];
-        }
-      }
-      if (kUniformBlk && !M::kDw) {
-        // T = M^T (P A) on lanes 0..7 and S = M^T (P M) on lanes 8..11 as ONE block product with per-lane operands:
-        // moment rows Cf^T Y_A + h Y_W, force rows c1 Y_P + h Y_V = (h I)^T Y_V + c1 Y_P
-        if (lane < 12) {
-          const bool isS = lane >= 8;
-          const int r = isS ? (lane >> 1) & 1 : br, cc = isS ? (lane & 1) : bc, ldy = isS ? 6 : 12;
-          blk_left(isS ? PM + 3 * cc : Yc, ldy, r == 1 ? oA : oV, r == 1 ? oW : oP, r == 1 ? Cf : c.hI3, r == 1 ? hd : c1,
-                   isS ? S + 18 * r + 3 * cc : T + 36 * r + 3 * cc, ldy);
-        }
-      } else if (kUniformBlk) {
-        // Euler model: the moment rows need the two-matrix product (Cf^T Y_A + Dw^T Y_W), so T and S share one call
-        // per row type instead of one call each
-        if (lane < 12) {
-          const bool isS = lane >= 8;
-          const int r = isS ? (lane >> 1) & 1 : br, cc = isS ? (lane & 1) : bc, ldy = isS ? 6 : 12;
-          const double* Y = isS ? PM + 3 * cc : Yc;
-          double* dst = isS ? S + 18 * r + 3 * cc : T + 36 * r + 3 * cc;
+          // Euler model: the moment rows need the two-matrix product (Cf^T Y_A + Dw^T Y_W): one call per row type
           if (r == 1) blk_left2(Y, ldy, oA, oW, Cf, Dw, dst, ldy);
           else blk_evenT(Y, ldy, oP, oV, c1, hd, dst, ldy);
         }
-      } else {
-      if (br < 2) {
-        if (br == 1) {
-          if (M::kDw) blk_left2(Yc, 12, oA, oW, Cf, Dw, T + 36 * br + 3 * bc, 12);
-          else blk_left(Yc, 12, oA, oW, Cf, hd, T + 36 * br + 3 * bc, 12);
-        } else blk_evenT(Yc, 12, oP, oV, c1, hd, T + 36 * br + 3 * bc, 12);
-      }
-      if (lane >= 8 && lane < 12) {
-        const int r = (lane >> 1) & 1, cc = lane & 1;
-        const double* Ym = PM + 3 * cc;
-        if (r == 1) {
-          if (M::kDw) blk_left2(Ym, 6, oA, oW, Cf, Dw, S + 18 * r + 3 * cc, 6);
-          else blk_left(Ym, 6, oA, oW, Cf, hd, S + 18 * r + 3 * cc, 6);
-        } else blk_evenT(Ym, 6, oP, oV, c1, hd, S + 18 * r + 3 * cc, 6);
-      }
       }
     }
     COOP_SYNC();
@@ -1428,39 +1313,23 @@ QMPC_HD inline void coop_phase_backward(CoopCtx<M, G>& c, COOP_ARGS_DECL) {
         rd[j] = rdg;
 #pragma unroll
         for (int i = j + 1; i < NU; ++i) {
-#ifndef QMPC_COOP_CHOL_RDG_SCALE
           // first guess and correction with r0 itself (within an ulp of 1 / dg): the correction step returns the
           // correctly rounded a / dg from either reciprocal, and the pivot chain no longer waits for rdg
           const double a = Lr[QMPC_TRI(i, j)], q = a * r0;
           Lr[QMPC_TRI(i, j)] = fma(fma(-q, dg, a), r0, q);   // a / dg
-#else
-          const double a = Lr[QMPC_TRI(i, j)], q = a * rdg;
-          Lr[QMPC_TRI(i, j)] = fma(fma(-q, dg, a), rdg, q);   // a / dg
-#endif
         }
 #endif
 #pragma unroll
         for (int i = j + 1; i < NU; ++i)
 #pragma unroll
           for (int l = j + 1; l <= i; ++l) Lr[QMPC_TRI(i, l)] -= Lr[QMPC_TRI(i, j)] * Lr[QMPC_TRI(l, j)];
-#ifndef QMPC_COOP_CHOL_SEPARATE_FWD
         // forward substitution riding along: column j of L is final, so y_j and its updates can go now (same
         // operations, same order per entry as a separate loop: bit-identical; +0.3 % measured)
         QMPC_DIVD(rhs[j], j);
 #pragma unroll
         for (int l = j + 1; l < NU; ++l) rhs[l] -= Lr[QMPC_TRI(l, j)] * rhs[j];
-#endif
       }
       if (!ok) bp_ok = false;
-#ifdef QMPC_COOP_CHOL_SEPARATE_FWD
-      // forward substitution, column oriented: after y_i is final every remaining entry updates independently
-#pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        QMPC_DIVD(rhs[i], i);
-#pragma unroll
-        for (int l = i + 1; l < NU; ++l) rhs[l] -= Lr[QMPC_TRI(l, i)] * rhs[i];
-      }
-#endif
       if (ok && lane <= 12) {
         if (cix < 12) {
 #pragma unroll
@@ -1585,7 +1454,6 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
   if (acc_j < 0) { c.status = QMPC_STATUS_LINESEARCH_FAILED; return; }
   // ---------------- accepted step: the winning lane's trial trajectory is already in the scratch.
   const int acc_lane = acc_j % NCAND;
-#ifndef QMPC_COOP_ACCEPT_OLD
   // (1) lane k <- knot k: dx_k = x_new (-) x_old into the shared dx buffer; (2) Riccati duals y_k = P_k dx_k + p_k
   // with lane a <- ROW a of every knot: the 12 active lanes read 12 consecutive rows of P_k (1152 contiguous
   // bytes per knot, 16-byte loads), four knots' loads in flight before the first FMA - three L2 round trips for
@@ -1603,14 +1471,11 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
       state_diff<M>(xn, X + k * NX, dx);
 #pragma unroll
       for (int i = 0; i < NE; ++i) dxs[k * NE + i] = dx[i];
-#ifndef QMPC_COOP_ACCEPT_COPY_LAST
       // X <- accepted states right here: the lane holds its knot's new state in registers and nobody reads the old
       // one again (the copy loop at the end took one L2 round trip per element: `unroll 1`, load -> store)
 #pragma unroll
       for (int i = 0; i < NX; ++i) X[k * NX + i] = xn[i];
-#endif
     }
-#ifndef QMPC_COOP_ACCEPT_COPY_LAST
     // U <- accepted inputs, four independent loads in flight per lane
 #pragma unroll 1
     for (int e0 = 0; e0 < N * NU; e0 += 4 * G) {
@@ -1626,7 +1491,6 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
         if (e < N * NU) U[e] = t[q];
       }
     }
-#endif
   }
   COOP_SYNC();
   COOP_PHASE {
@@ -1662,36 +1526,6 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
     }
   }
   COOP_SYNC();
-#else
-  COOP_PHASE {
-#pragma unroll 1
-    for (int k = lane; k <= N; k += G) {
-      double xn[NX], dx[NE];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) xn[i] = ld_stream(gTX + (size_t)(k * NX + i) * NCAND + acc_lane);
-      state_diff<M>(xn, X + k * NX, dx);
-      const double* Pk = c.gP + (size_t)k * 144;
-#pragma unroll 3
-      for (int a = 0; a < NE; ++a) {
-        double t = ld_keep(c.gpv + k * 12 + a);
-#pragma unroll
-        for (int b = 0; b < NE; ++b) t += ld_keep(Pk + 12 * a + b) * dx[b];
-        DX[k * NE + a] = t;
-      }
-    }
-  }
-  COOP_SYNC();
-#endif
-#if defined(QMPC_COOP_ACCEPT_OLD) || defined(QMPC_COOP_ACCEPT_COPY_LAST)
-  // ... then X, U <- accepted trajectory (cooperative strided copy)
-  COOP_PHASE {
-#pragma unroll 1
-    for (int e = lane; e < (N + 1) * NX; e += G) X[e] = ld_stream(gTX + (size_t)e * NCAND + acc_lane);
-#pragma unroll 1
-    for (int e = lane; e < N * NU; e += G) U[e] = ld_stream(gTU + (size_t)e * NCAND + acc_lane);
-  }
-  COOP_SYNC();
-#endif
 #if defined(__CUDA_ARCH__) && !defined(QMPC_COOP_NO_DISCARD)
   // The 16 trial trajectories (33.7 KB per slot at N = 10) are dead from here on, and they were 78 % of the DRAM
   // traffic of round 1's kernel (769 kB per solve against 536 B algorithmic): dirty L2 lines written back to HBM when
