@@ -1422,6 +1422,8 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
   double *X = c.X, *U = c.U, *red = c.red, *DX = c.DX, *gTX = c.gTX, *gTU = c.gTU;
   int acc_j = -1;
   double phin = 0, violn = 0;
+  // (prefetch.global.L2 of the P_k rows the accepted step will read - issued here, or right after the roll-out - was
+  // measured 0.5 ... 0.7 % slower, run 23: those rows are not what the accepted step waits for)
 #pragma unroll 1
   for (int round = 0; round * G < o.ls_iters_max && acc_j < 0; ++round) {
     COOP_PHASE {
