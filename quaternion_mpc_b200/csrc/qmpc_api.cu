@@ -272,6 +272,9 @@ extern "C" int qmpc_create_ex(const QmpcConfig* cfg, int32_t max_batch, int32_t 
     h->ws_bytes = ws_elems(*cfg, h->kernel) * h->stride * sizeof(double);
   }
   CU(cudaMalloc(&h->ws, h->ws_bytes));
+  // once, at creation: the 16-byte cp.async copies of the knot rows / linearisation blocks also move the padding double
+  // at the end of an odd-length row, which no phase ever writes (compute-sanitizer initcheck reports exactly those reads)
+  CU(cudaMemset(h->ws, 0, h->ws_bytes));
   size_t in_sz = cfg->model == QMPC_MODEL_EULER_CONVEX ? sizeof(QmpcConvexProblem) : sizeof(QmpcProblem);
   CU(cudaMalloc(&h->d_in, in_sz * (size_t)max_batch));
   CU(cudaMalloc(&h->d_out, sizeof(QmpcResult) * (size_t)max_batch));
