@@ -213,6 +213,8 @@ static void soc_project(const double* z, int p, double* out, double* J) {
     }
   }
 }
+/* exported for the unit test of the projection (tests/test_oracle_kats.py) */
+void altro_ref_soc_project(const double* z, int p, double* out, double* J) { soc_project(z, p, out, J); }
 /* distance of c from the cone, largest component of c - Pi_K(c) */
 static double soc_violation(const double* c, int p) {
   double pr[16], v = 0;

@@ -76,6 +76,8 @@ typedef struct AltroRefStats {
 } AltroRefStats;
 
 void altro_ref_default_options(AltroRefOptions* o);
+/* projection onto the second-order cone {(v, s): |v| <= s} (scalar last) and, if J != NULL, its p x p Jacobian (row-major) */
+void altro_ref_soc_project(const double* z, int p, double* out, double* J);
 
 /* U (N*m): in = initial guess (SetInput), out = solution.  X ((N+1)*n): out = state trajectory.
  * Returns 0, or -1 on bad dimensions. */

@@ -217,6 +217,18 @@ def kat_double_integrator(variant, penalty_initial=0.0, penalty_scaling=0.0, ite
     return X, U, st
 
 
+def soc_project(z):
+    """Projection of z = (v, s) onto the second-order cone |v| <= s and its Jacobian (oracle/altro_ref.c)."""
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    p = z.shape[0]
+    out, J = np.zeros(p), np.zeros((p, p))
+    fn = lib().altro_ref_soc_project
+    fn.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    fn.restype = None
+    fn(_dp(z), p, _dp(out), _dp(J))
+    return out, J
+
+
 def kat_pendulum(variant, cubic=False):
     N = 50 if variant == 0 else 20
     X, U, st = np.zeros((N + 1, 2)), np.zeros((N, 1)), Stats()

@@ -103,6 +103,32 @@ def test_double_integrator_iteration_counts_cubic_linesearch(oracle):
     assert np.allclose(U[0], -1.0, atol=1e-4)
 
 
+def test_second_order_cone_projection_and_jacobian(oracle):
+    """The conic AL of the SOC test stands on this projection: inside the cone it is the identity, inside the polar
+    cone it is 0, elsewhere it lands on the boundary, is idempotent, leaves a residual orthogonal to the image
+    (Moreau), and its Jacobian matches central differences and is symmetric."""
+    rng = np.random.default_rng(0)
+    for z in ([0.3, -0.2, 1.0], [0.3, -0.2, -1.0], [3.0, 4.0, 1.0], [3.0, 4.0, -1.0], [1e-3, 0.0, 0.0]):
+        z = np.array(z)
+        pz, J = oracle.soc_project(z)
+        a, s = np.linalg.norm(z[:-1]), z[-1]
+        if a <= s:
+            assert np.array_equal(pz, z) and np.array_equal(J, np.eye(3))
+        elif a <= -s:
+            assert not pz.any() and not J.any()
+        else:
+            assert abs(np.linalg.norm(pz[:-1]) - pz[-1]) < 1e-14              # on the boundary
+            assert abs(pz @ (z - pz)) < 1e-13                                  # Moreau: residual orthogonal to the image
+            assert np.linalg.norm(oracle.soc_project(pz)[0] - pz) < 1e-14     # idempotent
+    for _ in range(20):
+        z = rng.normal(size=4)
+        z[-1] *= 0.3                                                           # mostly outside both cones
+        pz, J = oracle.soc_project(z)
+        h = 1e-6
+        Jn = np.stack([(oracle.soc_project(z + h * e)[0] - oracle.soc_project(z - h * e)[0]) / (2 * h) for e in np.eye(4)], 1)
+        assert np.abs(J - Jn).max() < 1e-8 and np.abs(J - J.T).max() < 1e-15
+
+
 @pytest.mark.parametrize("cubic", [False, True])
 def test_double_integrator_second_order_cone_control_bound(oracle, cubic):
     # TestDoubleIntegrator.cpp:377-491 (ConstraintType::SECOND_ORDER_CONE, penalty_initial 1, scaling 100): Success,
