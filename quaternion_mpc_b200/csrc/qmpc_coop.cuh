@@ -1464,9 +1464,11 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
   // (Dealing the 12 (N + 1) rows over all 16 lanes, two batches with the first one's loads issued before step (1),
   // measured 1.4 % SLOWER, run 15: not adopted.)
   double* dxs = c.dxs;
+  // after the LAST iteration only the inputs are read again (result, warm-start buffer): no dx, no new X, no duals
+  const bool more = it + 1 < o.iterations_max;
   COOP_PHASE {
 #pragma unroll 1
-    for (int k = lane; k <= N; k += G) {
+    for (int k = lane; more && k <= N; k += G) {
       double xn[NX], dx[NE];
 #pragma unroll
       for (int i = 0; i < NX; ++i) xn[i] = ld_stream(gTX + (size_t)(k * NX + i) * NCAND + acc_lane);
@@ -1496,7 +1498,8 @@ QMPC_HD inline void coop_phase_forward(CoopCtx<M, G>& c, const QmpcConfig& cfg, 
   }
   COOP_SYNC();
   COOP_PHASE {
-    if (lane < NE) {
+    // (the duals are only read by the NEXT iteration's stationarity test)
+    if (lane < NE && more) {
       const int a = lane;
 #ifndef QMPC_COOP_ACCEPT_KB
 #define QMPC_COOP_ACCEPT_KB 4
